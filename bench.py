@@ -1,0 +1,445 @@
+#!/usr/bin/env python
+"""bench.py -- 3D U-Net training throughput (voxels/s, fwd + loss + bwd + optimizer) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
+  value  : whole-job voxels/s with the batch resident in HBM (max-over-ranks device time)
+  e2e    : the same step fed from pinned HOST buffers each iteration (H2D of image + targets inside the
+           timed region, D2H of the loss components), through the public TrainStep API
+  roofline / cpu_baseline : the dominant kernel against the measured B200 peaks; the CPU oracle
+           (a port of the reference's PyTorch path, oracle/unet_oracle.py) timed on the host cores
+--impl reference times that CPU port alone (the reference itself is pure Python and cannot travel to
+the GPU box; the port is pinned to it by tests/test_oracle_pinned.py).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "3D U-Net train voxels/sec (fwd+bwd, 128^3)"
+UNIT = "voxels/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default="UNetSP")
+    ap.add_argument("--batch", type=int, default=4)
+    ap.add_argument("--size", type=int, default=128)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    return ap.parse_args()
+
+
+HANDLER = {"UNetSP": "double", "UNetDO": "double", "UNetSPSmall": "double", "UNet4_2IC": "single",
+           "recAE_v2_fixed": "single", "UNet": "single"}
+
+
+def workload_name(a):
+    return ("%s + %s loss (dice_lambda=1, ce_lambda=1) + Adam(amsgrad) lr 1e-4, batch %d/GPU, %dx%d^3 synthetic "
+            "skull CT" % (a.model, "FlapRecWithShapePriorDoubleOut" if HANDLER[a.model] == "double" else "ProblemHandler",
+                          a.batch, 2 if a.model in ("UNetSP", "UNetSPSmall", "UNet4_2IC") else 1, a.size))
+
+
+def in_channels(model):
+    return 2 if model in ("UNetSP", "UNetSPSmall", "UNet4_2IC", "UNet4b2i3o", "UNet5b2i3o") else 1
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_step_time(model, batch, size, steps, warmup, threads=None):
+    """The CPU oracle (port of the reference's PyTorch path): fwd + loss + bwd + Adam(amsgrad), fp32,
+    checkpoint semantics as shipped, anomaly mode off.  Returns (seconds per step, threads)."""
+    import torch
+    from oracle import unet_oracle as O
+    if threads:
+        torch.set_num_threads(threads)
+    cfg = O.PRESETS[model]
+    sd = O.build_state_dict(cfg, seed=0)
+    names = [k for k in sd if not k.endswith(("running_mean", "running_var", "num_batches_tracked"))]
+    for k in names:
+        sd[k].requires_grad_()
+    opt = torch.optim.Adam([sd[k] for k in names], lr=1e-4, amsgrad=True)
+    x, (sk_t, fl_t) = O.make_training_batch(batch, cfg.input_channels, size, seed=1234)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        out = O.unet_forward(sd, x.clone().requires_grad_(), cfg, training=True)
+        if HANDLER[model] == "double":
+            loss, _ = O.loss_double_output(out, (sk_t, fl_t), 1.0, 1.0)
+        else:
+            loss, _ = O.loss_single_output(out, sk_t, 1.0, 1.0)
+        loss.backward()
+        opt.step()
+        for k in names:
+            sd[k].grad = None
+        float(loss)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    return sum(times) / len(times), torch.get_num_threads()
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    threads = os.cpu_count() or 1
+    size, batch = a.size, 1                       # bounded sample: one volume of the batch per step
+    sec, used = cpu_reference_step_time(a.model, batch, size, a.steps, a.warmup, threads)
+    value = batch * size ** 3 / sec
+    sample = "batch %d of the %d-volume batch, %d^3, fp32, %d steps after %d warm-up" % (batch, a.batch, size, a.steps, a.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "CPU port of the reference's PyTorch path (oracle/unet_oracle.py, pinned to the reference by golden "
+                "vectors); the reference itself is pure Python and is not present on the GPU box",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ roofline
+class CallProfiler:
+    """CUDA-event timing of every C-ABI call on the launching stream (resolved after the final sync)."""
+
+    def __init__(self, torch):
+        self.torch = torch
+        self.records = []
+
+    def wrap(self, lib_mod):
+        orig = lib_mod.call
+        prof = self
+
+        def timed(name, *args):
+            s = prof.torch.cuda.Event(enable_timing=True)
+            e = prof.torch.cuda.Event(enable_timing=True)
+            s.record()
+            orig(name, *args)
+            e.record()
+            prof.records.append((name, args, s, e))
+        return orig, timed
+
+    def summarize(self, esize):
+        agg = {}
+        for name, args, s, e in self.records:
+            ms = s.elapsed_time(e)
+            key, flops, nbytes = describe(name, args, esize)
+            a = agg.setdefault(key, [0.0, 0, flops, nbytes])
+            a[0] += ms
+            a[1] += 1
+        return agg
+
+
+def describe(name, args, esize):
+    """(key, algorithmic FLOPs, algorithmic bytes) of one call -- un-padded channels, each tensor crossing
+    the kernel boundary once."""
+    try:
+        if name in ("ctu_conv3d_fprop", "ctu_conv3d_wgrad"):
+            ca, ns = args[2], args[3]
+            cin = sum(ca[i] for i in range(ns))
+            cout, k, n, d, h, w = args[7], args[8], args[9], args[10], args[11], args[12]
+            vox = n * d * h * w
+            fl = 2.0 * vox * cin * cout * k ** 3
+            by = esize * vox * (cin + cout) + 4.0 * cin * cout * k ** 3
+            return "%s k%d %d->%d @%dx%dx%dx%d" % (name, k, cin, cout, n, d, h, w), fl, by
+        if name in ("ctu_convt2_fprop", "ctu_convt2_wgrad"):
+            ca, ns = args[2], args[3]
+            cin = sum(ca[i] for i in range(ns))
+            cout, n, d, h, w = args[7], args[8], args[9], args[10], args[11]
+            vox = n * d * h * w
+            return ("%s %d->%d @%dx%dx%dx%d" % (name, cin, cout, n, d, h, w), 2.0 * vox * cin * cout * 8,
+                    esize * vox * (cin + 8 * cout) + 4.0 * cin * cout * 8)
+        if name == "ctu_convt2_dgrad":
+            cout, cs, n, d, h, w = args[4], args[5], args[6], args[7], args[8], args[9]
+            vox = n * d * h * w
+            return ("%s %d->%d @%dx%dx%dx%d" % (name, cout, cs, n, d, h, w), 2.0 * vox * cs * cout * 8,
+                    esize * vox * (cs + 8 * cout))
+        if name == "ctu_bn_stats":
+            c, n, sp = args[2], args[3], args[4]
+            return "%s c%d @%dx%d" % (name, c, n, sp), 0.0, esize * c * n * sp
+        if name == "ctu_bn_relu_fwd":
+            c, n, d, h, w = args[5], args[6], args[7], args[8], args[9]
+            pooled = args[4] is not None
+            return ("%s c%d @%dx%dx%dx%d%s" % (name, c, n, d, h, w, " +pool" if pooled else ""), 0.0,
+                    esize * c * n * d * h * w * (2 + (0.125 if pooled else 0)))
+        if name in ("ctu_bn_relu_bwd_reduce", "ctu_bn_relu_bwd_apply"):
+            off = 6 if name.endswith("reduce") else 11
+            c, n, d, h, w = args[off], args[off + 1], args[off + 2], args[off + 3], args[off + 4]
+            dA, dP = (args[3], args[4]) if name.endswith("reduce") else (args[4], args[5])
+            tensors = 1 + (1 if dA else 0) + (0.125 if dP else 0) + (1 if name.endswith("apply") else 0)
+            return "%s c%d @%dx%dx%dx%d" % (name, c, n, d, h, w), 0.0, esize * c * n * d * h * w * tensors
+        if name in ("ctu_head_fwd", "ctu_head_bwd"):
+            ca, ns = args[2], args[3]
+            cin = sum(ca[i] for i in range(ns))
+            n, sp = (args[10], args[11]) if name == "ctu_head_fwd" else (args[13], args[14])
+            outs = 4 if (args[7] & 12) else args[6]
+            by = n * sp * (esize * cin * (1 if name == "ctu_head_fwd" else 2) + 4 * outs)
+            return "%s %d->%d @%dx%d" % (name, cin, args[6], n, sp), 2.0 * n * sp * cin * args[6], by
+        if name in ("ctu_dice_ce_fwd", "ctu_dice_ce_bwd"):
+            b, c, sp = args[2], args[3], args[4]
+            return "%s @%dx%dx%d" % (name, b, c, sp), 0.0, 4.0 * b * c * sp * (2 if name.endswith("fwd") else 3)
+        if name in ("ctu_pack_ncdhw", "ctu_unpack_ncdhw"):
+            n, c, sp = args[3], args[4], args[5]
+            return "%s c%d @%dx%d" % (name, c, n, sp), 0.0, (4.0 + esize) * n * c * sp
+    except Exception:
+        pass
+    return name, 0.0, 0.0
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        p = json.load(open(path))
+        return {"hbm": float(p["hbm_gbs"]), "tensor": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                "source": "measured (MEASURED_PEAKS.json; sustained bf16 figure: the kernel is timed inside a long step)"}
+    return {"hbm": 6650.0, "tensor": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# ------------------------------------------------------------------------------------------ B200 arm
+def run_b200_arm(a):
+    import torch
+    import torch.distributed as dist
+    import ctunet_b200 as C
+    from ctunet_b200 import _lib
+    from ctunet_b200.parallel import GradSync
+    from ctunet_b200.synthetic import make_training_batch
+    from ctunet_b200.trainer import TrainStep
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("NCCL_IB_DISABLE", "1")       # NVLink / NVSwitch only
+        os.environ.setdefault("NCCL_P2P_LEVEL", "NVL")
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+
+    C.set_compute_dtype(a.dtype)
+    torch.manual_seed(0)
+    net = getattr(C, a.model)().to(dev)
+    sync = GradSync(net) if world > 1 else None
+    step = TrainStep(net, HANDLER[a.model], 1.0, 1.0, lr=1e-4, grad_sync=sync)
+    cin = in_channels(a.model)
+    img, (sk_t, fl_t) = make_training_batch(a.batch, cin, a.size, seed=1234 + 1000 * rank, device=dev)
+    target = (sk_t, fl_t) if HANDLER[a.model] == "double" else sk_t
+    host = [t.cpu().pin_memory() for t in ((img, sk_t, fl_t) if HANDLER[a.model] == "double" else (img, sk_t))]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host)
+    # L2 hygiene: a step streams several GB of activations (>> 126 MB L2) between consecutive uses of any buffer
+    flush_note = "inputs+activations per step (GBs) exceed the 126 MB L2; no explicit flush"
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(steps):
+            fn()
+        e.record()
+        barrier()
+        ms = torch.tensor([s.elapsed_time(e)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps
+
+    # ---- device-resident steps (value) with per-call events for the roofline -------------------
+    def resident():
+        step(img, target)
+
+    for _ in range(max(a.warmup, 3)):
+        resident()
+    prof = CallProfiler(torch)
+    orig, timed_call = prof.wrap(_lib)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = _lib.launches
+    import ctunet_b200.engine as E
+    import ctunet_b200.losses as LS
+    E.call = LS.call = timed_call
+    try:
+        ms_resident = timed(resident, a.steps)
+    finally:
+        E.call = LS.call = orig
+    launches = _lib.launches - l0
+    clk = clocks.stop() if rank == 0 else None
+
+    # ---- end-to-end steps: pinned host -> device every iteration, loss read back ----------------
+    copy_stream = torch.cuda.Stream(device=dev)
+    dbuf = [[torch.empty_like(t, device=dev) for t in host] for _ in range(2)]
+    state = {"i": 0, "ready": None}
+
+    def prefetch(slot):
+        with torch.cuda.stream(copy_stream):
+            for dst, src in zip(dbuf[slot], host):
+                dst.copy_(src, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return ev
+
+    d2h_bytes = 0
+
+    def e2e_step():
+        nonlocal d2h_bytes
+        slot = state["i"] & 1
+        if state["ready"] is None:
+            state["ready"] = prefetch(slot)
+        torch.cuda.current_stream().wait_event(state["ready"])
+        bufs = dbuf[slot]
+        copy_stream.wait_stream(torch.cuda.current_stream())      # the other slot's consumer has been enqueued
+        state["ready"] = prefetch(slot ^ 1)                        # overlap next batch's H2D with this step
+        comps = step(bufs[0], (bufs[1], bufs[2]) if len(bufs) == 3 else bufs[1])
+        vals = comps.tolist()                                      # the D2H of the step's result (one sync)
+        d2h_bytes = 4 * len(vals)
+        state["i"] += 1
+        return vals
+
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, a.steps)
+
+    vox_per_step = a.batch * a.size ** 3 * world
+    value = vox_per_step / (ms_resident * 1e-3)
+    e2e_value = vox_per_step / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ----------------------------------------------------------
+    esize = 2 if a.dtype == "bf16" else 4
+    agg = prof.summarize(esize)
+    total_ms = sum(v[0] for v in agg.values())
+    ranked = sorted(agg.items(), key=lambda kv: -kv[1][0])
+    peaks = load_peaks()
+    roof = None
+    for key, (ms, cnt, fl, by) in ranked:
+        if fl == 0 and by == 0:
+            continue
+        avg_s = ms / cnt * 1e-3
+        t_tc, t_hbm = fl / (peaks["tensor"] * 1e12), by / (peaks["hbm"] * 1e9)
+        if fl > 0 and t_tc >= t_hbm:
+            roof = {"bound": "tensor", "achieved": fl / avg_s / 1e12, "peak": peaks["tensor"], "unit": "TFLOP/s"}
+        else:
+            roof = {"bound": "hbm", "achieved": by / avg_s / 1e9, "peak": peaks["hbm"], "unit": "GB/s"}
+        roof["frac"] = roof["achieved"] / roof["peak"]
+        roof["traffic"] = None
+        roof["kernel"] = key
+        roof["avg_launch_ms"] = ms / cnt
+        roof["launches_per_step"] = cnt / a.steps
+        roof["share_of_step"] = ms / total_ms
+        roof["peak_source"] = peaks["source"]
+        break
+    top = [{"kernel": k, "ms_per_step": v[0] / a.steps, "share": v[0] / total_ms} for k, v in ranked[:8]]
+
+    cpu = None
+    if world == 1 and not a.no_cpu_baseline:
+        cs, cb = 64, 1
+        sec, used = cpu_reference_step_time(a.model, cb, cs, steps=3, warmup=1, threads=os.cpu_count())
+        cpu = {"value": cb * cs ** 3 / sec, "unit": UNIT, "cores": used, "kind": "port",
+               "sample": "batch %d x %d^3 (BASELINE config 0 shape), fp32, 3 steps after 1 warm-up, %.2f s/step" % (cb, cs, sec)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+        "ms_per_step": ms_resident, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": a.dtype, "data": "synthetic",
+        "config": {"workload": workload_name(a), "global_batch": a.batch * world, "parallelism": "dp%d" % world,
+                   "l2": flush_note, "conv_path": "tcgen05" if _lib.load().ctu_has_tensor_path() else "cuda-core"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": d2h_bytes},
+        "gpu_launches": launches,
+        "gpu_launches_note": "C-ABI entry points called in the timed region (each enqueues >= 1 kernel of this library)",
+        "clocks": clk,
+        "roofline": roof,
+        "cpu_baseline": cpu,
+        "top_kernels": top,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_b200_arm(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,113 @@
+"""ctypes binding of the C ABI declared in include/ctunet_b200.h.
+
+The shared library is built in-tree (``ctunet_b200/libctunet_b200.so``) by ``__graft_entry__.build()``
+or ``make -C ctunet_b200/csrc``.  There is no CPU fallback: if the library is missing, or a call
+fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_float, c_int, c_longlong, c_void_p
+
+import torch  # noqa: F401  (loads libcudart / libcuda into the process before our library)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libctunet_b200.so")
+
+CTU_F32, CTU_BF16 = 0, 1
+HEAD_SOFTMAX, HEAD_SIGMOID, HEAD_SP, HEAD_SP_SOFTMAX = 1, 2, 4, 8
+
+P = c_void_p
+I = c_int
+LL = c_longlong
+D = c_double
+F = c_float
+
+# name -> (restype, argtypes); must list every function of include/ctunet_b200.h
+SIGNATURES = {
+    "ctu_last_error": (c_char_p, []),
+    "ctu_version": (I, []),
+    "ctu_has_tensor_path": (I, []),
+    "ctu_pack_ncdhw": (I, [P, P, I, I, I, LL, P]),
+    "ctu_unpack_ncdhw": (I, [P, P, I, I, I, LL, P]),
+    "ctu_conv_wpack_floats": (LL, [I, I, I, P]),
+    "ctu_conv_pack_weight": (I, [P, P, I, I, I, P, P]),
+    "ctu_conv_wpack_dgrad_floats": (LL, [I, I, I]),
+    "ctu_conv_pack_weight_dgrad": (I, [P, P, I, I, I, P, I, P]),
+    "ctu_conv_unpack_wgrad": (I, [P, P, I, I, I, P, P]),
+    "ctu_conv3d_fprop": (I, [I, P, P, I, P, P, P, I, I, I, I, I, I, I, P]),
+    "ctu_conv3d_wgrad": (I, [I, P, P, I, P, P, P, I, I, I, I, I, I, I, P]),
+    "ctu_convt_wpack_floats": (LL, [I, I, P]),
+    "ctu_convt_pack_weight": (I, [P, P, I, I, P, P]),
+    "ctu_convt_wpack_dgrad_floats": (LL, [I, I]),
+    "ctu_convt_pack_weight_dgrad": (I, [P, P, I, I, P, I, P]),
+    "ctu_convt_unpack_wgrad": (I, [P, P, I, I, P, P]),
+    "ctu_convt2_fprop": (I, [I, P, P, I, P, P, P, I, I, I, I, I, P]),
+    "ctu_convt2_dgrad": (I, [I, P, P, P, I, I, I, I, I, I, P]),
+    "ctu_convt2_wgrad": (I, [I, P, P, I, P, P, P, I, I, I, I, I, P]),
+    "ctu_bn_stats": (I, [I, P, I, I, LL, P, P]),
+    "ctu_bn_finalize": (I, [P, D, P, P, P, P, P, F, F, I, I, I, P, P]),
+    "ctu_bn_running_update": (I, [P, D, P, P, P, F, I, I, P]),
+    "ctu_bn_relu_fwd": (I, [I, P, P, P, P, I, I, I, I, I, P]),
+    "ctu_bn_relu_bwd_reduce": (I, [I, P, P, P, P, P, I, I, I, I, I, P]),
+    "ctu_bn_relu_bwd_apply": (I, [I, P, P, P, P, P, P, D, P, P, P, I, I, I, I, I, P]),
+    "ctu_head_fwd": (I, [I, P, P, I, P, P, I, I, P, P, I, LL, P]),
+    "ctu_head_bwd": (I, [I, P, P, I, P, P, I, I, P, P, P, P, P, I, LL, P]),
+    "ctu_dice_ce_fwd": (I, [P, P, I, I, LL, I, I, P, P, P]),
+    "ctu_dice_ce_bwd": (I, [P, P, I, I, LL, I, I, P, P, P, P]),
+    "ctu_argmax_channels": (I, [P, P, I, I, LL, P]),
+    "ctu_count_nonzero_u8": (I, [P, LL, P, P]),
+    "ctu_kth_nonzero_u8": (I, [P, I, I, I, LL, P, P, P]),
+    "ctu_flap_mask_u8": (I, [P, P, P, I, I, I, P, D, I, P]),
+    "ctu_hu_window": (I, [P, P, LL, F, F, P]),
+    "ctu_hu_threshold": (I, [P, P, LL, I, P]),
+    "ctu_resample_nearest_f32": (I, [P, P, I, I, I, I, I, I, P]),
+    "ctu_resample_nearest_u8": (I, [P, P, I, I, I, I, I, I, P]),
+    "ctu_resample_nearest_index": (I, [P, I, I, P]),
+    "ctu_resample_trilinear_f32": (I, [P, P, I, I, I, I, I, I, P]),
+}
+
+_lib = None
+launches = 0   # number of library entry points that enqueued GPU work (bench.py reports it)
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(
+                "ctunet_b200: %s is missing -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU or PyTorch fallback for the hot path)" % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)      # AttributeError if the build is stale
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def last_error() -> str:
+    return load().ctu_last_error().decode("utf-8", "replace")
+
+
+def call(name: str, *args):
+    """Invoke a status-returning entry point; raises RuntimeError on failure."""
+    global launches
+    rc = getattr(load(), name)(*args)
+    if rc != 0:
+        raise RuntimeError("%s failed (%d): %s" % (name, rc, last_error()))
+    launches += 1
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def int_array(values):
+    return (c_int * len(values))(*values)
+
+
+def ptr_array(values):
+    return (c_void_p * len(values))(*values)

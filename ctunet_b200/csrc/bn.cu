@@ -1,0 +1,412 @@
+// BatchNorm3d (+ ReLU, + MaxPool3d(2,2)) forward / backward on the blocked layout.
+// Reference: nn.BatchNorm3d + nn.ReLU(True) at ctunet/pytorch/models.py:27-28,31-32,39-40,43-44,
+// nn.MaxPool3d(2,2) at models.py:190-191,233 (indices discarded).  HBM-bound glue: every thread
+// moves whole 16/32-byte channel groups, statistics are reduced with warp shuffles.
+#include "common.cuh"
+
+namespace ctu {
+
+constexpr int kBnThreads = 256;
+constexpr int kStatVoxPerThread = 32;
+
+// Block-level reduction of NV per-thread values followed by one double atomic per value.
+template <int NV>
+__device__ __forceinline__ void block_atomic_add(const float (&vals)[NV], double* dst, int stride, int cvalid) {
+    __shared__ float red[kBnThreads / 32][NV];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        float s = warp_sum(vals[i]);
+        if (lane == 0) red[warp][i] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double s = 0.0;
+#pragma unroll
+        for (int wq = 0; wq < kBnThreads / 32; ++wq) s += (double)red[wq][threadIdx.x];
+        // value i -> channel (i % 8), quantity (i / 8)
+        const int ch = threadIdx.x & 7, q = threadIdx.x >> 3;
+        if (ch < cvalid) atomicAdd(dst + (long long)q * stride + ch, s);
+    }
+    __syncthreads();
+}
+
+// sums[0*cpad + ch] = sum, sums[1*cpad + ch] = sum of squares.  grid = (chunks, cb, n)
+template <typename T>
+__global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const T* __restrict__ y, double* __restrict__ sums, int c,
+                                                              int cb, long long spatial) {
+    const int b = blockIdx.y, n = blockIdx.z;
+    const T* base = y + ((long long)n * cb + b) * spatial * 8;
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+    const long long s0 = (long long)blockIdx.x * kBnThreads * kStatVoxPerThread;
+#pragma unroll 4
+    for (int it = 0; it < kStatVoxPerThread; ++it) {
+        long long s = s0 + (long long)it * kBnThreads + threadIdx.x;
+        if (s < spatial) {
+            V8 v = Vec8<T>::load(base + s * 8);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                acc[j] += v.v[j];
+                acc[8 + j] = fmaf(v.v[j], v.v[j], acc[8 + j]);
+            }
+        }
+    }
+    const int cpad = cb * 8;
+    int cvalid = c - b * 8;
+    if (cvalid > 8) cvalid = 8;
+    block_atomic_add<16>(acc, sums + b * 8, cpad, cvalid);
+}
+
+// One thread per channel.  ss = scale | shift | mean | invstd (each cpad floats).
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* running_mean, float* running_var,
+                                   long long* nbt, float momentum, float eps, int c, int cpad, int training,
+                                   int n_updates, float* __restrict__ ss) {
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= cpad) return;
+    float scale = 0.f, shift = 0.f, meanf = 0.f, invstd = 0.f;
+    if (ch < c) {
+        double mean, var;
+        if (training) {
+            mean = sums[ch] / count;
+            var = sums[cpad + ch] / count - mean * mean;
+            if (var < 0.0) var = 0.0;
+            if (running_mean != nullptr && running_var != nullptr) {
+                const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+                float rm = running_mean[ch], rv = running_var[ch];
+                for (int u = 0; u < n_updates; ++u) {
+                    rm = (1.f - momentum) * rm + momentum * (float)mean;
+                    rv = (1.f - momentum) * rv + momentum * (float)unbiased;
+                }
+                running_mean[ch] = rm;
+                running_var[ch] = rv;
+            }
+        } else {
+            mean = (double)running_mean[ch];
+            var = (double)running_var[ch];
+        }
+        invstd = (float)(1.0 / sqrt(var + (double)eps));
+        meanf = (float)mean;
+        scale = gamma[ch] * invstd;
+        shift = beta[ch] - meanf * scale;
+    }
+    ss[ch] = scale;
+    ss[cpad + ch] = shift;
+    ss[2 * cpad + ch] = meanf;
+    ss[3 * cpad + ch] = invstd;
+    if (ch == 0 && training && nbt != nullptr) *nbt += n_updates;
+}
+
+__global__ void bn_running_update_kernel(const double* __restrict__ sums, double count, float* running_mean,
+                                         float* running_var, long long* nbt, float momentum, int c, int cpad,
+                                         int n_updates) {
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch < c) {
+        double mean = sums[ch] / count;
+        double var = sums[cpad + ch] / count - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+        float rm = running_mean[ch], rv = running_var[ch];
+        for (int u = 0; u < n_updates; ++u) {
+            rm = (1.f - momentum) * rm + momentum * (float)mean;
+            rv = (1.f - momentum) * rv + momentum * (float)unbiased;
+        }
+        running_mean[ch] = rm;
+        running_var[ch] = rv;
+    }
+    if (ch == 0 && nbt != nullptr) *nbt += n_updates;
+}
+
+template <typename T>
+__device__ __forceinline__ V8 bn_relu_apply(const V8& y, const float (&sc)[8], const float (&sh)[8]) {
+    V8 a;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a.v[j] = round_to<T>(fmaxf(fmaf(y.v[j], sc[j], sh[j]), 0.f));
+    return a;
+}
+
+// a = relu(scale*y + shift); grid = (chunks, cb, n), one thread per voxel
+template <typename T>
+__global__ void __launch_bounds__(kBnThreads) bn_relu_fwd_kernel(const T* __restrict__ y, const float* __restrict__ ss,
+                                                                 T* __restrict__ a, int cb, long long spatial) {
+    const int b = blockIdx.y, n = blockIdx.z;
+    const int cpad = cb * 8;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        sc[j] = __ldg(ss + b * 8 + j);
+        sh[j] = __ldg(ss + cpad + b * 8 + j);
+    }
+    const long long s = (long long)blockIdx.x * kBnThreads + threadIdx.x;
+    if (s >= spatial) return;
+    const long long off = (((long long)n * cb + b) * spatial + s) * 8;
+    V8 v = Vec8<T>::load(y + off);
+    Vec8<T>::store(a + off, bn_relu_apply<T>(v, sc, sh));
+}
+
+// Same, plus pooled = maxpool 2x2x2 of a.  One thread per POOLED voxel (reads its 8 children).
+template <typename T>
+__global__ void __launch_bounds__(kBnThreads) bn_relu_pool_fwd_kernel(const T* __restrict__ y,
+                                                                      const float* __restrict__ ss, T* __restrict__ a,
+                                                                      T* __restrict__ pooled, int cb, int d, int h,
+                                                                      int w) {
+    const int b = blockIdx.y, n = blockIdx.z;
+    const int cpad = cb * 8;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        sc[j] = __ldg(ss + b * 8 + j);
+        sh[j] = __ldg(ss + cpad + b * 8 + j);
+    }
+    const int pd = d / 2, ph = h / 2, pw = w / 2;
+    const long long pspatial = (long long)pd * ph * pw;
+    const long long ps = (long long)blockIdx.x * kBnThreads + threadIdx.x;
+    if (ps >= pspatial) return;
+    const int px = (int)(ps % pw);
+    const int py = (int)((ps / pw) % ph);
+    const int pz = (int)(ps / ((long long)pw * ph));
+    const long long spatial = (long long)d * h * w;
+    const long long base = ((long long)n * cb + b) * spatial;
+    V8 mx;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mx.v[j] = 0.f;   // a >= 0 after ReLU
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int z = 2 * pz + (q >> 2), yy = 2 * py + ((q >> 1) & 1), x = 2 * px + (q & 1);
+        const long long off = (base + ((long long)z * h + yy) * w + x) * 8;
+        V8 r = bn_relu_apply<T>(Vec8<T>::load(y + off), sc, sh);
+        Vec8<T>::store(a + off, r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mx.v[j] = fmaxf(mx.v[j], r.v[j]);
+    }
+    Vec8<T>::store(pooled + (((long long)n * cb + b) * pspatial + ps) * 8, mx);
+}
+
+// ---------------------------------------------------------------------------- backward
+// Gradient entering the BatchNorm output for the 8 children of one pooled voxel (POOL) or for one
+// voxel: dz = (dA + [child is the first max of its window] * dP) * [a > 0].
+struct BwdArgs {
+    const void* y;
+    const float* ss;
+    const float* gamma;
+    const void* dA;
+    const void* dP;
+    double* sums2;        // reduce: output; apply: input
+    double count;
+    void* dy;
+    float* dgamma;
+    float* dbeta;
+    int c, cb, d, h, w;
+};
+
+template <typename T, bool POOL, bool APPLY>
+__global__ void __launch_bounds__(kBnThreads) bn_relu_bwd_kernel(BwdArgs p) {
+    const int b = blockIdx.y, n = blockIdx.z;
+    const int cpad = p.cb * 8;
+    float sc[8], sh[8], mean[8], invstd[8], k1[8], k2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        sc[j] = __ldg(p.ss + b * 8 + j);
+        sh[j] = __ldg(p.ss + cpad + b * 8 + j);
+        mean[j] = __ldg(p.ss + 2 * cpad + b * 8 + j);
+        invstd[j] = __ldg(p.ss + 3 * cpad + b * 8 + j);
+        if (APPLY) {
+            k1[j] = (float)(p.sums2[b * 8 + j] / p.count);          // mean(dz)
+            k2[j] = (float)(p.sums2[cpad + b * 8 + j] / p.count);   // mean(dz * xhat)
+        }
+    }
+    if (APPLY && blockIdx.x == 0 && n == 0 && threadIdx.x < 8) {
+        const int ch = b * 8 + threadIdx.x;
+        if (ch < p.c) {
+            p.dgamma[ch] = (float)p.sums2[cpad + ch];
+            p.dbeta[ch] = (float)p.sums2[ch];
+        }
+    }
+    const T* y = reinterpret_cast<const T*>(p.y);
+    const T* dA = reinterpret_cast<const T*>(p.dA);
+    const T* dP = reinterpret_cast<const T*>(p.dP);
+    T* dy = reinterpret_cast<T*>(p.dy);
+    const long long spatial = (long long)p.d * p.h * p.w;
+    const long long base = ((long long)n * p.cb + b) * spatial;
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+
+    constexpr int NCH = POOL ? 8 : 1;
+    long long offs[NCH];
+    bool active;
+    V8 gp;
+    if (POOL) {
+        const int pd = p.d / 2, ph = p.h / 2, pw = p.w / 2;
+        const long long pspatial = (long long)pd * ph * pw;
+        const long long ps = (long long)blockIdx.x * kBnThreads + threadIdx.x;
+        active = ps < pspatial;
+        if (active) {
+            const int px = (int)(ps % pw);
+            const int py = (int)((ps / pw) % ph);
+            const int pz = (int)(ps / ((long long)pw * ph));
+#pragma unroll
+            for (int q = 0; q < NCH; ++q) {
+                const int z = 2 * pz + (q >> 2), yy = 2 * py + ((q >> 1) & 1), x = 2 * px + (q & 1);
+                offs[q] = (base + ((long long)z * p.h + yy) * p.w + x) * 8;
+            }
+            gp = Vec8<T>::load(dP + (((long long)n * p.cb + b) * pspatial + ps) * 8);
+        }
+    } else {
+        const long long s = (long long)blockIdx.x * kBnThreads + threadIdx.x;
+        active = s < spatial;
+        offs[0] = (base + s) * 8;
+    }
+    if (active) {
+        V8 yv[NCH], av[NCH];
+#pragma unroll
+        for (int q = 0; q < NCH; ++q) {
+            yv[q] = Vec8<T>::load(y + offs[q]);
+            av[q] = bn_relu_apply<T>(yv[q], sc, sh);
+        }
+        int win[8];
+        if (POOL) {
+            // first maximum in (d, h, w) scan order, strict '>' like torch's max_pool3d
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float best = av[0].v[j];
+                int bi = 0;
+#pragma unroll
+                for (int q = 1; q < NCH; ++q)
+                    if (av[q].v[j] > best) {
+                        best = av[q].v[j];
+                        bi = q;
+                    }
+                win[j] = bi;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < NCH; ++q) {
+            V8 g;
+            if (dA != nullptr) {
+                g = Vec8<T>::load(dA + offs[q]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) g.v[j] = 0.f;
+            }
+            V8 o;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float dz = g.v[j];
+                if (POOL) dz += (win[j] == q) ? gp.v[j] : 0.f;
+                dz = av[q].v[j] > 0.f ? dz : 0.f;
+                const float xhat = (yv[q].v[j] - mean[j]) * invstd[j];
+                if (APPLY) {
+                    o.v[j] = sc[j] * (dz - k1[j] - xhat * k2[j]);
+                } else {
+                    acc[j] += dz;
+                    acc[8 + j] = fmaf(dz, xhat, acc[8 + j]);
+                }
+            }
+            if (APPLY) Vec8<T>::store(dy + offs[q], o);
+        }
+    }
+    if (!APPLY) {
+        int cvalid = p.c - b * 8;
+        if (cvalid > 8) cvalid = 8;
+        block_atomic_add<16>(acc, p.sums2 + b * 8, cpad, cvalid);
+    }
+}
+
+}  // namespace ctu
+
+using namespace ctu;
+
+extern "C" {
+
+int ctu_bn_stats(int dtype, const void* y, int c, int n, long long spatial, double* sums, ctu_stream stream) {
+    CTU_REQUIRE(y && sums && c > 0 && n > 0 && spatial > 0, "ctu_bn_stats: bad arguments");
+    const int cb = (c + 7) / 8;
+    cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * cb * 8, (cudaStream_t)stream);
+    if (e != cudaSuccess) {
+        set_error("ctu_bn_stats: memset: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    dim3 grid(cdiv(spatial, (long long)kBnThreads * kStatVoxPerThread), cb, n);
+    CTU_DISPATCH_DTYPE(dtype, (bn_stats_kernel<T><<<grid, kBnThreads, 0, (cudaStream_t)stream>>>((const T*)y, sums, c, cb, spatial)));
+    return check_launch("ctu_bn_stats");
+}
+
+int ctu_bn_finalize(const double* sums, double count, const float* gamma, const float* beta, float* running_mean,
+                    float* running_var, long long* num_batches_tracked, float momentum, float eps, int c,
+                    int training, int n_updates, float* ss, ctu_stream stream) {
+    CTU_REQUIRE(gamma && beta && ss && c > 0, "ctu_bn_finalize: bad arguments");
+    CTU_REQUIRE(training ? (sums != nullptr && count > 0) : (running_mean && running_var), "ctu_bn_finalize: missing statistics");
+    const int cpad = (c + 7) / 8 * 8;
+    bn_finalize_kernel<<<cdiv(cpad, 128), 128, 0, (cudaStream_t)stream>>>(sums, count, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, c, cpad, training, n_updates, ss);
+    return check_launch("ctu_bn_finalize");
+}
+
+int ctu_bn_running_update(const double* sums, double count, float* running_mean, float* running_var,
+                          long long* num_batches_tracked, float momentum, int c, int n_updates, ctu_stream stream) {
+    CTU_REQUIRE(sums && running_mean && running_var && c > 0 && count > 0, "ctu_bn_running_update: bad arguments");
+    const int cpad = (c + 7) / 8 * 8;
+    bn_running_update_kernel<<<cdiv(cpad, 128), 128, 0, (cudaStream_t)stream>>>(sums, count, running_mean, running_var, num_batches_tracked, momentum, c, cpad, n_updates);
+    return check_launch("ctu_bn_running_update");
+}
+
+int ctu_bn_relu_fwd(int dtype, const void* y, const float* ss, void* a, void* pooled, int c, int n, int d, int h, int w,
+                    ctu_stream stream) {
+    CTU_REQUIRE(y && ss && a && c > 0 && n > 0 && d > 0 && h > 0 && w > 0, "ctu_bn_relu_fwd: bad arguments");
+    const int cb = (c + 7) / 8;
+    const long long spatial = (long long)d * h * w;
+    if (pooled != nullptr) {
+        CTU_REQUIRE(d % 2 == 0 && h % 2 == 0 && w % 2 == 0, "ctu_bn_relu_fwd: pooling needs even dims (%d,%d,%d)", d, h, w);
+        dim3 grid(cdiv(spatial / 8, kBnThreads), cb, n);
+        CTU_DISPATCH_DTYPE(dtype, (bn_relu_pool_fwd_kernel<T><<<grid, kBnThreads, 0, (cudaStream_t)stream>>>((const T*)y, ss, (T*)a, (T*)pooled, cb, d, h, w)));
+    } else {
+        dim3 grid(cdiv(spatial, kBnThreads), cb, n);
+        CTU_DISPATCH_DTYPE(dtype, (bn_relu_fwd_kernel<T><<<grid, kBnThreads, 0, (cudaStream_t)stream>>>((const T*)y, ss, (T*)a, cb, spatial)));
+    }
+    return check_launch("ctu_bn_relu_fwd");
+}
+
+static int bn_bwd(int dtype, BwdArgs& p, int n, bool apply, cudaStream_t stream, const char* what) {
+    const long long spatial = (long long)p.d * p.h * p.w;
+    const bool pool = p.dP != nullptr;
+    if (pool && (p.d % 2 || p.h % 2 || p.w % 2)) {
+        set_error("%s: pooling needs even dims", what);
+        return CTU_ERR_INVALID;
+    }
+    dim3 grid(cdiv(pool ? spatial / 8 : spatial, kBnThreads), p.cb, n);
+    CTU_DISPATCH_DTYPE(dtype, {
+        if (pool && apply) bn_relu_bwd_kernel<T, true, true><<<grid, kBnThreads, 0, stream>>>(p);
+        else if (pool) bn_relu_bwd_kernel<T, true, false><<<grid, kBnThreads, 0, stream>>>(p);
+        else if (apply) bn_relu_bwd_kernel<T, false, true><<<grid, kBnThreads, 0, stream>>>(p);
+        else bn_relu_bwd_kernel<T, false, false><<<grid, kBnThreads, 0, stream>>>(p);
+    });
+    return check_launch(what);
+}
+
+int ctu_bn_relu_bwd_reduce(int dtype, const void* y, const float* ss, const void* dA, const void* dP, double* sums2,
+                           int c, int n, int d, int h, int w, ctu_stream stream) {
+    CTU_REQUIRE(y && ss && sums2 && (dA || dP) && c > 0 && n > 0 && d > 0 && h > 0 && w > 0, "ctu_bn_relu_bwd_reduce: bad arguments");
+    BwdArgs p = {};
+    p.y = y; p.ss = ss; p.dA = dA; p.dP = dP; p.sums2 = sums2; p.c = c; p.cb = (c + 7) / 8; p.d = d; p.h = h; p.w = w;
+    cudaError_t e = cudaMemsetAsync(sums2, 0, sizeof(double) * 2 * p.cb * 8, (cudaStream_t)stream);
+    if (e != cudaSuccess) {
+        set_error("ctu_bn_relu_bwd_reduce: memset: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    return bn_bwd(dtype, p, n, false, (cudaStream_t)stream, "ctu_bn_relu_bwd_reduce");
+}
+
+int ctu_bn_relu_bwd_apply(int dtype, const void* y, const float* ss, const float* gamma, const void* dA, const void* dP,
+                          const double* sums2, double count, void* dy, float* dgamma, float* dbeta, int c, int n, int d,
+                          int h, int w, ctu_stream stream) {
+    CTU_REQUIRE(y && ss && sums2 && dy && dgamma && dbeta && (dA || dP) && count > 0 && c > 0 && n > 0 && d > 0 && h > 0 && w > 0,
+                "ctu_bn_relu_bwd_apply: bad arguments");
+    BwdArgs p = {};
+    p.y = y; p.ss = ss; p.gamma = gamma; p.dA = dA; p.dP = dP; p.sums2 = const_cast<double*>(sums2); p.count = count;
+    p.dy = dy; p.dgamma = dgamma; p.dbeta = dbeta; p.c = c; p.cb = (c + 7) / 8; p.d = d; p.h = h; p.w = w;
+    return bn_bwd(dtype, p, n, true, (cudaStream_t)stream, "ctu_bn_relu_bwd_apply");
+}
+
+}  // extern "C"

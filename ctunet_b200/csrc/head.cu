@@ -1,0 +1,373 @@
+// Network head: last_conv 1x1x1 + bias over the (virtual) concatenation of blocked sources, then the
+// reference's output non-linearities, written as fp32 NCDHW (what the reference returns).
+//   generic UNet   : lc -> [softmax] -> [sigmoid]                      models.py:255-259
+//   UNetSP / UNetDO: ... -> skull = [s0, s1+s2], flap = [1-s1, s1]     models.py:319-330
+//   UNetSPSmall    : ... -> softmax(skull), softmax(flap)              models.py:364-365
+//   legacy         : softmax(lc)                                       models.py:535-538
+// Backward recomputes lc from the sources (they are needed for dW anyway) and chains back.
+#include "common.cuh"
+
+namespace ctu {
+
+constexpr int kHeadThreads = 256;
+constexpr int kHeadMaxCb = 4;
+
+struct HeadParams {
+    const void* src[CTU_MAX_SRC];
+    void* dsrc[CTU_MAX_SRC];
+    int src_cb[CTU_MAX_SRC];
+    int nsrc;
+    SrcMap m;
+    const float* w;       // native [cout][c_total]
+    const float* bias;
+    int cout, flags;
+    float* out0;
+    float* out1;
+    const float* dout0;
+    const float* dout1;
+    float* dw;
+    float* db;
+    int n;
+    long long spatial;
+};
+
+// wsm[o][cbt*8]: weight of output o for (blocked, padded) input lane; pad lanes 0.
+template <int CO>
+__device__ __forceinline__ void load_head_weights(const HeadParams& p, float* wsm, float* bsm) {
+    const int lanes = p.m.cb_total * 8;
+    for (int i = threadIdx.x; i < CO * lanes; i += blockDim.x) {
+        const int o = i / lanes, l = i % lanes;
+        const int cib = l >> 3, ci = l & 7;
+        int s = 0;
+        for (int q = 1; q < CTU_MAX_SRC; ++q)
+            if (q < p.m.nsrc && cib >= p.m.cboff[q]) s = q;
+        const int cl = (cib - p.m.cboff[s]) * 8 + ci;
+        wsm[i] = cl < p.m.ch[s] ? p.w[(long long)o * p.m.c_total + p.m.choff[s] + cl] : 0.f;
+    }
+    if (threadIdx.x < CO) bsm[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
+}
+
+template <int CO> struct HeadVals {
+    float lc[CO];   // logits
+    float sm[CO];   // after optional softmax
+    float sg[CO];   // after optional sigmoid (the plain output)
+    float o0[2], o1[2];   // SP outputs (after optional pair softmax)
+};
+
+template <int CO>
+__device__ __forceinline__ void head_forward_chain(HeadVals<CO>& h, int flags) {
+    if (flags & CTU_HEAD_SOFTMAX) {
+        float mx = h.lc[0];
+#pragma unroll
+        for (int o = 1; o < CO; ++o) mx = fmaxf(mx, h.lc[o]);
+        float sum = 0.f;
+#pragma unroll
+        for (int o = 0; o < CO; ++o) {
+            h.sm[o] = expf(h.lc[o] - mx);
+            sum += h.sm[o];
+        }
+#pragma unroll
+        for (int o = 0; o < CO; ++o) h.sm[o] /= sum;
+    } else {
+#pragma unroll
+        for (int o = 0; o < CO; ++o) h.sm[o] = h.lc[o];
+    }
+#pragma unroll
+    for (int o = 0; o < CO; ++o) h.sg[o] = (flags & CTU_HEAD_SIGMOID) ? 1.f / (1.f + expf(-h.sm[o])) : h.sm[o];
+    if (CO == 3 && (flags & (CTU_HEAD_SP | CTU_HEAD_SP_SOFTMAX))) {
+        h.o0[0] = h.sg[0];
+        h.o0[1] = h.sg[1] + h.sg[CO - 1];
+        h.o1[0] = 1.f - h.sg[1];
+        h.o1[1] = h.sg[1];
+        if (flags & CTU_HEAD_SP_SOFTMAX) {
+            float m0 = fmaxf(h.o0[0], h.o0[1]);
+            float e0 = expf(h.o0[0] - m0), e1 = expf(h.o0[1] - m0);
+            h.o0[0] = e0 / (e0 + e1);
+            h.o0[1] = e1 / (e0 + e1);
+            float m1 = fmaxf(h.o1[0], h.o1[1]);
+            e0 = expf(h.o1[0] - m1);
+            e1 = expf(h.o1[1] - m1);
+            h.o1[0] = e0 / (e0 + e1);
+            h.o1[1] = e1 / (e0 + e1);
+        }
+    }
+}
+
+// Source of blocked input lane group c (compile-time c after unrolling keeps xs[] in registers).
+__device__ __forceinline__ int head_block_source(const HeadParams& p, int c) {
+    int q = 0;
+#pragma unroll
+    for (int qq = 1; qq < CTU_MAX_SRC; ++qq)
+        if (qq < p.m.nsrc && c >= p.m.cboff[qq]) q = qq;
+    return q;
+}
+
+template <typename T, int CO, int CBT>
+__device__ __forceinline__ void head_logits(const HeadParams& p, const float* wsm, const float* bsm, int n, long long s,
+                                            HeadVals<CO>& h, V8 (&xs)[CBT]) {
+#pragma unroll
+    for (int o = 0; o < CO; ++o) h.lc[o] = bsm[o];
+#pragma unroll
+    for (int c = 0; c < CBT; ++c) {
+        const int q = head_block_source(p, c);
+        const int b = c - p.m.cboff[q];
+        const T* sp = reinterpret_cast<const T*>(p.src[q]);
+        xs[c] = Vec8<T>::load(sp + (((long long)n * p.src_cb[q] + b) * p.spatial + s) * 8);
+#pragma unroll
+        for (int o = 0; o < CO; ++o)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) h.lc[o] = fmaf(xs[c].v[j], wsm[o * CBT * 8 + c * 8 + j], h.lc[o]);
+    }
+}
+
+template <typename T, int CO, int CBT>
+__global__ void __launch_bounds__(kHeadThreads) head_fwd_kernel(HeadParams p) {
+    extern __shared__ float hsm[];
+    float* wsm = hsm;
+    float* bsm = hsm + CO * CBT * 8;
+    load_head_weights<CO>(p, wsm, bsm);
+    __syncthreads();
+    const long long total = (long long)p.n * p.spatial;
+    const bool sp = (p.flags & (CTU_HEAD_SP | CTU_HEAD_SP_SOFTMAX)) != 0;
+    for (long long i = (long long)blockIdx.x * kHeadThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kHeadThreads) {
+        const int n = (int)(i / p.spatial);
+        const long long s = i % p.spatial;
+        HeadVals<CO> h;
+        V8 xs[CBT];
+        head_logits<T, CO, CBT>(p, wsm, bsm, n, s, h, xs);
+        head_forward_chain<CO>(h, p.flags);
+        if (sp) {
+            p.out0[((long long)n * 2 + 0) * p.spatial + s] = h.o0[0];
+            p.out0[((long long)n * 2 + 1) * p.spatial + s] = h.o0[1];
+            p.out1[((long long)n * 2 + 0) * p.spatial + s] = h.o1[0];
+            p.out1[((long long)n * 2 + 1) * p.spatial + s] = h.o1[1];
+        } else {
+#pragma unroll
+            for (int o = 0; o < CO; ++o) p.out0[((long long)n * CO + o) * p.spatial + s] = h.sg[o];
+        }
+    }
+}
+
+template <typename T, int CO, int CBT>
+__global__ void __launch_bounds__(kHeadThreads) head_bwd_kernel(HeadParams p) {
+    extern __shared__ float hsm[];
+    float* wsm = hsm;
+    float* bsm = hsm + CO * CBT * 8;
+    float* red = bsm + 8;                           // [8 warps][CO*CBT*8 + CO]
+    load_head_weights<CO>(p, wsm, bsm);
+    __syncthreads();
+    const long long total = (long long)p.n * p.spatial;
+    const bool sp = (p.flags & (CTU_HEAD_SP | CTU_HEAD_SP_SOFTMAX)) != 0;
+    float gw[CO][CBT * 8], gb[CO];
+#pragma unroll
+    for (int o = 0; o < CO; ++o) {
+        gb[o] = 0.f;
+#pragma unroll
+        for (int l = 0; l < CBT * 8; ++l) gw[o][l] = 0.f;
+    }
+    for (long long i = (long long)blockIdx.x * kHeadThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kHeadThreads) {
+        const int n = (int)(i / p.spatial);
+        const long long s = i % p.spatial;
+        HeadVals<CO> h;
+        V8 xs[CBT];
+        head_logits<T, CO, CBT>(p, wsm, bsm, n, s, h, xs);
+        head_forward_chain<CO>(h, p.flags);
+        float dsg[CO];
+        if (sp) {
+            float g00 = p.dout0 ? p.dout0[((long long)n * 2 + 0) * p.spatial + s] : 0.f;
+            float g01 = p.dout0 ? p.dout0[((long long)n * 2 + 1) * p.spatial + s] : 0.f;
+            float g10 = p.dout1 ? p.dout1[((long long)n * 2 + 0) * p.spatial + s] : 0.f;
+            float g11 = p.dout1 ? p.dout1[((long long)n * 2 + 1) * p.spatial + s] : 0.f;
+            if (p.flags & CTU_HEAD_SP_SOFTMAX) {
+                // out = softmax(pair): d(pair_j) = out_j * (g_j - sum_i g_i out_i)
+                float d0 = g00 * h.o0[0] + g01 * h.o0[1];
+                g00 = h.o0[0] * (g00 - d0);
+                g01 = h.o0[1] * (g01 - d0);
+                float d1 = g10 * h.o1[0] + g11 * h.o1[1];
+                g10 = h.o1[0] * (g10 - d1);
+                g11 = h.o1[1] * (g11 - d1);
+            }
+            // skull = [s0, s1+s2], flap = [1-s1, s1]
+            dsg[0] = g00;
+            dsg[1] = g01 - g10 + g11;
+            dsg[CO - 1] = g01;
+        } else {
+#pragma unroll
+            for (int o = 0; o < CO; ++o) dsg[o] = p.dout0[((long long)n * CO + o) * p.spatial + s];
+        }
+        float dsm[CO], dlc[CO];
+#pragma unroll
+        for (int o = 0; o < CO; ++o) dsm[o] = (p.flags & CTU_HEAD_SIGMOID) ? dsg[o] * h.sg[o] * (1.f - h.sg[o]) : dsg[o];
+        if (p.flags & CTU_HEAD_SOFTMAX) {
+            float dot = 0.f;
+#pragma unroll
+            for (int o = 0; o < CO; ++o) dot += dsm[o] * h.sm[o];
+#pragma unroll
+            for (int o = 0; o < CO; ++o) dlc[o] = h.sm[o] * (dsm[o] - dot);
+        } else {
+#pragma unroll
+            for (int o = 0; o < CO; ++o) dlc[o] = dsm[o];
+        }
+        // parameter gradients (per-thread partials) and source gradients
+#pragma unroll
+        for (int c = 0; c < CBT; ++c) {
+            const int q = head_block_source(p, c);
+            const int b = c - p.m.cboff[q];
+            T* dp = reinterpret_cast<T*>(p.dsrc[q]);
+            V8 g;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float a = 0.f;
+#pragma unroll
+                for (int o = 0; o < CO; ++o) a = fmaf(dlc[o], wsm[o * CBT * 8 + c * 8 + j], a);
+                g.v[j] = a;
+            }
+            if (dp != nullptr) Vec8<T>::store(dp + (((long long)n * p.src_cb[q] + b) * p.spatial + s) * 8, g);
+        }
+#pragma unroll
+        for (int o = 0; o < CO; ++o) {
+            gb[o] += dlc[o];
+#pragma unroll
+            for (int c = 0; c < CBT; ++c)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) gw[o][c * 8 + j] = fmaf(dlc[o], xs[c].v[j], gw[o][c * 8 + j]);
+        }
+    }
+    // block reduction of the CO*(CBT*8+1) partials, then one atomic each
+    constexpr int NV = CO * CBT * 8 + CO;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 0; o < CO; ++o) {
+#pragma unroll
+        for (int l = 0; l < CBT * 8; ++l) {
+            float v = warp_sum(gw[o][l]);
+            if (lane == 0) red[warp * NV + o * CBT * 8 + l] = v;
+        }
+        float v = warp_sum(gb[o]);
+        if (lane == 0) red[warp * NV + CO * CBT * 8 + o] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NV; i += kHeadThreads) {
+        float v = 0.f;
+        for (int wq = 0; wq < kHeadThreads / 32; ++wq) v += red[wq * NV + i];
+        if (i < CO * CBT * 8) {
+            const int o = i / (CBT * 8), l = i % (CBT * 8);
+            const int cib = l >> 3, ci = l & 7;
+            int s = 0;
+            for (int q = 1; q < CTU_MAX_SRC; ++q)
+                if (q < p.m.nsrc && cib >= p.m.cboff[q]) s = q;
+            const int cl = (cib - p.m.cboff[s]) * 8 + ci;
+            if (cl < p.m.ch[s]) atomicAdd(p.dw + (long long)o * p.m.c_total + p.m.choff[s] + cl, v);
+        } else {
+            atomicAdd(p.db + (i - CO * CBT * 8), v);
+        }
+    }
+}
+
+static int head_setup(HeadParams& p, const void* const* h_srcs, const int* h_src_channels, int nsrc, const float* w,
+                      const float* bias, int cout, int flags, int n, long long spatial, const char* what) {
+    int rc = make_srcmap(p.m, nsrc, h_src_channels);
+    if (rc != CTU_OK) return rc;
+    CTU_REQUIRE(h_srcs && w && cout >= 1 && cout <= 4 && n > 0 && spatial > 0, "%s: bad arguments (cout must be 1..4)", what);
+    CTU_REQUIRE(p.m.cb_total <= kHeadMaxCb, "%s: at most %d input blocks supported (got %d)", what, kHeadMaxCb, p.m.cb_total);
+    if (flags & (CTU_HEAD_SP | CTU_HEAD_SP_SOFTMAX)) CTU_REQUIRE(cout == 3, "%s: the SP head needs 3 output channels", what);
+    for (int i = 0; i < CTU_MAX_SRC; ++i) {
+        p.src[i] = i < nsrc ? h_srcs[i] : nullptr;
+        p.dsrc[i] = nullptr;
+        p.src_cb[i] = i < nsrc ? (p.m.ch[i] + 7) / 8 : 0;
+        if (i < nsrc) CTU_REQUIRE(h_srcs[i] != nullptr, "%s: null source %d", what, i);
+    }
+    p.nsrc = nsrc; p.w = w; p.bias = bias; p.cout = cout; p.flags = flags; p.n = n; p.spatial = spatial;
+    return CTU_OK;
+}
+
+static int head_grid(long long total) {
+    long long g = (total + kHeadThreads - 1) / kHeadThreads;
+    const long long cap = 148 * 8;
+    return (int)(g < cap ? g : cap);
+}
+
+template <typename T, int CO>
+static int head_fwd_launch(const HeadParams& p, int grid, size_t smem, cudaStream_t stream) {
+    switch (p.m.cb_total) {
+        case 1: head_fwd_kernel<T, CO, 1><<<grid, kHeadThreads, smem, stream>>>(p); break;
+        case 2: head_fwd_kernel<T, CO, 2><<<grid, kHeadThreads, smem, stream>>>(p); break;
+        case 3: head_fwd_kernel<T, CO, 3><<<grid, kHeadThreads, smem, stream>>>(p); break;
+        default: head_fwd_kernel<T, CO, 4><<<grid, kHeadThreads, smem, stream>>>(p); break;
+    }
+    return check_launch("ctu_head_fwd");
+}
+
+template <typename T, int CO>
+static int head_bwd_launch(const HeadParams& p, cudaStream_t stream) {
+    const int cbt = p.m.cb_total;
+    const int nv = CO * cbt * 8 + CO;
+    const size_t smem = (size_t)(CO * cbt * 8 + 8 + (kHeadThreads / 32) * nv) * sizeof(float);
+    const int grid = head_grid((long long)p.n * p.spatial);
+    switch (cbt) {
+        case 1: head_bwd_kernel<T, CO, 1><<<grid, kHeadThreads, smem, stream>>>(p); break;
+        case 2: head_bwd_kernel<T, CO, 2><<<grid, kHeadThreads, smem, stream>>>(p); break;
+        case 3: head_bwd_kernel<T, CO, 3><<<grid, kHeadThreads, smem, stream>>>(p); break;
+        default: head_bwd_kernel<T, CO, 4><<<grid, kHeadThreads, smem, stream>>>(p); break;
+    }
+    return check_launch("ctu_head_bwd");
+}
+
+}  // namespace ctu
+
+using namespace ctu;
+
+extern "C" {
+
+int ctu_head_fwd(int dtype, const void* const* h_srcs, const int* h_src_channels, int nsrc, const float* w,
+                 const float* bias, int cout, int flags, float* out0, float* out1, int n, long long spatial,
+                 ctu_stream stream) {
+    HeadParams p = {};
+    int rc = head_setup(p, h_srcs, h_src_channels, nsrc, w, bias, cout, flags, n, spatial, "ctu_head_fwd");
+    if (rc != CTU_OK) return rc;
+    const bool sp = (flags & (CTU_HEAD_SP | CTU_HEAD_SP_SOFTMAX)) != 0;
+    CTU_REQUIRE(out0 && (!sp || out1), "ctu_head_fwd: missing output");
+    p.out0 = out0; p.out1 = out1;
+    const size_t smem = (size_t)(cout * p.m.cb_total * 8 + 8) * sizeof(float);
+    const long long total = (long long)n * spatial;
+    // forward has no reduction: use the full grid
+    const int grid = (int)((total + kHeadThreads - 1) / kHeadThreads > 148 * 32 ? 148 * 32 : (total + kHeadThreads - 1) / kHeadThreads);
+    CTU_DISPATCH_DTYPE(dtype, {
+        switch (cout) {
+            case 1: return head_fwd_launch<T, 1>(p, grid, smem, (cudaStream_t)stream);
+            case 2: return head_fwd_launch<T, 2>(p, grid, smem, (cudaStream_t)stream);
+            case 3: return head_fwd_launch<T, 3>(p, grid, smem, (cudaStream_t)stream);
+            default: return head_fwd_launch<T, 4>(p, grid, smem, (cudaStream_t)stream);
+        }
+    });
+    return CTU_OK;
+}
+
+int ctu_head_bwd(int dtype, const void* const* h_srcs, const int* h_src_channels, int nsrc, const float* w,
+                 const float* bias, int cout, int flags, const float* dout0, const float* dout1, void* const* h_dsrcs,
+                 float* dw, float* db, int n, long long spatial, ctu_stream stream) {
+    HeadParams p = {};
+    int rc = head_setup(p, h_srcs, h_src_channels, nsrc, w, bias, cout, flags, n, spatial, "ctu_head_bwd");
+    if (rc != CTU_OK) return rc;
+    const bool sp = (flags & (CTU_HEAD_SP | CTU_HEAD_SP_SOFTMAX)) != 0;
+    CTU_REQUIRE(dw && db && (sp ? (dout0 || dout1) : dout0 != nullptr), "ctu_head_bwd: missing gradient buffers");
+    for (int i = 0; i < nsrc; ++i) p.dsrc[i] = h_dsrcs ? h_dsrcs[i] : nullptr;
+    p.dout0 = dout0; p.dout1 = dout1; p.dw = dw; p.db = db;
+    cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * cout * p.m.c_total, (cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(db, 0, sizeof(float) * cout, (cudaStream_t)stream);
+    if (e != cudaSuccess) {
+        set_error("ctu_head_bwd: memset: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    CTU_DISPATCH_DTYPE(dtype, {
+        switch (cout) {
+            case 1: return head_bwd_launch<T, 1>(p, (cudaStream_t)stream);
+            case 2: return head_bwd_launch<T, 2>(p, (cudaStream_t)stream);
+            case 3: return head_bwd_launch<T, 3>(p, (cudaStream_t)stream);
+            default: return head_bwd_launch<T, 4>(p, (cudaStream_t)stream);
+        }
+    });
+    return CTU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,116 @@
+"""Data-parallel gradient synchronisation: one process per GPU, NCCL all-reduce over NVLink.
+
+The reference's only multi-GPU mechanism is single-process ``nn.DataParallel``
+(ctunet/pytorch/Model.py:481-486): scatter the batch, replicate the module, gather outputs, reduce
+gradients onto GPU 0; BatchNorm statistics stay per replica.  The B200 equivalent is one process per
+GPU with gradient averaging, which is mathematically the same step when the per-rank batches are
+equal: the Dice term is a mean of per-sample terms (utilities.py:50) and the CE
+term a mean over all voxels (ProblemHandler.py:251).  BatchNorm stays per-rank, as in the reference.
+
+All live gradients of a step land in ONE flat fp32 buffer (UNetSP: 4.6 MB) split into a few buckets
+in gradient-production order (head first, first encoder block last).  The engine writes each
+parameter gradient straight into its slice; when the last gradient of a bucket has been written the
+bucket is all-reduced (AVG) on a side stream while the remaining backward kernels keep running.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+class GradSync:
+    def __init__(self, module: torch.nn.Module, process_group=None, n_buckets: int = 3, skip_prefixes=("cblock.",)):
+        """``skip_prefixes``: parameters that never receive a gradient (the generic UNet's discarded
+        center block, models.py:241) -- they are left with ``grad = None`` exactly like the reference."""
+        self.module = module
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        named = [(n, p) for n, p in module.named_parameters() if p.requires_grad]
+        if type(module).__name__ in ("recAE_v2_fixed", "UNet4_2IC"):
+            skip_prefixes = ()
+        live = [(n, p) for n, p in named if not n.startswith(tuple(skip_prefixes))] if skip_prefixes else named
+        live = list(reversed(live))                       # production order of the backward pass
+        total = sum(p.numel() for _, p in live)
+        ref = live[0][1]
+        self.flat = torch.zeros(total, dtype=torch.float32, device=ref.device)
+        self.slices: Dict[int, torch.Tensor] = {}
+        self.bucket_of: Dict[int, int] = {}
+        self.names = [n for n, _ in live]
+        per = (total + n_buckets - 1) // n_buckets
+        self.bucket_ranges: List[List[int]] = []
+        off, b_start, b = 0, 0, 0
+        for i, (n, p) in enumerate(live):
+            self.slices[id(p)] = self.flat[off:off + p.numel()].view_as(p)
+            self.bucket_of[id(p)] = b
+            off += p.numel()
+            last = i == len(live) - 1
+            if off - b_start >= per or last:
+                self.bucket_ranges.append([b_start, off])
+                b_start = off
+                b += 1
+        self.n_in_bucket = [0] * len(self.bucket_ranges)
+        for k, bi in self.bucket_of.items():
+            self.n_in_bucket[bi] += 1
+        self.params = [p for _, p in live]
+        self.cuda = self.flat.is_cuda
+        self.comm_stream = torch.cuda.Stream(device=self.flat.device) if self.cuda else None
+        self._remaining: List[int] = []
+        self._handles = []
+        self.begin_step()
+
+    # -- engine-facing ---------------------------------------------------------------------------
+    def buffer_for(self, param) -> Optional[torch.Tensor]:
+        """Slice of the flat buffer the gradient kernels write into (None: not a synced parameter)."""
+        return self.slices.get(id(param))
+
+    def delivered(self, param) -> None:
+        """The gradient of ``param`` is fully written (on the current stream)."""
+        bi = self.bucket_of.get(id(param))
+        if bi is None:
+            return
+        self._remaining[bi] -= 1
+        if self._remaining[bi] == 0:
+            self._launch(bi)
+
+    # -- step protocol ---------------------------------------------------------------------------
+    def begin_step(self) -> None:
+        self._remaining = list(self.n_in_bucket)
+        self._handles = []
+
+    def _launch(self, bi: int) -> None:
+        lo, hi = self.bucket_ranges[bi]
+        view = self.flat[lo:hi]
+        if self.world == 1:
+            return
+        if self.cuda:
+            self.comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm_stream):
+                dist.all_reduce(view, op=dist.ReduceOp.AVG, group=self.group)
+        else:  # gloo (CPU tests): no AVG, no streams
+            h = dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            self._handles.append((h, view))
+
+    def finish(self) -> None:
+        """Make the averaged gradients visible to the optimizer (current stream) and publish them as
+        ``param.grad`` views of the flat buffer."""
+        if any(r != 0 for r in self._remaining):
+            missing = [n for n, p in zip(self.names, self.params) if self._remaining[self.bucket_of[id(p)]] != 0]
+            raise RuntimeError("gradient sync: some gradients were never produced, e.g. %s" % missing[:3])
+        if self.cuda:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        for h, view in self._handles:
+            h.wait()
+            view.div_(self.world)
+        for p in self.params:
+            p.grad = self.slices[id(p)]
+        self.begin_step()
+
+
+def shard_range(n_items: int, rank: int, world: int):
+    """Contiguous, balanced partition of ``n_items`` independent units (patches / volumes) over ranks:
+    inference and preprocessing shard with no data-path collective."""
+    base, rem = divmod(n_items, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)

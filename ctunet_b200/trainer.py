@@ -1,0 +1,75 @@
+"""One training iteration of the reference's step driver on the B200 path.
+
+Restates the 'train' branch of ``Model.forward_pass`` (ctunet/pytorch/Model.py:342-374):
+H2D copy, ``input.requires_grad_()``, forward, ``comp_losses_metrics``, ``backward``,
+``optimizer.step()``, ``param.grad = None`` -- with the optimizer of ``Model.initialize_optimizer``
+(Model.py:510-520: Adam, amsgrad=True).  The reference reads every loss component back with
+``float(...)`` (five host syncs per batch, ProblemHandler.py:253-302); here the step enqueues
+everything and returns device tensors, the caller decides when to read them (one sync).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from .losses import dice_ce
+from .parallel import GradSync
+
+
+class TrainStep:
+    def __init__(self, model, handler: str = "double", dice_lambda: float = 1.0, ce_lambda: float = 1.0,
+                 lr: float = 1e-4, weight_decay: float = 0.0, optimizer: str = "adam",
+                 grad_sync: Optional[GradSync] = None, input_requires_grad: bool = True):
+        if handler not in ("double", "single"):
+            raise ValueError("handler: 'double' (FlapRecWithShapePriorDoubleOut) or 'single' (ProblemHandler)")
+        self.model = model
+        self.handler = handler
+        self.dice_lambda, self.ce_lambda = float(dice_lambda), float(ce_lambda)
+        self.grad_sync = grad_sync
+        self.input_requires_grad = input_requires_grad       # Model.py:351-352
+        model._grad_sink = grad_sync
+        params = list(model.parameters())
+        if optimizer == "adam":                               # Model.py:514-520
+            self.optimizer = torch.optim.Adam(params, lr=lr, weight_decay=weight_decay, amsgrad=True)
+        elif optimizer == "adamw":                            # Model.py:521-527
+            self.optimizer = torch.optim.AdamW(params, lr=lr, weight_decay=weight_decay, amsgrad=True)
+        elif optimizer == "sgd":                              # Model.py:535-541
+            self.optimizer = torch.optim.SGD(params, lr=lr, momentum=0.99, weight_decay=weight_decay)
+        else:
+            raise ValueError("optimizer %r" % optimizer)
+
+    def loss(self, out, target):
+        """Weighted sum in the reference's order; returns (total, stacked components)."""
+        ce_on, terms = self.ce_lambda != 0, []
+        if self.handler == "double":                          # ProblemHandler.py:228-298
+            (sk_p, fl_p), (sk_t, fl_t) = out, target
+            ce_s, d_s = dice_ce(sk_p, sk_t, True, ce_on)
+            ce_f, d_f = dice_ce(fl_p, fl_t, True, ce_on)
+            if ce_on:
+                terms += [self.ce_lambda * ce_s, self.ce_lambda * ce_f]
+            if self.dice_lambda != 0:
+                terms += [self.dice_lambda * d_s, self.dice_lambda * d_f]
+        else:                                                 # ProblemHandler.py:59-91
+            ce, d = dice_ce(out, target, False, ce_on)
+            if ce_on:
+                terms.append(self.ce_lambda * ce)
+            if self.dice_lambda != 0:
+                terms.append(self.dice_lambda * d)
+        total = sum(terms)
+        return total, torch.stack([t.detach() for t in terms] + [total.detach()])
+
+    def __call__(self, image: torch.Tensor, target):
+        """Enqueues one full iteration; returns the device tensor [components..., total] (no host sync)."""
+        self.model.train()
+        if self.input_requires_grad:
+            image = image.detach().requires_grad_()
+        out = self.model(image)
+        total, comps = self.loss(out, target)
+        total.backward()
+        if self.grad_sync is not None:
+            self.grad_sync.finish()
+        self.optimizer.step()
+        for p in self.model.parameters():                     # Model.py:373-374
+            p.grad = None
+        return comps

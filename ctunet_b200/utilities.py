@@ -1,0 +1,140 @@
+"""GPU versions of the hot-path helpers of ``ctunet.utilities`` / ``ctunet.pytorch.transforms``.
+
+  hard_segm_from_tensor   ctunet/utilities.py:103-124
+  shape_3d (sphere, box)  ctunet/utilities.py:127-178
+  random_blank_patch      ctunet/pytorch/transforms.py:241-300
+  SkullRandomHole         ctunet/pytorch/transforms.py:52-94
+
+The 'flap' shape of shape_3d calls the un-vendored ``raster_geometry`` package in the reference
+(utilities.py:145-166): its exact voxelisation cannot be verified here (parity unpinned), so it is not
+offered; ``random_blank_patch`` draws its shape from ("sphere", "box").
+"""
+from __future__ import annotations
+
+import random
+
+import numpy as np
+import torch
+
+from ._lib import call, stream_ptr
+from .losses import dice_loss  # noqa: F401  (re-export: utils.dice_loss)
+
+_SHAPES = {"circle": 0, "sphere": 0, "square": 1, "box": 1, "cube": 1}
+
+
+def _need_cuda(t, what):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError("%s runs on CUDA tensors only (no CPU fallback)" % what)
+
+
+def hard_segm_from_tensor(prob_map: torch.Tensor, keep_dims: bool = False) -> torch.Tensor:
+    """Channel argmax as float32; ties go to the lowest index (utilities.py:118-124)."""
+    _need_cuda(prob_map, "hard_segm_from_tensor")
+    x = prob_map.float().contiguous()
+    five = x.dim() == 5
+    if not five:
+        x = x.unsqueeze(0)
+    b, c = x.shape[0], x.shape[1]
+    spatial = x[0, 0].numel()
+    out = torch.empty((b,) + tuple(x.shape[2:]), dtype=torch.float32, device=x.device)
+    call("ctu_argmax_channels", x.data_ptr(), out.data_ptr(), b, c, spatial, stream_ptr())
+    if five:
+        return out.unsqueeze(1) if keep_dims else out
+    out = out[0]
+    return out.unsqueeze(0) if keep_dims else out
+
+
+def blank_patch(image: torch.Tensor, center, size, shape: str):
+    """``masked = image AND outside``, ``extracted = image AND inside`` (uint8), the arithmetic of
+    transforms.py:286-296 for a given centre / radius / shape.  ``center`` is a host triple or a device int32[3]."""
+    _need_cuda(image, "blank_patch")
+    if shape not in _SHAPES:
+        raise NotImplementedError("shape %r is not available (the 'flap' shape needs raster_geometry)" % (shape,))
+    img = image.to(torch.uint8).contiguous()
+    if img.dim() != 3:
+        raise ValueError("expected a [D, H, W] volume")
+    if not isinstance(center, torch.Tensor):
+        center = torch.tensor([int(c) for c in center], dtype=torch.int32, device=img.device)
+    masked, extracted = torch.empty_like(img), torch.empty_like(img)
+    d, h, w = img.shape
+    call("ctu_flap_mask_u8", img.data_ptr(), masked.data_ptr(), extracted.data_ptr(), d, h, w, center.data_ptr(),
+         float(size), _SHAPES[shape], stream_ptr())
+    return masked, extracted
+
+
+def shape_3d(center, size, image_size, shape="sphere", device="cuda") -> torch.Tensor:
+    """utilities.py:127-178 for 'sphere' / 'box': float64 volume, 0 inside (bound inclusive), 1 outside."""
+    ones = torch.ones(tuple(image_size), dtype=torch.uint8, device=device)
+    masked, _ = blank_patch(ones, center, size, shape)
+    return masked.to(torch.float64)
+
+
+def count_nonzero(image: torch.Tensor) -> int:
+    img = image.to(torch.uint8).contiguous()
+    cnt = torch.empty(1, dtype=torch.int64, device=img.device)
+    call("ctu_count_nonzero_u8", img.data_ptr(), img.numel(), cnt.data_ptr(), stream_ptr())
+    return int(cnt.item())
+
+
+def kth_nonzero(image: torch.Tensor, k: int) -> torch.Tensor:
+    """Device int32[3] = ``np.argwhere(image > 0)[k]`` (C order), transforms.py:249-252."""
+    img = image.to(torch.uint8).contiguous()
+    d, h, w = img.shape
+    scratch = torch.empty((img.numel() + 4095) // 4096 + 1, dtype=torch.int64, device=img.device)
+    coords = torch.empty(3, dtype=torch.int32, device=img.device)
+    call("ctu_kth_nonzero_u8", img.data_ptr(), d, h, w, int(k), scratch.data_ptr(), coords.data_ptr(), stream_ptr())
+    return coords
+
+
+def radius_bounds(image_size):
+    """transforms.py:266-267"""
+    min_radius = (int(np.min(image_size)) // 5) - 1
+    max_radius = np.max([min_radius, np.max(image_size) // 3.5])
+    return min_radius, max_radius
+
+
+def random_blank_patch(image: torch.Tensor, prob=1, return_extracted=False, p_type="random",
+                       valid_shapes=("sphere", "box")):
+    """transforms.py:241-300 on a CUDA volume.  Consumes the host RNGs in the reference's order
+    (random.uniform, np.random.choice, np.random.randint, np.random.randint) so a seeded run picks the
+    same voxel index, radius and shape index as the reference would for the same nonzero count."""
+    _need_cuda(image, "random_blank_patch")
+    img = image.to(torch.uint8).contiguous()
+    r = random.uniform(0, 1)
+    if prob >= r:
+        n = count_nonzero(img)
+        if n:
+            center = kth_nonzero(img, int(np.random.choice(n)))
+            min_radius, max_radius = radius_bounds(tuple(img.shape))
+            size = np.random.randint(min_radius, max_radius)
+            if p_type not in valid_shapes:
+                p_type = valid_shapes[np.random.randint(0, len(valid_shapes))]
+            masked, extracted = blank_patch(img, center, size, p_type)
+            return (masked, extracted) if return_extracted else masked
+    return (img, torch.zeros_like(img)) if return_extracted else img
+
+
+class SkullRandomHole(object):
+    """transforms.py:52-94 for CUDA tensors: ``sample['image']`` is [D,H,W] or [B,D,H,W]."""
+
+    def __init__(self, p=1, double_output=False):
+        self.p = p
+        self.double_output = double_output
+
+    def __call__(self, sample):
+        img = sample["image"]
+        _need_cuda(img, "SkullRandomHole")
+        is_batch = img.dim() == 4
+        vols = img if is_batch else img.unsqueeze(0)
+        full = vols.to(torch.uint8)
+        brk, flap = [], []
+        for i in range(vols.shape[0]):
+            m, e = random_blank_patch(full[i], self.p, True)
+            brk.append(m)
+            flap.append(e)
+        brk, flap = torch.stack(brk), torch.stack(flap)
+        if not is_batch:
+            brk, flap = brk[0], flap[0]
+        if self.double_output:
+            return {"image": brk, "target": (full, flap)}
+        return {"image": brk, "target": flap}

@@ -1,0 +1,176 @@
+/*
+ * ctunet_b200 -- C ABI of the B200-native (sm_100a) hot path of vfmatzkin/ct-unet.
+ *
+ * The reference is pure Python/PyTorch and has NO FFI of its own: its hot
+ * path is the `torch.nn` module graph built in ctunet/pytorch/models.py plus the loss in
+ * ctunet/pytorch/ProblemHandler.py and ctunet/utilities.py.  This header is therefore the
+ * boundary a maintainer would bind (ctypes stub in INTEGRATION.md); each entry point cites the
+ * reference code it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless its name starts with `h_` (host array of small
+ *    metadata such as a list of source pointers); PyTorch (the caller) owns all memory, the library
+ *    never allocates, frees or retains device memory;
+ *  - all work is enqueued on `stream` (a cudaStream_t passed as void*); no call synchronises, so
+ *    every entry point is CUDA-graph capturable;
+ *  - return value: 0 ok, <0 invalid argument / unsupported shape, >0 a cudaError_t; the message
+ *    is available (thread-local) from ctu_last_error();
+ *  - there is NO CPU fallback.
+ *
+ * Activation layout ("blocked"): [N][Cb][D][H][W][8], Cb = ceil(C/8); the 8 channels of one
+ * voxel are contiguous (16 B in bf16, 32 B in fp32); pad lanes (channel >= C) are always zero.
+ * `dtype` selects the storage type of blocked activations: CTU_BF16 is the product mode
+ * (fp32 accumulation everywhere), CTU_F32 is the fp32 "accumulate-check" mode of north_star.
+ * A convolution / head input may be the channel concatenation of up to CTU_MAX_SRC blocked tensors
+ * (the reference's `cat((ubl, d[-i-1]), 1)`, models.py:249, is never materialised): `h_srcs[i]`
+ * with `h_src_channels[i]` real channels each, concatenated in order.
+ */
+#ifndef CTUNET_B200_H
+#define CTUNET_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define CTU_OK 0
+#define CTU_ERR_INVALID (-1)
+#define CTU_ERR_UNSUPPORTED (-2)
+#define CTU_MAX_SRC 4
+
+typedef enum { CTU_F32 = 0, CTU_BF16 = 1 } ctu_dtype;
+typedef void* ctu_stream; /* cudaStream_t */
+
+/* head flags (ctu_head_fwd / ctu_head_bwd) */
+#define CTU_HEAD_SOFTMAX 1    /* F.softmax(lc, dim=1)            models.py:258, :538 */
+#define CTU_HEAD_SIGMOID 2    /* torch.sigmoid(out)              models.py:259       */
+#define CTU_HEAD_SP 4         /* UNetSP/UNetDO encode            models.py:319-330   */
+#define CTU_HEAD_SP_SOFTMAX 8 /* UNetSPSmall softmax of each pair models.py:364-365  */
+
+const char* ctu_last_error(void);
+int ctu_version(void);
+/* 1 if the library contains the tcgen05/TMA implicit-GEMM convolution kernels */
+int ctu_has_tensor_path(void);
+
+/* ---- layout: fp32 NCDHW (the reference's tensors, Model.py:343) <-> blocked ---------------- */
+int ctu_pack_ncdhw(const float* src, void* dst, int dtype, int n, int c, long long spatial, ctu_stream stream);
+int ctu_unpack_ncdhw(const void* src, float* dst, int dtype, int n, int c, long long spatial, ctu_stream stream);
+
+/* ---- Conv3d k^3, stride 1, "same" zero padding (nn.Conv3d at models.py:26,29,38,41,71,76,
+ *      403,407,430,434,483,487), k in {1,3,5}.  Weights are re-packed from the native
+ *      [Cout][Cin][k][k][k] fp32 parameter into [cob][cib][tap][ci8][co8] fp32. -------------- */
+long long ctu_conv_wpack_floats(int cout, int k, int nsrc, const int* h_src_channels);
+int ctu_conv_pack_weight(const float* w, float* wp, int cout, int k, int nsrc, const int* h_src_channels,
+                         ctu_stream stream);
+/* packed weights of the data-gradient convolution dy -> d(src[which]) (flipped taps, transposed) */
+long long ctu_conv_wpack_dgrad_floats(int cout, int k, int src_channels);
+int ctu_conv_pack_weight_dgrad(const float* w, float* wpd, int cout, int k, int nsrc, const int* h_src_channels,
+                               int which, ctu_stream stream);
+int ctu_conv_unpack_wgrad(const float* dwp, float* dw, int cout, int k, int nsrc, const int* h_src_channels,
+                          ctu_stream stream);
+/* y = conv(cat(srcs)) (+ bias).  The data gradient is the same call on dy with dgrad-packed
+ * weights.  use_tensor_path: 0 = CUDA-core direct kernel (both dtypes), 1 = tcgen05 implicit GEMM
+ * (bf16 only; returns CTU_ERR_UNSUPPORTED for shapes it does not cover). */
+int ctu_conv3d_fprop(int dtype, const void* const* h_srcs, const int* h_src_channels, int nsrc, const float* wp,
+                     const float* bias, void* y, int cout, int k, int n, int d, int h, int w, int use_tensor_path,
+                     ctu_stream stream);
+/* dwp (packed layout, fp32) and dbias (nullable, [cout]) are zeroed by the call, then accumulated */
+int ctu_conv3d_wgrad(int dtype, const void* const* h_srcs, const int* h_src_channels, int nsrc, const void* dy,
+                     float* dwp, float* dbias, int cout, int k, int n, int d, int h, int w, int use_tensor_path,
+                     ctu_stream stream);
+
+/* ---- ConvTranspose3d k=2, stride 2, with bias (models.py:37, :427).  Native weight
+ *      [Cin][Cout][2][2][2]; packed [cob][cib][abc][ci8][co8].  n,d,h,w are the INPUT dims. --- */
+long long ctu_convt_wpack_floats(int cout, int nsrc, const int* h_src_channels);
+int ctu_convt_pack_weight(const float* w, float* wp, int cout, int nsrc, const int* h_src_channels, ctu_stream stream);
+long long ctu_convt_wpack_dgrad_floats(int cout, int src_channels);
+int ctu_convt_pack_weight_dgrad(const float* w, float* wpd, int cout, int nsrc, const int* h_src_channels, int which,
+                                ctu_stream stream);
+int ctu_convt_unpack_wgrad(const float* dwp, float* dw, int cout, int nsrc, const int* h_src_channels,
+                           ctu_stream stream);
+int ctu_convt2_fprop(int dtype, const void* const* h_srcs, const int* h_src_channels, int nsrc, const float* wp,
+                     const float* bias, void* y, int cout, int n, int d, int h, int w, ctu_stream stream);
+int ctu_convt2_dgrad(int dtype, const void* dy, const float* wpd, void* dx, int cout, int src_channels, int n, int d,
+                     int h, int w, ctu_stream stream);
+int ctu_convt2_wgrad(int dtype, const void* const* h_srcs, const int* h_src_channels, int nsrc, const void* dy,
+                     float* dwp, float* dbias, int cout, int n, int d, int h, int w, ctu_stream stream);
+
+/* ---- BatchNorm3d (+ReLU, + MaxPool3d(2,2)) (models.py:27-28,31-32,39-40,43-44,190-191,233) ---
+ * sums: double[2*cpad] = per-channel sum and sum of squares (zeroed by ctu_bn_stats).
+ * ss:   float[4*cpad]  = scale | shift | mean | invstd, cpad = 8*ceil(c/8).                    */
+int ctu_bn_stats(int dtype, const void* y, int c, int n, long long spatial, double* sums, ctu_stream stream);
+int ctu_bn_finalize(const double* sums, double count, const float* gamma, const float* beta, float* running_mean,
+                    float* running_var, long long* num_batches_tracked, float momentum, float eps, int c,
+                    int training, int n_updates, float* ss, ctu_stream stream);
+/* extra running-stat update(s) with the same batch statistics: the reentrant-checkpoint
+ * recomputation of models.py:232 */
+int ctu_bn_running_update(const double* sums, double count, float* running_mean, float* running_var,
+                          long long* num_batches_tracked, float momentum, int c, int n_updates, ctu_stream stream);
+/* a = relu(scale*y+shift); if pooled != NULL also pooled = maxpool2(a) (d,h,w even) */
+int ctu_bn_relu_fwd(int dtype, const void* y, const float* ss, void* a, void* pooled, int c, int n, int d, int h, int w,
+                    ctu_stream stream);
+/* backward, pass 1: sums2 = double[2*cpad] = sum(dz), sum(dz*xhat) with
+ * dz = (dA + unpool(dP)) * [a > 0]; dA and dP are nullable (not both) */
+int ctu_bn_relu_bwd_reduce(int dtype, const void* y, const float* ss, const void* dA, const void* dP, double* sums2,
+                           int c, int n, int d, int h, int w, ctu_stream stream);
+/* backward, pass 2: dy, dgamma[c], dbeta[c] */
+int ctu_bn_relu_bwd_apply(int dtype, const void* y, const float* ss, const float* gamma, const void* dA, const void* dP,
+                          const double* sums2, double count, void* dy, float* dgamma, float* dbeta, int c, int n, int d,
+                          int h, int w, ctu_stream stream);
+
+/* ---- head: last_conv 1x1x1 + bias (models.py:224,255 / :507,535), optional softmax / sigmoid,
+ *      UNetSP encode.  w is the NATIVE [cout][cin_total] fp32 parameter.  Outputs are fp32 NCDHW:
+ *      out0 = [n][cout] planes (plain) or the encoded full skull [n][2]; out1 = encoded flap. --- */
+int ctu_head_fwd(int dtype, const void* const* h_srcs, const int* h_src_channels, int nsrc, const float* w,
+                 const float* bias, int cout, int flags, float* out0, float* out1, int n, long long spatial,
+                 ctu_stream stream);
+/* dsrcs[i] nullable; dw [cout][cin_total] and db [cout] are zeroed by the call */
+int ctu_head_bwd(int dtype, const void* const* h_srcs, const int* h_src_channels, int nsrc, const float* w,
+                 const float* bias, int cout, int flags, const float* dout0, const float* dout1, void* const* h_dsrcs,
+                 float* dw, float* db, int n, long long spatial, ctu_stream stream);
+
+/* ---- loss: soft Dice (utilities.py:39-50) + CrossEntropy (ProblemHandler.py:67-70, 247-257) on
+ *      one prediction/target pair, fp32 NCDHW [b][c][spatial], c <= 4.
+ * sums: double[4*b] (zeroed by the call): sum p*t, sum p*p, sum t*t, CE sum.
+ * out:  float[2] = { ce_mean, dice_loss }.                                                      */
+int ctu_dice_ce_fwd(const float* pred, const float* target, int b, int c, long long spatial, int softmax_for_dice,
+                    int want_ce, double* sums, float* out, ctu_stream stream);
+/* dpred = g[0] * dCE/dpred + g[1] * dDice/dpred; g is a DEVICE float[2] */
+int ctu_dice_ce_bwd(const float* pred, const float* target, int b, int c, long long spatial, int softmax_for_dice,
+                    int want_ce, const double* sums, const float* g, float* dpred, ctu_stream stream);
+
+/* ---- hard segmentation: argmax over channels as float32, ties -> lowest index
+ *      (utilities.py:103-124) ------------------------------------------------------------------ */
+int ctu_argmax_channels(const float* x, float* out, int b, int c, long long spatial, ctu_stream stream);
+
+/* ---- virtual craniectomy (transforms.py:241-300, utilities.py:127-178), uint8 volumes -------- */
+/* count[0] = number of voxels > 0 (np.argwhere(image > 0).shape[0], transforms.py:249) */
+int ctu_count_nonzero_u8(const unsigned char* img, long long nvox, long long* count, ctu_stream stream);
+/* coords[0..2] = np.argwhere(img > 0)[k] in C order; block_counts is scratch: long long[ceil(nvox/4096)+1] */
+int ctu_kth_nonzero_u8(const unsigned char* img, int d, int h, int w, long long k, long long* block_counts, int* coords,
+                       ctu_stream stream);
+/* shape: 0 sphere (2-norm), 1 box (inf-norm); centre read from DEVICE int[3];
+ * masked = img AND outside, extracted = img AND inside (distance <= size, float64 like numpy) */
+int ctu_flap_mask_u8(const unsigned char* img, unsigned char* masked, unsigned char* extracted, int d, int h, int w,
+                     const int* center, double size, int shape, ctu_stream stream);
+
+/* ---- CT preprocessing (no reference implementation: oracle/unet_oracle.py defines it) -------- */
+int ctu_hu_window(const short* hu, float* out, long long nvox, float lo, float hi, ctu_stream stream);
+int ctu_hu_threshold(const short* hu, unsigned char* out, long long nvox, int thr, ctu_stream stream);
+int ctu_resample_nearest_f32(const float* src, float* dst, int sd, int sh, int sw, int dd, int dh, int dw,
+                             ctu_stream stream);
+int ctu_resample_nearest_u8(const unsigned char* src, unsigned char* dst, int sd, int sh, int sw, int dd, int dh, int dw,
+                            ctu_stream stream);
+int ctu_resample_nearest_index(int* idx, int out_size, int in_size, ctu_stream stream);
+int ctu_resample_trilinear_f32(const float* src, float* dst, int sd, int sh, int sw, int dd, int dh, int dw,
+                               ctu_stream stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTUNET_B200_H */

@@ -1,0 +1,262 @@
+"""Model-level parity (GPU): the drop-in modules against the CPU oracle (oracle/unet_oracle.py,
+pinned to the reference by tests/test_oracle_pinned.py) and against the golden vectors produced by
+the unmodified reference (tests/golden/reference_golden.pt).
+
+Tolerances (north_star): fp32 accumulate-check mode 1e-4; bf16 mode logits within 2e-2 relative,
+Dice within 0.5 % absolute.
+"""
+import copy
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+CLASSES = ["UNet", "UNetSP", "UNetSPSmall", "UNetDO", "UNet4_2IC", "recAE_v2_fixed"]
+
+
+def _x(cin, size, seed, batch=1, thr=0.7):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.rand(batch, cin, size, size, size, generator=g) > thr).float()
+
+
+def _targets(batch, size, seed):
+    g = torch.Generator().manual_seed(seed)
+    sk = (torch.rand(batch, size, size, size, generator=g) > 0.6).long()
+    fl = ((torch.rand(batch, size, size, size, generator=g) > 0.8) & (sk > 0)).long()
+    oh = lambda t: torch.nn.functional.one_hot(t, 2).permute(0, 4, 1, 2, 3).float().contiguous()
+    return oh(sk), oh(fl)
+
+
+def _build(name, mode):
+    import ctunet_b200 as C
+    C.set_compute_dtype(mode)
+    torch.manual_seed(0)
+    net = getattr(C, name)()
+    C.set_compute_dtype("bf16")
+    return net
+
+
+def _relerr(a, b):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
+
+
+@pytest.mark.parametrize("name", CLASSES)
+def test_eval_forward_fp32_matches_reference_golden(golden, name):
+    """fp32 accumulate-check mode against the reference's own outputs (same seed, same input)."""
+    from oracle import unet_oracle as O
+    g = golden["classes"][name]
+    net = _build(name, "fp32").to(DEV).eval()
+    x = _x(O.PRESETS[name].input_channels, 32, 1)
+    with torch.no_grad():
+        out = net(x.to(DEV))
+    outs = out if isinstance(out, tuple) else (out,)
+    assert len(outs) == len(g["eval32"]["out_sums"])
+    for o, s, sl, am, hs in zip(outs, g["eval32"]["out_sums"], g["eval32"]["out_slices"], g["eval32"]["argmax_ones"],
+                                g["eval32"]["hard_segm_slice"]):
+        assert o.dtype == torch.float32 and o.shape[0] == 1 and o.shape[2:] == (32, 32, 32)
+        assert _relerr(o[:, :, 12:20, 12:20, 12:20], sl) < 1e-4
+        assert float(o.double().sum()) == pytest.approx(s, rel=1e-5)
+        import ctunet_b200 as C
+        lab = C.hard_segm_from_tensor(o)
+        # label agreement with the reference away from (numerical) ties
+        ref_lab = hs
+        mism = (lab[:, 12:20, 12:20, 12:20].cpu() != ref_lab)
+        margin = (sl[:, 0] - sl[:, 1]).abs() if sl.shape[1] == 2 else None
+        if margin is not None:
+            assert not bool((mism & (margin > 1e-4)).any())
+        assert abs(int(lab.sum()) - am) <= max(2, int(1e-3 * lab.numel()))
+
+
+@pytest.mark.parametrize("name", CLASSES)
+def test_eval_forward_bf16_within_tolerance(name):
+    from oracle import unet_oracle as O
+    cfg = O.PRESETS[name]
+    sd = O.build_state_dict(cfg, seed=0)
+    net = _build(name, "bf16").to(DEV).eval()
+    x = _x(cfg.input_channels, 32, 1)
+    with torch.no_grad():
+        ref = O.unet_forward(sd, x, cfg, training=False)
+        out = net(x.to(DEV))
+    outs = out if isinstance(out, tuple) else (out,)
+    refs = ref if isinstance(ref, tuple) else (ref,)
+    for o, r in zip(outs, refs):
+        assert _relerr(o, r) < 2e-2
+
+
+def _train_step(name, mode, size, batch, handler):
+    """One training step of the product path; returns everything the parity checks look at."""
+    import ctunet_b200 as C
+    import types
+    from oracle import unet_oracle as O
+    cfg = O.PRESETS[name]
+    net = _build(name, mode).to(DEV).train()
+    x = _x(cfg.input_channels, size, 7, batch).to(DEV)
+    sk_t, fl_t = _targets(batch, size, 11)
+    fake = types.SimpleNamespace(params=dict(dice_lambda=1.0, ce_lambda=1.0, save_dice_plots=False,
+                                             save_hd_plots=False), losses_and_metrics={}, pt_loss=None)
+    x.requires_grad_()
+    out = net(x)
+    if handler == "double":
+        C.FlapRecWithShapePriorDoubleOut.comp_losses_metrics(fake, out, (sk_t.to(DEV), fl_t.to(DEV)), 0, 1, verbose=False)
+    else:
+        C.ProblemHandler.comp_losses_metrics(fake, out, sk_t.to(DEV), 0, 1, verbose=False)
+    fake.pt_loss.backward()
+    return net, x, out, fake
+
+
+@pytest.mark.parametrize("name", ["UNetSP", "UNetDO", "UNetSPSmall", "UNet4_2IC", "recAE_v2_fixed"])
+def test_train_step_fp32_matches_reference_golden(golden, name):
+    g = golden["train_step"][name]
+    net, x, out, fake = _train_step(name, "fp32", g["size"], g["batch"], g["handler"])
+    assert float(fake.pt_loss) == pytest.approx(g["loss"], rel=1e-4)
+    for k, v in g["components"].items():
+        assert fake.losses_and_metrics[k][0] == pytest.approx(v, rel=1e-4), k
+    named = dict(net.named_parameters())
+    assert [n for n, p in named.items() if p.grad is None] == g["grad_none"]
+    for k, v in g["grad_abs_sum"].items():
+        assert float(named[k].grad.double().abs().sum()) == pytest.approx(v, rel=2e-3, abs=1e-6), k
+        ref = g["grad_head"][k]
+        got = named[k].grad.flatten()[:8].cpu()
+        scale = max(v / named[k].numel(), 1e-8)        # mean |grad| of this tensor
+        assert float((got - ref).abs().max()) <= 1e-3 * max(float(ref.abs().max()), scale) + 1e-7, k
+    assert float(x.grad.double().abs().sum()) == pytest.approx(g["x_grad_abs_sum"], rel=2e-3)
+    sd = net.state_dict()
+    for k, v in g["bn_after"].items():
+        if k.endswith("num_batches_tracked"):
+            assert int(sd[k]) == int(v), k
+        else:
+            assert torch.allclose(sd[k].cpu(), v, rtol=1e-4, atol=1e-6), k
+
+
+@pytest.mark.parametrize("name,handler,size,batch", [("UNetSP", "double", 32, 2), ("recAE_v2_fixed", "single", 16, 2)])
+def test_train_step_bf16_within_tolerance(name, handler, size, batch):
+    """bf16 product mode against the fp32 oracle: loss (Dice) within 0.5 % absolute, gradients close in
+    the normwise sense."""
+    from oracle import unet_oracle as O
+    cfg = O.PRESETS[name]
+    sd = O.build_state_dict(cfg, seed=0)
+    pn = [k for k in sd if not k.endswith(("running_mean", "running_var", "num_batches_tracked"))]
+    for k in pn:
+        sd[k].requires_grad_()
+    x = _x(cfg.input_channels, size, 7, batch)
+    sk_t, fl_t = _targets(batch, size, 11)
+    ref_out = O.unet_forward(sd, x, cfg, training=True)
+    if handler == "double":
+        ref_loss, comps = O.loss_double_output(ref_out, (sk_t, fl_t), 1.0, 1.0)
+    else:
+        ref_loss, comps = O.loss_single_output(ref_out, sk_t, 1.0, 1.0)
+    ref_loss.backward()
+    net, xg, out, fake = _train_step(name, "bf16", size, batch, handler)
+    for k, v in comps.items():
+        assert abs(fake.losses_and_metrics[k][0] - float(v)) < 5e-3, k
+    outs = out if isinstance(out, tuple) else (out,)
+    refs = ref_out if isinstance(ref_out, tuple) else (ref_out,)
+    for o, r in zip(outs, refs):
+        assert _relerr(o, r) < 2e-2
+    named = dict(net.named_parameters())
+    worst = 0.0
+    for k in pn:
+        if sd[k].grad is None:
+            assert named[k].grad is None
+            continue
+        gr, gg = sd[k].grad.double(), named[k].grad.cpu().double()
+        rel = ((gg - gr).norm() / gr.norm().clamp_min(1e-12)).item()
+        worst = max(worst, rel)
+    assert worst < 0.15, "worst normwise gradient error %.3f" % worst
+
+
+def test_checkpoint_roundtrip_and_state_dict_layout(golden, tmp_path):
+    """Appendix B layout: keys/shapes equal the reference's; a reference-style checkpoint (bare
+    state_dict, optionally 'module.'-prefixed through nn.DataParallel) loads and re-saves."""
+    import ctunet_b200 as C
+    from oracle import unet_oracle as O
+    for name in CLASSES:
+        g = golden["classes"][name]
+        net = _build(name, "bf16")
+        sd = net.state_dict()
+        assert list(sd.keys()) == g["keys"] and [tuple(v.shape) for v in sd.values()] == g["shapes"]
+        ref_sd = O.build_state_dict(O.PRESETS[name], seed=3)
+        net.load_state_dict(ref_sd)                          # strict
+        p = tmp_path / (name + ".pt")
+        torch.save(net.state_dict(), p)
+        back = torch.load(p)
+        assert all(torch.equal(back[k], ref_sd[k]) for k in ref_sd)
+    net = _build("UNetSP", "bf16")
+    dp = torch.nn.DataParallel(net)
+    assert all(k.startswith("module.") for k in dp.state_dict())
+
+
+def test_training_reduces_loss_and_matches_oracle_trajectory():
+    """Three Adam(amsgrad) steps (Model.py:515-520) in fp32 check mode track the oracle's losses."""
+    import types
+    import ctunet_b200 as C
+    from oracle import unet_oracle as O
+    cfg = O.PRESETS["UNetSP"]
+    sd = O.build_state_dict(cfg, seed=0)
+    pn = [k for k in sd if not k.endswith(("running_mean", "running_var", "num_batches_tracked"))]
+    for k in pn:
+        sd[k].requires_grad_()
+    live = [sd[k] for k in pn if not k.startswith("cblock")]
+    opt_r = torch.optim.Adam([sd[k] for k in pn], lr=1e-3, amsgrad=True)
+    net = _build("UNetSP", "fp32").to(DEV).train()
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3, amsgrad=True)
+    x = _x(2, 16, 7, 2)
+    sk_t, fl_t = _targets(2, 16, 11)
+    ref_losses, losses = [], []
+    for it in range(3):
+        out = O.unet_forward(sd, x.clone().requires_grad_(), cfg, training=True)
+        loss, _ = O.loss_double_output(out, (sk_t, fl_t), 1.0, 1.0)
+        loss.backward()
+        opt_r.step()
+        for p in live:
+            p.grad = None
+        ref_losses.append(float(loss))
+        fake = types.SimpleNamespace(params=dict(dice_lambda=1.0, ce_lambda=1.0, save_dice_plots=False,
+                                                 save_hd_plots=False), losses_and_metrics={}, pt_loss=None)
+        o = net(x.to(DEV).requires_grad_())
+        C.FlapRecWithShapePriorDoubleOut.comp_losses_metrics(fake, o, (sk_t.to(DEV), fl_t.to(DEV)), it, 3, verbose=False)
+        fake.pt_loss.backward()
+        opt.step()
+        for p in net.parameters():
+            p.grad = None
+        losses.append(float(fake.pt_loss))
+    assert losses[-1] < losses[0]
+    for a, b in zip(losses, ref_losses):
+        assert a == pytest.approx(b, rel=2e-3)
+
+
+def test_no_grad_training_mode_updates_buffers_once():
+    """Train mode under torch.no_grad(): checkpoint never recomputes, so every BatchNorm moves once."""
+    net = _build("UNetSP", "fp32").to(DEV).train()
+    with torch.no_grad():
+        net(_x(2, 16, 1, 2).to(DEV))
+    sd = net.state_dict()
+    assert int(sd["d_blocks.0.block.1.num_batches_tracked"]) == 1
+    assert int(sd["cblock.block.1.num_batches_tracked"]) == 1
+
+
+def test_sliding_window_argmax_matches_oracle():
+    from oracle import unet_oracle as O
+    from ctunet_b200 import preprocess as P
+    cfg = O.PRESETS["UNetSP"]
+    sd = O.build_state_dict(cfg, seed=0)
+    net = _build("UNetSP", "fp32").to(DEV).eval()
+    g = torch.Generator().manual_seed(9)
+    vol = (torch.rand(2, 32, 64, 32, generator=g) > 0.7).float()
+    ref = O.sliding_window_argmax(sd, vol, cfg, patch=32)
+    out = P.sliding_window_argmax(net, vol.to(DEV), patch=32, batch=2)
+    for o, r in zip(out, ref):
+        agree = (o.cpu() == r).float().mean().item()
+        assert agree > 0.9999, agree
+
+
+def test_cpu_input_raises():
+    net = _build("UNetSP", "bf16")
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(1, 2, 16, 16, 16))
+    net = net.to(DEV)
+    with pytest.raises(ValueError):
+        net(torch.zeros(1, 2, 24, 16, 16, device=DEV))

@@ -1,0 +1,132 @@
+"""CPU: host-side logic of the drop-in surface -- constructors, state_dict layout, same-seed
+initialisation, loud failure without CUDA, and the name-rebinding plug-in used by the reference's
+``eval(model_class)`` lookup (ctunet/pytorch/Model.py:101,485,488)."""
+import types
+
+import pytest
+import torch
+
+CLASSES = ["UNet", "UNetSP", "UNetSPSmall", "UNetDO", "UNet4_2IC", "recAE_v2_fixed"]
+
+
+@pytest.mark.parametrize("name", CLASSES)
+def test_state_dict_layout_and_same_seed_init(golden, name):
+    import ctunet_b200 as C
+    g = golden["classes"][name]
+    torch.manual_seed(0)
+    net = getattr(C, name)()
+    sd = net.state_dict()
+    assert list(sd.keys()) == g["keys"]
+    assert [tuple(v.shape) for v in sd.values()] == g["shapes"]
+    assert len(sd) == g["n_state_entries"]
+    params = list(net.parameters())
+    assert sum(p.numel() for p in params) == g["n_params"]
+    assert abs(float(sum(p.detach().double().abs().sum() for p in params)) - g["abs_sum"]) < 1e-9
+    assert torch.equal(params[0].detach().flatten()[:3], g["first3"])
+    assert all(v.dtype == torch.float32 for k, v in sd.items() if not k.endswith("num_batches_tracked"))
+    assert sd[[k for k in sd if k.endswith("num_batches_tracked")][0]].dtype == torch.int64
+
+
+def test_reference_attributes_present():
+    import ctunet_b200 as C
+    net = C.UNet()
+    for attr in ["chk", "skip", "apply_softmax", "apply_sigmoid", "fc_layer", "cat", "mp", "d_blocks", "cblock",
+                 "u_blocks", "last_conv"]:
+        assert hasattr(net, attr), attr
+    assert net.chk is True and net.apply_sigmoid is True and net.apply_softmax is False
+    assert len(net.d_blocks) == 4 and len(net.u_blocks) == 4
+    leg = C.recAE_v2_fixed()
+    for attr in ["chk", "mp", "dblock1", "dblock4", "cblock_center", "ublock1", "ublock4", "last_conv"]:
+        assert hasattr(leg, attr), attr
+    custom = C.UNet(input_channels=3, out_channels=4, n_blocks=2, i_size=5)
+    assert custom.last_conv.weight.shape == (4, 10, 1, 1, 1)
+
+
+def test_unsupported_variants_raise():
+    import ctunet_b200 as C
+    with pytest.raises(NotImplementedError):
+        C.UNet(residual=True)
+    with pytest.raises(NotImplementedError):
+        C.UNet(fc_layer=[8, 4])
+    with pytest.raises(NotImplementedError):
+        C.UNet(cat=False)
+    with pytest.raises(NotImplementedError):
+        C.UNet(kern_sz_conv=3, padding=0)
+    with pytest.raises(NotImplementedError):
+        C.UNetBlock(2, 4).forward(torch.zeros(1))
+
+
+def test_no_cpu_fallback():
+    import ctunet_b200 as C
+    net = C.UNetSP()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net(torch.zeros(1, 2, 16, 16, 16))
+    with pytest.raises(RuntimeError):
+        C.hard_segm_from_tensor(torch.zeros(1, 2, 4, 4, 4))
+    with pytest.raises(RuntimeError):
+        C.dice_loss()(torch.zeros(1, 2, 4), torch.zeros(1, 2, 4))
+    with pytest.raises(RuntimeError):
+        C.blank_patch(torch.zeros(4, 4, 4, dtype=torch.uint8), (1, 1, 1), 1, "sphere")
+
+
+def test_product_package_never_imports_the_oracle():
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "ctunet_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), fn
+            assert "/root/reference" not in src, fn
+
+
+def test_install_rebinds_reference_names():
+    """``install`` makes eval('UNetSP')() inside the trainer module resolve to the B200 class and swaps
+    the loss half of the handlers, leaving the reference's dataset/writer halves alone."""
+    import ctunet_b200 as C
+
+    class RefHandler:                      # stands in for ctunet.pytorch.ProblemHandler.ProblemHandler
+        @staticmethod
+        def comp_losses_metrics(model, prediction, target, idx, n_imgs):
+            raise AssertionError("reference loss must have been replaced")
+
+        def write_predictions(self, *a):
+            return "reference writer kept"
+
+    class RefDouble(RefHandler):
+        pass
+
+    trainer = types.ModuleType("fake_trainer")
+    trainer.ProblemHandler = RefHandler
+    trainer.FlapRecWithShapePriorDoubleOut = RefDouble
+    trainer.UNetSP = object
+    done = C.install(trainer)
+    assert eval("UNetSP", vars(trainer)) is C.UNetSP
+    assert eval("recAE_v2_fixed", vars(trainer)) is C.recAE_v2_fixed
+    assert "UNetSP" in done and "FlapRecWithShapePriorDoubleOut.comp_losses_metrics" in done
+    assert RefDouble().write_predictions() == "reference writer kept"
+    assert RefDouble.comp_losses_metrics is not RefHandler.comp_losses_metrics
+    assert RefDouble.comp_losses_metrics.__doc__.startswith("ProblemHandler.py:213")
+
+
+def test_install_into_real_reference_when_present():
+    from oracle.reference_loader import reference_available, load_reference
+    if not reference_available():
+        pytest.skip("reference tree not mounted (GPU box)")
+    import importlib
+    import ctunet_b200 as C
+    load_reference()
+    trainer = importlib.import_module("ctunet.pytorch.Model")
+    saved = {k: getattr(trainer, k) for k in C.MODEL_CLASSES}
+    ph = trainer.FlapRecWithShapePriorDoubleOut.comp_losses_metrics
+    base = trainer.ProblemHandler.comp_losses_metrics
+    try:
+        C.install()
+        assert type(eval("UNetSP", vars(trainer))()).__module__ == "ctunet_b200.models"
+    finally:
+        for k, v in saved.items():
+            setattr(trainer, k, v)
+        trainer.FlapRecWithShapePriorDoubleOut.comp_losses_metrics = staticmethod(ph)
+        trainer.ProblemHandler.comp_losses_metrics = staticmethod(base)
+        torch.autograd.set_detect_anomaly(False)
