@@ -260,11 +260,15 @@ __global__ void __launch_bounds__(kBnThreads) bn_relu_bwd_kernel(BwdArgs p) {
         offs[0] = (base + s) * 8;
     }
     if (active) {
+        // av: the activation BEFORE rounding to the storage type.  Rounding is monotone, so the maximum of
+        // the rounded values is the rounded maximum (forward/backward stay consistent) while values that
+        // collide in bf16 still elect the arg-max an fp32 evaluation would.
         V8 yv[NCH], av[NCH];
 #pragma unroll
         for (int q = 0; q < NCH; ++q) {
             yv[q] = Vec8<T>::load(y + offs[q]);
-            av[q] = bn_relu_apply<T>(yv[q], sc, sh);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) av[q].v[j] = fmaxf(fmaf(yv[q].v[j], sc[j], sh[j]), 0.f);
         }
         int win[8];
         if (POOL) {

@@ -20,7 +20,7 @@ struct ConvParams {
     void* y;
     int cout, cob_n;
     int n, d, h, w;
-    int tw, th, dg;           // thread tile: tw*th*dg == 256, tile depth td = dg*RD
+    int tw, th, dg;           // thread tile: tw*th*dg <= 256, tile depth td = dg*RD
     int tiles_w, tiles_h, tiles_d;
 };
 
@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(kThreads) conv3d_direct_kernel(ConvParams p) {
     const int r = tid / p.tw;
     const int lh = r % p.th;
     const int dgi = r / p.th;
+    const bool active = dgi < p.dg;       // small volumes: the tile is capped, surplus threads only help loading
 
     float acc[RD][8];
 #pragma unroll
@@ -82,6 +83,7 @@ __global__ void __launch_bounds__(kThreads) conv3d_direct_kernel(ConvParams p) {
                 Vec8<T>::store(tile + (long long)i * 8, v);
             }
             __syncthreads();
+            if (!active) continue;
             for (int kd = 0; kd < K; ++kd)
                 for (int kh = 0; kh < K; ++kh)
 #pragma unroll
@@ -122,7 +124,7 @@ __global__ void __launch_bounds__(kThreads) conv3d_direct_kernel(ConvParams p) {
     }
     T* yb = reinterpret_cast<T*>(p.y) + ((long long)n * p.cob_n + cob) * plane * 8;
     const int gx = x0 + lw, gy = y0 + lh;
-    if (gx < p.w && gy < p.h && lw < p.tw && lh < p.th) {
+    if (active && gx < p.w && gy < p.h) {
 #pragma unroll
         for (int j = 0; j < RD; ++j) {
             int gz = z0 + dgi * RD + j;
@@ -268,7 +270,7 @@ __global__ void __launch_bounds__(kThreads) conv3d_wgrad_kernel(WgradParams p) {
     }
 }
 
-static void pick_tile(int w, int h, int& tw, int& th, int& dg) {
+static void pick_tile(int w, int h, int d, int& tw, int& th, int& dg) {
     tw = 32;
     while (tw > 1 && tw / 2 >= w) tw /= 2;      // smallest power of two >= min(w, 32)
     int rest = kThreads / tw;
@@ -277,6 +279,8 @@ static void pick_tile(int w, int h, int& tw, int& th, int& dg) {
     while (th > 1 && th / 2 >= h) th /= 2;
     while (th * 2 <= rest && th < h && th < 16 && tw < 32) th *= 2;
     dg = rest / th;
+    const int need = (d + RD - 1) / RD;          // never tile deeper than the volume
+    if (dg > need) dg = need;
 }
 
 template <typename T>
@@ -355,7 +359,7 @@ int ctu_conv3d_fprop(int dtype, const void* const* h_srcs, const int* h_src_chan
     }
     p.nsrc = nsrc; p.cb_total = m.cb_total; p.wp = wp; p.bias = bias; p.y = y;
     p.cout = cout; p.cob_n = (cout + 7) / 8; p.n = n; p.d = d; p.h = h; p.w = w;
-    pick_tile(w, h, p.tw, p.th, p.dg);
+    pick_tile(w, h, d, p.tw, p.th, p.dg);
     p.tiles_w = cdiv(w, p.tw); p.tiles_h = cdiv(h, p.th); p.tiles_d = cdiv(d, p.dg * RD);
     CTU_DISPATCH_DTYPE(dtype, return launch_fprop<T>(p, k, (cudaStream_t)stream));
     return CTU_OK;
