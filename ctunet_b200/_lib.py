@@ -36,7 +36,10 @@ SIGNATURES = {
     "ctu_conv_wpack_dgrad_floats": (LL, [I, I, I]),
     "ctu_conv_pack_weight_dgrad": (I, [P, P, I, I, I, P, I, P]),
     "ctu_conv_unpack_wgrad": (I, [P, P, I, I, I, P, P]),
-    "ctu_conv3d_fprop": (I, [I, P, P, I, P, P, P, I, I, I, I, I, I, I, P]),
+    "ctu_conv3d_fprop": (I, [I, P, P, I, P, P, P, P, I, I, I, I, I, I, I, P]),
+    "ctu_conv_tc_supported": (I, [I, I, I, I, I, I]),
+    "ctu_conv_tc_wimg_bytes": (LL, [I, I, I]),
+    "ctu_conv_tc_pack_weight": (I, [P, P, I, I, I, P]),
     "ctu_conv3d_wgrad": (I, [I, P, P, I, P, P, P, I, I, I, I, I, I, I, P]),
     "ctu_convt_wpack_floats": (LL, [I, I, P]),
     "ctu_convt_pack_weight": (I, [P, P, I, I, P, P]),

@@ -327,7 +327,7 @@ static int launch_wgrad(const WgradParams& p, int k, cudaStream_t stream) {
 
 // implemented in conv_tc.cu
 int conv3d_fprop_tc(const void* const* h_srcs, const int* h_src_channels, int nsrc, const float* wp, const float* bias,
-                    void* y, int cout, int k, int n, int d, int h, int w, cudaStream_t stream);
+                    void* y, double* stats, int cout, int k, int n, int d, int h, int w, cudaStream_t stream);
 int conv3d_wgrad_tc(const void* const* h_srcs, const int* h_src_channels, int nsrc, const void* dy, float* dwp,
                     float* dbias, int cout, int k, int n, int d, int h, int w, cudaStream_t stream);
 
@@ -337,9 +337,9 @@ using namespace ctu;
 
 extern "C" {
 
-int ctu_conv3d_fprop(int dtype, const void* const* h_srcs, const int* h_src_channels, int nsrc, const float* wp,
-                     const float* bias, void* y, int cout, int k, int n, int d, int h, int w, int use_tensor_path,
-                     ctu_stream stream) {
+int ctu_conv3d_fprop(int dtype, const void* const* h_srcs, const int* h_src_channels, int nsrc, const void* wp,
+                     const float* bias, void* y, double* bn_sums, int cout, int k, int n, int d, int h, int w,
+                     int use_tensor_path, ctu_stream stream) {
     SrcMap m;
     int rc = make_srcmap(m, nsrc, h_src_channels);
     if (rc != CTU_OK) return rc;
@@ -350,19 +350,22 @@ int ctu_conv3d_fprop(int dtype, const void* const* h_srcs, const int* h_src_chan
             set_error("ctu_conv3d_fprop: the tensor path is bf16 only");
             return CTU_ERR_UNSUPPORTED;
         }
-        return conv3d_fprop_tc(h_srcs, h_src_channels, nsrc, wp, bias, y, cout, k, n, d, h, w, (cudaStream_t)stream);
+        return conv3d_fprop_tc(h_srcs, h_src_channels, nsrc, (const float*)wp, bias, y, bn_sums, cout, k, n, d, h, w,
+                               (cudaStream_t)stream);
     }
     ConvParams p;
     for (int i = 0; i < CTU_MAX_SRC; ++i) {
         p.src[i] = i < nsrc ? h_srcs[i] : nullptr;
         p.src_cb[i] = i < nsrc ? (m.ch[i] + 7) / 8 : 0;
     }
-    p.nsrc = nsrc; p.cb_total = m.cb_total; p.wp = wp; p.bias = bias; p.y = y;
+    p.nsrc = nsrc; p.cb_total = m.cb_total; p.wp = (const float*)wp; p.bias = bias; p.y = y;
     p.cout = cout; p.cob_n = (cout + 7) / 8; p.n = n; p.d = d; p.h = h; p.w = w;
     pick_tile(w, h, d, p.tw, p.th, p.dg);
     p.tiles_w = cdiv(w, p.tw); p.tiles_h = cdiv(h, p.th); p.tiles_d = cdiv(d, p.dg * RD);
-    CTU_DISPATCH_DTYPE(dtype, return launch_fprop<T>(p, k, (cudaStream_t)stream));
-    return CTU_OK;
+    CTU_DISPATCH_DTYPE(dtype, rc = launch_fprop<T>(p, k, (cudaStream_t)stream));
+    if (rc == CTU_OK && bn_sums != nullptr)
+        rc = ctu_bn_stats(dtype, y, cout, n, (long long)d * h * w, bn_sums, stream);
+    return rc;
 }
 
 int ctu_conv3d_wgrad(int dtype, const void* const* h_srcs, const int* h_src_channels, int nsrc, const void* dy,

@@ -31,10 +31,11 @@ CONV_PATH = "auto"
 
 class Act:
     """A channel-blocked activation [N][Cb][D][H][W][8] (bf16 in product mode, fp32 in check mode)."""
-    __slots__ = ("buf", "c", "n", "d", "h", "w")
+    __slots__ = ("buf", "c", "n", "d", "h", "w", "sums")
 
     def __init__(self, buf, c, n, d, h, w):
         self.buf, self.c, self.n, self.d, self.h, self.w = buf, c, n, d, h, w
+        self.sums = None        # per-channel sum / sum of squares written by the producing conv's epilogue
 
     @property
     def cb(self):
@@ -99,6 +100,22 @@ class Engine:
     def _tc_ok(self, k, srcs, cout):
         return self.use_tc and tc_supported(k, [s.c for s in srcs], cout, srcs[0].d, srcs[0].h, srcs[0].w)
 
+    def _conv_launch(self, srcs, wp, bias, y: Act, cout, k, sums):
+        """One forward-style convolution launch (also used for the data gradient): tcgen05 implicit GEMM when
+        the kernel covers the shape, CUDA-core direct kernel otherwise."""
+        s0 = srcs[0]
+        pa, ca, ns = self._src_args(srcs)
+        tc = self._tc_ok(k, srcs, cout)
+        wptr = wp.data_ptr()
+        if tc:
+            lib = _lib.load()
+            wimg = torch.empty(lib.ctu_conv_tc_wimg_bytes(k, s0.c, cout), dtype=torch.uint8, device=self.device)
+            call("ctu_conv_tc_pack_weight", wp.data_ptr(), wimg.data_ptr(), k, s0.c, cout, stream_ptr())
+            wptr = wimg.data_ptr()
+        call("ctu_conv3d_fprop", self.dtype, pa, ca, ns, wptr, bias.data_ptr() if bias is not None else None,
+             y.ptr, sums.data_ptr() if sums is not None else None, cout, k, s0.n, s0.d, s0.h, s0.w, int(tc),
+             stream_ptr())
+
     # ------------------------------------------------------------------ layout
     def pack(self, x: torch.Tensor) -> Act:
         n, c, d, h, w = x.shape
@@ -112,7 +129,9 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ Conv3d
-    def conv(self, srcs: Sequence[Act], weight, bias, k: int, need_src_grad: Sequence[bool]) -> Act:
+    def conv(self, srcs: Sequence[Act], weight, bias, k: int, need_src_grad: Sequence[bool],
+             bn_stats: bool = False) -> Act:
+        """``bn_stats``: also produce the batch statistics of the output (``y.sums``) for the BatchNorm that follows."""
         cout = weight.shape[0]
         s0 = srcs[0]
         pa, ca, ns = self._src_args(srcs)
@@ -120,8 +139,9 @@ class Engine:
         wp = self.f32(lib.ctu_conv_wpack_floats(cout, k, ns, ca))
         call("ctu_conv_pack_weight", weight.data_ptr(), wp.data_ptr(), cout, k, ns, ca, stream_ptr())
         y = self.new_act(cout, s0.n, s0.d, s0.h, s0.w)
-        call("ctu_conv3d_fprop", self.dtype, pa, ca, ns, wp.data_ptr(), bias.data_ptr() if bias is not None else None,
-             y.ptr, cout, k, s0.n, s0.d, s0.h, s0.w, int(self._tc_ok(k, srcs, cout)), stream_ptr())
+        if bn_stats:
+            y.sums = self.f64(2 * y.cb * 8)
+        self._conv_launch(srcs, wp, bias, y, cout, k, y.sums)
         if self.record:
             srcs = list(srcs)
             need = list(need_src_grad)
@@ -134,7 +154,7 @@ class Engine:
                     db = self._grad_buffer(bias) if (bias is not None and bias.requires_grad) else None
                     call("ctu_conv3d_wgrad", self.dtype, pa, ca, ns, dy.ptr, dwp.data_ptr(),
                          db.data_ptr() if db is not None else None, cout, k, s0.n, s0.d, s0.h, s0.w,
-                         int(self._tc_ok(k, srcs, cout)), stream_ptr())
+                         0, stream_ptr())
                     dw = self._grad_buffer(weight)
                     call("ctu_conv_unpack_wgrad", dwp.data_ptr(), dw.data_ptr(), cout, k, ns, ca, stream_ptr())
                     self._add_pgrad(weight, dw)
@@ -146,9 +166,7 @@ class Engine:
                     wpd = self.f32(lib.ctu_conv_wpack_dgrad_floats(cout, k, s.c))
                     call("ctu_conv_pack_weight_dgrad", weight.data_ptr(), wpd.data_ptr(), cout, k, ns, ca, i, stream_ptr())
                     dx = self.new_act(s.c, s.n, s.d, s.h, s.w)
-                    dpa, dca, _ = self._src_args([dy])
-                    call("ctu_conv3d_fprop", self.dtype, dpa, dca, 1, wpd.data_ptr(), None, dx.ptr, s.c, k,
-                         s.n, s.d, s.h, s.w, int(self._tc_ok(k, [dy], s.c)), stream_ptr())
+                    self._conv_launch([dy], wpd, None, dx, s.c, k, None)
                     self._set_agrad(s, dx)
 
             self.tape.append(bwd)
@@ -211,8 +229,10 @@ class Engine:
         sums = None
         st = stream_ptr()
         if training:
-            sums = self.f64(2 * cpad)
-            call("ctu_bn_stats", self.dtype, y.ptr, c, y.n, y.spatial, sums.data_ptr(), st)
+            sums = y.sums
+            if sums is None:
+                sums = self.f64(2 * cpad)
+                call("ctu_bn_stats", self.dtype, y.ptr, c, y.n, y.spatial, sums.data_ptr(), st)
             track = bn.track_running_stats and bn.running_mean is not None
             mom = BN_MOMENTUM if bn.momentum is None else float(bn.momentum)
             call("ctu_bn_finalize", sums.data_ptr(), count, bn.weight.data_ptr(), bn.bias.data_ptr(),
@@ -296,5 +316,7 @@ class Engine:
 
 
 def tc_supported(k, src_channels, cout, d, h, w) -> bool:
-    """Shapes covered by the tcgen05 implicit-GEMM kernels (must mirror conv_tc.cu)."""
-    return False
+    """Shapes covered by the tcgen05 implicit-GEMM convolution (the predicate lives in conv_tc.cu)."""
+    if len(src_channels) != 1:
+        return False
+    return bool(_lib.load().ctu_conv_tc_supported(k, src_channels[0], cout, d, h, w))

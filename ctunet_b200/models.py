@@ -251,9 +251,9 @@ class UNet(_FusedNet):
         skips = []
         for i, blk in enumerate(self.d_blocks):
             seq = blk.block
-            y = eng.conv([cur], seq[0].weight, seq[0].bias, k, [eng.want_input_grad if i == 0 else True])
+            y = eng.conv([cur], seq[0].weight, seq[0].bias, k, [eng.want_input_grad if i == 0 else True], training)
             a = eng.bn_relu(y, seq[1], training, extra)
-            y = eng.conv([a], seq[3].weight, seq[3].bias, k, [True])
+            y = eng.conv([a], seq[3].weight, seq[3].bias, k, [True], training)
             s, cur = eng.bn_relu(y, seq[4], training, extra, pool=True)        # skip tensor + MaxPool (models.py:233)
             skips.append(s)
         if training:
@@ -261,18 +261,18 @@ class UNet(_FusedNet):
             # discarded: no gradient ever reaches it.
             rec, eng.record = eng.record, False
             seq = self.cblock.block
-            y = eng.conv([cur], seq[0].weight, seq[0].bias, k, [False])
+            y = eng.conv([cur], seq[0].weight, seq[0].bias, k, [False], True)
             a = eng.bn_relu(y, seq[1], True)
-            y = eng.conv([a], seq[3].weight, seq[3].bias, k, [False])
+            y = eng.conv([a], seq[3].weight, seq[3].bias, k, [False], True)
             eng.bn_relu(y, seq[4], True)
             eng.record = rec
         srcs = [cur]
         for i, blk in enumerate(self.u_blocks):
             seq = blk.block
             t = eng.convt(srcs, seq[0].weight, seq[0].bias, [True] * len(srcs))
-            y = eng.conv([t], seq[1].weight, seq[1].bias, k, [True])
+            y = eng.conv([t], seq[1].weight, seq[1].bias, k, [True], training)
             a = eng.bn_relu(y, seq[2], training, extra)
-            y = eng.conv([a], seq[4].weight, seq[4].bias, k, [True])
+            y = eng.conv([a], seq[4].weight, seq[4].bias, k, [True], training)
             ubl = eng.bn_relu(y, seq[5], training, extra)
             srcs = [ubl, skips[-i - 1]] if self.skip else [ubl]                  # models.py:247-253 (cat folded)
         return eng.head(srcs, self.last_conv.weight, self.last_conv.bias, self._head_flags())
@@ -393,22 +393,22 @@ class recAE_v2_fixed(_FusedNet):
         eng.input_act = cur
         skips = []
         for i, seq in enumerate([self.dblock1, self.dblock2, self.dblock3, self.dblock4]):
-            y = eng.conv([cur], seq[0].weight, seq[0].bias, k, [eng.want_input_grad if i == 0 else True])
+            y = eng.conv([cur], seq[0].weight, seq[0].bias, k, [eng.want_input_grad if i == 0 else True], training)
             a = eng.bn_relu(y, seq[1], training, extra)
-            y = eng.conv([a], seq[3].weight, seq[3].bias, k, [True])
+            y = eng.conv([a], seq[3].weight, seq[3].bias, k, [True], training)
             s, cur = eng.bn_relu(y, seq[4], training, extra, pool=True)
             skips.append(s)
         seq = self.cblock_center
-        y = eng.conv([cur], seq[0].weight, seq[0].bias, k, [True])
+        y = eng.conv([cur], seq[0].weight, seq[0].bias, k, [True], training)
         a = eng.bn_relu(y, seq[1], training, extra)
-        y = eng.conv([a], seq[3].weight, seq[3].bias, k, [True])
+        y = eng.conv([a], seq[3].weight, seq[3].bias, k, [True], training)
         cur = eng.bn_relu(y, seq[4], training, extra)
         srcs = [cur]
         for i, seq in enumerate([self.ublock1, self.ublock2, self.ublock3, self.ublock4]):
             t = eng.convt(srcs, seq[0].weight, seq[0].bias, [True] * len(srcs))
-            y = eng.conv([t], seq[1].weight, seq[1].bias, k, [True])
+            y = eng.conv([t], seq[1].weight, seq[1].bias, k, [True], training)
             a = eng.bn_relu(y, seq[2], training, extra)
-            y = eng.conv([a], seq[4].weight, seq[4].bias, k, [True])
+            y = eng.conv([a], seq[4].weight, seq[4].bias, k, [True], training)
             up = eng.bn_relu(y, seq[5], training, extra)
             srcs = [up, skips[3 - i]]                                            # models.py:528-534
         return eng.head(srcs, self.last_conv.weight, self.last_conv.bias, _lib.HEAD_SOFTMAX)   # models.py:538

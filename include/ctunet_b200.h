@@ -71,11 +71,18 @@ int ctu_conv_pack_weight_dgrad(const float* w, float* wpd, int cout, int k, int 
 int ctu_conv_unpack_wgrad(const float* dwp, float* dw, int cout, int k, int nsrc, const int* h_src_channels,
                           ctu_stream stream);
 /* y = conv(cat(srcs)) (+ bias).  The data gradient is the same call on dy with dgrad-packed
- * weights.  use_tensor_path: 0 = CUDA-core direct kernel (both dtypes), 1 = tcgen05 implicit GEMM
- * (bf16 only; returns CTU_ERR_UNSUPPORTED for shapes it does not cover). */
-int ctu_conv3d_fprop(int dtype, const void* const* h_srcs, const int* h_src_channels, int nsrc, const float* wp,
-                     const float* bias, void* y, int cout, int k, int n, int d, int h, int w, int use_tensor_path,
-                     ctu_stream stream);
+ * weights.  bn_sums (nullable, double[2*cpad]): per-channel sum / sum of squares of y for the
+ * BatchNorm that follows (fused into the epilogue where possible, so ctu_bn_stats is not needed).
+ * use_tensor_path: 0 = CUDA-core direct kernel (both dtypes; wp = fp32 packed weights),
+ * 1 = tcgen05/TMA implicit GEMM (bf16, one source, shapes accepted by ctu_conv_tc_supported;
+ * wp = the bf16 B-tile image written by ctu_conv_tc_pack_weight). */
+int ctu_conv3d_fprop(int dtype, const void* const* h_srcs, const int* h_src_channels, int nsrc, const void* wp,
+                     const float* bias, void* y, double* bn_sums, int cout, int k, int n, int d, int h, int w,
+                     int use_tensor_path, ctu_stream stream);
+/* tcgen05 path: coverage predicate, size of the weight image, and the re-pack fp32 packed -> image */
+int ctu_conv_tc_supported(int k, int cin, int cout, int d, int h, int w);
+long long ctu_conv_tc_wimg_bytes(int k, int cin, int cout);
+int ctu_conv_tc_pack_weight(const float* wp, void* wimg, int k, int cin, int cout, ctu_stream stream);
 /* dwp (packed layout, fp32) and dbias (nullable, [cout]) are zeroed by the call, then accumulated */
 int ctu_conv3d_wgrad(int dtype, const void* const* h_srcs, const int* h_src_channels, int nsrc, const void* dy,
                      float* dwp, float* dbias, int cout, int k, int n, int d, int h, int w, int use_tensor_path,

@@ -1,0 +1,97 @@
+"""tcgen05/TMA implicit-GEMM convolution (conv_tc.cu) against fp32 PyTorch on the CPU and against the
+CUDA-core direct kernel, on the layer shapes of the networks (GPU)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+# (k, cin, cout, bias, (n, d, h, w))
+CASES = [
+    (3, 2, 7, False, (1, 4, 16, 16)),
+    (3, 7, 7, False, (2, 9, 32, 16)),
+    (3, 14, 14, False, (1, 8, 16, 32)),
+    (3, 28, 7, False, (1, 6, 16, 16)),
+    (3, 7, 14, False, (1, 3, 16, 16)),
+    (3, 14, 28, False, (1, 5, 32, 32)),
+    (3, 56, 14, False, (1, 4, 16, 16)),      # odd number of channel blocks (7): tap-paired tail
+    (3, 24, 24, False, (1, 4, 16, 16)),      # 3 blocks
+    (3, 28, 28, False, (1, 40, 16, 16)),     # several d-chunks
+    (5, 1, 8, True, (1, 6, 16, 16)),
+    (5, 8, 8, True, (1, 5, 16, 32)),
+    (5, 16, 8, True, (1, 4, 16, 16)),
+    (3, 7, 7, True, (1, 2, 16, 16)),
+    (3, 7, 7, False, (1, 1, 16, 16)),
+]
+
+
+def _bf(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_tc_conv_matches_reference(case):
+    from ctunet_b200.engine import Engine, tc_supported
+    from ctunet_b200 import _lib
+    k, cin, cout, use_bias, (n, d, h, w) = case
+    assert _lib.load().ctu_has_tensor_path() == 1
+    assert tc_supported(k, [cin], cout, d, h, w)
+    g = torch.Generator().manual_seed(k * 100 + cin)
+    x = _bf(torch.randn(n, cin, d, h, w, generator=g))
+    wt = torch.randn(cout, cin, k, k, k, generator=g) / (cin * k ** 3) ** 0.5
+    bs = torch.randn(cout, generator=g) if use_bias else None
+    dy = _bf(torch.randn(n, cout, d, h, w, generator=g))
+    xr = x.clone().requires_grad_()
+    yr = F.conv3d(xr, _bf(wt), bs, 1, k // 2)       # the tensor path rounds the weights to bf16
+    yr.backward(dy)
+
+    eng = Engine(torch.device(DEV), "bf16", record=True)
+    assert eng.use_tc
+    wg = wt.to(DEV).requires_grad_()
+    bg = bs.to(DEV).requires_grad_() if use_bias else None
+    xa = eng.pack(x.to(DEV))
+    y = eng.conv([xa], wg, bg, k, [True], bn_stats=True)
+    yo = eng.unpack(y).cpu()
+    scale = yr.abs().max().item()
+    err = (yo - yr.detach()).abs().max().item()
+    assert err <= 1e-2 * scale, "fprop err %.3e (scale %.3e)" % (err, scale)
+    # fused BatchNorm statistics = sums of the stored (bf16-rounded) outputs
+    sums = y.sums.cpu()
+    cpad = (cout + 7) // 8 * 8
+    ref_sum = yo.double().sum((0, 2, 3, 4))
+    ref_sq = (yo.double() ** 2).sum((0, 2, 3, 4))
+    assert torch.allclose(sums[:cout], ref_sum, rtol=1e-4, atol=1e-2 * scale)
+    assert torch.allclose(sums[cpad:cpad + cout], ref_sq, rtol=1e-4, atol=1e-3)
+    # data gradient through the same kernel (flipped / transposed weights)
+    eng.agrads[id(y)] = eng.pack(dy.to(DEV))
+    for fn in reversed(eng.tape):
+        fn()
+    dx = eng.unpack(eng.agrads[id(xa)]).cpu()
+    gs = xr.grad.abs().max().item()
+    gerr = (dx - xr.grad).abs().max().item()
+    assert gerr <= 1.2e-2 * gs, "dgrad err %.3e (scale %.3e)" % (gerr, gs)
+
+
+def test_tc_and_direct_agree_on_network_layer():
+    """Same bf16 inputs through both kernels: only weight rounding and accumulation order differ."""
+    import ctunet_b200.engine as E
+    g = torch.Generator().manual_seed(3)
+    x = _bf(torch.rand(2, 7, 8, 32, 32, generator=g))
+    wt = (torch.randn(7, 7, 3, 3, 3, generator=g) * 0.1).to(DEV)
+    outs = []
+    for path in ("auto", "direct"):
+        E.CONV_PATH = path
+        try:
+            eng = E.Engine(torch.device(DEV), "bf16", record=False)
+            outs.append(eng.unpack(eng.conv([eng.pack(x.to(DEV))], wt, None, 3, [False])).cpu())
+        finally:
+            E.CONV_PATH = "auto"
+    assert (outs[0] - outs[1]).abs().max().item() <= 1e-2 * outs[1].abs().max().item()
+
+
+def test_unsupported_shapes_fall_back_to_direct():
+    from ctunet_b200.engine import tc_supported
+    assert not tc_supported(3, [7], 7, 8, 8, 8)          # h, w not multiples of 16
+    assert not tc_supported(1, [7], 7, 16, 16, 16)       # 1x1x1 is the head kernel's job
+    assert not tc_supported(3, [7, 7], 7, 16, 16, 16)    # concatenated sources go through ConvTranspose / head
