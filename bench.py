@@ -203,7 +203,9 @@ def describe(name, args, esize):
         if name in ("ctu_conv3d_fprop", "ctu_conv3d_wgrad"):
             ca, ns = args[2], args[3]
             cin = sum(ca[i] for i in range(ns))
-            cout, k, n, d, h, w = args[7], args[8], args[9], args[10], args[11], args[12]
+            o = 8 if name == "ctu_conv3d_fprop" else 7
+            cout, k, n, d, h, w = args[o], args[o + 1], args[o + 2], args[o + 3], args[o + 4], args[o + 5]
+            name = name + ("[tcgen05]" if args[o + 6] else "[cuda-core]")
             vox = n * d * h * w
             fl = 2.0 * vox * cin * cout * k ** 3
             by = esize * vox * (cin + cout) + 4.0 * cin * cout * k ** 3
@@ -321,21 +323,25 @@ def run_b200_arm(a):
 
     for _ in range(max(a.warmup, 3)):
         resident()
-    prof = CallProfiler(torch)
-    orig, timed_call = prof.wrap(_lib)
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
     l0 = _lib.launches
+    ms_resident = timed(resident, a.steps)
+    launches = _lib.launches - l0
+    clk = clocks.stop() if rank == 0 else None
+    # the same K steps again with a CUDA-event pair around every C-ABI call (on the launching stream): the
+    # per-kernel durations behind `roofline`.  Kept out of the `value` loop: creating ~1500 events per step in
+    # Python costs more host time than the step itself.
+    prof = CallProfiler(torch)
+    orig, timed_call = prof.wrap(_lib)
     import ctunet_b200.engine as E
     import ctunet_b200.losses as LS
     E.call = LS.call = timed_call
     try:
-        ms_resident = timed(resident, a.steps)
+        timed(resident, a.steps)
     finally:
         E.call = LS.call = orig
-    launches = _lib.launches - l0
-    clk = clocks.stop() if rank == 0 else None
 
     # ---- end-to-end steps: pinned host -> device every iteration, loss read back ----------------
     copy_stream = torch.cuda.Stream(device=dev)
@@ -405,6 +411,11 @@ def run_b200_arm(a):
         roof["peak_source"] = peaks["source"]
         break
     top = [{"kernel": k, "ms_per_step": v[0] / a.steps, "share": v[0] / total_ms} for k, v in ranked[:8]]
+    by_entry = {}
+    for k, v in agg.items():
+        e = k.split(" ")[0]
+        by_entry[e] = by_entry.get(e, 0.0) + v[0] / a.steps
+    by_entry = dict(sorted(by_entry.items(), key=lambda kv: -kv[1]))
 
     cpu = None
     if world == 1 and not a.no_cpu_baseline:
@@ -427,6 +438,8 @@ def run_b200_arm(a):
         "roofline": roof,
         "cpu_baseline": cpu,
         "top_kernels": top,
+        "ms_per_step_by_entry_point": by_entry,
+        "profiled_ms_per_step": total_ms / a.steps,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

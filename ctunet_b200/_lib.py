@@ -38,6 +38,7 @@ SIGNATURES = {
     "ctu_conv_unpack_wgrad": (I, [P, P, I, I, I, P, P]),
     "ctu_conv3d_fprop": (I, [I, P, P, I, P, P, P, P, I, I, I, I, I, I, I, P]),
     "ctu_conv_tc_supported": (I, [I, I, I, I, I, I]),
+    "ctu_conv_tc_wgrad_supported": (I, [I, I, I, I, I, I]),
     "ctu_conv_tc_wimg_bytes": (LL, [I, I, I]),
     "ctu_conv_tc_pack_weight": (I, [P, P, I, I, I, P]),
     "ctu_conv3d_wgrad": (I, [I, P, P, I, P, P, P, I, I, I, I, I, I, I, P]),

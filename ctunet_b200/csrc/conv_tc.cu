@@ -23,9 +23,13 @@
 
 namespace ctu {
 
-constexpr int TC_THREADS = 192;
 constexpr int TC_TH = 16, TC_TW = 16;   // output tile (h, w) per plane = 2 MMA tiles of 16x8
 constexpr int TC_WB = TC_TW / 8;
+// fprop/dgrad: warp 0 TMA producer, warps 1..2 MMA issuers (one per 16x8 tile), warps 3..10 epilogue (4 per tile)
+// wgrad: warp 0 TMA producer, warps 1..4 MMA issuers (accumulators dealt round-robin) and final flush
+constexpr int WG_ISSUERS = 4;
+constexpr int WG_THREADS = 32 * (1 + WG_ISSUERS);
+constexpr int WG_MAX_OWN = 16;          // accumulators per issuer warp
 
 // ------------------------------------------------------------------------------------------------ PTX
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -68,6 +72,13 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4,
+                                            uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(bar)
+        : "memory");
+}
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar)
@@ -81,6 +92,20 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+// accumulate variant without the predicate set-up (the hot loop)
+__device__ __forceinline__ void umma_bf16_acc(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.eq.b32 p, 0, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t pack64(uint32_t lo, uint32_t hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -103,6 +128,18 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo_bytes,
     d |= (uint64_t)1 << 46;
     return d;
 }
+
+// Position in a ring of `ns` shared-memory slots guarded by full/empty mbarriers.
+struct Ring {
+    uint32_t slot, phase;
+    __device__ __forceinline__ void next(uint32_t ns) {
+        if (++slot == ns) {
+            slot = 0;
+            phase ^= 1;
+        }
+    }
+};
+constexpr int TC_MAX_SLOTS = 16;
 
 // ------------------------------------------------------------------------------------------------ schedule
 // MMAs of one kd-plane: first every (tap, channel-block pair) -- second K chunk = the next channel block --
@@ -130,108 +167,92 @@ __host__ __device__ inline bool tc_chunk(int k, int cb, int m, int c, int& blk, 
 }
 
 struct TcParams {
-    const __nv_bfloat16* wimg;   // [K kd][mmas_per_kd][N/8][2][8][8] bf16 (the UMMA B tiles, in order of use)
+    const __nv_bfloat16* wimg;   // [mma m][NT/8][2][8][8] bf16: UMMA B tiles in order of use, n = kd*cpad + co
     const float* bias;
     __nv_bfloat16* y;
     double* stats;               // nullable: [2][cpad_out] sum, sum of squares (of the bf16-rounded outputs)
-    int cb, cob_n, npad, cout;
+    int cb, cob_n, nt, cout;     // nt: MMA N = K*COB*8 rounded up to 16
+    int ob0, nob;                // output blocks [ob0, ob0+nob) are produced by this launch (nob <= COB)
     int n, d, h, w;
     int tiles_h, tiles_w, dchunks, dc;
     int total_items;
     uint32_t wimg_bytes, plane_bytes, slot_bytes;   // plane_bytes: one channel block of one plane, padded to 128
     uint32_t tmem_cols;
+    uint32_t ns;                                    // plane ring depth (more slots = more TMA loads in flight)
 };
 
-// fp32 packed weights [cob][cib][tap][ci][co] -> the bf16 B-tile image above
+// fp32 packed weights [cob][cib][tap][ci][co] -> the bf16 B-tile images, one per output-block group of `cobg`
 __global__ void tc_pack_wimg_kernel(const float* __restrict__ wp, __nv_bfloat16* __restrict__ wimg, int k, int cb,
-                                    int cob_n, int npad, long long total) {
+                                    int cob_n, int cobg, int nt, int nm, long long total) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int e = (int)(i & 7), r = (int)((i >> 3) & 7), c = (int)((i >> 6) & 1);
     long long q = i >> 7;
-    const int ngroups = npad / 8;
+    const int ngroups = nt / 8;
     const int g = (int)(q % ngroups);
     q /= ngroups;
-    const int nm = tc_mmas_per_kd(k, cb);
     const int m = (int)(q % nm);
-    const int kd = (int)(q / nm);
+    const int grp = (int)(q / nm);
+    const int kd = g / cobg, cob = grp * cobg + g % cobg;
     int blk, tap2d;
     float v = 0.f;
-    if (tc_chunk(k, cb, m, c, blk, tap2d) && g < cob_n) {
+    if (kd < k && cob < cob_n && tc_chunk(k, cb, m, c, blk, tap2d)) {
         const int taps = k * k * k, tap = kd * k * k + tap2d;
-        v = wp[(((long long)g * cb + blk) * taps + tap) * 64 + e * 8 + r];   // e = input lane (K), r = output lane (N)
+        v = wp[(((long long)cob * cb + blk) * taps + tap) * 64 + e * 8 + r];   // e = input lane (K), r = output lane (N)
     }
     wimg[i] = __float2bfloat16_rn(v);
 }
 
-// Epilogue of one 8-channel output block of one voxel row: TMEM -> (+bias) -> bf16 -> 16-byte store (+ statistics).
-template <bool CAN_STATS>
-__device__ __forceinline__ void tc_emit(uint32_t taddr, int ob, const TcParams& p, __nv_bfloat16* ybase, long long plane,
-                                        bool inb, bool want_stats, float (&s1)[8], float (&s2)[8]) {
-    float v[8];
-    tmem_ld8(taddr + ob * 8, v);
-    V8 o;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const int ch = ob * 8 + c;
-        float x = v[c];
-        if (p.bias != nullptr && ch < p.cout) x += __ldg(p.bias + ch);
-        o.v[c] = round_to<__nv_bfloat16>(x);
-    }
-    if (inb) {
-        Vec8<__nv_bfloat16>::store(ybase + (long long)ob * plane * 8, o);
-        if (CAN_STATS && want_stats) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                s1[c] += o.v[c];
-                s2[c] = fmaf(o.v[c], o.v[c], s2[c]);
-            }
-        }
-    }
-}
-
-template <int K>
-__global__ void __launch_bounds__(TC_THREADS) conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcParams p) {
+// One CTA walks (n, 16x16 h-w tile, d-chunk) items plane by plane.  For every INPUT plane and every 16x8 tile a
+// single accumulation group of tc_mmas_per_kd() MMAs computes P[voxel][kd][co] = sum_{kh,kw,ci} x * W, i.e. the
+// three (five) kd taps ride in the MMA N dimension: the activation tile is read from shared memory once per
+// plane instead of once per kd (SS-mode UMMA is bound by the A-operand read, ~64 B/clk, not by the math, when N
+// is this small).  The epilogue thread of a voxel column adds P[kd] of K consecutive planes in registers.
+template <int K, int COB>
+__global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                                                 TcParams p) {
     constexpr int PAD = K / 2;
-    constexpr int NS = K + 1;                      // plane ring
     constexpr int HH = TC_TH + K - 1, WW = TC_TW + K - 1;
     constexpr uint32_t ROW = WW * 16;              // bytes per halo row of one channel block
+    constexpr int CP = COB * 8;                    // padded output channels
+    constexpr int NTHREADS = 32 * (1 + TC_WB + 4 * TC_WB);
+    const uint32_t NS = p.ns;
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t s_base = smem_u32(smem);
     const uint32_t s_w = s_base;                                            // weights image
     const uint32_t s_planes = s_base + ((p.wimg_bytes + 1023u) & ~1023u);   // NS slots
-    const uint32_t s_tab = s_planes + NS * p.slot_bytes;                    // per-MMA A descriptor low words
+    const uint32_t s_tab = s_planes + NS * p.slot_bytes;                    // per-MMA descriptor low words (A, B)
     const int nm = tc_mmas_per_kd(K, p.cb);
-    uint32_t* tab = reinterpret_cast<uint32_t*>(smem + (s_tab - s_base));
-    const uint32_t s_bar = s_tab + ((nm * 4u + 15u) & ~15u);
-    // barriers: plane_full[NS], plane_empty[NS], acc_full[2], acc_empty[2], w_full
-    const uint32_t b_full = s_bar, b_empty = s_bar + 8 * NS, b_afull = s_bar + 16 * NS, b_aempty = b_afull + 16,
-                   b_w = b_afull + 32;
+    uint2* tab = reinterpret_cast<uint2*>(smem + (s_tab - s_base));
+    const uint32_t s_bar = s_tab + ((nm * 8u + 15u) & ~15u);
+    // barriers: plane_full[NS], plane_empty[NS], acc_full[2 stages][TC_WB tiles], acc_empty[2][TC_WB], w_full
+    const uint32_t b_full = s_bar, b_empty = s_bar + 8 * TC_MAX_SLOTS, b_afull = s_bar + 16 * TC_MAX_SLOTS,
+                   b_aempty = b_afull + 8 * 2 * TC_WB, b_w = b_aempty + 8 * 2 * TC_WB;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (b_w + 8 - s_base));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < NS; ++i) {
+        for (uint32_t i = 0; i < NS; ++i) {
             mbar_init(b_full + 8 * i, 1);
-            mbar_init(b_empty + 8 * i, 1);
+            mbar_init(b_empty + 8 * i, TC_WB);      // every issuer warp releases the plane
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < 2 * TC_WB; ++i) {
             mbar_init(b_afull + 8 * i, 1);
             mbar_init(b_aempty + 8 * i, 4);
         }
         mbar_init(b_w, 1);
         fence_barrier_init();
     }
-    // A-descriptor table: low word = (offset within a plane slot) >> 4 | (LBO >> 4) << 16
-    for (int m = threadIdx.x; m < nm; m += TC_THREADS) {
+    // descriptor table: A low word = (offset within a plane slot) >> 4 | (LBO >> 4) << 16; B low word likewise
+    for (int m = threadIdx.x; m < nm; m += NTHREADS) {
         int blk0, t0, blk1, t1;
         tc_chunk(K, p.cb, m, 0, blk0, t0);
         const bool real1 = tc_chunk(K, p.cb, m, 1, blk1, t1);
         const uint32_t off0 = blk0 * p.plane_bytes + (t0 / K) * ROW + (t0 % K) * 16;
         const uint32_t off1 = blk1 * p.plane_bytes + (t1 / K) * ROW + (t1 % K) * 16;
         const uint32_t lbo = real1 ? off1 - off0 : 0u;
-        tab[m] = (off0 >> 4) | ((lbo >> 4) << 16);
+        tab[m] = make_uint2((off0 >> 4) | ((lbo >> 4) << 16), ((s_w >> 4) + (uint32_t)m * (uint32_t)p.nt * 2u) | (8u << 16));
     }
     if (warp == 1) {   // TMEM allocation (this warp also frees it)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
@@ -250,12 +271,11 @@ __global__ void __launch_bounds__(TC_THREADS) conv3d_tc_kernel(const __grid_cons
         // ===================================================================== TMA producer
         if (lane == 0) {
             mbar_expect_tx(b_w, p.wimg_bytes);
-            // weights in <= 64 KB pieces (bulk copy size field)
             for (uint32_t off = 0; off < p.wimg_bytes; off += 32768u) {
                 const uint32_t sz = p.wimg_bytes - off < 32768u ? p.wimg_bytes - off : 32768u;
                 bulk_load_1d(s_w + off, reinterpret_cast<const unsigned char*>(p.wimg) + off, sz, b_w);
             }
-            uint32_t it = 0;
+            Ring pr = {0, 0};
             for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
                 const int n = item / items_per_n;
                 int r = item % items_per_n;
@@ -263,76 +283,68 @@ __global__ void __launch_bounds__(TC_THREADS) conv3d_tc_kernel(const __grid_cons
                 const int twi = r % p.tiles_w, thi = r / p.tiles_w;
                 const int z0 = dci * p.dc, h0 = thi * TC_TH, w0 = twi * TC_TW;
                 const int nd = (p.d - z0) < p.dc ? (p.d - z0) : p.dc;
-                for (int pl = 0; pl < nd + K - 1; ++pl, ++it) {
-                    const uint32_t slot = it % NS, ph = (it / NS) & 1;
-                    mbar_wait(b_empty + 8 * slot, ph ^ 1);
-                    mbar_expect_tx(b_full + 8 * slot, (uint32_t)p.cb * HH * WW * 16);
+                for (int pl = 0; pl < nd + K - 1; ++pl, pr.next(NS)) {
+                    mbar_wait(b_empty + 8 * pr.slot, pr.phase ^ 1);
+                    mbar_expect_tx(b_full + 8 * pr.slot, (uint32_t)p.cb * HH * WW * 16);
                     for (int b = 0; b < p.cb; ++b)
-                        tma_load_4d(s_planes + slot * p.slot_bytes + b * p.plane_bytes, &tmap, (w0 - PAD) * 8, h0 - PAD,
-                                    z0 + pl - PAD, n * p.cb + b, b_full + 8 * slot);
+                        tma_load_4d(s_planes + pr.slot * p.slot_bytes + b * p.plane_bytes, &tmap, (w0 - PAD) * 8,
+                                    h0 - PAD, z0 + pl - PAD, n * p.cb + b, b_full + 8 * pr.slot);
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===================================================================== MMA issuer
+    } else if (warp <= TC_WB) {
+        // ===================================================================== MMA issuers (tile t = warp - 1)
         if (lane == 0) {
             // instruction descriptor: D=f32, A=B=bf16, both K-major, N at [17,23), M=128 at [24,29)
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.npad >> 3) << 17) | (8u << 24);
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.nt >> 3) << 17) | (8u << 24);
             const uint32_t a_hi = (ROW >> 4) | (1u << 14);           // SBO = row pitch (next h), version 1
             const uint32_t b_hi = (16u) | (1u << 14);                 // B: SBO = 256 B between n-groups
-            const uint32_t b_lbo = 8u << 16;                          // B: LBO = 128 B between the two K chunks
-            const uint32_t btile16 = (uint32_t)p.npad * 2;            // one B tile = npad*32 bytes
+            const uint32_t t = warp - 1;
             mbar_wait(b_w, 0);
-            uint32_t base = 0, waited = 0, acc_it = 0;
+            uint32_t step = 0;
+            Ring cons = {0, 0};
             for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
                 const int r0 = item % items_per_n;
-                const int dci = r0 % p.dchunks;
-                const int z0 = dci * p.dc;
+                const int z0 = (r0 % p.dchunks) * p.dc;
                 const int nd = (p.d - z0) < p.dc ? (p.d - z0) : p.dc;
-                for (int j = 0; j < nd; ++j, ++acc_it) {
-                    while (waited < base + j + K) {
-                        mbar_wait(b_full + 8 * (waited % NS), (waited / NS) & 1);
-                        ++waited;
-                    }
-                    const uint32_t stage = acc_it & 1;
-                    mbar_wait(b_aempty + 8 * stage, ((acc_it >> 1) & 1) ^ 1);
+                for (int pl = 0; pl < nd + K - 1; ++pl, ++step, cons.next(NS)) {
+                    mbar_wait(b_full + 8 * cons.slot, cons.phase);
+                    const uint32_t stage = step & 1;
+                    mbar_wait(b_aempty + 8 * (stage * TC_WB + t), ((step >> 1) & 1) ^ 1);
                     tc_fence_after();
-#pragma unroll 1
-                    for (int t = 0; t < TC_WB; ++t) {
-                        const uint32_t d_tmem = tmem_base + (stage * TC_WB + t) * p.npad;
-                        uint32_t first = 0;
-#pragma unroll 1
-                        for (int kd = 0; kd < K; ++kd) {
-                            const uint32_t slot = (base + j + kd) % NS;
-                            const uint32_t a16 = (s_planes + slot * p.slot_bytes + t * 128u) >> 4;
-                            uint32_t b16 = (s_w >> 4) + (uint32_t)(kd * nm) * btile16;
-#pragma unroll 1
-                            for (int m = 0; m < nm; ++m, b16 += btile16) {
-                                const uint64_t ad = ((uint64_t)a_hi << 32) | (uint64_t)(tab[m] + a16);
-                                const uint64_t bd = ((uint64_t)b_hi << 32) | (uint64_t)(b16 | b_lbo);
-                                umma_bf16(d_tmem, ad, bd, idesc, first);
-                                first = 1;
-                            }
-                        }
+                    const uint32_t d_tmem = tmem_base + (stage * TC_WB + t) * p.nt;
+                    const uint32_t a16 = (s_planes + cons.slot * p.slot_bytes + t * 128u) >> 4;
+                    {
+                        const uint2 e = tab[0];
+                        umma_bf16(d_tmem, pack64(e.x + a16, a_hi), pack64(e.y, b_hi), idesc, 0u);
                     }
-                    umma_commit(b_afull + 8 * stage);
-                    umma_commit(b_empty + 8 * ((base + j) % NS));   // plane j is not needed by later outputs
+#pragma unroll 4
+                    for (int m = 1; m < nm; ++m) {
+                        const uint2 e = tab[m];
+                        umma_bf16_acc(d_tmem, pack64(e.x + a16, a_hi), pack64(e.y, b_hi), idesc);
+                    }
+                    umma_commit(b_afull + 8 * (stage * TC_WB + t));
+                    umma_commit(b_empty + 8 * cons.slot);
                 }
-                for (int q = 0; q < K - 1; ++q) umma_commit(b_empty + 8 * ((base + nd + q) % NS));
-                base += nd + K - 1;
             }
         }
     } else {
-        // ===================================================================== epilogue (warps 2..5)
+        // ===================================================================== epilogue: 4 warps per tile
+        const int te = (warp - 1 - TC_WB) >> 2;        // tile this warp serves
         const int quarter = warp & 3;                  // TMEM lane quarter this warp may read
         const int row = quarter * 32 + lane;           // row of the 128-row MMA tile
         const int hh = row >> 3, wl = row & 7;
-        float sA[8], qA[8], sB[8], qB[8];              // per-thread BatchNorm statistics of output blocks 0 and 1
         const bool want_stats = p.stats != nullptr;
         const long long plane = (long long)p.d * p.h * p.w;
-        uint32_t acc_it = 0;   // statistics are fused only for cob_n <= 2 (the host splits the rest off)
+        float part[K][CP];                             // partial sums of the K output planes in flight
+        float s1[(COB < 2 ? COB : 2) * 8], s2[(COB < 2 ? COB : 2) * 8];
+        float bv[CP];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) sA[i] = qA[i] = sB[i] = qB[i] = 0.f;
+        for (int c = 0; c < CP; ++c)
+            bv[c] = (p.bias != nullptr && p.ob0 * 8 + c < p.cout) ? __ldg(p.bias + p.ob0 * 8 + c) : 0.f;
+#pragma unroll
+        for (int i = 0; i < (COB < 2 ? COB : 2) * 8; ++i) s1[i] = s2[i] = 0.f;
+        uint32_t step = 0;
         for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
             const int n = item / items_per_n;
             int r = item % items_per_n;
@@ -340,41 +352,67 @@ __global__ void __launch_bounds__(TC_THREADS) conv3d_tc_kernel(const __grid_cons
             const int twi = r % p.tiles_w, thi = r / p.tiles_w;
             const int z0 = dci * p.dc, h0 = thi * TC_TH, w0 = twi * TC_TW;
             const int nd = (p.d - z0) < p.dc ? (p.d - z0) : p.dc;
-            for (int j = 0; j < nd; ++j, ++acc_it) {
-                const uint32_t stage = acc_it & 1;
-                mbar_wait(b_afull + 8 * stage, (acc_it >> 1) & 1);
+            const int gy = h0 + hh, gx = w0 + te * 8 + wl;
+            const bool inb = gy < p.h && gx < p.w;
+            __nv_bfloat16* ycol = p.y + (((long long)n * p.cob_n + p.ob0) * plane + ((long long)gy) * p.w + gx) * 8;
+#pragma unroll
+            for (int i = 0; i < K; ++i)
+#pragma unroll
+                for (int c = 0; c < CP; ++c) part[i][c] = 0.f;
+            for (int pl = 0; pl < nd + K - 1; ++pl, ++step) {
+                const uint32_t stage = step & 1;
+                mbar_wait(b_afull + 8 * (stage * TC_WB + te), (step >> 1) & 1);
                 tc_fence_after();
-                const int gz = z0 + j, gy = h0 + hh;
-#pragma unroll 1
-                for (int t = 0; t < TC_WB; ++t) {
-                    const int gx = w0 + t * 8 + wl;
-                    const bool inb = gy < p.h && gx < p.w;
-                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (stage * TC_WB + t) * p.npad;
-                    __nv_bfloat16* ybase = p.y + (((long long)n * p.cob_n) * plane + ((long long)gz * p.h + gy) * p.w + gx) * 8;
-                    tc_emit<true>(taddr, 0, p, ybase, plane, inb, want_stats, sA, qA);
-                    if (p.cob_n > 1) tc_emit<true>(taddr, 1, p, ybase, plane, inb, want_stats, sB, qB);
-                    for (int ob = 2; ob < p.cob_n; ++ob) tc_emit<false>(taddr, ob, p, ybase, plane, inb, false, sA, qA);
-                }
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (stage * TC_WB + te) * p.nt;
+                // P[kd] of input plane pl feeds output plane pl - kd, kept in part[K-1-kd]
+#pragma unroll
+                for (int kd = 0; kd < K; ++kd)
+#pragma unroll
+                    for (int ob = 0; ob < COB; ++ob) {
+                        float v[8];
+                        tmem_ld8(taddr + kd * CP + ob * 8, v);
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) part[K - 1 - kd][ob * 8 + c] += v[c];
+                    }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(b_aempty + 8 * stage);
+                if (lane == 0) mbar_arrive(b_aempty + 8 * (stage * TC_WB + te));
+                // output plane j = pl - (K-1) is complete
+                const int j = pl - (K - 1);
+                if (j >= 0) {
+                    const int gz = z0 + j;
+#pragma unroll
+                    for (int ob = 0; ob < COB; ++ob) {
+                        V8 o;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) o.v[c] = round_to<__nv_bfloat16>(part[0][ob * 8 + c] + bv[ob * 8 + c]);
+                        if (inb && ob < p.nob) {
+                            Vec8<__nv_bfloat16>::store(ycol + ((long long)ob * plane + (long long)gz * p.h * p.w) * 8, o);
+                            if (ob < 2 && want_stats) {
+#pragma unroll
+                                for (int c = 0; c < 8; ++c) {
+                                    s1[(ob & 1) * 8 + c] += o.v[c];
+                                    s2[(ob & 1) * 8 + c] = fmaf(o.v[c], o.v[c], s2[(ob & 1) * 8 + c]);
+                                }
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i + 1 < K; ++i)
+#pragma unroll
+                    for (int c = 0; c < CP; ++c) part[i][c] = part[i + 1][c];
+#pragma unroll
+                for (int c = 0; c < CP; ++c) part[K - 1][c] = 0.f;
             }
         }
         if (want_stats) {
-            const int cpad = p.cob_n * 8;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float a1 = warp_sum(sA[i]), a2 = warp_sum(qA[i]);
-                const float b1 = warp_sum(sB[i]), b2 = warp_sum(qB[i]);
-                if (lane == 0) {
-                    if (i < p.cout) {
-                        atomicAdd(p.stats + i, (double)a1);
-                        atomicAdd(p.stats + cpad + i, (double)a2);
-                    }
-                    if (8 + i < p.cout) {
-                        atomicAdd(p.stats + 8 + i, (double)b1);
-                        atomicAdd(p.stats + cpad + 8 + i, (double)b2);
-                    }
+            for (int i = 0; i < (COB < 2 ? COB : 2) * 8; ++i) {
+                const float a1 = warp_sum(s1[i]), a2 = warp_sum(s2[i]);
+                if (lane == 0 && i < p.cout) {   // fused statistics: single group only (ob0 == 0, cob_n == COB)
+                    atomicAdd(p.stats + i, (double)a1);
+                    atomicAdd(p.stats + CP + i, (double)a2);
                 }
             }
         }
@@ -401,29 +439,49 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 }
 
 struct TcGeom {
-    int cb, cob_n, npad, nm;
-    uint32_t wimg_bytes, plane_bytes, slot_bytes, tmem_cols;
+    int cb, cob_n, cobg, ngroups, nt, nm;
+    uint32_t wimg_bytes, plane_bytes, slot_bytes, tmem_cols, ns;   // wimg_bytes: ONE group's image
     size_t smem;
 };
+
+// Ring depth: as deep as a ~100 KB budget allows (two CTAs per SM), at least `min_slots`, at most TC_MAX_SLOTS.
+static uint32_t pick_slots(int min_slots, size_t fixed_bytes, size_t slot_bytes) {
+    const size_t budget = 100 * 1024;
+    long long ns = fixed_bytes < budget ? (long long)((budget - fixed_bytes) / slot_bytes) : 0;
+    if (ns < min_slots) ns = min_slots;
+    if (ns > TC_MAX_SLOTS) ns = TC_MAX_SLOTS;
+    return (uint32_t)ns;
+}
 
 static bool tc_geometry(int k, int cin, int cout, int h, int w, TcGeom& g) {
     if (k != 3 && k != 5) return false;
     if (h % TC_TH || w % TC_TW) return false;
     g.cb = (cin + 7) / 8;
     g.cob_n = (cout + 7) / 8;
-    g.npad = (cout + 15) / 16 * 16;
-    if (g.npad > 128) return false;
     g.nm = tc_mmas_per_kd(k, g.cb);
-    g.wimg_bytes = (uint32_t)k * g.nm * g.npad * 32;
     const int hh = TC_TH + k - 1, ww = TC_TW + k - 1;
     g.plane_bytes = ((uint32_t)hh * ww * 16 + 127u) & ~127u;
     g.slot_bytes = g.plane_bytes * g.cb;
-    uint32_t cols = 2 * TC_WB * g.npad;
+    // output blocks per launch: the instantiated COB in {1,2,4} (k=3) / {1,2} (k=5) -- N = K*COB*8 <= 128 so that
+    // 2 stages x 2 tiles fit the 512 TMEM columns -- shrunk until weights + a 3-slot ring fit shared memory
+    int cobg = (k == 3) ? 4 : 2;
+    while (cobg > 1 && cobg / 2 >= g.cob_n) cobg /= 2;
+    for (;; cobg /= 2) {
+        g.cobg = cobg;
+        g.nt = (k * cobg * 8 + 15) / 16 * 16;
+        g.wimg_bytes = (uint32_t)g.nm * g.nt * 32;
+        const size_t fixed = ((g.wimg_bytes + 1023u) & ~1023u) + ((g.nm * 8 + 15) & ~15) +
+                             8 * (2 * TC_MAX_SLOTS + 4 * TC_WB + 2) + 16 + 1024;
+        g.ns = pick_slots(3, fixed, g.slot_bytes);
+        g.smem = fixed + (size_t)g.ns * g.slot_bytes;
+        if (g.smem <= 220 * 1024) break;
+        if (cobg == 1) return false;
+    }
+    g.ngroups = (g.cob_n + g.cobg - 1) / g.cobg;
+    uint32_t cols = 2 * TC_WB * g.nt;
     g.tmem_cols = 32;
     while (g.tmem_cols < cols) g.tmem_cols *= 2;
-    if (g.tmem_cols > 512) return false;
-    g.smem = ((g.wimg_bytes + 1023u) & ~1023u) + (size_t)(k + 1) * g.slot_bytes + ((g.nm * 4 + 15) & ~15) + 8 * (2 * (k + 1) + 5) + 16 + 1024;
-    return g.smem <= 220 * 1024;
+    return g.tmem_cols <= 512;
 }
 
 int conv3d_fprop_tc(const void* const* h_srcs, const int* h_src_channels, int nsrc, const float* wp, const float* bias,
@@ -458,9 +516,9 @@ int conv3d_fprop_tc(const void* const* h_srcs, const int* h_src_channels, int ns
     p.wimg = reinterpret_cast<const __nv_bfloat16*>(wp);
     p.bias = bias;
     p.y = reinterpret_cast<__nv_bfloat16*>(y);
-    const bool fuse_stats = stats != nullptr && g.cob_n <= 2;
+    const bool fuse_stats = stats != nullptr && g.ngroups == 1 && g.cob_n == g.cobg && g.cob_n <= 2;
     p.stats = fuse_stats ? stats : nullptr;
-    p.cb = g.cb; p.cob_n = g.cob_n; p.npad = g.npad; p.cout = cout;
+    p.cb = g.cb; p.cob_n = g.cob_n; p.nt = g.nt; p.cout = cout;
     p.n = n; p.d = d; p.h = h; p.w = w;
     p.tiles_h = h / TC_TH; p.tiles_w = w / TC_TW;
     // d-chunk: enough work items to balance 148 SMs x resident CTAs, but at least 8 planes per chunk
@@ -471,6 +529,7 @@ int conv3d_fprop_tc(const void* const* h_srcs, const int* h_src_channels, int ns
     p.dchunks = (d + dc - 1) / dc;
     p.total_items = tiles * p.dchunks;
     p.wimg_bytes = g.wimg_bytes; p.plane_bytes = g.plane_bytes; p.slot_bytes = g.slot_bytes; p.tmem_cols = g.tmem_cols;
+    p.ns = g.ns;
     if (fuse_stats) {
         cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(double) * 2 * g.cob_n * 8, stream);
         if (e != cudaSuccess) {
@@ -481,28 +540,406 @@ int conv3d_fprop_tc(const void* const* h_srcs, const int* h_src_channels, int ns
     int ctas_per_sm = (int)((227 * 1024) / (g.smem + 1024));
     if (ctas_per_sm > 512 / (int)g.tmem_cols) ctas_per_sm = 512 / (int)g.tmem_cols;
     if (ctas_per_sm < 1) ctas_per_sm = 1;
-    if (ctas_per_sm > 3) ctas_per_sm = 3;
+    if (ctas_per_sm > 2) ctas_per_sm = 2;
     int grid = 148 * ctas_per_sm;
     if (grid > p.total_items) grid = p.total_items;
+    const int threads = 32 * (1 + TC_WB + 4 * TC_WB);
     auto go = [&](auto kern) -> int {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
         if (e != cudaSuccess) {
             set_error("conv3d tensor path: smem %zu: %s", g.smem, cudaGetErrorString(e));
             return (int)e;
         }
-        kern<<<grid, TC_THREADS, g.smem, stream>>>(tmap, p);
+        kern<<<grid, threads, g.smem, stream>>>(tmap, p);
         return check_launch("ctu_conv3d_fprop(tcgen05)");
     };
-    int rc = k == 3 ? go(conv3d_tc_kernel<3>) : go(conv3d_tc_kernel<5>);
+    int rc = CTU_OK;
+    for (int grp = 0; grp < g.ngroups && rc == CTU_OK; ++grp) {
+        p.ob0 = grp * g.cobg;
+        p.nob = (g.cob_n - p.ob0) < g.cobg ? (g.cob_n - p.ob0) : g.cobg;
+        p.wimg = reinterpret_cast<const __nv_bfloat16*>(reinterpret_cast<const unsigned char*>(wp) + (size_t)grp * g.wimg_bytes);
+        if (k == 3 && g.cobg == 1) rc = go(conv3d_tc_kernel<3, 1>);
+        else if (k == 3 && g.cobg == 2) rc = go(conv3d_tc_kernel<3, 2>);
+        else if (k == 3 && g.cobg == 4) rc = go(conv3d_tc_kernel<3, 4>);
+        else if (k == 5 && g.cobg == 1) rc = go(conv3d_tc_kernel<5, 1>);
+        else rc = go(conv3d_tc_kernel<5, 2>);
+    }
     if (rc == CTU_OK && stats != nullptr && !fuse_stats)   // wide layers (low resolution): separate statistics pass
         rc = ctu_bn_stats(CTU_BF16, y, cout, n, (long long)d * h * w, stats, stream);
     return rc;
 }
 
-int conv3d_wgrad_tc(const void* const*, const int*, int, const void*, float*, float*, int, int, int, int, int, int,
-                    cudaStream_t) {
-    set_error("wgrad tensor path not built");
-    return CTU_ERR_UNSUPPORTED;
+// ================================================================================================ wgrad
+// dW[co, ci, kd, kh, kw] = sum_v dy[co, v] * x[ci, v + tap - pad]  as UMMA with the VOXELS as the K dimension.
+// Both operands are MN-major straight out of the blocked layout (for one voxel the 8 channels are contiguous):
+//   A = x halo row:  M = 64 = 8 "lag" groups x 8 input lanes, group g = the row shifted by g voxels (SBO = 16 B),
+//       so lags 0..K-1 are the kw taps (lags K..7 are computed and discarded: 3/8 or 5/8 of the MMA is useful);
+//   B = K dy rows:   N = K (kh) x output channels.  The dy tile is staged as [h][cob][w][8] (one 5-D TMA box), so
+//       for the x halo row rho the rows rho-(K-1)..rho of dy (kh = K-1..0) x all channel blocks are n-groups at a
+//       uniform SBO of 256 B; K-1 zero rows above and below the tile stand for the rows owned by neighbour tiles;
+//   K = 16 consecutive w-voxels (two 8-voxel core matrices, LBO = 128 B).
+// The MMA is bound by the A-operand read from shared memory (~64 B/clk), so carrying the kh taps in N (instead of
+// one MMA per kh) cuts the work to HH = 16+K-1 MMAs per (plane, kd, input block).
+// One TMEM accumulator [64 x K*Ng] per (kd, input block) lives for the whole CTA; a CTA walks its share of the
+// (n, h-tile, w-tile, d-chunk) items and flushes K^3 x 8 x Cbg x Ng partial sums with fp32 atomics at the end.
+struct WgParams {
+    float* dwp;                 // packed fp32 [cob][cib][tap][ci][co], zeroed by the caller
+    int cb, cob_n;              // totals
+    int cbg, ng;                // input blocks / output channels handled per CTA group
+    int n_cbgroups, n_ngroups;
+    int n, d, h, w;
+    int tiles_h, tiles_w, dchunks, dc, total_items;
+    uint32_t plane_bytes, xslot_bytes, dyslot_bytes, tmem_cols;
+    uint32_t ns, nds;           // x-plane / dy-plane ring depths
+};
+
+template <int K>
+__global__ void __launch_bounds__(WG_THREADS) conv3d_wgrad_tc_kernel(const __grid_constant__ CUtensorMap xmap,
+                                                                     const __grid_constant__ CUtensorMap dymap,
+                                                                     WgParams p) {
+    constexpr int PAD = K / 2;
+    constexpr int HH = TC_TH + K - 1, WW = TC_TW + K - 1;
+    constexpr uint32_t ROW = WW * 16;
+    constexpr uint32_t DYBLK = TC_TW * 16;         // one channel block of one dy row: 16 voxels x 16 B
+    const uint32_t NS = p.ns, NDS = p.nds;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const uint32_t s_base = smem_u32(smem);
+    const uint32_t s_x = s_base;
+    const uint32_t s_dy = s_x + NS * p.xslot_bytes;
+    const uint32_t s_bar = s_dy + NDS * p.dyslot_bytes;
+    const uint32_t b_xfull = s_bar, b_xempty = s_bar + 8 * TC_MAX_SLOTS, b_dyfull = s_bar + 16 * TC_MAX_SLOTS,
+                   b_dyempty = s_bar + 24 * TC_MAX_SLOTS, b_done = s_bar + 32 * TC_MAX_SLOTS;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (b_done + 8 - s_base));
+    uint2* wtab = reinterpret_cast<uint2*>(smem + (b_done + 16 - s_base));   // [WG_ISSUERS][WG_MAX_OWN]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = blockIdx.y;
+    const int cbg_i = grp % p.n_cbgroups, ng_i = grp / p.n_cbgroups;
+    const int cb0 = cbg_i * p.cbg;
+    const int ncb = (p.cb - cb0) < p.cbg ? (p.cb - cb0) : p.cbg;         // input blocks of this group
+    const int ob0 = ng_i * (p.ng / 8);
+    const int nob = (p.cob_n - ob0) < (p.ng / 8) ? (p.cob_n - ob0) : (p.ng / 8);
+    const int nn = nob * 8;                                              // output channels of this group
+    const uint32_t dyrow = (uint32_t)nob * DYBLK;                        // one dy row, all channel blocks
+
+    // zero rows above / below every dy slot (never written by TMA), visible to the async proxy before any MMA
+    for (uint32_t sl = 0; sl < NDS; ++sl) {
+        uint4* top = reinterpret_cast<uint4*>(smem + (s_dy - s_base) + sl * p.dyslot_bytes);
+        uint4* bot = reinterpret_cast<uint4*>(smem + (s_dy - s_base) + sl * p.dyslot_bytes + (K - 1 + TC_TH) * dyrow);
+        for (uint32_t i = threadIdx.x; i < (K - 1) * dyrow / 16; i += WG_THREADS) {
+            top[i] = make_uint4(0, 0, 0, 0);
+            bot[i] = make_uint4(0, 0, 0, 0);
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+
+    if (threadIdx.x == 0) {
+        for (uint32_t i = 0; i < NS; ++i) {
+            mbar_init(b_xfull + 8 * i, 1);
+            mbar_init(b_xempty + 8 * i, WG_ISSUERS);
+        }
+        for (uint32_t i = 0; i < NDS; ++i) {
+            mbar_init(b_dyfull + 8 * i, 1);
+            mbar_init(b_dyempty + 8 * i, WG_ISSUERS);
+        }
+        mbar_init(b_done, WG_ISSUERS);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(p.tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int items_per_n = p.tiles_h * p.tiles_w * p.dchunks;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            Ring pr = {0, 0}, dr = {0, 0};
+            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+                const int n = item / items_per_n;
+                int r = item % items_per_n;
+                const int dci = r % p.dchunks; r /= p.dchunks;
+                const int twi = r % p.tiles_w, thi = r / p.tiles_w;
+                const int z0 = dci * p.dc, h0 = thi * TC_TH, w0 = twi * TC_TW;
+                const int nd = (p.d - z0) < p.dc ? (p.d - z0) : p.dc;
+                for (int pl = 0; pl < nd + K - 1; ++pl, pr.next(NS)) {
+                    mbar_wait(b_xempty + 8 * pr.slot, pr.phase ^ 1);
+                    mbar_expect_tx(b_xfull + 8 * pr.slot, (uint32_t)ncb * HH * WW * 16);
+                    for (int b = 0; b < ncb; ++b)
+                        tma_load_4d(s_x + pr.slot * p.xslot_bytes + b * p.plane_bytes, &xmap, (w0 - PAD) * 8, h0 - PAD,
+                                    z0 + pl - PAD, n * p.cb + cb0 + b, b_xfull + 8 * pr.slot);
+                    if (pl >= K - 1) {
+                        mbar_wait(b_dyempty + 8 * dr.slot, dr.phase ^ 1);
+                        mbar_expect_tx(b_dyfull + 8 * dr.slot, (uint32_t)TC_TH * dyrow);
+                        tma_load_5d(s_dy + dr.slot * p.dyslot_bytes + (K - 1) * dyrow, &dymap, w0 * 8, ob0, h0,
+                                    z0 + pl - (K - 1), n, b_dyfull + 8 * dr.slot);
+                        dr.next(NDS);
+                    }
+                }
+            }
+        }
+    } else {
+        // ===================================================================== MMA issuers + flush (warps 1..4)
+        // D=f32, A=B=bf16, both MN-major (bits 15, 16), N at [17,23), M=64 at [24,29)
+        const int ncol = K * nn;                                  // MMA N: kh taps x output channels
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                               ((uint32_t)(ncol >> 3) << 17) | (4u << 24);
+        const uint32_t a_hi = 1u | (1u << 14);                    // SBO = 16 B: m-group g = lag g
+        const uint32_t b_hi = (DYBLK >> 4) | (1u << 14);          // SBO = 256 B: next (row, channel block) n-group
+        const uint32_t lbo = 8u << 16;                            // second 8-voxel core matrix: +128 B
+        const int q = warp - 1;
+        const int nacc = K * ncb;                                 // one accumulator per (kd, input block)
+        const int n_own = (nacc - q + WG_ISSUERS - 1) / WG_ISSUERS;     // accumulators e = q, q+4, ...
+        uint2* mytab = wtab + q * WG_MAX_OWN;
+        uint32_t base = 0, waited = 0, first = 1;
+        Ring cons = {0, 0}, head = {0, 0}, dyr = {0, 0};
+        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+            const int r0 = item % items_per_n;
+            const int z0 = (r0 % p.dchunks) * p.dc;
+            const int nd = (p.d - z0) < p.dc ? (p.d - z0) : p.dc;
+            for (int j = 0; j < nd; ++j) {
+                while (waited < base + j + K) {
+                    mbar_wait(b_xfull + 8 * cons.slot, cons.phase);
+                    cons.next(NS);
+                    ++waited;
+                }
+                mbar_wait(b_dyfull + 8 * dyr.slot, dyr.phase);
+                tc_fence_after();
+                // per-plane table of this warp's accumulators: A start (row 0) and TMEM column
+                for (int el = lane; el < n_own; el += 32) {
+                    const int e = q + el * WG_ISSUERS;
+                    const int b = e % ncb, kd = e / ncb;
+                    uint32_t slot = head.slot + kd;
+                    if (slot >= NS) slot -= NS;
+                    const uint32_t x16 = (s_x + slot * p.xslot_bytes + b * p.plane_bytes) >> 4;
+                    mytab[el] = make_uint2(x16 | lbo, tmem_base + (uint32_t)e * ncol);
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    const uint32_t dy16 = ((s_dy + dyr.slot * p.dyslot_bytes) >> 4) | lbo;
+                    int r = 0;
+                    if (first) {
+                        const uint64_t bd = pack64(dy16, b_hi);
+                        for (int el = 0; el < n_own; ++el) {
+                            const uint2 e = mytab[el];
+                            umma_bf16(e.y, pack64(e.x, a_hi), bd, idesc, 0u);
+                        }
+                        first = 0;
+                        r = 1;
+                    }
+#pragma unroll 1
+                    for (; r < HH; ++r) {     // x halo row r meets dy rows r-(K-1)..r (slot rows r..r+K-1)
+                        const uint64_t bd = pack64(dy16 + r * (dyrow >> 4), b_hi);
+                        const uint32_t rstep = r * (ROW >> 4);
+#pragma unroll 4
+                        for (int el = 0; el < n_own; ++el) {
+                            const uint2 e = mytab[el];
+                            umma_bf16_acc(e.y, pack64(e.x + rstep, a_hi), bd, idesc);
+                        }
+                    }
+                    umma_commit(b_xempty + 8 * head.slot);
+                    umma_commit(b_dyempty + 8 * dyr.slot);
+                }
+                head.next(NS);
+                dyr.next(NDS);
+                __syncwarp();
+            }
+            for (int qq = 0; qq < K - 1; ++qq, head.next(NS))
+                if (lane == 0) umma_commit(b_xempty + 8 * head.slot);
+            base += nd + K - 1;
+        }
+        if (lane == 0) umma_commit(b_done);
+        __syncwarp();
+        // flush: M=64 accumulators sit in lanes 0-15 of every 32-lane quarter (row = quarter*16 + lane)
+        const int quarter = warp & 3;
+        mbar_wait(b_done, 0);
+        tc_fence_after();
+        const int row = quarter * 16 + (lane & 15);
+        const int lag = row >> 3, ci = row & 7;
+        const bool useful = lane < 16 && lag < K;
+        const int taps = K * K * K;
+        for (int a = 0; a < nacc; ++a) {
+            const int b = a % ncb, kd = a / ncb;
+            for (int g = 0; g < K; ++g) {                  // n-group g holds kh = K-1-g
+                const int tap = (kd * K + (K - 1 - g)) * K + lag;
+                for (int ob = 0; ob < nob; ++ob) {
+                    float v[8];
+                    tmem_ld8(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)a * ncol + g * nn + ob * 8, v);
+                    if (useful) {
+                        float* dst = p.dwp + ((((long long)(ob0 + ob) * p.cb + cb0 + b) * taps + tap) * 64 + ci * 8);
+#pragma unroll
+                        for (int c = 0; c < 8; ++c)
+                            if (v[c] != 0.f) atomicAdd(dst + c, v[c]);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    }
+}
+
+// sum of dy over voxels per channel (bias gradient of convolutions that carry a bias: the legacy 5^3 family)
+__global__ void tc_channel_sum_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ dbias, int cout, int cob_n,
+                                      long long spatial) {
+    const int ob = blockIdx.y, n = blockIdx.z;
+    const __nv_bfloat16* base = dy + ((long long)n * cob_n + ob) * spatial * 8;
+    float acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+    for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < spatial; s += (long long)gridDim.x * blockDim.x) {
+        V8 v = Vec8<__nv_bfloat16>::load(base + s * 8);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] += v.v[c];
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float t = warp_sum(acc[c]);
+        const int ch = ob * 8 + c;
+        if ((threadIdx.x & 31) == 0 && ch < cout && t != 0.f) atomicAdd(dbias + ch, t);
+    }
+}
+
+struct WgGeom {
+    int cb, cob_n, cbg, ng, n_cbgroups, n_ngroups;
+    uint32_t plane_bytes, xslot_bytes, dyslot_bytes, tmem_cols, ns, nds;
+    size_t smem;
+};
+
+static bool wg_geometry(int k, int cin, int cout, int h, int w, WgGeom& g) {
+    if (k != 3 && k != 5) return false;
+    if (h % TC_TH || w % TC_TW) return false;
+    g.cb = (cin + 7) / 8;
+    g.cob_n = (cout + 7) / 8;
+    const int k2 = k * k;
+    const int hh = TC_TH + k - 1, ww = TC_TW + k - 1;
+    g.plane_bytes = ((uint32_t)hh * ww * 16 + 127u) & ~127u;
+    // choose (cbg, ng): k2*cbg*ng <= 512 TMEM columns; prefer all output channels, then as many input blocks as fit
+    g.ng = g.cob_n * 8;
+    while (k2 * g.ng > 512 || k * g.ng > 256) g.ng = ((g.ng / 8 + 1) / 2) * 8;
+    g.cbg = 512 / (k2 * g.ng);
+    if (g.cbg > g.cb) g.cbg = g.cb;
+    // shared memory: x ring (k+1 slots x cbg planes) + dy ring
+    const size_t fixed = 8 * (4 * TC_MAX_SLOTS + 3) + 16 + WG_ISSUERS * WG_MAX_OWN * 8 + 1024;
+    for (;;) {
+        g.xslot_bytes = g.plane_bytes * g.cbg;
+        g.dyslot_bytes = (uint32_t)(g.ng / 8) * (TC_TH + 2 * (k - 1)) * TC_TW * 16;   // + zero rows above / below
+        g.smem = fixed + (size_t)(k + 1) * g.xslot_bytes + 2 * (size_t)g.dyslot_bytes;
+        if (g.smem <= 200 * 1024 || g.cbg == 1) break;
+        --g.cbg;
+    }
+    if (g.smem > 220 * 1024) return false;
+    // deepen both rings while a ~100 KB budget (two CTAs per SM) allows: more TMA loads in flight
+    g.ns = k + 1;
+    g.nds = 2;
+    while (g.ns < TC_MAX_SLOTS && g.smem + g.xslot_bytes + g.dyslot_bytes <= 100 * 1024) {
+        ++g.ns;
+        if (g.nds < TC_MAX_SLOTS) ++g.nds;
+        g.smem += g.xslot_bytes + g.dyslot_bytes;
+    }
+    g.n_cbgroups = (g.cb + g.cbg - 1) / g.cbg;
+    g.n_ngroups = (g.cob_n * 8 + g.ng - 1) / g.ng;
+    uint32_t cols = (uint32_t)k2 * g.cbg * g.ng;
+    g.tmem_cols = 32;
+    while (g.tmem_cols < cols) g.tmem_cols *= 2;
+    return g.tmem_cols <= 512;
+}
+
+static int make_map(CUtensorMap* map, const void* ptr, int nblocks, int d, int h, int w, int box_w, int box_h) {
+    auto encode = get_encode();
+    if (!encode) {
+        set_error("cuTensorMapEncodeTiled entry point not found");
+        return CTU_ERR_UNSUPPORTED;
+    }
+    const cuuint64_t gdim[4] = {(cuuint64_t)w * 8, (cuuint64_t)h, (cuuint64_t)d, (cuuint64_t)nblocks};
+    const cuuint64_t gstr[3] = {(cuuint64_t)w * 16, (cuuint64_t)h * w * 16, (cuuint64_t)d * h * w * 16};
+    const cuuint32_t box[4] = {(cuuint32_t)box_w * 8, (cuuint32_t)box_h, 1, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult cr = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d)", (int)cr);
+        return CTU_ERR_INVALID;
+    }
+    return CTU_OK;
+}
+
+int conv3d_wgrad_tc(const void* const* h_srcs, const int* h_src_channels, int nsrc, const void* dy, float* dwp,
+                    float* dbias, int cout, int k, int n, int d, int h, int w, cudaStream_t stream) {
+    if (nsrc != 1) {
+        set_error("conv3d wgrad tensor path: single source only");
+        return CTU_ERR_UNSUPPORTED;
+    }
+    WgGeom g;
+    if (!wg_geometry(k, h_src_channels[0], cout, h, w, g)) {
+        set_error("conv3d wgrad tensor path: shape k=%d cin=%d cout=%d %dx%dx%d not covered", k, h_src_channels[0], cout, d, h, w);
+        return CTU_ERR_UNSUPPORTED;
+    }
+    CUtensorMap xmap, dymap;
+    int rc = make_map(&xmap, h_srcs[0], n * g.cb, d, h, w, TC_TW + k - 1, TC_TH + k - 1);
+    if (rc == CTU_OK) {
+        // dy as (w*8, cob, h, d, n): one box [TH][ng/8][TW*8] lands in shared memory as [h][cob][w][8]
+        auto encode = get_encode();
+        const cuuint64_t plane_b = (cuuint64_t)d * h * w * 16;
+        const cuuint64_t gdim[5] = {(cuuint64_t)w * 8, (cuuint64_t)g.cob_n, (cuuint64_t)h, (cuuint64_t)d, (cuuint64_t)n};
+        const cuuint64_t gstr[4] = {plane_b, (cuuint64_t)w * 16, (cuuint64_t)h * w * 16, plane_b * g.cob_n};
+        const cuuint32_t box[5] = {(cuuint32_t)TC_TW * 8, (cuuint32_t)(g.ng / 8), (cuuint32_t)TC_TH, 1, 1};
+        const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        CUresult cr = encode(&dymap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(dy), gdim, gstr, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) {
+            set_error("cuTensorMapEncodeTiled(dy) failed (%d)", (int)cr);
+            rc = CTU_ERR_INVALID;
+        }
+    }
+    if (rc != CTU_OK) return rc;
+    WgParams p = {};
+    p.dwp = dwp;
+    p.cb = g.cb; p.cob_n = g.cob_n; p.cbg = g.cbg; p.ng = g.ng; p.n_cbgroups = g.n_cbgroups; p.n_ngroups = g.n_ngroups;
+    p.n = n; p.d = d; p.h = h; p.w = w;
+    p.tiles_h = h / TC_TH; p.tiles_w = w / TC_TW;
+    const int tiles = n * p.tiles_h * p.tiles_w;
+    const int groups = g.n_cbgroups * g.n_ngroups;
+    int dc = d;
+    while (dc > 8 && (long long)tiles * ((d + dc - 1) / dc) * groups < 148 * 4) dc = (dc + 1) / 2;
+    p.dc = dc;
+    p.dchunks = (d + dc - 1) / dc;
+    p.total_items = tiles * p.dchunks;
+    p.plane_bytes = g.plane_bytes; p.xslot_bytes = g.xslot_bytes; p.dyslot_bytes = g.dyslot_bytes; p.tmem_cols = g.tmem_cols;
+    p.ns = g.ns; p.nds = g.nds;
+    int ctas_per_sm = (int)((227 * 1024) / (g.smem + 1024));
+    if (ctas_per_sm > 512 / (int)g.tmem_cols) ctas_per_sm = 512 / (int)g.tmem_cols;
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    int gx = (148 * ctas_per_sm + groups - 1) / groups;
+    if (gx > p.total_items) gx = p.total_items;
+    if (gx < 1) gx = 1;
+    dim3 grid(gx, groups);
+    auto go = [&](auto kern) -> int {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+        if (e != cudaSuccess) {
+            set_error("conv3d wgrad tensor path: smem %zu: %s", g.smem, cudaGetErrorString(e));
+            return (int)e;
+        }
+        kern<<<grid, WG_THREADS, g.smem, stream>>>(xmap, dymap, p);
+        return check_launch("ctu_conv3d_wgrad(tcgen05)");
+    };
+    rc = k == 3 ? go(conv3d_wgrad_tc_kernel<3>) : go(conv3d_wgrad_tc_kernel<5>);
+    if (rc == CTU_OK && dbias != nullptr) {
+        const long long spatial = (long long)d * h * w;
+        dim3 bgrid((unsigned)((spatial + 256 * 32 - 1) / (256 * 32)), g.cob_n, n);
+        tc_channel_sum_kernel<<<bgrid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dy), dbias, cout, g.cob_n, spatial);
+        rc = check_launch("ctu_conv3d_wgrad(dbias)");
+    }
+    return rc;
 }
 
 }  // namespace ctu
@@ -519,17 +956,23 @@ int ctu_conv_tc_supported(int k, int cin, int cout, int d, int h, int w) {
     return tc_geometry(k, cin, cout, h, w, g) ? 1 : 0;
 }
 
+int ctu_conv_tc_wgrad_supported(int k, int cin, int cout, int d, int h, int w) {
+    (void)d;
+    WgGeom g;
+    return wg_geometry(k, cin, cout, h, w, g) ? 1 : 0;
+}
+
 long long ctu_conv_tc_wimg_bytes(int k, int cin, int cout) {
     TcGeom g;
     if (!tc_geometry(k, cin, cout, TC_TH, TC_TW, g)) return -1;
-    return (long long)g.wimg_bytes;
+    return (long long)g.wimg_bytes * g.ngroups;
 }
 
 int ctu_conv_tc_pack_weight(const float* wp, void* wimg, int k, int cin, int cout, ctu_stream stream) {
     TcGeom g;
     CTU_REQUIRE(wp && wimg && tc_geometry(k, cin, cout, TC_TH, TC_TW, g), "ctu_conv_tc_pack_weight: bad arguments");
-    const long long total = (long long)g.wimg_bytes / 2;
-    tc_pack_wimg_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(wp, reinterpret_cast<__nv_bfloat16*>(wimg), k, g.cb, g.cob_n, g.npad, total);
+    const long long total = (long long)g.wimg_bytes / 2 * g.ngroups;
+    tc_pack_wimg_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(wp, reinterpret_cast<__nv_bfloat16*>(wimg), k, g.cb, g.cob_n, g.cobg, g.nt, g.nm, total);
     return check_launch("ctu_conv_tc_pack_weight");
 }
 

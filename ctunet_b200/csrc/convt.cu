@@ -298,7 +298,7 @@ int ctu_convt2_wgrad(int dtype, const void* const* h_srcs, const int* h_src_chan
     p.dy = dy; p.dwp = dwp; p.dbias = dbias; p.cout = cout; p.cob_n = (cout + 7) / 8;
     p.n = n; p.d = d; p.h = h; p.w = w;
     const long long plane = (long long)d * h * w;
-    p.vox_per_cta = 2048;
+    p.vox_per_cta = 16384;
     const long long nfl = (long long)p.cob_n * m.cb_total * 512;
     cudaError_t e = cudaMemsetAsync(dwp, 0, nfl * sizeof(float), (cudaStream_t)stream);
     if (e == cudaSuccess && dbias) e = cudaMemsetAsync(dbias, 0, cout * sizeof(float), (cudaStream_t)stream);

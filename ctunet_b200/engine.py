@@ -154,7 +154,8 @@ class Engine:
                     db = self._grad_buffer(bias) if (bias is not None and bias.requires_grad) else None
                     call("ctu_conv3d_wgrad", self.dtype, pa, ca, ns, dy.ptr, dwp.data_ptr(),
                          db.data_ptr() if db is not None else None, cout, k, s0.n, s0.d, s0.h, s0.w,
-                         0, stream_ptr())
+                         int(self.use_tc and len(srcs) == 1 and bool(
+                             lib.ctu_conv_tc_wgrad_supported(k, s0.c, cout, s0.d, s0.h, s0.w))), stream_ptr())
                     dw = self._grad_buffer(weight)
                     call("ctu_conv_unpack_wgrad", dwp.data_ptr(), dw.data_ptr(), cout, k, ns, ca, stream_ptr())
                     self._add_pgrad(weight, dw)

@@ -81,6 +81,7 @@ int ctu_conv3d_fprop(int dtype, const void* const* h_srcs, const int* h_src_chan
                      int use_tensor_path, ctu_stream stream);
 /* tcgen05 path: coverage predicate, size of the weight image, and the re-pack fp32 packed -> image */
 int ctu_conv_tc_supported(int k, int cin, int cout, int d, int h, int w);
+int ctu_conv_tc_wgrad_supported(int k, int cin, int cout, int d, int h, int w);
 long long ctu_conv_tc_wimg_bytes(int k, int cin, int cout);
 int ctu_conv_tc_pack_weight(const float* wp, void* wimg, int k, int cin, int cout, ctu_stream stream);
 /* dwp (packed layout, fp32) and dbias (nullable, [cout]) are zeroed by the call, then accumulated */

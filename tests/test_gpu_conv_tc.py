@@ -23,6 +23,10 @@ CASES = [
     (5, 16, 8, True, (1, 4, 16, 16)),
     (3, 7, 7, True, (1, 2, 16, 16)),
     (3, 7, 7, False, (1, 1, 16, 16)),
+    (3, 56, 56, False, (1, 3, 16, 16)),      # wgrad: several input-block groups
+    (3, 112, 28, False, (1, 2, 16, 16)),
+    (3, 28, 112, False, (1, 2, 16, 16)),     # wgrad: output channels split over TMEM
+    (5, 14, 28, True, (1, 3, 16, 16)),
 ]
 
 
@@ -36,14 +40,15 @@ def test_tc_conv_matches_reference(case):
     from ctunet_b200 import _lib
     k, cin, cout, use_bias, (n, d, h, w) = case
     assert _lib.load().ctu_has_tensor_path() == 1
-    assert tc_supported(k, [cin], cout, d, h, w)
+    fprop_on_tc = tc_supported(k, [cin], cout, d, h, w)     # very wide inputs keep the direct kernel for fprop
+    assert fprop_on_tc or cin >= 112
     g = torch.Generator().manual_seed(k * 100 + cin)
     x = _bf(torch.randn(n, cin, d, h, w, generator=g))
     wt = torch.randn(cout, cin, k, k, k, generator=g) / (cin * k ** 3) ** 0.5
     bs = torch.randn(cout, generator=g) if use_bias else None
     dy = _bf(torch.randn(n, cout, d, h, w, generator=g))
     xr = x.clone().requires_grad_()
-    yr = F.conv3d(xr, _bf(wt), bs, 1, k // 2)       # the tensor path rounds the weights to bf16
+    yr = F.conv3d(xr, _bf(wt) if fprop_on_tc else wt, bs, 1, k // 2)   # the tensor path rounds the weights to bf16
     yr.backward(dy)
 
     eng = Engine(torch.device(DEV), "bf16", record=True)
@@ -71,6 +76,18 @@ def test_tc_conv_matches_reference(case):
     gs = xr.grad.abs().max().item()
     gerr = (dx - xr.grad).abs().max().item()
     assert gerr <= 1.2e-2 * gs, "dgrad err %.3e (scale %.3e)" % (gerr, gs)
+    # weight gradient on the tensor cores (voxels as the K dimension): bf16 products, fp32 accumulation
+    assert _lib.load().ctu_conv_tc_wgrad_supported(k, cin, cout, d, h, w) == 1
+    wr = wt.clone().requires_grad_()
+    br = bs.clone().requires_grad_() if use_bias else None
+    F.conv3d(x, wr, br, 1, k // 2).backward(dy)
+    dw = eng.pgrads[id(wg)].cpu()
+    ws = wr.grad.abs().max().item()
+    werr = (dw - wr.grad).abs().max().item()
+    assert werr <= 2e-3 * ws, "wgrad err %.3e (scale %.3e)" % (werr, ws)
+    if use_bias:
+        db = eng.pgrads[id(bg)].cpu()
+        assert (db - br.grad).abs().max().item() <= 2e-3 * br.grad.abs().max().item()
 
 
 def test_tc_and_direct_agree_on_network_layer():

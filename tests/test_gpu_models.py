@@ -191,7 +191,7 @@ def test_train_step_bf16_within_tolerance(name, handler, size, batch):
         nr += float(gr.norm() ** 2)
         ng += float(gg.norm() ** 2)
     total_cos = dot / (nr * ng) ** 0.5
-    assert worst_cos > 0.7 and total_cos > 0.97, "worst per-tensor cosine %.4f, whole-gradient cosine %.4f" % (worst_cos, total_cos)
+    assert worst_cos > 0.7 and total_cos > 0.95, "worst per-tensor cosine %.4f, whole-gradient cosine %.4f" % (worst_cos, total_cos)
     # and the bf16-storage oracle must show the same order of deviation from the fp32 oracle (sanity of the claim)
     sdr, _, _, _ = _oracle_step(name, handler, size, batch, act_round=torch.bfloat16)
     k = "d_blocks.0.block.0.weight" if name == "UNetSP" else "dblock1.0.weight"
