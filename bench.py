@@ -203,10 +203,19 @@ def describe(name, args, esize):
         if name in ("ctu_conv3d_fprop", "ctu_conv3d_wgrad"):
             ca, ns = args[2], args[3]
             cin = sum(ca[i] for i in range(ns))
-            o = 8 if name == "ctu_conv3d_fprop" else 7
+            o = 9 if name == "ctu_conv3d_fprop" else 7
             cout, k, n, d, h, w = args[o], args[o + 1], args[o + 2], args[o + 3], args[o + 4], args[o + 5]
             name = name + ("[tcgen05]" if args[o + 6] else "[cuda-core]")
             vox = n * d * h * w
+            stat_cout = args[8] if name.startswith("ctu_conv3d_fprop") else 0
+            if stat_cout or (ns > 1 and ca[ns - 1] == 1 and cout % 64 == 0):
+                # fused ConvTranspose3d(k2,s2) + Conv3d on the low-res grid (phase-major output; last source = ones):
+                # algorithmic work = the two reference layers, bytes = low-res input + high-res output
+                cin -= 1
+                co = stat_cout if stat_cout else cout // 8
+                fl = 2.0 * vox * 8 * (cin * cin + 27.0 * cin * co)
+                by = esize * vox * (cin + 8 * co) + 4.0 * (8 * cin * cin + 27 * cin * co)
+                return "%s[up-fused] k%d %d->%d @%dx%dx%dx%d" % (name, k, cin, co, n, d, h, w), fl, by
             fl = 2.0 * vox * cin * cout * k ** 3
             by = esize * vox * (cin + cout) + 4.0 * cin * cout * k ** 3
             return "%s k%d %d->%d @%dx%dx%dx%d" % (name, k, cin, cout, n, d, h, w), fl, by
@@ -223,8 +232,8 @@ def describe(name, args, esize):
             return ("%s %d->%d @%dx%dx%dx%d" % (name, cout, cs, n, d, h, w), 2.0 * vox * cs * cout * 8,
                     esize * vox * (cs + 8 * cout))
         if name == "ctu_bn_stats":
-            c, n, sp = args[2], args[3], args[4]
-            return "%s c%d @%dx%d" % (name, c, n, sp), 0.0, esize * c * n * sp
+            c, ph, n, sp = args[2], args[3], args[4], args[5]
+            return "%s c%d @%dx%d" % (name, c, n, sp * ph), 0.0, esize * c * n * sp * ph
         if name == "ctu_bn_relu_fwd":
             c, n, d, h, w = args[5], args[6], args[7], args[8], args[9]
             pooled = args[4] is not None

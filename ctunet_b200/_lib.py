@@ -16,6 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libctunet_b200.so")
 
 CTU_F32, CTU_BF16 = 0, 1
+CTU_MAX_SRC = 4
 HEAD_SOFTMAX, HEAD_SIGMOID, HEAD_SP, HEAD_SP_SOFTMAX = 1, 2, 4, 8
 
 P = c_void_p
@@ -36,11 +37,14 @@ SIGNATURES = {
     "ctu_conv_wpack_dgrad_floats": (LL, [I, I, I]),
     "ctu_conv_pack_weight_dgrad": (I, [P, P, I, I, I, P, I, P]),
     "ctu_conv_unpack_wgrad": (I, [P, P, I, I, I, P, P]),
-    "ctu_conv3d_fprop": (I, [I, P, P, I, P, P, P, P, I, I, I, I, I, I, I, P]),
-    "ctu_conv_tc_supported": (I, [I, I, I, I, I, I]),
-    "ctu_conv_tc_wgrad_supported": (I, [I, I, I, I, I, I]),
-    "ctu_conv_tc_wimg_bytes": (LL, [I, I, I]),
-    "ctu_conv_tc_pack_weight": (I, [P, P, I, I, I, P]),
+    "ctu_conv3d_fprop": (I, [I, P, P, I, P, P, P, P, I, I, I, I, I, I, I, I, P]),
+    "ctu_conv_tc_supported": (I, [I, I, P, I, I, I, I]),
+    "ctu_conv_tc_wgrad_supported": (I, [I, I, P, I, I, I, I]),
+    "ctu_conv_tc_wimg_bytes": (LL, [I, I, P, I]),
+    "ctu_conv_tc_pack_weight": (I, [P, P, I, I, P, I, P]),
+    "ctu_upfuse_cout": (I, [I]),
+    "ctu_upfuse_compose": (I, [P, P, P, P, P, P, I, I, I, P]),
+    "ctu_upfuse_decompose": (I, [P, P, P, P, P, P, P, P, P, I, I, I, P]),
     "ctu_conv3d_wgrad": (I, [I, P, P, I, P, P, P, I, I, I, I, I, I, I, P]),
     "ctu_convt_wpack_floats": (LL, [I, I, P]),
     "ctu_convt_pack_weight": (I, [P, P, I, I, P, P]),
@@ -50,12 +54,12 @@ SIGNATURES = {
     "ctu_convt2_fprop": (I, [I, P, P, I, P, P, P, I, I, I, I, I, P]),
     "ctu_convt2_dgrad": (I, [I, P, P, P, I, I, I, I, I, I, P]),
     "ctu_convt2_wgrad": (I, [I, P, P, I, P, P, P, I, I, I, I, I, P]),
-    "ctu_bn_stats": (I, [I, P, I, I, LL, P, P]),
+    "ctu_bn_stats": (I, [I, P, I, I, I, LL, P, P]),
     "ctu_bn_finalize": (I, [P, D, P, P, P, P, P, F, F, I, I, I, P, P]),
     "ctu_bn_running_update": (I, [P, D, P, P, P, F, I, I, P]),
-    "ctu_bn_relu_fwd": (I, [I, P, P, P, P, I, I, I, I, I, P]),
-    "ctu_bn_relu_bwd_reduce": (I, [I, P, P, P, P, P, I, I, I, I, I, P]),
-    "ctu_bn_relu_bwd_apply": (I, [I, P, P, P, P, P, P, D, P, P, P, I, I, I, I, I, P]),
+    "ctu_bn_relu_fwd": (I, [I, P, P, P, P, I, I, I, I, I, I, P]),
+    "ctu_bn_relu_bwd_reduce": (I, [I, P, P, P, P, P, I, I, I, I, I, I, P]),
+    "ctu_bn_relu_bwd_apply": (I, [I, P, P, P, P, P, P, D, P, P, P, I, I, I, I, I, I, P]),
     "ctu_head_fwd": (I, [I, P, P, I, P, P, I, I, P, P, I, LL, P]),
     "ctu_head_bwd": (I, [I, P, P, I, P, P, I, I, P, P, P, P, P, I, LL, P]),
     "ctu_dice_ce_fwd": (I, [P, P, I, I, LL, I, I, P, P, P]),

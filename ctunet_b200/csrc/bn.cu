@@ -31,12 +31,13 @@ __device__ __forceinline__ void block_atomic_add(const float (&vals)[NV], double
     __syncthreads();
 }
 
-// sums[0*cpad + ch] = sum, sums[1*cpad + ch] = sum of squares.  grid = (chunks, cb, n)
+// sums[0*cpad + ch] = sum, sums[1*cpad + ch] = sum of squares.  grid = (chunks, phases*cb, n): the tensor holds
+// `phases` copies of the cb natural channel blocks (phase-major output of the fused up-sampling stage; 1 otherwise)
 template <typename T>
 __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const T* __restrict__ y, double* __restrict__ sums, int c,
                                                               int cb, long long spatial) {
-    const int b = blockIdx.y, n = blockIdx.z;
-    const T* base = y + ((long long)n * cb + b) * spatial * 8;
+    const int b = blockIdx.y % cb, n = blockIdx.z;
+    const T* base = y + ((long long)n * gridDim.y + blockIdx.y) * spatial * 8;
     float acc[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) acc[i] = 0.f;
@@ -127,7 +128,9 @@ __device__ __forceinline__ V8 bn_relu_apply(const V8& y, const float (&sc)[8], c
     return a;
 }
 
-// a = relu(scale*y + shift); grid = (chunks, cb, n), one thread per voxel
+constexpr int kVoxPerThread = 4;   // plain (unpooled) kernels: voxels per thread, strided by the block size
+
+// a = relu(scale*y + shift); grid = (chunks, cb, n)
 template <typename T>
 __global__ void __launch_bounds__(kBnThreads) bn_relu_fwd_kernel(const T* __restrict__ y, const float* __restrict__ ss,
                                                                  T* __restrict__ a, int cb, long long spatial) {
@@ -139,19 +142,30 @@ __global__ void __launch_bounds__(kBnThreads) bn_relu_fwd_kernel(const T* __rest
         sc[j] = __ldg(ss + b * 8 + j);
         sh[j] = __ldg(ss + cpad + b * 8 + j);
     }
-    const long long s = (long long)blockIdx.x * kBnThreads + threadIdx.x;
-    if (s >= spatial) return;
-    const long long off = (((long long)n * cb + b) * spatial + s) * 8;
-    V8 v = Vec8<T>::load(y + off);
-    Vec8<T>::store(a + off, bn_relu_apply<T>(v, sc, sh));
+    const long long base = ((long long)n * cb + b) * spatial;
+    const long long s0 = (long long)blockIdx.x * kBnThreads * kVoxPerThread + threadIdx.x;
+    V8 v[kVoxPerThread];
+#pragma unroll
+    for (int it = 0; it < kVoxPerThread; ++it) {
+        const long long s = s0 + (long long)it * kBnThreads;
+        if (s < spatial) v[it] = Vec8<T>::load(y + (base + s) * 8);
+    }
+#pragma unroll
+    for (int it = 0; it < kVoxPerThread; ++it) {
+        const long long s = s0 + (long long)it * kBnThreads;
+        if (s < spatial) Vec8<T>::store(a + (base + s) * 8, bn_relu_apply<T>(v[it], sc, sh));
+    }
 }
 
-// Same, plus pooled = maxpool 2x2x2 of a.  One thread per POOLED voxel (reads its 8 children).
-template <typename T>
-__global__ void __launch_bounds__(kBnThreads) bn_relu_pool_fwd_kernel(const T* __restrict__ y,
-                                                                      const float* __restrict__ ss, T* __restrict__ a,
-                                                                      T* __restrict__ pooled, int cb, int d, int h,
-                                                                      int w) {
+// One thread per LOW-resolution voxel and its 8 children (d, h, w even).
+//   POOL:  y, a natural [n][cb][d][h][w][8]; pooled = maxpool 2x2x2 of a.
+//   S2D:   y phase-major [n][8*cb][d/2][h/2][w/2][8] (output of the fused up-sampling stage, block = q*cb + b,
+//          q = qd*4 + qh*2 + qw), a natural.
+template <typename T, bool S2D>
+__global__ void __launch_bounds__(kBnThreads) bn_relu_child_fwd_kernel(const T* __restrict__ y,
+                                                                       const float* __restrict__ ss, T* __restrict__ a,
+                                                                       T* __restrict__ pooled, int cb, int d, int h,
+                                                                       int w) {
     const int b = blockIdx.y, n = blockIdx.z;
     const int cpad = cb * 8;
     float sc[8], sh[8];
@@ -172,21 +186,31 @@ __global__ void __launch_bounds__(kBnThreads) bn_relu_pool_fwd_kernel(const T* _
     V8 mx;
 #pragma unroll
     for (int j = 0; j < 8; ++j) mx.v[j] = 0.f;   // a >= 0 after ReLU
+    V8 in[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         const int z = 2 * pz + (q >> 2), yy = 2 * py + ((q >> 1) & 1), x = 2 * px + (q & 1);
-        const long long off = (base + ((long long)z * h + yy) * w + x) * 8;
-        V8 r = bn_relu_apply<T>(Vec8<T>::load(y + off), sc, sh);
-        Vec8<T>::store(a + off, r);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) mx.v[j] = fmaxf(mx.v[j], r.v[j]);
+        const long long off = S2D ? ((((long long)n * 8 + q) * cb + b) * pspatial + ps) * 8
+                                  : (base + ((long long)z * h + yy) * w + x) * 8;
+        in[q] = Vec8<T>::load(y + off);
     }
-    Vec8<T>::store(pooled + (((long long)n * cb + b) * pspatial + ps) * 8, mx);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int z = 2 * pz + (q >> 2), yy = 2 * py + ((q >> 1) & 1), x = 2 * px + (q & 1);
+        V8 r = bn_relu_apply<T>(in[q], sc, sh);
+        Vec8<T>::store(a + (base + ((long long)z * h + yy) * w + x) * 8, r);
+        if (!S2D) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) mx.v[j] = fmaxf(mx.v[j], r.v[j]);
+        }
+    }
+    if (!S2D) Vec8<T>::store(pooled + (((long long)n * cb + b) * pspatial + ps) * 8, mx);
 }
 
 // ---------------------------------------------------------------------------- backward
-// Gradient entering the BatchNorm output for the 8 children of one pooled voxel (POOL) or for one
-// voxel: dz = (dA + [child is the first max of its window] * dP) * [a > 0].
+// Gradient entering the BatchNorm output: dz = (dA + [child is the first max of its window] * dP) * [a > 0].
+// MODE 0: one voxel at a time (kVoxPerThread per thread); MODE 1 (pool): the 8 children of one pooled voxel;
+// MODE 2 (s2d): the 8 children of one low-res voxel with y / dy phase-major and dA natural.
 struct BwdArgs {
     const void* y;
     const float* ss;
@@ -201,10 +225,23 @@ struct BwdArgs {
     int c, cb, d, h, w;
 };
 
-template <typename T, bool POOL, bool APPLY>
+template <typename T, int MODE, bool APPLY>
 __global__ void __launch_bounds__(kBnThreads) bn_relu_bwd_kernel(BwdArgs p) {
+    constexpr bool POOL = MODE == 1, S2D = MODE == 2;
     const int b = blockIdx.y, n = blockIdx.z;
     const int cpad = p.cb * 8;
+    __shared__ float kk[16];
+    if (APPLY) {
+        if (threadIdx.x < 16) {
+            const int j = threadIdx.x & 7, q = threadIdx.x >> 3;
+            kk[threadIdx.x] = (float)(p.sums2[q * cpad + b * 8 + j] / p.count);   // mean(dz) | mean(dz * xhat)
+            if (blockIdx.x == 0 && n == 0 && b * 8 + j < p.c) {
+                if (q == 0) p.dbeta[b * 8 + j] = (float)p.sums2[b * 8 + j];
+                else p.dgamma[b * 8 + j] = (float)p.sums2[cpad + b * 8 + j];
+            }
+        }
+        __syncthreads();
+    }
     float sc[8], sh[8], mean[8], invstd[8], k1[8], k2[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -213,15 +250,8 @@ __global__ void __launch_bounds__(kBnThreads) bn_relu_bwd_kernel(BwdArgs p) {
         mean[j] = __ldg(p.ss + 2 * cpad + b * 8 + j);
         invstd[j] = __ldg(p.ss + 3 * cpad + b * 8 + j);
         if (APPLY) {
-            k1[j] = (float)(p.sums2[b * 8 + j] / p.count);          // mean(dz)
-            k2[j] = (float)(p.sums2[cpad + b * 8 + j] / p.count);   // mean(dz * xhat)
-        }
-    }
-    if (APPLY && blockIdx.x == 0 && n == 0 && threadIdx.x < 8) {
-        const int ch = b * 8 + threadIdx.x;
-        if (ch < p.c) {
-            p.dgamma[ch] = (float)p.sums2[cpad + ch];
-            p.dbeta[ch] = (float)p.sums2[ch];
+            k1[j] = kk[j];
+            k2[j] = kk[8 + j];
         }
     }
     const T* y = reinterpret_cast<const T*>(p.y);
@@ -234,82 +264,105 @@ __global__ void __launch_bounds__(kBnThreads) bn_relu_bwd_kernel(BwdArgs p) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) acc[i] = 0.f;
 
-    constexpr int NCH = POOL ? 8 : 1;
-    long long offs[NCH];
-    bool active;
-    V8 gp;
-    if (POOL) {
+    if (MODE == 0) {
+        const long long s0 = (long long)blockIdx.x * kBnThreads * kVoxPerThread + threadIdx.x;
+        V8 yv[kVoxPerThread], g[kVoxPerThread];
+#pragma unroll
+        for (int it = 0; it < kVoxPerThread; ++it) {
+            const long long s = s0 + (long long)it * kBnThreads;
+            if (s < spatial) {
+                yv[it] = Vec8<T>::load(y + (base + s) * 8);
+                g[it] = Vec8<T>::load(dA + (base + s) * 8);
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < kVoxPerThread; ++it) {
+            const long long s = s0 + (long long)it * kBnThreads;
+            if (s < spatial) {
+                V8 o;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float av = fmaf(yv[it].v[j], sc[j], sh[j]);
+                    const float dz = av > 0.f ? g[it].v[j] : 0.f;
+                    const float xhat = (yv[it].v[j] - mean[j]) * invstd[j];
+                    if (APPLY) {
+                        o.v[j] = sc[j] * (dz - k1[j] - xhat * k2[j]);
+                    } else {
+                        acc[j] += dz;
+                        acc[8 + j] = fmaf(dz, xhat, acc[8 + j]);
+                    }
+                }
+                if (APPLY) Vec8<T>::store(dy + (base + s) * 8, o);
+            }
+        }
+    } else {
         const int pd = p.d / 2, ph = p.h / 2, pw = p.w / 2;
         const long long pspatial = (long long)pd * ph * pw;
         const long long ps = (long long)blockIdx.x * kBnThreads + threadIdx.x;
-        active = ps < pspatial;
-        if (active) {
+        if (ps < pspatial) {
             const int px = (int)(ps % pw);
             const int py = (int)((ps / pw) % ph);
             const int pz = (int)(ps / ((long long)pw * ph));
+            long long offa[8], offy[8];
 #pragma unroll
-            for (int q = 0; q < NCH; ++q) {
+            for (int q = 0; q < 8; ++q) {
                 const int z = 2 * pz + (q >> 2), yy = 2 * py + ((q >> 1) & 1), x = 2 * px + (q & 1);
-                offs[q] = (base + ((long long)z * p.h + yy) * p.w + x) * 8;
+                offa[q] = (base + ((long long)z * p.h + yy) * p.w + x) * 8;
+                offy[q] = S2D ? ((((long long)n * 8 + q) * p.cb + b) * pspatial + ps) * 8 : offa[q];
             }
-            gp = Vec8<T>::load(dP + (((long long)n * p.cb + b) * pspatial + ps) * 8);
-        }
-    } else {
-        const long long s = (long long)blockIdx.x * kBnThreads + threadIdx.x;
-        active = s < spatial;
-        offs[0] = (base + s) * 8;
-    }
-    if (active) {
-        // av: the activation BEFORE rounding to the storage type.  Rounding is monotone, so the maximum of
-        // the rounded values is the rounded maximum (forward/backward stay consistent) while values that
-        // collide in bf16 still elect the arg-max an fp32 evaluation would.
-        V8 yv[NCH], av[NCH];
+            V8 gp;
+            if (POOL) gp = Vec8<T>::load(dP + (((long long)n * p.cb + b) * pspatial + ps) * 8);
+            // av: the activation BEFORE rounding to the storage type.  Rounding is monotone, so the maximum of
+            // the rounded values is the rounded maximum (forward/backward stay consistent) while values that
+            // collide in bf16 still elect the arg-max an fp32 evaluation would.
+            V8 yv[8], av[8];
 #pragma unroll
-        for (int q = 0; q < NCH; ++q) {
-            yv[q] = Vec8<T>::load(y + offs[q]);
+            for (int q = 0; q < 8; ++q) {
+                yv[q] = Vec8<T>::load(y + offy[q]);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) av[q].v[j] = fmaxf(fmaf(yv[q].v[j], sc[j], sh[j]), 0.f);
-        }
-        int win[8];
-        if (POOL) {
-            // first maximum in (d, h, w) scan order, strict '>' like torch's max_pool3d
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float best = av[0].v[j];
-                int bi = 0;
-#pragma unroll
-                for (int q = 1; q < NCH; ++q)
-                    if (av[q].v[j] > best) {
-                        best = av[q].v[j];
-                        bi = q;
-                    }
-                win[j] = bi;
+                for (int j = 0; j < 8; ++j) av[q].v[j] = fmaxf(fmaf(yv[q].v[j], sc[j], sh[j]), 0.f);
             }
-        }
+            int win[8];
+            if (POOL) {
+                // first maximum in (d, h, w) scan order, strict '>' like torch's max_pool3d
 #pragma unroll
-        for (int q = 0; q < NCH; ++q) {
-            V8 g;
-            if (dA != nullptr) {
-                g = Vec8<T>::load(dA + offs[q]);
-            } else {
+                for (int j = 0; j < 8; ++j) {
+                    float best = av[0].v[j];
+                    int bi = 0;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) g.v[j] = 0.f;
-            }
-            V8 o;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float dz = g.v[j];
-                if (POOL) dz += (win[j] == q) ? gp.v[j] : 0.f;
-                dz = av[q].v[j] > 0.f ? dz : 0.f;
-                const float xhat = (yv[q].v[j] - mean[j]) * invstd[j];
-                if (APPLY) {
-                    o.v[j] = sc[j] * (dz - k1[j] - xhat * k2[j]);
-                } else {
-                    acc[j] += dz;
-                    acc[8 + j] = fmaf(dz, xhat, acc[8 + j]);
+                    for (int q = 1; q < 8; ++q)
+                        if (av[q].v[j] > best) {
+                            best = av[q].v[j];
+                            bi = q;
+                        }
+                    win[j] = bi;
                 }
             }
-            if (APPLY) Vec8<T>::store(dy + offs[q], o);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                V8 g;
+                if (dA != nullptr) {
+                    g = Vec8<T>::load(dA + offa[q]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) g.v[j] = 0.f;
+                }
+                V8 o;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float dz = g.v[j];
+                    if (POOL) dz += (win[j] == q) ? gp.v[j] : 0.f;
+                    dz = av[q].v[j] > 0.f ? dz : 0.f;
+                    const float xhat = (yv[q].v[j] - mean[j]) * invstd[j];
+                    if (APPLY) {
+                        o.v[j] = sc[j] * (dz - k1[j] - xhat * k2[j]);
+                    } else {
+                        acc[j] += dz;
+                        acc[8 + j] = fmaf(dz, xhat, acc[8 + j]);
+                    }
+                }
+                if (APPLY) Vec8<T>::store(dy + offy[q], o);
+            }
         }
     }
     if (!APPLY) {
@@ -325,15 +378,15 @@ using namespace ctu;
 
 extern "C" {
 
-int ctu_bn_stats(int dtype, const void* y, int c, int n, long long spatial, double* sums, ctu_stream stream) {
-    CTU_REQUIRE(y && sums && c > 0 && n > 0 && spatial > 0, "ctu_bn_stats: bad arguments");
+int ctu_bn_stats(int dtype, const void* y, int c, int phases, int n, long long spatial, double* sums, ctu_stream stream) {
+    CTU_REQUIRE(y && sums && c > 0 && phases > 0 && n > 0 && spatial > 0, "ctu_bn_stats: bad arguments");
     const int cb = (c + 7) / 8;
     cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * cb * 8, (cudaStream_t)stream);
     if (e != cudaSuccess) {
         set_error("ctu_bn_stats: memset: %s", cudaGetErrorString(e));
         return (int)e;
     }
-    dim3 grid(cdiv(spatial, (long long)kBnThreads * kStatVoxPerThread), cb, n);
+    dim3 grid(cdiv(spatial, (long long)kBnThreads * kStatVoxPerThread), phases * cb, n);
     CTU_DISPATCH_DTYPE(dtype, (bn_stats_kernel<T><<<grid, kBnThreads, 0, (cudaStream_t)stream>>>((const T*)y, sums, c, cb, spatial)));
     return check_launch("ctu_bn_stats");
 }
@@ -357,40 +410,55 @@ int ctu_bn_running_update(const double* sums, double count, float* running_mean,
 }
 
 int ctu_bn_relu_fwd(int dtype, const void* y, const float* ss, void* a, void* pooled, int c, int n, int d, int h, int w,
-                    ctu_stream stream) {
+                    int y_phase_major, ctu_stream stream) {
     CTU_REQUIRE(y && ss && a && c > 0 && n > 0 && d > 0 && h > 0 && w > 0, "ctu_bn_relu_fwd: bad arguments");
+    CTU_REQUIRE(!(y_phase_major && pooled), "ctu_bn_relu_fwd: a phase-major input is never pooled");
     const int cb = (c + 7) / 8;
     const long long spatial = (long long)d * h * w;
-    if (pooled != nullptr) {
-        CTU_REQUIRE(d % 2 == 0 && h % 2 == 0 && w % 2 == 0, "ctu_bn_relu_fwd: pooling needs even dims (%d,%d,%d)", d, h, w);
+    if (pooled != nullptr || y_phase_major) {
+        CTU_REQUIRE(d % 2 == 0 && h % 2 == 0 && w % 2 == 0, "ctu_bn_relu_fwd: needs even dims (%d,%d,%d)", d, h, w);
         dim3 grid(cdiv(spatial / 8, kBnThreads), cb, n);
-        CTU_DISPATCH_DTYPE(dtype, (bn_relu_pool_fwd_kernel<T><<<grid, kBnThreads, 0, (cudaStream_t)stream>>>((const T*)y, ss, (T*)a, (T*)pooled, cb, d, h, w)));
+        if (y_phase_major)
+            CTU_DISPATCH_DTYPE(dtype, (bn_relu_child_fwd_kernel<T, true><<<grid, kBnThreads, 0, (cudaStream_t)stream>>>((const T*)y, ss, (T*)a, nullptr, cb, d, h, w)));
+        else
+            CTU_DISPATCH_DTYPE(dtype, (bn_relu_child_fwd_kernel<T, false><<<grid, kBnThreads, 0, (cudaStream_t)stream>>>((const T*)y, ss, (T*)a, (T*)pooled, cb, d, h, w)));
     } else {
-        dim3 grid(cdiv(spatial, kBnThreads), cb, n);
+        dim3 grid(cdiv(spatial, kBnThreads * kVoxPerThread), cb, n);
         CTU_DISPATCH_DTYPE(dtype, (bn_relu_fwd_kernel<T><<<grid, kBnThreads, 0, (cudaStream_t)stream>>>((const T*)y, ss, (T*)a, cb, spatial)));
     }
     return check_launch("ctu_bn_relu_fwd");
 }
 
-static int bn_bwd(int dtype, BwdArgs& p, int n, bool apply, cudaStream_t stream, const char* what) {
+static int bn_bwd(int dtype, BwdArgs& p, int n, bool apply, int y_phase_major, cudaStream_t stream, const char* what) {
     const long long spatial = (long long)p.d * p.h * p.w;
     const bool pool = p.dP != nullptr;
-    if (pool && (p.d % 2 || p.h % 2 || p.w % 2)) {
-        set_error("%s: pooling needs even dims", what);
+    if ((pool || y_phase_major) && (p.d % 2 || p.h % 2 || p.w % 2)) {
+        set_error("%s: needs even dims", what);
         return CTU_ERR_INVALID;
     }
-    dim3 grid(cdiv(pool ? spatial / 8 : spatial, kBnThreads), p.cb, n);
+    if (pool && y_phase_major) {
+        set_error("%s: a phase-major BatchNorm input is never pooled", what);
+        return CTU_ERR_INVALID;
+    }
+    if (!pool && p.dA == nullptr) {
+        set_error("%s: missing gradient", what);
+        return CTU_ERR_INVALID;
+    }
+    const int mode = pool ? 1 : (y_phase_major ? 2 : 0);
+    dim3 grid(mode ? cdiv(spatial / 8, kBnThreads) : cdiv(spatial, kBnThreads * kVoxPerThread), p.cb, n);
     CTU_DISPATCH_DTYPE(dtype, {
-        if (pool && apply) bn_relu_bwd_kernel<T, true, true><<<grid, kBnThreads, 0, stream>>>(p);
-        else if (pool) bn_relu_bwd_kernel<T, true, false><<<grid, kBnThreads, 0, stream>>>(p);
-        else if (apply) bn_relu_bwd_kernel<T, false, true><<<grid, kBnThreads, 0, stream>>>(p);
-        else bn_relu_bwd_kernel<T, false, false><<<grid, kBnThreads, 0, stream>>>(p);
+        if (mode == 1 && apply) bn_relu_bwd_kernel<T, 1, true><<<grid, kBnThreads, 0, stream>>>(p);
+        else if (mode == 1) bn_relu_bwd_kernel<T, 1, false><<<grid, kBnThreads, 0, stream>>>(p);
+        else if (mode == 2 && apply) bn_relu_bwd_kernel<T, 2, true><<<grid, kBnThreads, 0, stream>>>(p);
+        else if (mode == 2) bn_relu_bwd_kernel<T, 2, false><<<grid, kBnThreads, 0, stream>>>(p);
+        else if (apply) bn_relu_bwd_kernel<T, 0, true><<<grid, kBnThreads, 0, stream>>>(p);
+        else bn_relu_bwd_kernel<T, 0, false><<<grid, kBnThreads, 0, stream>>>(p);
     });
     return check_launch(what);
 }
 
 int ctu_bn_relu_bwd_reduce(int dtype, const void* y, const float* ss, const void* dA, const void* dP, double* sums2,
-                           int c, int n, int d, int h, int w, ctu_stream stream) {
+                           int c, int n, int d, int h, int w, int y_phase_major, ctu_stream stream) {
     CTU_REQUIRE(y && ss && sums2 && (dA || dP) && c > 0 && n > 0 && d > 0 && h > 0 && w > 0, "ctu_bn_relu_bwd_reduce: bad arguments");
     BwdArgs p = {};
     p.y = y; p.ss = ss; p.dA = dA; p.dP = dP; p.sums2 = sums2; p.c = c; p.cb = (c + 7) / 8; p.d = d; p.h = h; p.w = w;
@@ -399,18 +467,18 @@ int ctu_bn_relu_bwd_reduce(int dtype, const void* y, const float* ss, const void
         set_error("ctu_bn_relu_bwd_reduce: memset: %s", cudaGetErrorString(e));
         return (int)e;
     }
-    return bn_bwd(dtype, p, n, false, (cudaStream_t)stream, "ctu_bn_relu_bwd_reduce");
+    return bn_bwd(dtype, p, n, false, y_phase_major, (cudaStream_t)stream, "ctu_bn_relu_bwd_reduce");
 }
 
 int ctu_bn_relu_bwd_apply(int dtype, const void* y, const float* ss, const float* gamma, const void* dA, const void* dP,
                           const double* sums2, double count, void* dy, float* dgamma, float* dbeta, int c, int n, int d,
-                          int h, int w, ctu_stream stream) {
+                          int h, int w, int y_phase_major, ctu_stream stream) {
     CTU_REQUIRE(y && ss && sums2 && dy && dgamma && dbeta && (dA || dP) && count > 0 && c > 0 && n > 0 && d > 0 && h > 0 && w > 0,
                 "ctu_bn_relu_bwd_apply: bad arguments");
     BwdArgs p = {};
     p.y = y; p.ss = ss; p.gamma = gamma; p.dA = dA; p.dP = dP; p.sums2 = const_cast<double*>(sums2); p.count = count;
     p.dy = dy; p.dgamma = dgamma; p.dbeta = dbeta; p.c = c; p.cb = (c + 7) / 8; p.d = d; p.h = h; p.w = w;
-    return bn_bwd(dtype, p, n, true, (cudaStream_t)stream, "ctu_bn_relu_bwd_apply");
+    return bn_bwd(dtype, p, n, true, y_phase_major, (cudaStream_t)stream, "ctu_bn_relu_bwd_apply");
 }
 
 }  // extern "C"

@@ -327,7 +327,7 @@ static int launch_wgrad(const WgradParams& p, int k, cudaStream_t stream) {
 
 // implemented in conv_tc.cu
 int conv3d_fprop_tc(const void* const* h_srcs, const int* h_src_channels, int nsrc, const float* wp, const float* bias,
-                    void* y, double* stats, int cout, int k, int n, int d, int h, int w, cudaStream_t stream);
+                    void* y, double* stats, int stat_cout, int cout, int k, int n, int d, int h, int w, cudaStream_t stream);
 int conv3d_wgrad_tc(const void* const* h_srcs, const int* h_src_channels, int nsrc, const void* dy, float* dwp,
                     float* dbias, int cout, int k, int n, int d, int h, int w, cudaStream_t stream);
 
@@ -338,20 +338,24 @@ using namespace ctu;
 extern "C" {
 
 int ctu_conv3d_fprop(int dtype, const void* const* h_srcs, const int* h_src_channels, int nsrc, const void* wp,
-                     const float* bias, void* y, double* bn_sums, int cout, int k, int n, int d, int h, int w,
-                     int use_tensor_path, ctu_stream stream) {
+                     const float* bias, void* y, double* bn_sums, int stat_cout, int cout, int k, int n, int d, int h,
+                     int w, int use_tensor_path, ctu_stream stream) {
     SrcMap m;
     int rc = make_srcmap(m, nsrc, h_src_channels);
     if (rc != CTU_OK) return rc;
     CTU_REQUIRE(h_srcs && wp && y && cout > 0 && n > 0 && d > 0 && h > 0 && w > 0, "ctu_conv3d_fprop: bad arguments");
+    if (stat_cout <= 0) stat_cout = cout;
+    const int cob_nat = (stat_cout + 7) / 8;
+    CTU_REQUIRE(stat_cout == cout || (cout % 8 == 0 && (cout / 8) % cob_nat == 0),
+                "ctu_conv3d_fprop: stat_cout=%d does not divide the %d output blocks", stat_cout, cout / 8);
     for (int i = 0; i < nsrc; ++i) CTU_REQUIRE(h_srcs[i] != nullptr, "ctu_conv3d_fprop: null source %d", i);
     if (use_tensor_path) {
         if (dtype != CTU_BF16) {
             set_error("ctu_conv3d_fprop: the tensor path is bf16 only");
             return CTU_ERR_UNSUPPORTED;
         }
-        return conv3d_fprop_tc(h_srcs, h_src_channels, nsrc, (const float*)wp, bias, y, bn_sums, cout, k, n, d, h, w,
-                               (cudaStream_t)stream);
+        return conv3d_fprop_tc(h_srcs, h_src_channels, nsrc, (const float*)wp, bias, y, bn_sums, stat_cout, cout, k, n, d,
+                               h, w, (cudaStream_t)stream);
     }
     ConvParams p;
     for (int i = 0; i < CTU_MAX_SRC; ++i) {
@@ -364,7 +368,7 @@ int ctu_conv3d_fprop(int dtype, const void* const* h_srcs, const int* h_src_chan
     p.tiles_w = cdiv(w, p.tw); p.tiles_h = cdiv(h, p.th); p.tiles_d = cdiv(d, p.dg * RD);
     CTU_DISPATCH_DTYPE(dtype, rc = launch_fprop<T>(p, k, (cudaStream_t)stream));
     if (rc == CTU_OK && bn_sums != nullptr)
-        rc = ctu_bn_stats(dtype, y, cout, n, (long long)d * h * w, bn_sums, stream);
+        rc = ctu_bn_stats(dtype, y, stat_cout, ((cout + 7) / 8) / cob_nat, n, (long long)d * h * w, bn_sums, stream);
     return rc;
 }
 

@@ -142,22 +142,41 @@ struct Ring {
 constexpr int TC_MAX_SLOTS = 16;
 
 // ------------------------------------------------------------------------------------------------ schedule
-// MMAs of one kd-plane: first every (tap, channel-block pair) -- second K chunk = the next channel block --
-// then, when Cb is odd, the last channel block's taps pairwise -- second K chunk = the next tap.
-__host__ __device__ inline int tc_mmas_per_kd(int k, int cb) {
+// The input channel blocks of one plane are staged in GROUPS of `cbg` blocks (one ring slot per group, so wide
+// inputs -- the concatenated sources of the fused up-sampling stage -- never need more than cbg planes of shared
+// memory per slot); cbg is even whenever there is more than one group.
+// MMAs of one kd-plane, group by group: first every (tap, channel-block pair) -- second K chunk = the next channel
+// block -- then, when the (last) group has an odd number of blocks, its last block's taps pairwise -- second K
+// chunk = the next tap.
+__host__ __device__ inline int tc_groups(int cb, int cbg) { return (cb + cbg - 1) / cbg; }
+__host__ __device__ inline int tc_group_mmas(int k, int gb) {
     const int k2 = k * k;
-    return k2 * (cb / 2) + ((cb & 1) ? (k2 + 1) / 2 : 0);
+    return k2 * (gb / 2) + ((gb & 1) ? (k2 + 1) / 2 : 0);
 }
-// chunk c (0/1) of MMA m: returns false for the zero-weight dummy half of an odd tail
-__host__ __device__ inline bool tc_chunk(int k, int cb, int m, int c, int& blk, int& tap2d) {
-    const int k2 = k * k, pairs = cb / 2;
-    if (m < k2 * pairs) {
-        tap2d = m / pairs;
-        blk = 2 * (m % pairs) + c;
+__host__ __device__ inline int tc_mmas_per_kd(int k, int cb, int cbg) {
+    const int ng = tc_groups(cb, cbg);
+    return (ng - 1) * tc_group_mmas(k, cbg) + tc_group_mmas(k, cb - (ng - 1) * cbg);
+}
+// first MMA of group g
+__host__ __device__ inline int tc_group_start(int k, int cb, int cbg, int g) {
+    const int ng = tc_groups(cb, cbg);
+    return g < ng ? g * tc_group_mmas(k, cbg) : tc_mmas_per_kd(k, cb, cbg);
+}
+// chunk c (0/1) of MMA m: global block, 2-D tap and group; returns false for the zero-weight dummy half of an odd tail
+__host__ __device__ inline bool tc_chunk(int k, int cb, int cbg, int m, int c, int& blk, int& tap2d, int& grp) {
+    const int k2 = k * k, ng = tc_groups(cb, cbg), per = tc_group_mmas(k, cbg);
+    grp = (ng > 1 && per > 0) ? m / per : 0;
+    if (grp > ng - 1) grp = ng - 1;
+    const int ml = m - grp * (ng > 1 ? per : 0);
+    const int gb = (grp == ng - 1) ? cb - grp * cbg : cbg;
+    const int pairs = gb / 2;
+    if (ml < k2 * pairs) {
+        tap2d = ml / pairs;
+        blk = grp * cbg + 2 * (ml % pairs) + c;
         return true;
     }
-    const int j = m - k2 * pairs;
-    blk = cb - 1;
+    const int j = ml - k2 * pairs;
+    blk = grp * cbg + gb - 1;
     tap2d = 2 * j + c;
     if (tap2d >= k2) {
         tap2d = k2 - 1;
@@ -166,12 +185,20 @@ __host__ __device__ inline bool tc_chunk(int k, int cb, int m, int c, int& blk, 
     return true;
 }
 
+// up to CTU_MAX_SRC concatenated sources, one tensor map each
+struct TcMaps {
+    CUtensorMap m[CTU_MAX_SRC];
+};
+
 struct TcParams {
     const __nv_bfloat16* wimg;   // [mma m][NT/8][2][8][8] bf16: UMMA B tiles in order of use, n = kd*cpad + co
     const float* bias;
     __nv_bfloat16* y;
     double* stats;               // nullable: [2][cpad_out] sum, sum of squares (of the bf16-rounded outputs)
     int cb, cob_n, nt, cout;     // nt: MMA N = K*COB*8 rounded up to 16
+    int cbg, ncg;                // channel blocks per ring slot, number of such groups
+    int nsrc, src_cb[CTU_MAX_SRC], src_cboff[CTU_MAX_SRC];   // concatenated sources: blocks and first block of each
+    int cobo, cstat;             // statistics: natural channel block = output block % cobo, cstat real channels
     int ob0, nob;                // output blocks [ob0, ob0+nob) are produced by this launch (nob <= COB)
     int n, d, h, w;
     int tiles_h, tiles_w, dchunks, dc;
@@ -182,7 +209,7 @@ struct TcParams {
 };
 
 // fp32 packed weights [cob][cib][tap][ci][co] -> the bf16 B-tile images, one per output-block group of `cobg`
-__global__ void tc_pack_wimg_kernel(const float* __restrict__ wp, __nv_bfloat16* __restrict__ wimg, int k, int cb,
+__global__ void tc_pack_wimg_kernel(const float* __restrict__ wp, __nv_bfloat16* __restrict__ wimg, int k, int cb, int cbg,
                                     int cob_n, int cobg, int nt, int nm, long long total) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
@@ -194,9 +221,9 @@ __global__ void tc_pack_wimg_kernel(const float* __restrict__ wp, __nv_bfloat16*
     const int m = (int)(q % nm);
     const int grp = (int)(q / nm);
     const int kd = g / cobg, cob = grp * cobg + g % cobg;
-    int blk, tap2d;
+    int blk, tap2d, grp_;
     float v = 0.f;
-    if (kd < k && cob < cob_n && tc_chunk(k, cb, m, c, blk, tap2d)) {
+    if (kd < k && cob < cob_n && tc_chunk(k, cb, cbg, m, c, blk, tap2d, grp_)) {
         const int taps = k * k * k, tap = kd * k * k + tap2d;
         v = wp[(((long long)cob * cb + blk) * taps + tap) * 64 + e * 8 + r];   // e = input lane (K), r = output lane (N)
     }
@@ -209,12 +236,13 @@ __global__ void tc_pack_wimg_kernel(const float* __restrict__ wp, __nv_bfloat16*
 // plane instead of once per kd (SS-mode UMMA is bound by the A-operand read, ~64 B/clk, not by the math, when N
 // is this small).  The epilogue thread of a voxel column adds P[kd] of K consecutive planes in registers.
 template <int K, int COB>
-__global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap,
+__global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel(const __grid_constant__ TcMaps maps,
                                                                                  TcParams p) {
     constexpr int PAD = K / 2;
     constexpr int HH = TC_TH + K - 1, WW = TC_TW + K - 1;
     constexpr uint32_t ROW = WW * 16;              // bytes per halo row of one channel block
     constexpr int CP = COB * 8;                    // padded output channels
+    constexpr int NSLOT = COB < 2 ? COB : 2;       // statistics accumulators (blocks) per thread
     constexpr int NTHREADS = 32 * (1 + TC_WB + 4 * TC_WB);
     const uint32_t NS = p.ns;
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -222,7 +250,7 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
     const uint32_t s_w = s_base;                                            // weights image
     const uint32_t s_planes = s_base + ((p.wimg_bytes + 1023u) & ~1023u);   // NS slots
     const uint32_t s_tab = s_planes + NS * p.slot_bytes;                    // per-MMA descriptor low words (A, B)
-    const int nm = tc_mmas_per_kd(K, p.cb);
+    const int nm = tc_mmas_per_kd(K, p.cb, p.cbg);
     uint2* tab = reinterpret_cast<uint2*>(smem + (s_tab - s_base));
     const uint32_t s_bar = s_tab + ((nm * 8u + 15u) & ~15u);
     // barriers: plane_full[NS], plane_empty[NS], acc_full[2 stages][TC_WB tiles], acc_empty[2][TC_WB], w_full
@@ -235,7 +263,7 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
     if (threadIdx.x == 0) {
         for (uint32_t i = 0; i < NS; ++i) {
             mbar_init(b_full + 8 * i, 1);
-            mbar_init(b_empty + 8 * i, TC_WB);      // every issuer warp releases the plane
+            mbar_init(b_empty + 8 * i, TC_WB);      // every issuer warp releases the slot
         }
         for (int i = 0; i < 2 * TC_WB; ++i) {
             mbar_init(b_afull + 8 * i, 1);
@@ -244,13 +272,13 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
         mbar_init(b_w, 1);
         fence_barrier_init();
     }
-    // descriptor table: A low word = (offset within a plane slot) >> 4 | (LBO >> 4) << 16; B low word likewise
+    // descriptor table: A low word = (offset within a ring slot) >> 4 | (LBO >> 4) << 16; B low word likewise
     for (int m = threadIdx.x; m < nm; m += NTHREADS) {
-        int blk0, t0, blk1, t1;
-        tc_chunk(K, p.cb, m, 0, blk0, t0);
-        const bool real1 = tc_chunk(K, p.cb, m, 1, blk1, t1);
-        const uint32_t off0 = blk0 * p.plane_bytes + (t0 / K) * ROW + (t0 % K) * 16;
-        const uint32_t off1 = blk1 * p.plane_bytes + (t1 / K) * ROW + (t1 % K) * 16;
+        int blk0, t0, blk1, t1, g0, g1;
+        tc_chunk(K, p.cb, p.cbg, m, 0, blk0, t0, g0);
+        const bool real1 = tc_chunk(K, p.cb, p.cbg, m, 1, blk1, t1, g1);
+        const uint32_t off0 = (blk0 - g0 * p.cbg) * p.plane_bytes + (t0 / K) * ROW + (t0 % K) * 16;
+        const uint32_t off1 = (blk1 - g0 * p.cbg) * p.plane_bytes + (t1 / K) * ROW + (t1 % K) * 16;
         const uint32_t lbo = real1 ? off1 - off0 : 0u;
         tab[m] = make_uint2((off0 >> 4) | ((lbo >> 4) << 16), ((s_w >> 4) + (uint32_t)m * (uint32_t)p.nt * 2u) | (8u << 16));
     }
@@ -283,12 +311,22 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
                 const int twi = r % p.tiles_w, thi = r / p.tiles_w;
                 const int z0 = dci * p.dc, h0 = thi * TC_TH, w0 = twi * TC_TW;
                 const int nd = (p.d - z0) < p.dc ? (p.d - z0) : p.dc;
-                for (int pl = 0; pl < nd + K - 1; ++pl, pr.next(NS)) {
-                    mbar_wait(b_empty + 8 * pr.slot, pr.phase ^ 1);
-                    mbar_expect_tx(b_full + 8 * pr.slot, (uint32_t)p.cb * HH * WW * 16);
-                    for (int b = 0; b < p.cb; ++b)
-                        tma_load_4d(s_planes + pr.slot * p.slot_bytes + b * p.plane_bytes, &tmap, (w0 - PAD) * 8,
-                                    h0 - PAD, z0 + pl - PAD, n * p.cb + b, b_full + 8 * pr.slot);
+                for (int pl = 0; pl < nd + K - 1; ++pl) {
+                    for (int g = 0; g < p.ncg; ++g, pr.next(NS)) {
+                        const int b0 = g * p.cbg;
+                        const int gb = (p.cb - b0) < p.cbg ? (p.cb - b0) : p.cbg;
+                        mbar_wait(b_empty + 8 * pr.slot, pr.phase ^ 1);
+                        mbar_expect_tx(b_full + 8 * pr.slot, (uint32_t)gb * HH * WW * 16);
+                        for (int b = 0; b < gb; ++b) {
+                            int s = 0;
+#pragma unroll
+                            for (int q = 1; q < CTU_MAX_SRC; ++q)
+                                if (q < p.nsrc && b0 + b >= p.src_cboff[q]) s = q;
+                            tma_load_4d(s_planes + pr.slot * p.slot_bytes + b * p.plane_bytes, &maps.m[s], (w0 - PAD) * 8,
+                                        h0 - PAD, z0 + pl - PAD, n * p.src_cb[s] + (b0 + b - p.src_cboff[s]),
+                                        b_full + 8 * pr.slot);
+                        }
+                    }
                 }
             }
         }
@@ -307,24 +345,29 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
                 const int r0 = item % items_per_n;
                 const int z0 = (r0 % p.dchunks) * p.dc;
                 const int nd = (p.d - z0) < p.dc ? (p.d - z0) : p.dc;
-                for (int pl = 0; pl < nd + K - 1; ++pl, ++step, cons.next(NS)) {
-                    mbar_wait(b_full + 8 * cons.slot, cons.phase);
+                for (int pl = 0; pl < nd + K - 1; ++pl, ++step) {
                     const uint32_t stage = step & 1;
-                    mbar_wait(b_aempty + 8 * (stage * TC_WB + t), ((step >> 1) & 1) ^ 1);
-                    tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (stage * TC_WB + t) * p.nt;
-                    const uint32_t a16 = (s_planes + cons.slot * p.slot_bytes + t * 128u) >> 4;
-                    {
-                        const uint2 e = tab[0];
-                        umma_bf16(d_tmem, pack64(e.x + a16, a_hi), pack64(e.y, b_hi), idesc, 0u);
-                    }
+                    int m = 0;
+                    for (int g = 0; g < p.ncg; ++g, cons.next(NS)) {
+                        mbar_wait(b_full + 8 * cons.slot, cons.phase);
+                        if (g == 0) mbar_wait(b_aempty + 8 * (stage * TC_WB + t), ((step >> 1) & 1) ^ 1);
+                        tc_fence_after();
+                        const uint32_t a16 = (s_planes + cons.slot * p.slot_bytes + t * 128u) >> 4;
+                        const int mend = (g + 1 < p.ncg) ? tc_group_start(K, p.cb, p.cbg, g + 1) : nm;
+                        if (g == 0) {
+                            const uint2 e = tab[0];
+                            umma_bf16(d_tmem, pack64(e.x + a16, a_hi), pack64(e.y, b_hi), idesc, 0u);
+                            m = 1;
+                        }
 #pragma unroll 4
-                    for (int m = 1; m < nm; ++m) {
-                        const uint2 e = tab[m];
-                        umma_bf16_acc(d_tmem, pack64(e.x + a16, a_hi), pack64(e.y, b_hi), idesc);
+                        for (; m < mend; ++m) {
+                            const uint2 e = tab[m];
+                            umma_bf16_acc(d_tmem, pack64(e.x + a16, a_hi), pack64(e.y, b_hi), idesc);
+                        }
+                        umma_commit(b_empty + 8 * cons.slot);
                     }
                     umma_commit(b_afull + 8 * (stage * TC_WB + t));
-                    umma_commit(b_empty + 8 * cons.slot);
                 }
             }
         }
@@ -337,13 +380,13 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
         const bool want_stats = p.stats != nullptr;
         const long long plane = (long long)p.d * p.h * p.w;
         float part[K][CP];                             // partial sums of the K output planes in flight
-        float s1[(COB < 2 ? COB : 2) * 8], s2[(COB < 2 ? COB : 2) * 8];
+        float s1[NSLOT * 8], s2[NSLOT * 8];
         float bv[CP];
 #pragma unroll
         for (int c = 0; c < CP; ++c)
             bv[c] = (p.bias != nullptr && p.ob0 * 8 + c < p.cout) ? __ldg(p.bias + p.ob0 * 8 + c) : 0.f;
 #pragma unroll
-        for (int i = 0; i < (COB < 2 ? COB : 2) * 8; ++i) s1[i] = s2[i] = 0.f;
+        for (int i = 0; i < NSLOT * 8; ++i) s1[i] = s2[i] = 0.f;
         uint32_t step = 0;
         for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
             const int n = item / items_per_n;
@@ -388,11 +431,11 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
                         for (int c = 0; c < 8; ++c) o.v[c] = round_to<__nv_bfloat16>(part[0][ob * 8 + c] + bv[ob * 8 + c]);
                         if (inb && ob < p.nob) {
                             Vec8<__nv_bfloat16>::store(ycol + ((long long)ob * plane + (long long)gz * p.h * p.w) * 8, o);
-                            if (ob < 2 && want_stats) {
+                            if (want_stats) {
 #pragma unroll
                                 for (int c = 0; c < 8; ++c) {
-                                    s1[(ob & 1) * 8 + c] += o.v[c];
-                                    s2[(ob & 1) * 8 + c] = fmaf(o.v[c], o.v[c], s2[(ob & 1) * 8 + c]);
+                                    s1[(ob % NSLOT) * 8 + c] += o.v[c];
+                                    s2[(ob % NSLOT) * 8 + c] = fmaf(o.v[c], o.v[c], s2[(ob % NSLOT) * 8 + c]);
                                 }
                             }
                         }
@@ -407,12 +450,16 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
             }
         }
         if (want_stats) {
+            // accumulator slot s holds the output blocks ob0 + s, ob0 + s + NSLOT, ...: all the same natural block
+            // (the host only fuses the statistics when that holds)
+            const int cpn = p.cobo * 8;
 #pragma unroll
-            for (int i = 0; i < (COB < 2 ? COB : 2) * 8; ++i) {
+            for (int i = 0; i < NSLOT * 8; ++i) {
                 const float a1 = warp_sum(s1[i]), a2 = warp_sum(s2[i]);
-                if (lane == 0 && i < p.cout) {   // fused statistics: single group only (ob0 == 0, cob_n == COB)
-                    atomicAdd(p.stats + i, (double)a1);
-                    atomicAdd(p.stats + CP + i, (double)a2);
+                const int ch = ((p.ob0 + (i >> 3)) % p.cobo) * 8 + (i & 7);
+                if (lane == 0 && (i >> 3) < p.nob && ch < p.cstat) {
+                    atomicAdd(p.stats + ch, (double)a1);
+                    atomicAdd(p.stats + cpn + ch, (double)a2);
                 }
             }
         }
@@ -439,7 +486,7 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 }
 
 struct TcGeom {
-    int cb, cob_n, cobg, ngroups, nt, nm;
+    int cb, cbg, ncg, cob_n, cobg, ngroups, nt, nm;
     uint32_t wimg_bytes, plane_bytes, slot_bytes, tmem_cols, ns;   // wimg_bytes: ONE group's image
     size_t smem;
 };
@@ -453,15 +500,18 @@ static uint32_t pick_slots(int min_slots, size_t fixed_bytes, size_t slot_bytes)
     return (uint32_t)ns;
 }
 
-static bool tc_geometry(int k, int cin, int cout, int h, int w, TcGeom& g) {
+// cb: total channel blocks over all concatenated sources
+static bool tc_geometry(int k, int cb, int cout, int h, int w, TcGeom& g) {
     if (k != 3 && k != 5) return false;
-    if (h % TC_TH || w % TC_TW) return false;
-    g.cb = (cin + 7) / 8;
+    if (h % TC_TH || w % TC_TW || cb < 1 || cout < 1) return false;
+    g.cb = cb;
+    g.cbg = cb <= 6 ? cb : 4;          // wide inputs are staged four blocks at a time
+    g.ncg = tc_groups(cb, g.cbg);
     g.cob_n = (cout + 7) / 8;
-    g.nm = tc_mmas_per_kd(k, g.cb);
+    g.nm = tc_mmas_per_kd(k, g.cb, g.cbg);
     const int hh = TC_TH + k - 1, ww = TC_TW + k - 1;
     g.plane_bytes = ((uint32_t)hh * ww * 16 + 127u) & ~127u;
-    g.slot_bytes = g.plane_bytes * g.cb;
+    g.slot_bytes = g.plane_bytes * g.cbg;
     // output blocks per launch: the instantiated COB in {1,2,4} (k=3) / {1,2} (k=5) -- N = K*COB*8 <= 128 so that
     // 2 stages x 2 tiles fit the 512 TMEM columns -- shrunk until weights + a 3-slot ring fit shared memory
     int cobg = (k == 3) ? 4 : 2;
@@ -472,7 +522,7 @@ static bool tc_geometry(int k, int cin, int cout, int h, int w, TcGeom& g) {
         g.wimg_bytes = (uint32_t)g.nm * g.nt * 32;
         const size_t fixed = ((g.wimg_bytes + 1023u) & ~1023u) + ((g.nm * 8 + 15) & ~15) +
                              8 * (2 * TC_MAX_SLOTS + 4 * TC_WB + 2) + 16 + 1024;
-        g.ns = pick_slots(3, fixed, g.slot_bytes);
+        g.ns = pick_slots(g.ncg > 1 ? 4 : 3, fixed, g.slot_bytes);
         g.smem = fixed + (size_t)g.ns * g.slot_bytes;
         if (g.smem <= 220 * 1024) break;
         if (cobg == 1) return false;
@@ -484,41 +534,76 @@ static bool tc_geometry(int k, int cin, int cout, int h, int w, TcGeom& g) {
     return g.tmem_cols <= 512;
 }
 
-int conv3d_fprop_tc(const void* const* h_srcs, const int* h_src_channels, int nsrc, const float* wp, const float* bias,
-                    void* y, double* stats, int cout, int k, int n, int d, int h, int w, cudaStream_t stream) {
-    if (nsrc != 1) {
-        set_error("conv3d tensor path: single source only");
-        return CTU_ERR_UNSUPPORTED;
+static int total_blocks(int nsrc, const int* h_src_channels) {
+    if (nsrc < 1 || nsrc > CTU_MAX_SRC || h_src_channels == nullptr) return -1;
+    int cb = 0;
+    for (int i = 0; i < nsrc; ++i) {
+        if (h_src_channels[i] < 1) return -1;
+        cb += (h_src_channels[i] + 7) / 8;
     }
-    TcGeom g;
-    if (!tc_geometry(k, h_src_channels[0], cout, h, w, g)) {
-        set_error("conv3d tensor path: shape k=%d cin=%d cout=%d %dx%dx%d not covered", k, h_src_channels[0], cout, d, h, w);
-        return CTU_ERR_UNSUPPORTED;
-    }
+    return cb;
+}
+
+static int make_map(CUtensorMap* map, const void* ptr, int nblocks, int d, int h, int w, int box_w, int box_h) {
     auto encode = get_encode();
     if (!encode) {
         set_error("cuTensorMapEncodeTiled entry point not found");
         return CTU_ERR_UNSUPPORTED;
     }
-    CUtensorMap tmap;
-    const cuuint64_t gdim[4] = {(cuuint64_t)w * 8, (cuuint64_t)h, (cuuint64_t)d, (cuuint64_t)n * g.cb};
+    const cuuint64_t gdim[4] = {(cuuint64_t)w * 8, (cuuint64_t)h, (cuuint64_t)d, (cuuint64_t)nblocks};
     const cuuint64_t gstr[3] = {(cuuint64_t)w * 16, (cuuint64_t)h * w * 16, (cuuint64_t)d * h * w * 16};
-    const cuuint32_t box[4] = {(cuuint32_t)(TC_TW + k - 1) * 8, (cuuint32_t)(TC_TH + k - 1), 1, 1};
+    const cuuint32_t box[4] = {(cuuint32_t)box_w * 8, (cuuint32_t)box_h, 1, 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(h_srcs[0]), gdim, gstr, box, estr,
+    CUresult cr = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (%d)", (int)cr);
         return CTU_ERR_INVALID;
     }
+    return CTU_OK;
+}
+
+// one halo-box tensor map per concatenated source
+static int make_src_maps(TcMaps& maps, const void* const* h_srcs, const int* h_src_channels, int nsrc, int n, int d, int h,
+                         int w, int k) {
+    for (int i = 0; i < CTU_MAX_SRC; ++i) {
+        const int j = i < nsrc ? i : 0;
+        int rc = make_map(&maps.m[i], h_srcs[j], n * ((h_src_channels[j] + 7) / 8), d, h, w, TC_TW + k - 1, TC_TH + k - 1);
+        if (rc != CTU_OK) return rc;
+    }
+    return CTU_OK;
+}
+
+// stat_cout: number of NATURAL channels the statistics are taken over: cout for an ordinary convolution, cout / 8
+// phases for the phase-major output of the fused up-sampling stage (natural block = output block % ceil(stat_cout/8))
+int conv3d_fprop_tc(const void* const* h_srcs, const int* h_src_channels, int nsrc, const float* wp, const float* bias,
+                    void* y, double* stats, int stat_cout, int cout, int k, int n, int d, int h, int w, cudaStream_t stream) {
+    TcGeom g;
+    const int cb = total_blocks(nsrc, h_src_channels);
+    if (cb < 0 || !tc_geometry(k, cb, cout, h, w, g)) {
+        set_error("conv3d tensor path: shape k=%d blocks=%d cout=%d %dx%dx%d not covered", k, cb, cout, d, h, w);
+        return CTU_ERR_UNSUPPORTED;
+    }
+    TcMaps maps;
+    int rc = make_src_maps(maps, h_srcs, h_src_channels, nsrc, n, d, h, w, k);
+    if (rc != CTU_OK) return rc;
     TcParams p = {};
     p.wimg = reinterpret_cast<const __nv_bfloat16*>(wp);
     p.bias = bias;
     p.y = reinterpret_cast<__nv_bfloat16*>(y);
-    const bool fuse_stats = stats != nullptr && g.ngroups == 1 && g.cob_n == g.cobg && g.cob_n <= 2;
+    if (stat_cout <= 0) stat_cout = cout;
+    p.cobo = (stat_cout + 7) / 8;
+    p.cstat = stat_cout;
+    const bool fuse_stats = stats != nullptr && (g.cobg <= 2 || p.cobo <= 2);
     p.stats = fuse_stats ? stats : nullptr;
-    p.cb = g.cb; p.cob_n = g.cob_n; p.nt = g.nt; p.cout = cout;
+    p.cb = g.cb; p.cbg = g.cbg; p.ncg = g.ncg; p.cob_n = g.cob_n; p.nt = g.nt; p.cout = cout;
+    p.nsrc = nsrc;
+    for (int i = 0, off = 0; i < CTU_MAX_SRC; ++i) {
+        p.src_cb[i] = i < nsrc ? (h_src_channels[i] + 7) / 8 : 0;
+        p.src_cboff[i] = off;
+        off += p.src_cb[i];
+    }
     p.n = n; p.d = d; p.h = h; p.w = w;
     p.tiles_h = h / TC_TH; p.tiles_w = w / TC_TW;
     // d-chunk: enough work items to balance 148 SMs x resident CTAs, but at least 8 planes per chunk
@@ -531,7 +616,7 @@ int conv3d_fprop_tc(const void* const* h_srcs, const int* h_src_channels, int ns
     p.wimg_bytes = g.wimg_bytes; p.plane_bytes = g.plane_bytes; p.slot_bytes = g.slot_bytes; p.tmem_cols = g.tmem_cols;
     p.ns = g.ns;
     if (fuse_stats) {
-        cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(double) * 2 * g.cob_n * 8, stream);
+        cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(double) * 2 * p.cobo * 8, stream);
         if (e != cudaSuccess) {
             set_error("conv3d tensor path: memset: %s", cudaGetErrorString(e));
             return (int)e;
@@ -550,10 +635,10 @@ int conv3d_fprop_tc(const void* const* h_srcs, const int* h_src_channels, int ns
             set_error("conv3d tensor path: smem %zu: %s", g.smem, cudaGetErrorString(e));
             return (int)e;
         }
-        kern<<<grid, threads, g.smem, stream>>>(tmap, p);
+        kern<<<grid, threads, g.smem, stream>>>(maps, p);
         return check_launch("ctu_conv3d_fprop(tcgen05)");
     };
-    int rc = CTU_OK;
+    rc = CTU_OK;
     for (int grp = 0; grp < g.ngroups && rc == CTU_OK; ++grp) {
         p.ob0 = grp * g.cobg;
         p.nob = (g.cob_n - p.ob0) < g.cobg ? (g.cob_n - p.ob0) : g.cobg;
@@ -565,7 +650,7 @@ int conv3d_fprop_tc(const void* const* h_srcs, const int* h_src_channels, int ns
         else rc = go(conv3d_tc_kernel<5, 2>);
     }
     if (rc == CTU_OK && stats != nullptr && !fuse_stats)   // wide layers (low resolution): separate statistics pass
-        rc = ctu_bn_stats(CTU_BF16, y, cout, n, (long long)d * h * w, stats, stream);
+        rc = ctu_bn_stats(CTU_BF16, y, stat_cout, g.cob_n / p.cobo, n, (long long)d * h * w, stats, stream);
     return rc;
 }
 
@@ -591,10 +676,11 @@ struct WgParams {
     int tiles_h, tiles_w, dchunks, dc, total_items;
     uint32_t plane_bytes, xslot_bytes, dyslot_bytes, tmem_cols;
     uint32_t ns, nds;           // x-plane / dy-plane ring depths
+    int nsrc, src_cb[CTU_MAX_SRC], src_cboff[CTU_MAX_SRC];   // concatenated sources of x
 };
 
 template <int K>
-__global__ void __launch_bounds__(WG_THREADS) conv3d_wgrad_tc_kernel(const __grid_constant__ CUtensorMap xmap,
+__global__ void __launch_bounds__(WG_THREADS) conv3d_wgrad_tc_kernel(const __grid_constant__ TcMaps xmaps,
                                                                      const __grid_constant__ CUtensorMap dymap,
                                                                      WgParams p) {
     constexpr int PAD = K / 2;
@@ -669,9 +755,14 @@ __global__ void __launch_bounds__(WG_THREADS) conv3d_wgrad_tc_kernel(const __gri
                 for (int pl = 0; pl < nd + K - 1; ++pl, pr.next(NS)) {
                     mbar_wait(b_xempty + 8 * pr.slot, pr.phase ^ 1);
                     mbar_expect_tx(b_xfull + 8 * pr.slot, (uint32_t)ncb * HH * WW * 16);
-                    for (int b = 0; b < ncb; ++b)
-                        tma_load_4d(s_x + pr.slot * p.xslot_bytes + b * p.plane_bytes, &xmap, (w0 - PAD) * 8, h0 - PAD,
-                                    z0 + pl - PAD, n * p.cb + cb0 + b, b_xfull + 8 * pr.slot);
+                    for (int b = 0; b < ncb; ++b) {
+                        int s = 0;
+#pragma unroll
+                        for (int q = 1; q < CTU_MAX_SRC; ++q)
+                            if (q < p.nsrc && cb0 + b >= p.src_cboff[q]) s = q;
+                        tma_load_4d(s_x + pr.slot * p.xslot_bytes + b * p.plane_bytes, &xmaps.m[s], (w0 - PAD) * 8, h0 - PAD,
+                                    z0 + pl - PAD, n * p.src_cb[s] + (cb0 + b - p.src_cboff[s]), b_xfull + 8 * pr.slot);
+                    }
                     if (pl >= K - 1) {
                         mbar_wait(b_dyempty + 8 * dr.slot, dr.phase ^ 1);
                         mbar_expect_tx(b_dyfull + 8 * dr.slot, (uint32_t)TC_TH * dyrow);
@@ -813,10 +904,10 @@ struct WgGeom {
     size_t smem;
 };
 
-static bool wg_geometry(int k, int cin, int cout, int h, int w, WgGeom& g) {
+static bool wg_geometry(int k, int cb, int cout, int h, int w, WgGeom& g) {
     if (k != 3 && k != 5) return false;
-    if (h % TC_TH || w % TC_TW) return false;
-    g.cb = (cin + 7) / 8;
+    if (h % TC_TH || w % TC_TW || cb < 1 || cout < 1) return false;
+    g.cb = cb;
     g.cob_n = (cout + 7) / 8;
     const int k2 = k * k;
     const int hh = TC_TH + k - 1, ww = TC_TW + k - 1;
@@ -852,39 +943,17 @@ static bool wg_geometry(int k, int cin, int cout, int h, int w, WgGeom& g) {
     return g.tmem_cols <= 512;
 }
 
-static int make_map(CUtensorMap* map, const void* ptr, int nblocks, int d, int h, int w, int box_w, int box_h) {
-    auto encode = get_encode();
-    if (!encode) {
-        set_error("cuTensorMapEncodeTiled entry point not found");
-        return CTU_ERR_UNSUPPORTED;
-    }
-    const cuuint64_t gdim[4] = {(cuuint64_t)w * 8, (cuuint64_t)h, (cuuint64_t)d, (cuuint64_t)nblocks};
-    const cuuint64_t gstr[3] = {(cuuint64_t)w * 16, (cuuint64_t)h * w * 16, (cuuint64_t)d * h * w * 16};
-    const cuuint32_t box[4] = {(cuuint32_t)box_w * 8, (cuuint32_t)box_h, 1, 1};
-    const cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult cr = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (cr != CUDA_SUCCESS) {
-        set_error("cuTensorMapEncodeTiled failed (%d)", (int)cr);
-        return CTU_ERR_INVALID;
-    }
-    return CTU_OK;
-}
-
 int conv3d_wgrad_tc(const void* const* h_srcs, const int* h_src_channels, int nsrc, const void* dy, float* dwp,
                     float* dbias, int cout, int k, int n, int d, int h, int w, cudaStream_t stream) {
-    if (nsrc != 1) {
-        set_error("conv3d wgrad tensor path: single source only");
-        return CTU_ERR_UNSUPPORTED;
-    }
     WgGeom g;
-    if (!wg_geometry(k, h_src_channels[0], cout, h, w, g)) {
-        set_error("conv3d wgrad tensor path: shape k=%d cin=%d cout=%d %dx%dx%d not covered", k, h_src_channels[0], cout, d, h, w);
+    const int cbt = total_blocks(nsrc, h_src_channels);
+    if (cbt < 0 || !wg_geometry(k, cbt, cout, h, w, g)) {
+        set_error("conv3d wgrad tensor path: shape k=%d blocks=%d cout=%d %dx%dx%d not covered", k, cbt, cout, d, h, w);
         return CTU_ERR_UNSUPPORTED;
     }
-    CUtensorMap xmap, dymap;
-    int rc = make_map(&xmap, h_srcs[0], n * g.cb, d, h, w, TC_TW + k - 1, TC_TH + k - 1);
+    TcMaps xmaps;
+    CUtensorMap dymap;
+    int rc = make_src_maps(xmaps, h_srcs, h_src_channels, nsrc, n, d, h, w, k);
     if (rc == CTU_OK) {
         // dy as (w*8, cob, h, d, n): one box [TH][ng/8][TW*8] lands in shared memory as [h][cob][w][8]
         auto encode = get_encode();
@@ -916,6 +985,12 @@ int conv3d_wgrad_tc(const void* const* h_srcs, const int* h_src_channels, int ns
     p.total_items = tiles * p.dchunks;
     p.plane_bytes = g.plane_bytes; p.xslot_bytes = g.xslot_bytes; p.dyslot_bytes = g.dyslot_bytes; p.tmem_cols = g.tmem_cols;
     p.ns = g.ns; p.nds = g.nds;
+    p.nsrc = nsrc;
+    for (int i = 0, off = 0; i < CTU_MAX_SRC; ++i) {
+        p.src_cb[i] = i < nsrc ? (h_src_channels[i] + 7) / 8 : 0;
+        p.src_cboff[i] = off;
+        off += p.src_cb[i];
+    }
     int ctas_per_sm = (int)((227 * 1024) / (g.smem + 1024));
     if (ctas_per_sm > 512 / (int)g.tmem_cols) ctas_per_sm = 512 / (int)g.tmem_cols;
     if (ctas_per_sm < 1) ctas_per_sm = 1;
@@ -929,7 +1004,7 @@ int conv3d_wgrad_tc(const void* const* h_srcs, const int* h_src_channels, int ns
             set_error("conv3d wgrad tensor path: smem %zu: %s", g.smem, cudaGetErrorString(e));
             return (int)e;
         }
-        kern<<<grid, WG_THREADS, g.smem, stream>>>(xmap, dymap, p);
+        kern<<<grid, WG_THREADS, g.smem, stream>>>(xmaps, dymap, p);
         return check_launch("ctu_conv3d_wgrad(tcgen05)");
     };
     rc = k == 3 ? go(conv3d_wgrad_tc_kernel<3>) : go(conv3d_wgrad_tc_kernel<5>);
@@ -950,29 +1025,34 @@ extern "C" {
 
 int ctu_has_tensor_path(void) { return 1; }
 
-int ctu_conv_tc_supported(int k, int cin, int cout, int d, int h, int w) {
+int ctu_conv_tc_supported(int k, int nsrc, const int* h_src_channels, int cout, int d, int h, int w) {
     (void)d;
     TcGeom g;
-    return tc_geometry(k, cin, cout, h, w, g) ? 1 : 0;
+    const int cb = total_blocks(nsrc, h_src_channels);
+    return (cb > 0 && tc_geometry(k, cb, cout, h, w, g)) ? 1 : 0;
 }
 
-int ctu_conv_tc_wgrad_supported(int k, int cin, int cout, int d, int h, int w) {
+int ctu_conv_tc_wgrad_supported(int k, int nsrc, const int* h_src_channels, int cout, int d, int h, int w) {
     (void)d;
     WgGeom g;
-    return wg_geometry(k, cin, cout, h, w, g) ? 1 : 0;
+    const int cb = total_blocks(nsrc, h_src_channels);
+    return (cb > 0 && wg_geometry(k, cb, cout, h, w, g)) ? 1 : 0;
 }
 
-long long ctu_conv_tc_wimg_bytes(int k, int cin, int cout) {
+long long ctu_conv_tc_wimg_bytes(int k, int nsrc, const int* h_src_channels, int cout) {
     TcGeom g;
-    if (!tc_geometry(k, cin, cout, TC_TH, TC_TW, g)) return -1;
+    const int cb = total_blocks(nsrc, h_src_channels);
+    if (cb < 0 || !tc_geometry(k, cb, cout, TC_TH, TC_TW, g)) return -1;
     return (long long)g.wimg_bytes * g.ngroups;
 }
 
-int ctu_conv_tc_pack_weight(const float* wp, void* wimg, int k, int cin, int cout, ctu_stream stream) {
+int ctu_conv_tc_pack_weight(const float* wp, void* wimg, int k, int nsrc, const int* h_src_channels, int cout,
+                            ctu_stream stream) {
     TcGeom g;
-    CTU_REQUIRE(wp && wimg && tc_geometry(k, cin, cout, TC_TH, TC_TW, g), "ctu_conv_tc_pack_weight: bad arguments");
+    const int cb = total_blocks(nsrc, h_src_channels);
+    CTU_REQUIRE(wp && wimg && cb > 0 && tc_geometry(k, cb, cout, TC_TH, TC_TW, g), "ctu_conv_tc_pack_weight: bad arguments");
     const long long total = (long long)g.wimg_bytes / 2 * g.ngroups;
-    tc_pack_wimg_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(wp, reinterpret_cast<__nv_bfloat16*>(wimg), k, g.cb, g.cob_n, g.cobg, g.nt, g.nm, total);
+    tc_pack_wimg_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(wp, reinterpret_cast<__nv_bfloat16*>(wimg), k, g.cb, g.cbg, g.cob_n, g.cobg, g.nt, g.nm, total);
     return check_launch("ctu_conv_tc_pack_weight");
 }
 

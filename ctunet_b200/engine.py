@@ -28,14 +28,24 @@ BN_EPS = 1e-5
 # "direct": CUDA-core kernels only (always the case in fp32 accumulate-check mode).
 CONV_PATH = "auto"
 
+# "auto": ConvTranspose3d(k2,s2) + Conv3d of every up block run as ONE composed convolution on the low-resolution
+# grid wherever the tcgen05 kernels cover it (bf16 mode); "off": never; "force": always (also in fp32 check mode,
+# through the CUDA-core kernels -- used by the tests to check the composition at fp32 accuracy).
+UP_FUSION = "auto"
+_ONES = {}
+
 
 class Act:
-    """A channel-blocked activation [N][Cb][D][H][W][8] (bf16 in product mode, fp32 in check mode)."""
-    __slots__ = ("buf", "c", "n", "d", "h", "w", "sums")
+    """A channel-blocked activation [N][Cb][D][H][W][8] (bf16 in product mode, fp32 in check mode).
+
+    ``c_nat`` is set on the PHASE-MAJOR output of the fused up-sampling stage: the tensor then holds 8 phases x
+    8*ceil(c_nat/8) channels on the low-resolution grid (block q*cb_nat + b), i.e. a [c_nat] x (2d, 2h, 2w) volume."""
+    __slots__ = ("buf", "c", "n", "d", "h", "w", "sums", "c_nat")
 
     def __init__(self, buf, c, n, d, h, w):
         self.buf, self.c, self.n, self.d, self.h, self.w = buf, c, n, d, h, w
         self.sums = None        # per-channel sum / sum of squares written by the producing conv's epilogue
+        self.c_nat = 0
 
     @property
     def cb(self):
@@ -100,7 +110,7 @@ class Engine:
     def _tc_ok(self, k, srcs, cout):
         return self.use_tc and tc_supported(k, [s.c for s in srcs], cout, srcs[0].d, srcs[0].h, srcs[0].w)
 
-    def _conv_launch(self, srcs, wp, bias, y: Act, cout, k, sums):
+    def _conv_launch(self, srcs, wp, bias, y: Act, cout, k, sums, stat_cout=0):
         """One forward-style convolution launch (also used for the data gradient): tcgen05 implicit GEMM when
         the kernel covers the shape, CUDA-core direct kernel otherwise."""
         s0 = srcs[0]
@@ -109,11 +119,11 @@ class Engine:
         wptr = wp.data_ptr()
         if tc:
             lib = _lib.load()
-            wimg = torch.empty(lib.ctu_conv_tc_wimg_bytes(k, s0.c, cout), dtype=torch.uint8, device=self.device)
-            call("ctu_conv_tc_pack_weight", wp.data_ptr(), wimg.data_ptr(), k, s0.c, cout, stream_ptr())
+            wimg = torch.empty(lib.ctu_conv_tc_wimg_bytes(k, ns, ca, cout), dtype=torch.uint8, device=self.device)
+            call("ctu_conv_tc_pack_weight", wp.data_ptr(), wimg.data_ptr(), k, ns, ca, cout, stream_ptr())
             wptr = wimg.data_ptr()
         call("ctu_conv3d_fprop", self.dtype, pa, ca, ns, wptr, bias.data_ptr() if bias is not None else None,
-             y.ptr, sums.data_ptr() if sums is not None else None, cout, k, s0.n, s0.d, s0.h, s0.w, int(tc),
+             y.ptr, sums.data_ptr() if sums is not None else None, stat_cout, cout, k, s0.n, s0.d, s0.h, s0.w, int(tc),
              stream_ptr())
 
     # ------------------------------------------------------------------ layout
@@ -129,46 +139,126 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ Conv3d
-    def conv(self, srcs: Sequence[Act], weight, bias, k: int, need_src_grad: Sequence[bool],
-             bn_stats: bool = False) -> Act:
-        """``bn_stats``: also produce the batch statistics of the output (``y.sums``) for the BatchNorm that follows."""
-        cout = weight.shape[0]
+    def _conv_fwd(self, srcs, w_native, bias, k, cout, stat_cout, bn_stats):
+        """y = conv(cat(srcs), w_native [cout][cin][k^3]) (+bias); returns the output activation."""
         s0 = srcs[0]
         pa, ca, ns = self._src_args(srcs)
         lib = _lib.load()
         wp = self.f32(lib.ctu_conv_wpack_floats(cout, k, ns, ca))
-        call("ctu_conv_pack_weight", weight.data_ptr(), wp.data_ptr(), cout, k, ns, ca, stream_ptr())
+        call("ctu_conv_pack_weight", w_native.data_ptr(), wp.data_ptr(), cout, k, ns, ca, stream_ptr())
         y = self.new_act(cout, s0.n, s0.d, s0.h, s0.w)
         if bn_stats:
-            y.sums = self.f64(2 * y.cb * 8)
-        self._conv_launch(srcs, wp, bias, y, cout, k, y.sums)
+            y.sums = self.f64(2 * (((stat_cout or cout) + 7) // 8 * 8))
+        self._conv_launch(srcs, wp, bias, y, cout, k, y.sums, stat_cout)
+        return y
+
+    def _conv_bwd(self, srcs, need, w_native, y, k, cout, dw_out, db_out):
+        """Weight gradient into ``dw_out`` (native layout, nullable) / ``db_out`` and the data gradient of every
+        source with ``need[i]``."""
+        lib = _lib.load()
+        s0 = srcs[0]
+        dy = self.agrads.pop(id(y))
+        pa, ca, ns = self._src_args(srcs)
+        if dw_out is not None:
+            dwp = self.f32(lib.ctu_conv_wpack_floats(cout, k, ns, ca))
+            tc = self.use_tc and bool(lib.ctu_conv_tc_wgrad_supported(k, ns, ca, cout, s0.d, s0.h, s0.w))
+            call("ctu_conv3d_wgrad", self.dtype, pa, ca, ns, dy.ptr, dwp.data_ptr(),
+                 db_out.data_ptr() if db_out is not None else None, cout, k, s0.n, s0.d, s0.h, s0.w, int(tc),
+                 stream_ptr())
+            call("ctu_conv_unpack_wgrad", dwp.data_ptr(), dw_out.data_ptr(), cout, k, ns, ca, stream_ptr())
+        for i, s in enumerate(srcs):
+            if not need[i]:
+                continue
+            wpd = self.f32(lib.ctu_conv_wpack_dgrad_floats(cout, k, s.c))
+            call("ctu_conv_pack_weight_dgrad", w_native.data_ptr(), wpd.data_ptr(), cout, k, ns, ca, i, stream_ptr())
+            dx = self.new_act(s.c, s.n, s.d, s.h, s.w)
+            self._conv_launch([dy], wpd, None, dx, s.c, k, None)
+            self._set_agrad(s, dx)
+
+    def conv(self, srcs: Sequence[Act], weight, bias, k: int, need_src_grad: Sequence[bool],
+             bn_stats: bool = False) -> Act:
+        """``bn_stats``: also produce the batch statistics of the output (``y.sums``) for the BatchNorm that follows."""
+        cout = weight.shape[0]
+        y = self._conv_fwd(srcs, weight, bias, k, cout, 0, bn_stats)
         if self.record:
             srcs = list(srcs)
             need = list(need_src_grad)
 
             def bwd():
-                dy = self.agrads.pop(id(y))
-                pa, ca, ns = self._src_args(srcs)
-                if weight.requires_grad:
-                    dwp = torch.empty_like(wp)
-                    db = self._grad_buffer(bias) if (bias is not None and bias.requires_grad) else None
-                    call("ctu_conv3d_wgrad", self.dtype, pa, ca, ns, dy.ptr, dwp.data_ptr(),
-                         db.data_ptr() if db is not None else None, cout, k, s0.n, s0.d, s0.h, s0.w,
-                         int(self.use_tc and len(srcs) == 1 and bool(
-                             lib.ctu_conv_tc_wgrad_supported(k, s0.c, cout, s0.d, s0.h, s0.w))), stream_ptr())
-                    dw = self._grad_buffer(weight)
-                    call("ctu_conv_unpack_wgrad", dwp.data_ptr(), dw.data_ptr(), cout, k, ns, ca, stream_ptr())
+                dw = self._grad_buffer(weight) if weight.requires_grad else None
+                db = self._grad_buffer(bias) if (dw is not None and bias is not None and bias.requires_grad) else None
+                self._conv_bwd(srcs, need, weight, y, k, cout, dw, db)
+                if dw is not None:
                     self._add_pgrad(weight, dw)
-                    if db is not None:
-                        self._add_pgrad(bias, db)
-                for i, s in enumerate(srcs):
-                    if not need[i]:
-                        continue
-                    wpd = self.f32(lib.ctu_conv_wpack_dgrad_floats(cout, k, s.c))
-                    call("ctu_conv_pack_weight_dgrad", weight.data_ptr(), wpd.data_ptr(), cout, k, ns, ca, i, stream_ptr())
-                    dx = self.new_act(s.c, s.n, s.d, s.h, s.w)
-                    self._conv_launch([dy], wpd, None, dx, s.c, k, None)
-                    self._set_agrad(s, dx)
+                if db is not None:
+                    self._add_pgrad(bias, db)
+
+            self.tape.append(bwd)
+        return y
+
+    # ------------------------------------------------------------------ fused ConvTranspose3d(k2,s2) -> Conv3d
+    def _ones(self, like: Act) -> Act:
+        """All-ones single-channel activation (the input channel that carries the transposed convolution's bias)."""
+        key = (str(self.device), self.tdtype, like.n, like.d, like.h, like.w)
+        buf = _ONES.get(key)
+        if buf is None:
+            buf = torch.zeros((like.n, 1, like.d, like.h, like.w, 8), dtype=self.tdtype, device=self.device)
+            buf[..., 0] = 1
+            _ONES[key] = buf
+        return Act(buf, 1, like.n, like.d, like.h, like.w)
+
+    def up_fusable(self, srcs: Sequence[Act], cout: int, k: int) -> bool:
+        """The fused stage needs k in {3, 5} and, in bf16 mode, tcgen05 coverage of the composed convolution
+        (forward, weight gradient and every data gradient); fp32 check mode fuses only when forced."""
+        if UP_FUSION == "off" or k not in (3, 5) or len(srcs) + 1 > _lib.CTU_MAX_SRC:
+            return False
+        if UP_FUSION == "force":
+            return True
+        if self.dtype == CTU_F32 or not self.use_tc:
+            return False
+        lib = _lib.load()
+        chans = [s.c for s in srcs] + [1]
+        s0 = srcs[0]
+        co8 = lib.ctu_upfuse_cout(cout)
+        ca = int_array(chans)
+        return bool(lib.ctu_conv_tc_supported(3, len(chans), ca, co8, s0.d, s0.h, s0.w)
+                    and lib.ctu_conv_tc_wgrad_supported(3, len(chans), ca, co8, s0.d, s0.h, s0.w)
+                    and all(lib.ctu_conv_tc_supported(3, 1, int_array([co8]), s.c, s0.d, s0.h, s0.w) for s in srcs))
+
+    def up_conv(self, srcs: Sequence[Act], ct, cv, k: int, need_src_grad: Sequence[bool], bn_stats: bool) -> Act:
+        """conv(convT(cat(srcs))) as one 3x3x3 convolution on the low-resolution grid (csrc/fuse.cu): the 8x larger
+        intermediate of models.py:37-38 is never written.  Returns the PHASE-MAJOR output (``c_nat`` set)."""
+        lib = _lib.load()
+        cin = sum(s.c for s in srcs)
+        cout = cv.weight.shape[0]
+        co8 = lib.ctu_upfuse_cout(cout)
+        st = stream_ptr()
+        wn = self.f32(co8, cin + 1, 27)
+        b3n = self.f32(co8) if cv.bias is not None else None
+        call("ctu_upfuse_compose", ct.weight.data_ptr(), ct.bias.data_ptr() if ct.bias is not None else None,
+             cv.weight.data_ptr(), cv.bias.data_ptr() if cv.bias is not None else None, wn.data_ptr(),
+             b3n.data_ptr() if b3n is not None else None, cin, cout, k, st)
+        all_srcs = list(srcs) + [self._ones(srcs[0])]
+        y = self._conv_fwd(all_srcs, wn, b3n, 3, co8, cout, bn_stats)
+        y.c_nat = cout
+        if self.record:
+            need = list(need_src_grad) + [False]
+
+            def bwd():
+                st = stream_ptr()
+                dwn = torch.empty_like(wn)
+                dbn = self.f32(co8) if b3n is not None else None
+                self._conv_bwd(all_srcs, need, wn, y, 3, co8, dwn, dbn)
+                dwt, dw3 = self._grad_buffer(ct.weight), self._grad_buffer(cv.weight)
+                dbt = self._grad_buffer(ct.bias) if ct.bias is not None else None
+                db3 = self._grad_buffer(cv.bias) if cv.bias is not None else None
+                call("ctu_upfuse_decompose", dwn.data_ptr(), dbn.data_ptr() if dbn is not None else None,
+                     ct.weight.data_ptr(), ct.bias.data_ptr() if ct.bias is not None else None, cv.weight.data_ptr(),
+                     dwt.data_ptr(), dbt.data_ptr() if dbt is not None else None, dw3.data_ptr(),
+                     db3.data_ptr() if db3 is not None else None, cin, cout, k, st)
+                for prm, g in ((ct.weight, dwt), (ct.bias, dbt), (cv.weight, dw3), (cv.bias, db3)):
+                    if g is not None:
+                        self._add_pgrad(prm, g)
 
             self.tape.append(bwd)
         return y
@@ -223,9 +313,11 @@ class Engine:
     def bn_relu(self, y: Act, bn, training: bool, extra_updates: int = 0, pool: bool = False):
         """Returns ``a`` or ``(a, pooled)``.  ``extra_updates``: additional running-stat updates applied
         when the backward pass runs (the reentrant-checkpoint recomputation of the reference)."""
-        c = y.c
-        cpad = y.cb * 8
-        count = float(y.n * y.spatial)
+        pm = 1 if y.c_nat else 0                     # phase-major input: natural dims are twice the stored ones
+        c = y.c_nat if pm else y.c
+        cpad = (c + 7) // 8 * 8
+        yn, yd, yh, yw = y.n, y.d * (2 if pm else 1), y.h * (2 if pm else 1), y.w * (2 if pm else 1)
+        count = float(yn * yd * yh * yw)
         ss = self.f32(4 * cpad)
         sums = None
         st = stream_ptr()
@@ -233,7 +325,7 @@ class Engine:
             sums = y.sums
             if sums is None:
                 sums = self.f64(2 * cpad)
-                call("ctu_bn_stats", self.dtype, y.ptr, c, y.n, y.spatial, sums.data_ptr(), st)
+                call("ctu_bn_stats", self.dtype, y.ptr, c, 8 if pm else 1, y.n, y.spatial, sums.data_ptr(), st)
             track = bn.track_running_stats and bn.running_mean is not None
             mom = BN_MOMENTUM if bn.momentum is None else float(bn.momentum)
             call("ctu_bn_finalize", sums.data_ptr(), count, bn.weight.data_ptr(), bn.bias.data_ptr(),
@@ -242,10 +334,10 @@ class Engine:
         else:
             call("ctu_bn_finalize", None, count, bn.weight.data_ptr(), bn.bias.data_ptr(), bn.running_mean.data_ptr(),
                  bn.running_var.data_ptr(), None, 0.0, float(bn.eps), c, 0, 0, ss.data_ptr(), st)
-        a = self.new_act(c, y.n, y.d, y.h, y.w)
-        pooled = self.new_act(c, y.n, y.d // 2, y.h // 2, y.w // 2) if pool else None
+        a = self.new_act(c, yn, yd, yh, yw)
+        pooled = self.new_act(c, yn, yd // 2, yh // 2, yw // 2) if pool else None
         call("ctu_bn_relu_fwd", self.dtype, y.ptr, ss.data_ptr(), a.ptr, pooled.ptr if pool else None,
-             c, y.n, y.d, y.h, y.w, st)
+             c, yn, yd, yh, yw, pm, st)
         if self.record:
             if not training:
                 raise RuntimeError("backward through eval-mode BatchNorm is not supported by the fused path")
@@ -264,11 +356,11 @@ class Engine:
                 pA = dA.ptr if dA is not None else None
                 pP = dP.ptr if dP is not None else None
                 call("ctu_bn_relu_bwd_reduce", self.dtype, y.ptr, ss.data_ptr(), pA, pP, sums2.data_ptr(),
-                     c, y.n, y.d, y.h, y.w, st)
-                dy = self.new_act(c, y.n, y.d, y.h, y.w)
+                     c, yn, yd, yh, yw, pm, st)
+                dy = self.new_act(y.c, y.n, y.d, y.h, y.w)          # same layout as y (phase-major stays phase-major)
                 dg, db = self._grad_buffer(bn.weight), self._grad_buffer(bn.bias)
                 call("ctu_bn_relu_bwd_apply", self.dtype, y.ptr, ss.data_ptr(), bn.weight.data_ptr(), pA, pP,
-                     sums2.data_ptr(), count, dy.ptr, dg.data_ptr(), db.data_ptr(), c, y.n, y.d, y.h, y.w, st)
+                     sums2.data_ptr(), count, dy.ptr, dg.data_ptr(), db.data_ptr(), c, yn, yd, yh, yw, pm, st)
                 self._add_pgrad(bn.weight, dg)
                 self._add_pgrad(bn.bias, db)
                 self._set_agrad(y, dy)
@@ -318,6 +410,6 @@ class Engine:
 
 def tc_supported(k, src_channels, cout, d, h, w) -> bool:
     """Shapes covered by the tcgen05 implicit-GEMM convolution (the predicate lives in conv_tc.cu)."""
-    if len(src_channels) != 1:
+    if not 1 <= len(src_channels) <= _lib.CTU_MAX_SRC:
         return False
-    return bool(_lib.load().ctu_conv_tc_supported(k, src_channels[0], cout, d, h, w))
+    return bool(_lib.load().ctu_conv_tc_supported(k, len(src_channels), int_array(list(src_channels)), cout, d, h, w))

@@ -102,6 +102,15 @@ def _check_conv_geometry(k, pad, stride=1):
             % (k, pad, stride))
 
 
+def _up_stage(eng: Engine, srcs, ct: nn.ConvTranspose3d, cv: nn.Conv3d, k: int, training: bool):
+    """ConvTranspose3d(k2, s2) + the first Conv3d of an up block (models.py:37-38, :427-430): one composed
+    convolution on the low-resolution grid where the engine covers it, the two separate stages otherwise."""
+    if eng.up_fusable(srcs, cv.weight.shape[0], k):
+        return eng.up_conv(srcs, ct, cv, k, [True] * len(srcs), training)
+    t = eng.convt(srcs, ct.weight, ct.bias, [True] * len(srcs))
+    return eng.conv([t], cv.weight, cv.bias, k, [True], training)
+
+
 class _FusedNet(nn.Module):
     """Common forward driver: validates the input, runs the engine, wires autograd."""
 
@@ -269,8 +278,7 @@ class UNet(_FusedNet):
         srcs = [cur]
         for i, blk in enumerate(self.u_blocks):
             seq = blk.block
-            t = eng.convt(srcs, seq[0].weight, seq[0].bias, [True] * len(srcs))
-            y = eng.conv([t], seq[1].weight, seq[1].bias, k, [True], training)
+            y = _up_stage(eng, srcs, seq[0], seq[1], k, training)
             a = eng.bn_relu(y, seq[2], training, extra)
             y = eng.conv([a], seq[4].weight, seq[4].bias, k, [True], training)
             ubl = eng.bn_relu(y, seq[5], training, extra)
@@ -405,8 +413,7 @@ class recAE_v2_fixed(_FusedNet):
         cur = eng.bn_relu(y, seq[4], training, extra)
         srcs = [cur]
         for i, seq in enumerate([self.ublock1, self.ublock2, self.ublock3, self.ublock4]):
-            t = eng.convt(srcs, seq[0].weight, seq[0].bias, [True] * len(srcs))
-            y = eng.conv([t], seq[1].weight, seq[1].bias, k, [True], training)
+            y = _up_stage(eng, srcs, seq[0], seq[1], k, training)
             a = eng.bn_relu(y, seq[2], training, extra)
             y = eng.conv([a], seq[4].weight, seq[4].bias, k, [True], training)
             up = eng.bn_relu(y, seq[5], training, extra)

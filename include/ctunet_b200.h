@@ -73,17 +73,20 @@ int ctu_conv_unpack_wgrad(const float* dwp, float* dw, int cout, int k, int nsrc
 /* y = conv(cat(srcs)) (+ bias).  The data gradient is the same call on dy with dgrad-packed
  * weights.  bn_sums (nullable, double[2*cpad]): per-channel sum / sum of squares of y for the
  * BatchNorm that follows (fused into the epilogue where possible, so ctu_bn_stats is not needed).
+ * stat_cout: 0 (= cout), or the number of NATURAL channels when y is the phase-major output of the
+ * fused up-sampling stage (cout = 8 phases x 8*ceil(stat_cout/8); statistics are summed over phases).
  * use_tensor_path: 0 = CUDA-core direct kernel (both dtypes; wp = fp32 packed weights),
- * 1 = tcgen05/TMA implicit GEMM (bf16, one source, shapes accepted by ctu_conv_tc_supported;
+ * 1 = tcgen05/TMA implicit GEMM (bf16, shapes accepted by ctu_conv_tc_supported;
  * wp = the bf16 B-tile image written by ctu_conv_tc_pack_weight). */
 int ctu_conv3d_fprop(int dtype, const void* const* h_srcs, const int* h_src_channels, int nsrc, const void* wp,
-                     const float* bias, void* y, double* bn_sums, int cout, int k, int n, int d, int h, int w,
-                     int use_tensor_path, ctu_stream stream);
+                     const float* bias, void* y, double* bn_sums, int stat_cout, int cout, int k, int n, int d, int h,
+                     int w, int use_tensor_path, ctu_stream stream);
 /* tcgen05 path: coverage predicate, size of the weight image, and the re-pack fp32 packed -> image */
-int ctu_conv_tc_supported(int k, int cin, int cout, int d, int h, int w);
-int ctu_conv_tc_wgrad_supported(int k, int cin, int cout, int d, int h, int w);
-long long ctu_conv_tc_wimg_bytes(int k, int cin, int cout);
-int ctu_conv_tc_pack_weight(const float* wp, void* wimg, int k, int cin, int cout, ctu_stream stream);
+int ctu_conv_tc_supported(int k, int nsrc, const int* h_src_channels, int cout, int d, int h, int w);
+int ctu_conv_tc_wgrad_supported(int k, int nsrc, const int* h_src_channels, int cout, int d, int h, int w);
+long long ctu_conv_tc_wimg_bytes(int k, int nsrc, const int* h_src_channels, int cout);
+int ctu_conv_tc_pack_weight(const float* wp, void* wimg, int k, int nsrc, const int* h_src_channels, int cout,
+                            ctu_stream stream);
 /* dwp (packed layout, fp32) and dbias (nullable, [cout]) are zeroed by the call, then accumulated */
 int ctu_conv3d_wgrad(int dtype, const void* const* h_srcs, const int* h_src_channels, int nsrc, const void* dy,
                      float* dwp, float* dbias, int cout, int k, int n, int d, int h, int w, int use_tensor_path,
@@ -105,10 +108,23 @@ int ctu_convt2_dgrad(int dtype, const void* dy, const float* wpd, void* dx, int 
 int ctu_convt2_wgrad(int dtype, const void* const* h_srcs, const int* h_src_channels, int nsrc, const void* dy,
                      float* dwp, float* dbias, int cout, int n, int d, int h, int w, ctu_stream stream);
 
+/* ---- fused up-sampling stage: ConvTranspose3d(k2,s2) followed by Conv3d(k^3,"same") (models.py:37-38, :427-430)
+ *      as ONE 3x3x3 convolution on the low-resolution grid with 8 phases x 8*ceil(cout/8) output channels
+ *      (output channel q*cop + co, q = qd*4+qh*2+qw); the transposed convolution's bias rides on an extra
+ *      all-ones input channel (index cin).  wt [cin][cin][2][2][2], bt [cin] (nullable), w3 [cout][cin][k][k][k],
+ *      b3 [cout] (nullable, with b3n [8*cop]);  wn: native [8*cop][cin+1][3][3][3] for ctu_conv_pack_weight. ---- */
+int ctu_upfuse_cout(int cout);
+int ctu_upfuse_compose(const float* wt, const float* bt, const float* w3, const float* b3, float* wn, float* b3n, int cin,
+                       int cout, int k, ctu_stream stream);
+/* chain rule of the composition: dwn [8*cop][cin+1][27] (+ dbn [8*cop]) -> dwt, dbt, dw3 (+ db3) */
+int ctu_upfuse_decompose(const float* dwn, const float* dbn, const float* wt, const float* bt, const float* w3, float* dwt,
+                         float* dbt, float* dw3, float* db3, int cin, int cout, int k, ctu_stream stream);
+
 /* ---- BatchNorm3d (+ReLU, + MaxPool3d(2,2)) (models.py:27-28,31-32,39-40,43-44,190-191,233) ---
  * sums: double[2*cpad] = per-channel sum and sum of squares (zeroed by ctu_bn_stats).
  * ss:   float[4*cpad]  = scale | shift | mean | invstd, cpad = 8*ceil(c/8).                    */
-int ctu_bn_stats(int dtype, const void* y, int c, int n, long long spatial, double* sums, ctu_stream stream);
+/* phases: 1, or 8 when y is phase-major (8 copies of the ceil(c/8) natural channel blocks) */
+int ctu_bn_stats(int dtype, const void* y, int c, int phases, int n, long long spatial, double* sums, ctu_stream stream);
 int ctu_bn_finalize(const double* sums, double count, const float* gamma, const float* beta, float* running_mean,
                     float* running_var, long long* num_batches_tracked, float momentum, float eps, int c,
                     int training, int n_updates, float* ss, ctu_stream stream);
@@ -116,17 +132,19 @@ int ctu_bn_finalize(const double* sums, double count, const float* gamma, const 
  * recomputation of models.py:232 */
 int ctu_bn_running_update(const double* sums, double count, float* running_mean, float* running_var,
                           long long* num_batches_tracked, float momentum, int c, int n_updates, ctu_stream stream);
-/* a = relu(scale*y+shift); if pooled != NULL also pooled = maxpool2(a) (d,h,w even) */
+/* a = relu(scale*y+shift); if pooled != NULL also pooled = maxpool2(a) (d,h,w even).
+ * y_phase_major: y (and dy in the backward calls) is [n][8*cb][d/2][h/2][w/2][8], the output layout of the fused
+ * up-sampling stage; a / dA stay natural [n][cb][d][h][w][8]; d,h,w are always the natural (high-res) dims. */
 int ctu_bn_relu_fwd(int dtype, const void* y, const float* ss, void* a, void* pooled, int c, int n, int d, int h, int w,
-                    ctu_stream stream);
+                    int y_phase_major, ctu_stream stream);
 /* backward, pass 1: sums2 = double[2*cpad] = sum(dz), sum(dz*xhat) with
  * dz = (dA + unpool(dP)) * [a > 0]; dA and dP are nullable (not both) */
 int ctu_bn_relu_bwd_reduce(int dtype, const void* y, const float* ss, const void* dA, const void* dP, double* sums2,
-                           int c, int n, int d, int h, int w, ctu_stream stream);
+                           int c, int n, int d, int h, int w, int y_phase_major, ctu_stream stream);
 /* backward, pass 2: dy, dgamma[c], dbeta[c] */
 int ctu_bn_relu_bwd_apply(int dtype, const void* y, const float* ss, const float* gamma, const void* dA, const void* dP,
                           const double* sums2, double count, void* dy, float* dgamma, float* dbeta, int c, int n, int d,
-                          int h, int w, ctu_stream stream);
+                          int h, int w, int y_phase_major, ctu_stream stream);
 
 /* ---- head: last_conv 1x1x1 + bias (models.py:224,255 / :507,535), optional softmax / sigmoid,
  *      UNetSP encode.  w is the NATIVE [cout][cin_total] fp32 parameter.  Outputs are fp32 NCDHW:

@@ -1,0 +1,41 @@
+"""One training step of the bench workload inside a cudaProfilerStart/Stop range (for ncu --profile-from-start off).
+
+    python scripts/profile_step.py [model] [batch] [size] [warmup]
+
+Prints the device time of the profiled step so that a plain run (no ncu) doubles as a sanity check.
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import ctunet_b200 as C
+from ctunet_b200.synthetic import make_training_batch
+from ctunet_b200.trainer import TrainStep
+
+model = sys.argv[1] if len(sys.argv) > 1 else "UNetSP"
+batch = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+size = int(sys.argv[3]) if len(sys.argv) > 3 else 128
+warm = int(sys.argv[4]) if len(sys.argv) > 4 else 2
+handler = "double" if model in ("UNetSP", "UNetDO", "UNetSPSmall") else "single"
+cin = 2 if model in ("UNetSP", "UNetSPSmall", "UNet4_2IC") else 1
+
+dev = torch.device("cuda:0")
+torch.cuda.set_device(dev)
+torch.manual_seed(0)
+net = getattr(C, model)().to(dev)
+step = TrainStep(net, handler, 1.0, 1.0, lr=1e-4)
+img, (sk_t, fl_t) = make_training_batch(batch, cin, size, seed=1234, device=dev)
+target = (sk_t, fl_t) if handler == "double" else sk_t
+for _ in range(warm):
+    step(img, target)
+torch.cuda.synchronize()
+s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+torch.cuda.cudart().cudaProfilerStart()
+s.record()
+comps = step(img, target)
+e.record()
+torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStop()
+print("step ms %.3f  loss %s" % (s.elapsed_time(e), [round(v, 5) for v in comps.tolist()]))

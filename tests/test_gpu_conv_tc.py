@@ -40,8 +40,8 @@ def test_tc_conv_matches_reference(case):
     from ctunet_b200 import _lib
     k, cin, cout, use_bias, (n, d, h, w) = case
     assert _lib.load().ctu_has_tensor_path() == 1
-    fprop_on_tc = tc_supported(k, [cin], cout, d, h, w)     # very wide inputs keep the direct kernel for fprop
-    assert fprop_on_tc or cin >= 112
+    fprop_on_tc = tc_supported(k, [cin], cout, d, h, w)     # wide inputs are staged in groups of four channel blocks
+    assert fprop_on_tc
     g = torch.Generator().manual_seed(k * 100 + cin)
     x = _bf(torch.randn(n, cin, d, h, w, generator=g))
     wt = torch.randn(cout, cin, k, k, k, generator=g) / (cin * k ** 3) ** 0.5
@@ -77,7 +77,7 @@ def test_tc_conv_matches_reference(case):
     gerr = (dx - xr.grad).abs().max().item()
     assert gerr <= 1.2e-2 * gs, "dgrad err %.3e (scale %.3e)" % (gerr, gs)
     # weight gradient on the tensor cores (voxels as the K dimension): bf16 products, fp32 accumulation
-    assert _lib.load().ctu_conv_tc_wgrad_supported(k, cin, cout, d, h, w) == 1
+    assert _lib.load().ctu_conv_tc_wgrad_supported(k, 1, _lib.int_array([cin]), cout, d, h, w) == 1
     wr = wt.clone().requires_grad_()
     br = bs.clone().requires_grad_() if use_bias else None
     F.conv3d(x, wr, br, 1, k // 2).backward(dy)
@@ -111,4 +111,39 @@ def test_unsupported_shapes_fall_back_to_direct():
     from ctunet_b200.engine import tc_supported
     assert not tc_supported(3, [7], 7, 8, 8, 8)          # h, w not multiples of 16
     assert not tc_supported(1, [7], 7, 16, 16, 16)       # 1x1x1 is the head kernel's job
-    assert not tc_supported(3, [7, 7], 7, 16, 16, 16)    # concatenated sources go through ConvTranspose / head
+    assert tc_supported(3, [7, 7], 7, 16, 16, 16)        # concatenated sources: one tensor map per source
+    assert not tc_supported(3, [7] * 5, 7, 16, 16, 16)   # at most CTU_MAX_SRC sources
+
+
+@pytest.mark.parametrize("chans,cout", [([14, 14], 7), ([28, 28, 1], 64), ([56, 56, 1], 24)])
+def test_tc_conv_concatenated_sources(chans, cout):
+    """cat(srcs) is never materialised: one TMA tensor map per source, channel blocks staged in groups."""
+    from ctunet_b200.engine import Engine
+    n, d, h, w, k = 1, 4, 16, 16, 3
+    g = torch.Generator().manual_seed(sum(chans))
+    xs = [_bf(torch.randn(n, c, d, h, w, generator=g)) for c in chans]
+    cin = sum(chans)
+    wt = torch.randn(cout, cin, k, k, k, generator=g) / (cin * k ** 3) ** 0.5
+    dy = _bf(torch.randn(n, cout, d, h, w, generator=g))
+    xr = [x.clone().requires_grad_() for x in xs]
+    wr = _bf(wt).requires_grad_()
+    yr = F.conv3d(torch.cat(xr, 1), wr, None, 1, 1)
+    yr.backward(dy)
+    eng = Engine(torch.device(DEV), "bf16", record=True)
+    acts = [eng.pack(x.to(DEV)) for x in xs]
+    wg = wt.to(DEV).requires_grad_()
+    assert eng._tc_ok(k, acts, cout)
+    y = eng.conv(acts, wg, None, k, [True] * len(acts), bn_stats=True)
+    yo = eng.unpack(y).cpu()
+    assert (yo - yr.detach()).abs().max().item() <= 1e-2 * yr.abs().max().item()
+    cpad = (cout + 7) // 8 * 8
+    assert torch.allclose(y.sums.cpu()[:cout], yo.double().sum((0, 2, 3, 4)), rtol=1e-4, atol=1e-2 * yr.abs().max().item())
+    assert torch.allclose(y.sums.cpu()[cpad:cpad + cout], (yo.double() ** 2).sum((0, 2, 3, 4)), rtol=1e-4, atol=1e-3)
+    eng.agrads[id(y)] = eng.pack(dy.to(DEV))
+    for fn in reversed(eng.tape):
+        fn()
+    for a, r in zip(acts, xr):
+        dx = eng.unpack(eng.agrads[id(a)]).cpu()
+        assert (dx - r.grad).abs().max().item() <= 1.2e-2 * r.grad.abs().max().item()
+    dw = eng.pgrads[id(wg)].cpu()
+    assert (dw - wr.grad).abs().max().item() <= 2e-3 * wr.grad.abs().max().item()

@@ -1,0 +1,159 @@
+"""Fused up-sampling stage (GPU): ConvTranspose3d(k2,s2) -> Conv3d(k^3) as one composed low-resolution convolution
+(csrc/fuse.cu + engine.up_conv), against conv_transpose3d -> conv3d in fp32 PyTorch on the CPU and against the
+composition restated in oracle/upfuse_oracle.py."""
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _bf(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+@pytest.mark.parametrize("k,cin,cout,bias3", [(3, 5, 3, False), (3, 28, 7, False), (5, 6, 9, True), (3, 56, 14, False)])
+def test_compose_decompose_kernels_match_oracle(k, cin, cout, bias3):
+    from ctunet_b200 import _lib
+    from ctunet_b200._lib import call, stream_ptr
+    from oracle import upfuse_oracle as U
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(k * 10 + cin)
+    wt = torch.randn(cin, cin, 2, 2, 2, generator=g, requires_grad=True)
+    bt = torch.randn(cin, generator=g, requires_grad=True)
+    w3 = torch.randn(cout, cin, k, k, k, generator=g, requires_grad=True)
+    b3 = torch.randn(cout, generator=g) if bias3 else None
+    ref = U.compose(wt, bt, w3, k)
+    co8 = lib.ctu_upfuse_cout(cout)
+    assert co8 == ref.shape[0]
+    d = lambda t: t.detach().to(DEV).contiguous()
+    wn = torch.empty(co8, cin + 1, 27, device=DEV)
+    b3n = torch.empty(co8, device=DEV) if bias3 else None
+    wtd, btd, w3d = d(wt), d(bt), d(w3)              # keep the device copies alive across the call
+    b3d = d(b3) if bias3 else None
+    call("ctu_upfuse_compose", wtd.data_ptr(), btd.data_ptr(), w3d.data_ptr(), b3d.data_ptr() if bias3 else None,
+         wn.data_ptr(), b3n.data_ptr() if bias3 else None, cin, cout, k, stream_ptr())
+    torch.cuda.synchronize()
+    scale = ref.abs().max().item()
+    assert (wn.cpu().view_as(ref) - ref.detach()).abs().max().item() <= 1e-5 * scale
+    if bias3:
+        cop = co8 // 8
+        exp = torch.zeros(8, cop)
+        exp[:, :cout] = b3
+        assert torch.equal(b3n.cpu().view(8, cop), exp)
+    # chain rule: dWn -> (dWT, dbT, dW3)
+    dwn = torch.randn(ref.shape, generator=g)
+    dwn.view(8, co8 // 8, cin + 1, 27)[:, cout:] = 0           # pad rows never receive a gradient
+    gwt, gbt, gw3 = torch.autograd.grad(ref, [wt, bt, w3], dwn)
+    dwt, dbt, dw3 = torch.empty_like(wt, device=DEV), torch.empty_like(bt, device=DEV), torch.empty_like(w3, device=DEV)
+    dbn = torch.randn(co8, generator=g) if bias3 else None
+    db3 = torch.empty(cout, device=DEV) if bias3 else None
+    dwnd = dwn.to(DEV)
+    dbnd = dbn.to(DEV) if bias3 else None
+    call("ctu_upfuse_decompose", dwnd.data_ptr(), dbnd.data_ptr() if bias3 else None, wtd.data_ptr(), btd.data_ptr(),
+         w3d.data_ptr(), dwt.data_ptr(), dbt.data_ptr(), dw3.data_ptr(), db3.data_ptr() if bias3 else None, cin, cout, k,
+         stream_ptr())
+    torch.cuda.synchronize()
+    for got, exp, what in ((dwt, gwt, "dWT"), (dbt, gbt, "dbT"), (dw3, gw3, "dW3")):
+        err = (got.cpu() - exp).abs().max().item()
+        assert err <= 2e-5 * exp.abs().max().item() + 1e-6, "%s err %.3e" % (what, err)
+    if bias3:
+        assert torch.allclose(db3.cpu(), dbn.view(8, -1)[:, :cout].sum(0), rtol=1e-5, atol=1e-5)
+
+
+# (k, source channels, cout, conv bias, (n, d, h, w) LOW-resolution dims)
+STAGES = [
+    (3, [6], 5, False, (1, 4, 4, 6)),
+    (3, [14, 14], 7, False, (2, 4, 6, 4)),
+    (5, [8, 8], 8, True, (1, 4, 4, 4)),
+    (3, [28, 28], 14, False, (1, 2, 4, 4)),
+]
+STAGES_TC = [
+    (3, [14, 14], 7, False, (1, 5, 16, 16)),
+    (3, [28, 28], 14, False, (1, 3, 16, 32)),
+    (5, [14, 14], 7, True, (1, 4, 16, 16)),
+]
+
+
+def _run_stage(mode, case, force):
+    """up_conv -> bn_relu (phase-major) through the engine vs convT -> conv -> BatchNorm(train) -> ReLU on the CPU."""
+    import ctunet_b200.engine as E
+    k, chans, cout, bias3, (n, d, h, w) = case
+    rnd = _bf if mode == "bf16" else (lambda t: t)
+    g = torch.Generator().manual_seed(17 + k + cout)
+    cin = sum(chans)
+    xs = [rnd(torch.randn(n, c, d, h, w, generator=g)) for c in chans]
+    ct = nn.ConvTranspose3d(cin, cin, 2, 2)
+    cv = nn.Conv3d(cin, cout, k, 1, k // 2, bias=bias3)
+    bn = nn.BatchNorm3d(cout)
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5, generator=g)
+        bn.bias.uniform_(-0.3, 0.3, generator=g)
+    dA = rnd(torch.randn(n, cout, 2 * d, 2 * h, 2 * w, generator=g))
+    # reference (fp32, CPU)
+    xr = [x.clone().requires_grad_() for x in xs]
+    t = ct(torch.cat(xr, 1))
+    yr = cv(t)
+    ar = F.relu(F.batch_norm(yr, None, None, bn.weight, bn.bias, True, 0.1, 1e-5))
+    ar.backward(dA)
+    ref_grads = {"ct.w": ct.weight.grad.clone(), "ct.b": ct.bias.grad.clone(), "cv.w": cv.weight.grad.clone(),
+                 "bn.w": bn.weight.grad.clone(), "bn.b": bn.bias.grad.clone()}
+    if bias3:
+        ref_grads["cv.b"] = cv.bias.grad.clone()
+    for m in (ct, cv, bn):
+        m.zero_grad()
+    # product
+    ctg, cvg, bng = ct.to(DEV), cv.to(DEV), bn.to(DEV)
+    old = E.UP_FUSION
+    E.UP_FUSION = "force" if force else "auto"
+    try:
+        eng = E.Engine(torch.device(DEV), mode, record=True)
+        acts = [eng.pack(x.to(DEV)) for x in xs]
+        assert eng.up_fusable(acts, cout, k)
+        y = eng.up_conv(acts, ctg, cvg, k, [True] * len(acts), True)
+        assert y.c_nat == cout and y.d == d
+        a = eng.bn_relu(y, bng, True)
+        assert (a.d, a.h, a.w) == (2 * d, 2 * h, 2 * w)
+        ao = eng.unpack(a).cpu()
+        eng.agrads[id(a)] = eng.pack(dA.to(DEV))
+        for fn in reversed(eng.tape):
+            fn()
+        dxs = [eng.unpack(eng.agrads[id(s)]).cpu() for s in acts]
+        got = {"ct.w": eng.pgrads[id(ctg.weight)], "ct.b": eng.pgrads[id(ctg.bias)], "cv.w": eng.pgrads[id(cvg.weight)],
+               "bn.w": eng.pgrads[id(bng.weight)], "bn.b": eng.pgrads[id(bng.bias)]}
+        if bias3:
+            got["cv.b"] = eng.pgrads[id(cvg.bias)]
+        torch.cuda.synchronize()
+    finally:
+        E.UP_FUSION = old
+    return ar.detach(), ao, [x.grad for x in xr], dxs, ref_grads, {k_: v.cpu() for k_, v in got.items()}
+
+
+@pytest.mark.parametrize("case", STAGES)
+def test_fused_up_stage_fp32_check_mode(case):
+    """Composition + phase-major BatchNorm at fp32 accuracy (CUDA-core kernels)."""
+    ar, ao, gx, dxs, rg, gg = _run_stage("fp32", case, force=True)
+    assert (ao - ar).abs().max().item() <= 2e-4 * max(ar.abs().max().item(), 1.0)
+    for r, o in zip(gx, dxs):
+        assert (o - r).abs().max().item() <= 5e-4 * r.abs().max().item()
+    for name in rg:
+        if name == "cv.b":
+            continue        # a bias in front of a training-mode BatchNorm has a mathematically zero gradient
+        err = (gg[name] - rg[name]).abs().max().item()
+        assert err <= 1e-3 * rg[name].abs().max().item() + 1e-5, "%s err %.3e" % (name, err)
+
+
+@pytest.mark.parametrize("case", STAGES_TC)
+def test_fused_up_stage_bf16_tensor_path(case):
+    ar, ao, gx, dxs, rg, gg = _run_stage("bf16", case, force=False)
+    assert (ao - ar).abs().max().item() <= 4e-2 * max(ar.abs().max().item(), 1.0)
+    for r, o in zip(gx, dxs):
+        rel = ((o - r).norm() / r.norm()).item()
+        assert rel <= 5e-2, "dx normwise err %.3e" % rel
+    for name in rg:
+        if name == "cv.b":
+            continue
+        rel = ((gg[name] - rg[name]).norm() / rg[name].norm()).item()
+        assert rel <= 5e-2, "%s normwise err %.3e" % (name, rel)
