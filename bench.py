@@ -39,6 +39,8 @@ def parse():
     ap.add_argument("--size", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="capture the training step in a CUDA graph (auto: on for a single GPU)")
     return ap.parse_args()
 
 
@@ -299,7 +301,8 @@ def run_b200_arm(a):
     torch.manual_seed(0)
     net = getattr(C, a.model)().to(dev)
     sync = GradSync(net) if world > 1 else None
-    step = TrainStep(net, HANDLER[a.model], 1.0, 1.0, lr=1e-4, grad_sync=sync)
+    use_graph = a.graph == "on" or (a.graph == "auto" and world == 1)
+    step = TrainStep(net, HANDLER[a.model], 1.0, 1.0, lr=1e-4, grad_sync=sync, graph=use_graph)
     cin = in_channels(a.model)
     img, (sk_t, fl_t) = make_training_batch(a.batch, cin, a.size, seed=1234 + 1000 * rank, device=dev)
     target = (sk_t, fl_t) if HANDLER[a.model] == "double" else sk_t
@@ -337,7 +340,7 @@ def run_b200_arm(a):
         clocks.start()
     l0 = _lib.launches
     ms_resident = timed(resident, a.steps)
-    launches = _lib.launches - l0
+    launches = (a.steps * step.launches_per_step) if use_graph else (_lib.launches - l0)
     clk = clocks.stop() if rank == 0 else None
     # the same K steps again with a CUDA-event pair around every C-ABI call (on the launching stream): the
     # per-kernel durations behind `roofline`.  Kept out of the `value` loop: creating ~1500 events per step in
@@ -347,10 +350,12 @@ def run_b200_arm(a):
     import ctunet_b200.engine as E
     import ctunet_b200.losses as LS
     E.call = LS.call = timed_call
+    eager_step = TrainStep(net, HANDLER[a.model], 1.0, 1.0, lr=1e-4, grad_sync=sync) if use_graph else step
     try:
-        timed(resident, a.steps)
+        timed(lambda: eager_step(img, target), a.steps)
     finally:
         E.call = LS.call = orig
+        net._grad_sink = sync
 
     # ---- end-to-end steps: pinned host -> device every iteration, loss read back ----------------
     copy_stream = torch.cuda.Stream(device=dev)
@@ -438,11 +443,13 @@ def run_b200_arm(a):
         "ms_per_step": ms_resident, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": a.dtype, "data": "synthetic",
         "config": {"workload": workload_name(a), "global_batch": a.batch * world, "parallelism": "dp%d" % world,
-                   "l2": flush_note, "conv_path": "tcgen05" if _lib.load().ctu_has_tensor_path() else "cuda-core"},
+                   "l2": flush_note, "conv_path": "tcgen05" if _lib.load().ctu_has_tensor_path() else "cuda-core",
+                   "cuda_graph": use_graph},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": d2h_bytes},
         "gpu_launches": launches,
-        "gpu_launches_note": "C-ABI entry points called in the timed region (each enqueues >= 1 kernel of this library)",
+        "gpu_launches_note": "C-ABI entry points in the timed region (each enqueues >= 1 kernel of this library)"
+                             + ("; the step is replayed from a CUDA graph captured once" if use_graph else ""),
         "clocks": clk,
         "roofline": roof,
         "cpu_baseline": cpu,

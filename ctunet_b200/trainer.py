@@ -6,6 +6,11 @@ H2D copy, ``input.requires_grad_()``, forward, ``comp_losses_metrics``, ``backwa
 (Model.py:510-520: Adam, amsgrad=True).  The reference reads every loss component back with
 ``float(...)`` (five host syncs per batch, ProblemHandler.py:253-302); here the step enqueues
 everything and returns device tensors, the caller decides when to read them (one sync).
+
+``graph=True``: the step is a fixed sequence of ~300 launches with no host
+synchronisation, so after ``GRAPH_WARMUP`` eager iterations it is captured ONCE in a CUDA graph and every
+later call is a copy of the batch into the graph's static input buffers plus one ``cudaGraphLaunch`` -- the
+Python / ctypes dispatch cost (longer than the GPU work at 128^3) disappears from the step.
 """
 from __future__ import annotations
 
@@ -13,14 +18,17 @@ from typing import Optional
 
 import torch
 
+from . import _lib
 from .losses import dice_ce
 from .parallel import GradSync
+
+GRAPH_WARMUP = 2      # eager iterations before the capture (allocator pools, lazy optimizer state, cached constants)
 
 
 class TrainStep:
     def __init__(self, model, handler: str = "double", dice_lambda: float = 1.0, ce_lambda: float = 1.0,
                  lr: float = 1e-4, weight_decay: float = 0.0, optimizer: str = "adam",
-                 grad_sync: Optional[GradSync] = None, input_requires_grad: bool = True):
+                 grad_sync: Optional[GradSync] = None, input_requires_grad: bool = True, graph: bool = False):
         if handler not in ("double", "single"):
             raise ValueError("handler: 'double' (FlapRecWithShapePriorDoubleOut) or 'single' (ProblemHandler)")
         self.model = model
@@ -30,10 +38,17 @@ class TrainStep:
         self.input_requires_grad = input_requires_grad       # Model.py:351-352
         model._grad_sink = grad_sync
         params = list(model.parameters())
+        self.graph = bool(graph)
+        self._graph = None
+        self._static = None
+        self._static_out = None
+        self._calls = 0
+        self.launches_per_step = None                         # C-ABI calls recorded in the captured step
+        cap = dict(capturable=True) if self.graph else {}
         if optimizer == "adam":                               # Model.py:514-520
-            self.optimizer = torch.optim.Adam(params, lr=lr, weight_decay=weight_decay, amsgrad=True)
+            self.optimizer = torch.optim.Adam(params, lr=lr, weight_decay=weight_decay, amsgrad=True, **cap)
         elif optimizer == "adamw":                            # Model.py:521-527
-            self.optimizer = torch.optim.AdamW(params, lr=lr, weight_decay=weight_decay, amsgrad=True)
+            self.optimizer = torch.optim.AdamW(params, lr=lr, weight_decay=weight_decay, amsgrad=True, **cap)
         elif optimizer == "sgd":                              # Model.py:535-541
             self.optimizer = torch.optim.SGD(params, lr=lr, momentum=0.99, weight_decay=weight_decay)
         else:
@@ -60,7 +75,34 @@ class TrainStep:
         return total, torch.stack([t.detach() for t in terms] + [total.detach()])
 
     def __call__(self, image: torch.Tensor, target):
-        """Enqueues one full iteration; returns the device tensor [components..., total] (no host sync)."""
+        """Enqueues one full iteration; returns the device tensor [components..., total] (no host sync).
+        In graph mode the returned tensor is the graph's static output: read it before the next call."""
+        if not self.graph:
+            return self._eager(image, target)
+        self._calls += 1
+        if self._graph is None and self._calls <= GRAPH_WARMUP:
+            return self._eager(image, target)
+        flat = [image] + (list(target) if isinstance(target, (tuple, list)) else [target])
+        if self._graph is None:
+            self._static = [torch.empty_like(t) for t in flat]
+        elif any(a.shape != b.shape or a.dtype != b.dtype for a, b in zip(flat, self._static)):
+            raise RuntimeError("graph mode: the batch shape changed after the step was captured")
+        for dst, src in zip(self._static, flat):
+            dst.copy_(src, non_blocking=True)
+        if self._graph is None:
+            st_img = self._static[0]
+            st_tgt = tuple(self._static[1:]) if isinstance(target, (tuple, list)) else self._static[1]
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            l0 = _lib.launches
+            with torch.cuda.graph(g):                         # records the launches; nothing executes here
+                self._static_out = self._eager(st_img, st_tgt)
+            self.launches_per_step = _lib.launches - l0
+            self._graph = g
+        self._graph.replay()
+        return self._static_out
+
+    def _eager(self, image: torch.Tensor, target):
         self.model.train()
         if self.input_requires_grad:
             image = image.detach().requires_grad_()

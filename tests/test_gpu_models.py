@@ -324,3 +324,38 @@ def test_cpu_input_raises():
     net = net.to(DEV)
     with pytest.raises(ValueError):
         net(torch.zeros(1, 2, 24, 16, 16, device=DEV))
+
+
+@pytest.mark.parametrize("mode,size", [("fp32", 16), ("bf16", 32)])
+def test_cuda_graph_step_matches_eager_step(mode, size):
+    """TrainStep(graph=True): two eager iterations, one capture, then replays -- same losses, parameters and
+    BatchNorm buffers as the eager driver fed the same batches."""
+    from ctunet_b200.trainer import TrainStep
+    nets, steps = [], []
+    for graph in (False, True):
+        torch.manual_seed(0)
+        net = _build("UNetSP", mode).to(DEV).train()
+        nets.append(net)
+        steps.append(TrainStep(net, "double", 1.0, 1.0, lr=1e-3, graph=graph))
+    hist = [[], []]
+    for it in range(5):
+        x = _x(2, size, 20 + it, 2).to(DEV)
+        sk_t, fl_t = _targets(2, size, 30 + it)
+        for i in range(2):
+            comps = steps[i](x, (sk_t.to(DEV), fl_t.to(DEV)))
+            hist[i].append(comps.tolist())
+    assert steps[1]._graph is not None and steps[1].launches_per_step > 50
+    tol = 1e-4 if mode == "fp32" else 2e-2
+    for a, b in zip(hist[0], hist[1]):
+        assert a == pytest.approx(b, rel=tol, abs=tol)
+    sa, sb = nets[0].state_dict(), nets[1].state_dict()
+    for k in sa:
+        if k.endswith("num_batches_tracked"):
+            assert int(sa[k]) == int(sb[k]), k
+        elif "running" in k:
+            assert torch.allclose(sa[k], sb[k], rtol=50 * tol, atol=50 * tol * float(sa[k].abs().max()) + 1e-6), k
+        elif not k.startswith("cblock"):
+            # Adam's normalised update turns rounding-level gradient differences (atomic accumulation order) into
+            # differences of up to lr per step on near-zero gradients: 5 steps x 1e-3
+            assert float((sa[k] - sb[k]).abs().max()) <= 5e-3, k
+            assert float((sa[k] - sb[k]).abs().mean()) <= (2e-4 if mode == "fp32" else 1.5e-3), k
