@@ -110,6 +110,37 @@ __device__ __forceinline__ uint64_t pack64(uint32_t lo, uint32_t hi) {
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// Warp-uniform issue path: the whole issuer warp runs the (branch-free) descriptor arithmetic so that it lives in
+// uniform registers, and only the elected lane's instruction takes effect.  `leader` comes from elect_one().
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred;
+}
+__device__ __forceinline__ void umma_bf16_lead(uint32_t leader, uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                               uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %7, 0;\n\t"
+        "setp.ne.b32 q, %0, 0;\n\t"
+        "mov.b64 da, {%2, %3};\n\t"
+        "mov.b64 db, {%4, %5};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%1], da, db, %6, p;\n\t}"
+        ::"r"(leader), "r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_lead(uint32_t leader, uint32_t bar) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "setp.ne.b32 q, %0, 0;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%1];\n\t}"
+        ::"r"(leader), "r"(bar)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
     uint32_t r[8];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -272,16 +303,6 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
         mbar_init(b_w, 1);
         fence_barrier_init();
     }
-    // descriptor table: A low word = (offset within a ring slot) >> 4 | (LBO >> 4) << 16; B low word likewise
-    for (int m = threadIdx.x; m < nm; m += NTHREADS) {
-        int blk0, t0, blk1, t1, g0, g1;
-        tc_chunk(K, p.cb, p.cbg, m, 0, blk0, t0, g0);
-        const bool real1 = tc_chunk(K, p.cb, p.cbg, m, 1, blk1, t1, g1);
-        const uint32_t off0 = (blk0 - g0 * p.cbg) * p.plane_bytes + (t0 / K) * ROW + (t0 % K) * 16;
-        const uint32_t off1 = (blk1 - g0 * p.cbg) * p.plane_bytes + (t1 / K) * ROW + (t1 % K) * 16;
-        const uint32_t lbo = real1 ? off1 - off0 : 0u;
-        tab[m] = make_uint2((off0 >> 4) | ((lbo >> 4) << 16), ((s_w >> 4) + (uint32_t)m * (uint32_t)p.nt * 2u) | (8u << 16));
-    }
     if (warp == 1) {   // TMEM allocation (this warp also frees it)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                      "r"(p.tmem_cols)
@@ -332,12 +353,20 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
         }
     } else if (warp <= TC_WB) {
         // ===================================================================== MMA issuers (tile t = warp - 1)
-        if (lane == 0) {
+        // All 32 lanes walk the schedule (so the descriptor arithmetic stays warp-uniform and branch-free); the
+        // MMAs and commits of the elected lane are the ones that issue.  The order is the weight image's order
+        // (tc_chunk): per group, (tap, block pair) with the tap outermost, then the odd block's tap pairs.
+        {
+            const uint32_t leader = elect_one();
             // instruction descriptor: D=f32, A=B=bf16, both K-major, N at [17,23), M=128 at [24,29)
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.nt >> 3) << 17) | (8u << 24);
             const uint32_t a_hi = (ROW >> 4) | (1u << 14);           // SBO = row pitch (next h), version 1
             const uint32_t b_hi = (16u) | (1u << 14);                 // B: SBO = 256 B between n-groups
             const uint32_t t = warp - 1;
+            const uint32_t plane16 = p.plane_bytes >> 4;
+            const uint32_t lbo_pair = plane16 << 16;                  // second K chunk = the next channel block
+            const uint32_t bstep = (uint32_t)p.nt * 2u;              // one MMA's B tile in 16-byte units
+            constexpr int K2 = K * K, NTAIL = (K2 + 1) / 2;
             mbar_wait(b_w, 0);
             uint32_t step = 0;
             Ring cons = {0, 0};
@@ -348,26 +377,43 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
                 for (int pl = 0; pl < nd + K - 1; ++pl, ++step) {
                     const uint32_t stage = step & 1;
                     const uint32_t d_tmem = tmem_base + (stage * TC_WB + t) * p.nt;
-                    int m = 0;
+                    uint32_t b_lo = (s_w >> 4) | (8u << 16);          // B: LBO = 128 B (second 8-wide K chunk)
+                    uint32_t acc = 0;
                     for (int g = 0; g < p.ncg; ++g, cons.next(NS)) {
                         mbar_wait(b_full + 8 * cons.slot, cons.phase);
                         if (g == 0) mbar_wait(b_aempty + 8 * (stage * TC_WB + t), ((step >> 1) & 1) ^ 1);
                         tc_fence_after();
                         const uint32_t a16 = (s_planes + cons.slot * p.slot_bytes + t * 128u) >> 4;
-                        const int mend = (g + 1 < p.ncg) ? tc_group_start(K, p.cb, p.cbg, g + 1) : nm;
-                        if (g == 0) {
-                            const uint2 e = tab[0];
-                            umma_bf16(d_tmem, pack64(e.x + a16, a_hi), pack64(e.y, b_hi), idesc, 0u);
-                            m = 1;
+                        const int gb = (p.cb - g * p.cbg) < p.cbg ? (p.cb - g * p.cbg) : p.cbg;
+                        const int pairs = gb >> 1;
+                        if (pairs > 0) {
+#pragma unroll
+                            for (int tp = 0; tp < K2; ++tp) {
+                                const uint32_t a_tap = a16 + (tp / K) * (ROW >> 4) + (tp % K);
+                                for (int pr = 0; pr < pairs; ++pr) {
+                                    umma_bf16_lead(leader, d_tmem, (a_tap + 2u * pr * plane16) | lbo_pair, a_hi, b_lo, b_hi,
+                                                   idesc, acc);
+                                    acc = 1;
+                                    b_lo += bstep;
+                                }
+                            }
                         }
-#pragma unroll 4
-                        for (; m < mend; ++m) {
-                            const uint2 e = tab[m];
-                            umma_bf16_acc(d_tmem, pack64(e.x + a16, a_hi), pack64(e.y, b_hi), idesc);
+                        if (gb & 1) {
+                            const uint32_t a_blk = a16 + (uint32_t)(gb - 1) * plane16;
+#pragma unroll
+                            for (int j = 0; j < NTAIL; ++j) {
+                                // taps 2j and 2j+1 of the last block; the dummy half of the last MMA has zero weights
+                                constexpr uint32_t R16 = ROW >> 4;
+                                const int t0 = 2 * j, t1 = (2 * j + 1 < K2) ? 2 * j + 1 : 2 * j;
+                                const uint32_t o0 = (t0 / K) * R16 + (t0 % K), o1 = (t1 / K) * R16 + (t1 % K);
+                                umma_bf16_lead(leader, d_tmem, (a_blk + o0) | ((o1 - o0) << 16), a_hi, b_lo, b_hi, idesc, acc);
+                                acc = 1;
+                                b_lo += bstep;
+                            }
                         }
-                        umma_commit(b_empty + 8 * cons.slot);
+                        umma_commit_lead(leader, b_empty + 8 * cons.slot);
                     }
-                    umma_commit(b_afull + 8 * (stage * TC_WB + t));
+                    umma_commit_lead(leader, b_afull + 8 * (stage * TC_WB + t));
                 }
             }
         }
@@ -784,8 +830,10 @@ __global__ void __launch_bounds__(WG_THREADS) conv3d_wgrad_tc_kernel(const __gri
         const uint32_t lbo = 8u << 16;                            // second 8-voxel core matrix: +128 B
         const int q = warp - 1;
         const int nacc = K * ncb;                                 // one accumulator per (kd, input block)
-        const int n_own = (nacc - q + WG_ISSUERS - 1) / WG_ISSUERS;     // accumulators e = q, q+4, ...
-        uint2* mytab = wtab + q * WG_MAX_OWN;
+        // All 32 lanes walk the schedule (warp-uniform, branch-free descriptor arithmetic); only the elected lane's
+        // MMAs / commits issue.  Per accumulator e = (kd, input block): HH back-to-back MMAs, A and B descriptors
+        // advancing by one halo row / one dy row.
+        const uint32_t leader = elect_one();
         uint32_t base = 0, waited = 0, first = 1;
         Ring cons = {0, 0}, head = {0, 0}, dyr = {0, 0};
         for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
@@ -800,50 +848,33 @@ __global__ void __launch_bounds__(WG_THREADS) conv3d_wgrad_tc_kernel(const __gri
                 }
                 mbar_wait(b_dyfull + 8 * dyr.slot, dyr.phase);
                 tc_fence_after();
-                // per-plane table of this warp's accumulators: A start (row 0) and TMEM column
-                for (int el = lane; el < n_own; el += 32) {
-                    const int e = q + el * WG_ISSUERS;
-                    const int b = e % ncb, kd = e / ncb;
+                const uint32_t dy16 = ((s_dy + dyr.slot * p.dyslot_bytes) >> 4) | lbo;
+                int b = q % ncb, kd = q / ncb;                // accumulator e = q, q + WG_ISSUERS, ...
+                for (int e = q; e < nacc; e += WG_ISSUERS) {
                     uint32_t slot = head.slot + kd;
                     if (slot >= NS) slot -= NS;
-                    const uint32_t x16 = (s_x + slot * p.xslot_bytes + b * p.plane_bytes) >> 4;
-                    mytab[el] = make_uint2(x16 | lbo, tmem_base + (uint32_t)e * ncol);
-                }
-                __syncwarp();
-                if (lane == 0) {
-                    const uint32_t dy16 = ((s_dy + dyr.slot * p.dyslot_bytes) >> 4) | lbo;
-                    int r = 0;
-                    if (first) {
-                        const uint64_t bd = pack64(dy16, b_hi);
-                        for (int el = 0; el < n_own; ++el) {
-                            const uint2 e = mytab[el];
-                            umma_bf16(e.y, pack64(e.x, a_hi), bd, idesc, 0u);
-                        }
-                        first = 0;
-                        r = 1;
+                    const uint32_t x16 = ((s_x + slot * p.xslot_bytes + b * p.plane_bytes) >> 4) | lbo;
+                    const uint32_t tcol = tmem_base + (uint32_t)e * ncol;
+#pragma unroll
+                    for (int r = 0; r < HH; ++r)    // x halo row r meets dy rows r-(K-1)..r (slot rows r..r+K-1)
+                        umma_bf16_lead(leader, tcol, x16 + r * (ROW >> 4), a_hi, dy16 + r * (dyrow >> 4), b_hi, idesc,
+                                       (r == 0) ? (first ^ 1u) : 1u);
+                    b += WG_ISSUERS;
+                    while (b >= ncb) {
+                        b -= ncb;
+                        ++kd;
                     }
-#pragma unroll 1
-                    for (; r < HH; ++r) {     // x halo row r meets dy rows r-(K-1)..r (slot rows r..r+K-1)
-                        const uint64_t bd = pack64(dy16 + r * (dyrow >> 4), b_hi);
-                        const uint32_t rstep = r * (ROW >> 4);
-#pragma unroll 4
-                        for (int el = 0; el < n_own; ++el) {
-                            const uint2 e = mytab[el];
-                            umma_bf16_acc(e.y, pack64(e.x + rstep, a_hi), bd, idesc);
-                        }
-                    }
-                    umma_commit(b_xempty + 8 * head.slot);
-                    umma_commit(b_dyempty + 8 * dyr.slot);
                 }
+                first = 0;
+                umma_commit_lead(leader, b_xempty + 8 * head.slot);
+                umma_commit_lead(leader, b_dyempty + 8 * dyr.slot);
                 head.next(NS);
                 dyr.next(NDS);
-                __syncwarp();
             }
-            for (int qq = 0; qq < K - 1; ++qq, head.next(NS))
-                if (lane == 0) umma_commit(b_xempty + 8 * head.slot);
+            for (int qq = 0; qq < K - 1; ++qq, head.next(NS)) umma_commit_lead(leader, b_xempty + 8 * head.slot);
             base += nd + K - 1;
         }
-        if (lane == 0) umma_commit(b_done);
+        umma_commit_lead(leader, b_done);
         __syncwarp();
         // flush: M=64 accumulators sit in lanes 0-15 of every 32-lane quarter (row = quarter*16 + lane)
         const int quarter = warp & 3;

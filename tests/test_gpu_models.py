@@ -357,5 +357,5 @@ def test_cuda_graph_step_matches_eager_step(mode, size):
         elif not k.startswith("cblock"):
             # Adam's normalised update turns rounding-level gradient differences (atomic accumulation order) into
             # differences of up to lr per step on near-zero gradients: 5 steps x 1e-3
-            assert float((sa[k] - sb[k]).abs().max()) <= 5e-3, k
+            assert float((sa[k] - sb[k]).abs().max()) <= (5e-3 if mode == "fp32" else 1e-2), k
             assert float((sa[k] - sb[k]).abs().mean()) <= (2e-4 if mode == "fp32" else 1.5e-3), k
