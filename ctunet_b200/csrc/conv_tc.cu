@@ -230,7 +230,6 @@ struct TcParams {
     int cbg, ncg;                // channel blocks per ring slot, number of such groups
     int nsrc, src_cb[CTU_MAX_SRC], src_cboff[CTU_MAX_SRC];   // concatenated sources: blocks and first block of each
     int cobo, cstat;             // statistics: natural channel block = output block % cobo, cstat real channels
-    int ob0, nob;                // output blocks [ob0, ob0+nob) are produced by this launch (nob <= COB)
     int n, d, h, w;
     int tiles_h, tiles_w, dchunks, dc;
     int total_items;
@@ -322,7 +321,7 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
             mbar_expect_tx(b_w, p.wimg_bytes);
             for (uint32_t off = 0; off < p.wimg_bytes; off += 32768u) {
                 const uint32_t sz = p.wimg_bytes - off < 32768u ? p.wimg_bytes - off : 32768u;
-                bulk_load_1d(s_w + off, reinterpret_cast<const unsigned char*>(p.wimg) + off, sz, b_w);
+                bulk_load_1d(s_w + off, reinterpret_cast<const unsigned char*>(p.wimg) + (size_t)blockIdx.y * p.wimg_bytes + off, sz, b_w);
             }
             Ring pr = {0, 0};
             for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
@@ -425,12 +424,14 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
         const int hh = row >> 3, wl = row & 7;
         const bool want_stats = p.stats != nullptr;
         const long long plane = (long long)p.d * p.h * p.w;
+        const int ob0 = blockIdx.y * COB;              // output blocks [ob0, ob0 + nob) belong to this CTA row
+        const int nob = (p.cob_n - ob0) < COB ? (p.cob_n - ob0) : COB;
         float part[K][CP];                             // partial sums of the K output planes in flight
         float s1[NSLOT * 8], s2[NSLOT * 8];
         float bv[CP];
 #pragma unroll
         for (int c = 0; c < CP; ++c)
-            bv[c] = (p.bias != nullptr && p.ob0 * 8 + c < p.cout) ? __ldg(p.bias + p.ob0 * 8 + c) : 0.f;
+            bv[c] = (p.bias != nullptr && ob0 * 8 + c < p.cout) ? __ldg(p.bias + ob0 * 8 + c) : 0.f;
 #pragma unroll
         for (int i = 0; i < NSLOT * 8; ++i) s1[i] = s2[i] = 0.f;
         uint32_t step = 0;
@@ -443,7 +444,7 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
             const int nd = (p.d - z0) < p.dc ? (p.d - z0) : p.dc;
             const int gy = h0 + hh, gx = w0 + te * 8 + wl;
             const bool inb = gy < p.h && gx < p.w;
-            __nv_bfloat16* ycol = p.y + (((long long)n * p.cob_n + p.ob0) * plane + ((long long)gy) * p.w + gx) * 8;
+            __nv_bfloat16* ycol = p.y + (((long long)n * p.cob_n + ob0) * plane + ((long long)gy) * p.w + gx) * 8;
 #pragma unroll
             for (int i = 0; i < K; ++i)
 #pragma unroll
@@ -475,7 +476,7 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
                         V8 o;
 #pragma unroll
                         for (int c = 0; c < 8; ++c) o.v[c] = round_to<__nv_bfloat16>(part[0][ob * 8 + c] + bv[ob * 8 + c]);
-                        if (inb && ob < p.nob) {
+                        if (inb && ob < nob) {
                             Vec8<__nv_bfloat16>::store(ycol + ((long long)ob * plane + (long long)gz * p.h * p.w) * 8, o);
                             if (want_stats) {
 #pragma unroll
@@ -502,8 +503,8 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
 #pragma unroll
             for (int i = 0; i < NSLOT * 8; ++i) {
                 const float a1 = warp_sum(s1[i]), a2 = warp_sum(s2[i]);
-                const int ch = ((p.ob0 + (i >> 3)) % p.cobo) * 8 + (i & 7);
-                if (lane == 0 && (i >> 3) < p.nob && ch < p.cstat) {
+                const int ch = ((ob0 + (i >> 3)) % p.cobo) * 8 + (i & 7);
+                if (lane == 0 && (i >> 3) < nob && ch < p.cstat) {
                     atomicAdd(p.stats + ch, (double)a1);
                     atomicAdd(p.stats + cpn + ch, (double)a2);
                 }
@@ -570,6 +571,10 @@ static bool tc_geometry(int k, int cb, int cout, int h, int w, TcGeom& g) {
                              8 * (2 * TC_MAX_SLOTS + 4 * TC_WB + 2) + 16 + 1024;
         g.ns = pick_slots(g.ncg > 1 ? 4 : 3, fixed, g.slot_bytes);
         g.smem = fixed + (size_t)g.ns * g.slot_bytes;
+        if (g.smem > 220 * 1024 && g.ns > 3) {
+            g.ns = 3;
+            g.smem = fixed + (size_t)g.ns * g.slot_bytes;
+        }
         if (g.smem <= 220 * 1024) break;
         if (cobg == 1) return false;
     }
@@ -655,7 +660,7 @@ int conv3d_fprop_tc(const void* const* h_srcs, const int* h_src_channels, int ns
     // d-chunk: enough work items to balance 148 SMs x resident CTAs, but at least 8 planes per chunk
     const int tiles = n * p.tiles_h * p.tiles_w;
     int dc = d;
-    while (dc > 8 && (long long)tiles * ((d + dc - 1) / dc) < 148 * 6) dc = (dc + 1) / 2;
+    while (dc > 8 && (long long)tiles * ((d + dc - 1) / dc) * g.ngroups < 148 * 6) dc = (dc + 1) / 2;
     p.dc = dc;
     p.dchunks = (d + dc - 1) / dc;
     p.total_items = tiles * p.dchunks;
@@ -672,8 +677,11 @@ int conv3d_fprop_tc(const void* const* h_srcs, const int* h_src_channels, int ns
     if (ctas_per_sm > 512 / (int)g.tmem_cols) ctas_per_sm = 512 / (int)g.tmem_cols;
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     if (ctas_per_sm > 2) ctas_per_sm = 2;
-    int grid = 148 * ctas_per_sm;
-    if (grid > p.total_items) grid = p.total_items;
+    // one grid row per group of COB output blocks (all rows stream the same input planes, so re-reads hit L2)
+    int gx = (148 * ctas_per_sm + g.ngroups - 1) / g.ngroups;
+    if (gx > p.total_items) gx = p.total_items;
+    if (gx < 1) gx = 1;
+    const dim3 grid(gx, g.ngroups);
     const int threads = 32 * (1 + TC_WB + 4 * TC_WB);
     auto go = [&](auto kern) -> int {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
@@ -684,17 +692,11 @@ int conv3d_fprop_tc(const void* const* h_srcs, const int* h_src_channels, int ns
         kern<<<grid, threads, g.smem, stream>>>(maps, p);
         return check_launch("ctu_conv3d_fprop(tcgen05)");
     };
-    rc = CTU_OK;
-    for (int grp = 0; grp < g.ngroups && rc == CTU_OK; ++grp) {
-        p.ob0 = grp * g.cobg;
-        p.nob = (g.cob_n - p.ob0) < g.cobg ? (g.cob_n - p.ob0) : g.cobg;
-        p.wimg = reinterpret_cast<const __nv_bfloat16*>(reinterpret_cast<const unsigned char*>(wp) + (size_t)grp * g.wimg_bytes);
-        if (k == 3 && g.cobg == 1) rc = go(conv3d_tc_kernel<3, 1>);
-        else if (k == 3 && g.cobg == 2) rc = go(conv3d_tc_kernel<3, 2>);
-        else if (k == 3 && g.cobg == 4) rc = go(conv3d_tc_kernel<3, 4>);
-        else if (k == 5 && g.cobg == 1) rc = go(conv3d_tc_kernel<5, 1>);
-        else rc = go(conv3d_tc_kernel<5, 2>);
-    }
+    if (k == 3 && g.cobg == 1) rc = go(conv3d_tc_kernel<3, 1>);
+    else if (k == 3 && g.cobg == 2) rc = go(conv3d_tc_kernel<3, 2>);
+    else if (k == 3 && g.cobg == 4) rc = go(conv3d_tc_kernel<3, 4>);
+    else if (k == 5 && g.cobg == 1) rc = go(conv3d_tc_kernel<5, 1>);
+    else rc = go(conv3d_tc_kernel<5, 2>);
     if (rc == CTU_OK && stats != nullptr && !fuse_stats)   // wide layers (low resolution): separate statistics pass
         rc = ctu_bn_stats(CTU_BF16, y, stat_cout, g.cob_n / p.cobo, n, (long long)d * h * w, stats, stream);
     return rc;

@@ -73,6 +73,7 @@ STAGES = [
 STAGES_TC = [
     (3, [14, 14], 7, False, (1, 5, 16, 16)),
     (3, [28, 28], 14, False, (1, 3, 16, 32)),
+    (3, [56, 56], 28, False, (1, 3, 16, 16)),      # 15 input blocks staged in groups, 32 output blocks over grid rows
     (5, [14, 14], 7, True, (1, 4, 16, 16)),
 ]
 
