@@ -657,13 +657,7 @@ int conv3d_fprop_tc(const void* const* h_srcs, const int* h_src_channels, int ns
     }
     p.n = n; p.d = d; p.h = h; p.w = w;
     p.tiles_h = h / TC_TH; p.tiles_w = w / TC_TW;
-    // d-chunk: enough work items to balance 148 SMs x resident CTAs, but at least 8 planes per chunk
     const int tiles = n * p.tiles_h * p.tiles_w;
-    int dc = d;
-    while (dc > 8 && (long long)tiles * ((d + dc - 1) / dc) * g.ngroups < 148 * 6) dc = (dc + 1) / 2;
-    p.dc = dc;
-    p.dchunks = (d + dc - 1) / dc;
-    p.total_items = tiles * p.dchunks;
     p.wimg_bytes = g.wimg_bytes; p.plane_bytes = g.plane_bytes; p.slot_bytes = g.slot_bytes; p.tmem_cols = g.tmem_cols;
     p.ns = g.ns;
     if (fuse_stats) {
@@ -677,11 +671,6 @@ int conv3d_fprop_tc(const void* const* h_srcs, const int* h_src_channels, int ns
     if (ctas_per_sm > 512 / (int)g.tmem_cols) ctas_per_sm = 512 / (int)g.tmem_cols;
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     if (ctas_per_sm > 2) ctas_per_sm = 2;
-    // one grid row per group of COB output blocks (all rows stream the same input planes, so re-reads hit L2)
-    int gx = (148 * ctas_per_sm + g.ngroups - 1) / g.ngroups;
-    if (gx > p.total_items) gx = p.total_items;
-    if (gx < 1) gx = 1;
-    const dim3 grid(gx, g.ngroups);
     const int threads = 32 * (1 + TC_WB + 4 * TC_WB);
     auto go = [&](auto kern) -> int {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
@@ -689,7 +678,23 @@ int conv3d_fprop_tc(const void* const* h_srcs, const int* h_src_channels, int ns
             set_error("conv3d tensor path: smem %zu: %s", g.smem, cudaGetErrorString(e));
             return (int)e;
         }
-        kern<<<grid, threads, g.smem, stream>>>(maps, p);
+        // persistent grid = exactly the CTAs that are resident at once (registers limit the wide-output variants
+        // to one per SM); one grid row per group of COB output blocks -- all rows stream the same input planes, so
+        // their re-reads hit L2
+        int occ = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, g.smem) != cudaSuccess || occ < 1) occ = 1;
+        if (occ > ctas_per_sm) occ = ctas_per_sm;
+        // d-chunk: about three work items per resident CTA (load balance), but at least 8 planes per chunk
+        // (every chunk re-reads K-1 halo planes)
+        int dc = d;
+        while (dc > 8 && (long long)tiles * ((d + dc - 1) / dc) * g.ngroups < 148 * occ * 3) dc = (dc + 1) / 2;
+        p.dc = dc;
+        p.dchunks = (d + dc - 1) / dc;
+        p.total_items = tiles * p.dchunks;
+        int gx = (148 * occ) / g.ngroups;
+        if (gx > p.total_items) gx = p.total_items;
+        if (gx < 1) gx = 1;
+        kern<<<dim3(gx, g.ngroups), threads, g.smem, stream>>>(maps, p);
         return check_launch("ctu_conv3d_fprop(tcgen05)");
     };
     if (k == 3 && g.cobg == 1) rc = go(conv3d_tc_kernel<3, 1>);

@@ -73,15 +73,17 @@ __global__ void __launch_bounds__(FT* FT) upfuse_compose_kernel(const float* __r
 }
 
 // dWTa[ci][cm][p3] = sum_{(q, kk) with phase p3} sum_co dWn[(q, co)][ci][delta(q, kk)] * W3[co][cm][kk]
-// one thread per (ci <= cin, cm, p3); row ci == cin is the bias: dbT[cm] += its value (dbt zeroed by the caller)
-__global__ void upfuse_dwt_kernel(const float* __restrict__ dwn, const float* __restrict__ w3, float* __restrict__ dwt,
-                                  float* __restrict__ dbt, FuseDims g, long long total) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int p3 = (int)(i & 7);
-    const int cm = (int)((i >> 3) % g.cm);
-    const int ci = (int)((i >> 3) / g.cm);
+// block = (cm tile, ci tile, p3): a 16x16 tile of (ci, cm), one thread per entry; shared-memory tiles over co.
+// Row ci == cin is the bias: dbT[cm] += its value (dbt zeroed by the caller).
+__global__ void __launch_bounds__(FT* FT) upfuse_dwt_kernel(const float* __restrict__ dwn, const float* __restrict__ w3,
+                                                            float* __restrict__ dwt, float* __restrict__ dbt, FuseDims g,
+                                                            int rows) {
+    __shared__ float As[FT][FT + 1];   // dWn[q][co][ci][d3]  as [ci][co]
+    __shared__ float Bs[FT][FT + 1];   // W3[co][cm][tap]     as [co][cm]
+    const int tx = threadIdx.x % FT, ty = threadIdx.x / FT;
+    const int p3 = blockIdx.z;
     const int pd = p3 >> 2, ph = (p3 >> 1) & 1, pw = p3 & 1;
+    const int cm0 = blockIdx.x * FT, ci0 = blockIdx.y * FT;
     float acc = 0.f;
     for (int qd = 0; qd < 2; ++qd)
         for (int kd = 0; kd < g.k; ++kd) {
@@ -100,28 +102,40 @@ __global__ void upfuse_dwt_kernel(const float* __restrict__ dwn, const float* __
                             if (p != pw) continue;
                             const int q = qd * 4 + qh * 2 + qw, d3 = ((dd + 1) * 3 + dh + 1) * 3 + dw + 1;
                             const int tap = (kd * g.k + kh) * g.k + kw;
-                            const float* a = dwn + (((long long)q * g.cop) * (g.cin + 1) + ci) * 27 + d3;
-                            const float* b = w3 + (long long)cm * g.k3 + tap;
-                            for (int co = 0; co < g.cout; ++co)
-                                acc = fmaf(a[(long long)co * (g.cin + 1) * 27], b[(long long)co * g.cm * g.k3], acc);
+                            for (int c0 = 0; c0 < g.cout; c0 += FT) {
+                                const int ci = ci0 + ty, co_a = c0 + tx;     // As[ty = ci][tx = co]
+                                As[ty][tx] = (ci < rows && co_a < g.cout)
+                                                 ? dwn[(((long long)q * g.cop + co_a) * (g.cin + 1) + ci) * 27 + d3] : 0.f;
+                                const int co_b = c0 + ty, cm = cm0 + tx;     // Bs[ty = co][tx = cm]
+                                Bs[ty][tx] = (co_b < g.cout && cm < g.cm) ? w3[((long long)co_b * g.cm + cm) * g.k3 + tap] : 0.f;
+                                __syncthreads();
+#pragma unroll
+                                for (int j = 0; j < FT; ++j) acc = fmaf(As[ty][j], Bs[j][tx], acc);
+                                __syncthreads();
+                            }
                         }
                 }
         }
-    if (ci < g.cin)
-        dwt[((long long)ci * g.cm + cm) * 8 + p3] = acc;
-    else if (dbt != nullptr)
-        atomicAdd(dbt + cm, acc);
+    const int ci = ci0 + ty, cm = cm0 + tx;
+    if (cm < g.cm) {
+        if (ci < g.cin)
+            dwt[((long long)ci * g.cm + cm) * 8 + p3] = acc;
+        else if (ci == g.cin && ci < rows)
+            atomicAdd(dbt + cm, acc);
+    }
 }
 
-// dW3[co][cm][kk] = sum_q sum_{ci <= cin} dWn[(q, co)][ci][delta(q, kk)] * WTa[ci][cm][p(q, kk)]; one thread per entry
-__global__ void upfuse_dw3_kernel(const float* __restrict__ dwn, const float* __restrict__ wt, const float* __restrict__ bt,
-                                  float* __restrict__ dw3, FuseDims g, long long total) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int tap = (int)(i % g.k3);
-    const int cm = (int)((i / g.k3) % g.cm);
-    const int co = (int)(i / ((long long)g.k3 * g.cm));
+// dW3[co][cm][kk] = sum_q sum_{ci <= cin} dWn[(q, co)][ci][delta(q, kk)] * WTa[ci][cm][p(q, kk)]
+// block = (cm tile, co tile, tap): a 16x16 tile of (co, cm); shared-memory tiles over ci.
+__global__ void __launch_bounds__(FT* FT) upfuse_dw3_kernel(const float* __restrict__ dwn, const float* __restrict__ wt,
+                                                            const float* __restrict__ bt, float* __restrict__ dw3,
+                                                            FuseDims g) {
+    __shared__ float As[FT][FT + 1];   // dWn[q][co][ci][d3] as [co][ci]
+    __shared__ float Bs[FT][FT + 1];   // WTa[ci][cm][p3]    as [ci][cm]
+    const int tx = threadIdx.x % FT, ty = threadIdx.x / FT;
+    const int tap = blockIdx.z;
     const int kd = tap / (g.k * g.k), kh = (tap / g.k) % g.k, kw = tap % g.k;
+    const int cm0 = blockIdx.x * FT, co0 = blockIdx.y * FT;
     float acc = 0.f;
     for (int q = 0; q < 8; ++q) {
         int dd, dh, dw, pd, ph, pw;
@@ -129,10 +143,19 @@ __global__ void upfuse_dw3_kernel(const float* __restrict__ dwn, const float* __
         tap_of((q >> 1) & 1, kh, g.pad, dh, ph);
         tap_of(q & 1, kw, g.pad, dw, pw);
         const int d3 = ((dd + 1) * 3 + dh + 1) * 3 + dw + 1, p3 = pd * 4 + ph * 2 + pw;
-        const float* a = dwn + (((long long)q * g.cop + co) * (g.cin + 1)) * 27 + d3;
-        for (int ci = 0; ci <= g.cin; ++ci) acc = fmaf(a[(long long)ci * 27], wta(wt, bt, g, ci, cm, p3), acc);
+        for (int c0 = 0; c0 <= g.cin; c0 += FT) {
+            const int co = co0 + ty, ci_a = c0 + tx;          // As[ty = co][tx = ci]
+            As[ty][tx] = (co < g.cout && ci_a <= g.cin) ? dwn[(((long long)q * g.cop + co) * (g.cin + 1) + ci_a) * 27 + d3] : 0.f;
+            const int ci_b = c0 + ty, cm = cm0 + tx;          // Bs[ty = ci][tx = cm]
+            Bs[ty][tx] = (ci_b <= g.cin && cm < g.cm) ? wta(wt, bt, g, ci_b, cm, p3) : 0.f;
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < FT; ++j) acc = fmaf(As[ty][j], Bs[j][tx], acc);
+            __syncthreads();
+        }
     }
-    dw3[i] = acc;
+    const int co = co0 + ty, cm = cm0 + tx;
+    if (co < g.cout && cm < g.cm) dw3[((long long)co * g.cm + cm) * g.k3 + tap] = acc;
 }
 
 // b3n[(q*cop + co)] = b3[co] (pad lanes 0); db3[co] = sum_q dbn[(q*cop + co)]
@@ -193,12 +216,11 @@ int ctu_upfuse_decompose(const float* dwn, const float* dbn, const float* wt, co
             return (int)e;
         }
     }
-    const long long t1 = (long long)(cin + (dbt != nullptr ? 1 : 0)) * g.cm * 8;
-    upfuse_dwt_kernel<<<cdiv(t1, 128), 128, 0, st>>>(dwn, w3, dwt, dbt, g, t1);
+    const int rows = cin + (dbt != nullptr ? 1 : 0);
+    upfuse_dwt_kernel<<<dim3(cdiv(g.cm, FT), cdiv(rows, FT), 8), FT * FT, 0, st>>>(dwn, w3, dwt, dbt, g, rows);
     int rc = check_launch("ctu_upfuse_decompose(dwt)");
     if (rc != CTU_OK) return rc;
-    const long long t2 = (long long)cout * g.cm * g.k3;
-    upfuse_dw3_kernel<<<cdiv(t2, 128), 128, 0, st>>>(dwn, wt, bt, dw3, g, t2);
+    upfuse_dw3_kernel<<<dim3(cdiv(g.cm, FT), cdiv(cout, FT), g.k3), FT * FT, 0, st>>>(dwn, wt, bt, dw3, g);
     rc = check_launch("ctu_upfuse_decompose(dw3)");
     if (rc == CTU_OK && db3 != nullptr) {
         upfuse_bias_kernel<<<cdiv(cout, 128), 128, 0, st>>>(nullptr, nullptr, dbn, db3, cout, g.cop);
