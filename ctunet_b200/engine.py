@@ -34,6 +34,17 @@ CONV_PATH = "auto"
 UP_FUSION = "auto"
 _ONES = {}
 
+# Re-pack all weights of a pass up front on a side stream (Engine.begin) instead of inline in the layer chain.
+WEIGHT_PREP_ASYNC = True
+_SIDE = {}
+
+
+def _side_stream(device):
+    key = str(device)
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=device)
+    return _SIDE[key]
+
 
 class Act:
     """A channel-blocked activation [N][Cb][D][H][W][8] (bf16 in product mode, fp32 in check mode).
@@ -75,6 +86,63 @@ class Engine:
         self.want_input_grad = False
         self.grad_sink = None                       # parallel.GradSync: gradients land in its flat buffer
         self.use_tc = (CONV_PATH == "auto" and compute_dtype == "bf16" and bool(_lib.load().ctu_has_tensor_path()))
+        # weight preparation plan (see begin()): None = not in use, every preparation runs inline
+        self._plan = None
+        self._recording = False
+        self._results = []
+        self._pi = 0
+        self._side = None
+
+    # ------------------------------------------------------------------ weight preparation on a side stream
+    def begin(self, store: dict, key) -> None:
+        """Weight re-packing (native fp32 -> packed -> bf16 UMMA image, data-gradient packs, the composed weights
+        of the fused up stage) depends on the parameters only.  The first pass with a given ``key`` (input shape,
+        mode, flags) runs those ~100 tiny kernels inline and records them; every later pass enqueues ALL of them up
+        front on a side stream -- off the critical path of the layer chain (parallel branches of the CUDA graph) --
+        and each consumer just waits for its event."""
+        if not WEIGHT_PREP_ASYNC:
+            return
+        plan = store.get(key)
+        if plan is None:
+            self._plan, self._recording = [], True
+            self._store, self._key = store, key
+            return
+        self._plan = plan
+        main = torch.cuda.current_stream()
+        side = _side_stream(self.device)
+        self._side = side
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            for tag, fn in plan:
+                out = fn(self)
+                ev = torch.cuda.Event()
+                ev.record(side)
+                for t in out:
+                    if isinstance(t, torch.Tensor):
+                        t.record_stream(main)
+                self._results.append((tag, out, ev))
+
+    def end_forward(self) -> None:
+        """Publish a freshly recorded plan / join the side stream (required before a graph capture ends)."""
+        if self._recording:
+            self._store[self._key] = self._plan
+            self._recording = False
+        elif self._side is not None:
+            torch.cuda.current_stream().wait_stream(self._side)
+
+    def _prepared(self, tag: str, fn):
+        """``fn(engine) -> tuple of tensors`` computed from parameters and static shapes only."""
+        if self._plan is None:
+            return fn(self)
+        if self._recording:
+            self._plan.append((tag, fn))
+            return fn(self)
+        if self._pi >= len(self._results) or self._results[self._pi][0] != tag:
+            raise RuntimeError("internal: weight preparation plan out of step at %r" % tag)
+        _, out, ev = self._results[self._pi]
+        self._pi += 1
+        torch.cuda.current_stream().wait_event(ev)
+        return out
 
     # ------------------------------------------------------------------ helpers
     def new_act(self, c, n, d, h, w) -> Act:
@@ -110,19 +178,32 @@ class Engine:
     def _tc_ok(self, k, srcs, cout):
         return self.use_tc and tc_supported(k, [s.c for s in srcs], cout, srcs[0].d, srcs[0].h, srcs[0].w)
 
-    def _conv_launch(self, srcs, wp, bias, y: Act, cout, k, sums, stat_cout=0):
-        """One forward-style convolution launch (also used for the data gradient): tcgen05 implicit GEMM when
-        the kernel covers the shape, CUDA-core direct kernel otherwise."""
+    def _kernel_weights(self, native, cout, k, chans, tc, dgrad_of=None):
+        """Kernel-ready weights of conv(cat(srcs with ``chans`` channels)) -> cout: the packed fp32 tensor (CUDA-core
+        kernel) or the bf16 UMMA image (tcgen05 kernel).  ``dgrad_of = (i, cs)``: instead the weights of the data
+        gradient dy (cout channels) -> d(src i) (cs channels)."""
+        lib = _lib.load()
+        ca, ns, st = int_array(chans), len(chans), stream_ptr()
+        if dgrad_of is None:
+            wp = self.f32(lib.ctu_conv_wpack_floats(cout, k, ns, ca))
+            call("ctu_conv_pack_weight", native.data_ptr(), wp.data_ptr(), cout, k, ns, ca, st)
+            kin, kout = (ns, ca), cout
+        else:
+            i, cs = dgrad_of
+            wp = self.f32(lib.ctu_conv_wpack_dgrad_floats(cout, k, cs))
+            call("ctu_conv_pack_weight_dgrad", native.data_ptr(), wp.data_ptr(), cout, k, ns, ca, i, st)
+            kin, kout = (1, int_array([cout])), cs
+        if not tc:
+            return wp
+        wimg = torch.empty(lib.ctu_conv_tc_wimg_bytes(k, kin[0], kin[1], kout), dtype=torch.uint8, device=self.device)
+        call("ctu_conv_tc_pack_weight", wp.data_ptr(), wimg.data_ptr(), k, kin[0], kin[1], kout, st)
+        return wimg
+
+    def _conv_launch(self, srcs, wk, tc, bias, y: Act, cout, k, sums, stat_cout=0):
+        """One forward-style convolution launch (also used for the data gradient) with kernel-ready weights."""
         s0 = srcs[0]
         pa, ca, ns = self._src_args(srcs)
-        tc = self._tc_ok(k, srcs, cout)
-        wptr = wp.data_ptr()
-        if tc:
-            lib = _lib.load()
-            wimg = torch.empty(lib.ctu_conv_tc_wimg_bytes(k, ns, ca, cout), dtype=torch.uint8, device=self.device)
-            call("ctu_conv_tc_pack_weight", wp.data_ptr(), wimg.data_ptr(), k, ns, ca, cout, stream_ptr())
-            wptr = wimg.data_ptr()
-        call("ctu_conv3d_fprop", self.dtype, pa, ca, ns, wptr, bias.data_ptr() if bias is not None else None,
+        call("ctu_conv3d_fprop", self.dtype, pa, ca, ns, wk.data_ptr(), bias.data_ptr() if bias is not None else None,
              y.ptr, sums.data_ptr() if sums is not None else None, stat_cout, cout, k, s0.n, s0.d, s0.h, s0.w, int(tc),
              stream_ptr())
 
@@ -139,22 +220,42 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ Conv3d
-    def _conv_fwd(self, srcs, w_native, bias, k, cout, stat_cout, bn_stats):
-        """y = conv(cat(srcs), w_native [cout][cin][k^3]) (+bias); returns the output activation."""
+    def _conv_weights(self, tag, srcs, need, w_native, k, cout, compose=None):
+        """Prepared weights of one convolution stage: (forward weights, [data-gradient weights per source or None],
+        extra).  ``compose(engine) -> (w_native, extra...)`` builds the native weights first (fused up stage)."""
+        chans = [s.c for s in srcs]
         s0 = srcs[0]
-        pa, ca, ns = self._src_args(srcs)
-        lib = _lib.load()
-        wp = self.f32(lib.ctu_conv_wpack_floats(cout, k, ns, ca))
-        call("ctu_conv_pack_weight", w_native.data_ptr(), wp.data_ptr(), cout, k, ns, ca, stream_ptr())
+        tc_f = self._tc_ok(k, srcs, cout)
+        tc_d = [bool(nd) and self.use_tc and tc_supported(k, [cout], s.c, s0.d, s0.h, s0.w) for s, nd in zip(srcs, need)]
+        need = list(need)
+
+        def prep(eng):
+            extra = ()
+            wn = w_native
+            if compose is not None:
+                res = compose(eng)
+                wn, extra = res[0], tuple(res[1:])
+            out = [eng._kernel_weights(wn, cout, k, chans, tc_f)]
+            for i, nd in enumerate(need):
+                out.append(eng._kernel_weights(wn, cout, k, chans, tc_d[i], (i, chans[i])) if nd else None)
+            return tuple(out) + (wn,) + extra
+
+        res = self._prepared(tag, prep)
+        ns = len(srcs)
+        return res[0], tc_f, list(res[1:1 + ns]), tc_d, res[1 + ns], res[2 + ns:]
+
+    def _conv_fwd(self, srcs, wk, tc, bias, k, cout, stat_cout, bn_stats):
+        """y = conv(cat(srcs)) (+bias) with kernel-ready weights; returns the output activation."""
+        s0 = srcs[0]
         y = self.new_act(cout, s0.n, s0.d, s0.h, s0.w)
         if bn_stats:
             y.sums = self.f64(2 * (((stat_cout or cout) + 7) // 8 * 8))
-        self._conv_launch(srcs, wp, bias, y, cout, k, y.sums, stat_cout)
+        self._conv_launch(srcs, wk, tc, bias, y, cout, k, y.sums, stat_cout)
         return y
 
-    def _conv_bwd(self, srcs, need, w_native, y, k, cout, dw_out, db_out):
+    def _conv_bwd(self, srcs, need, wkd, tc_d, y, k, cout, dw_out, db_out):
         """Weight gradient into ``dw_out`` (native layout, nullable) / ``db_out`` and the data gradient of every
-        source with ``need[i]``."""
+        source with ``need[i]`` (prepared weights ``wkd[i]``)."""
         lib = _lib.load()
         s0 = srcs[0]
         dy = self.agrads.pop(id(y))
@@ -169,25 +270,23 @@ class Engine:
         for i, s in enumerate(srcs):
             if not need[i]:
                 continue
-            wpd = self.f32(lib.ctu_conv_wpack_dgrad_floats(cout, k, s.c))
-            call("ctu_conv_pack_weight_dgrad", w_native.data_ptr(), wpd.data_ptr(), cout, k, ns, ca, i, stream_ptr())
             dx = self.new_act(s.c, s.n, s.d, s.h, s.w)
-            self._conv_launch([dy], wpd, None, dx, s.c, k, None)
+            self._conv_launch([dy], wkd[i], tc_d[i], None, dx, s.c, k, None)
             self._set_agrad(s, dx)
 
     def conv(self, srcs: Sequence[Act], weight, bias, k: int, need_src_grad: Sequence[bool],
              bn_stats: bool = False) -> Act:
         """``bn_stats``: also produce the batch statistics of the output (``y.sums``) for the BatchNorm that follows."""
         cout = weight.shape[0]
-        y = self._conv_fwd(srcs, weight, bias, k, cout, 0, bn_stats)
+        srcs = list(srcs)
+        need = [bool(n) and self.record for n in need_src_grad]
+        wk, tc, wkd, tc_d, _, _ = self._conv_weights("conv", srcs, need, weight, k, cout)
+        y = self._conv_fwd(srcs, wk, tc, bias, k, cout, 0, bn_stats)
         if self.record:
-            srcs = list(srcs)
-            need = list(need_src_grad)
-
             def bwd():
                 dw = self._grad_buffer(weight) if weight.requires_grad else None
                 db = self._grad_buffer(bias) if (dw is not None and bias is not None and bias.requires_grad) else None
-                self._conv_bwd(srcs, need, weight, y, k, cout, dw, db)
+                self._conv_bwd(srcs, need, wkd, tc_d, y, k, cout, dw, db)
                 if dw is not None:
                     self._add_pgrad(weight, dw)
                 if db is not None:
@@ -232,26 +331,31 @@ class Engine:
         cin = sum(s.c for s in srcs)
         cout = cv.weight.shape[0]
         co8 = lib.ctu_upfuse_cout(cout)
-        st = stream_ptr()
-        wn = self.f32(co8, cin + 1, 27)
-        b3n = self.f32(co8) if cv.bias is not None else None
-        call("ctu_upfuse_compose", ct.weight.data_ptr(), ct.bias.data_ptr() if ct.bias is not None else None,
-             cv.weight.data_ptr(), cv.bias.data_ptr() if cv.bias is not None else None, wn.data_ptr(),
-             b3n.data_ptr() if b3n is not None else None, cin, cout, k, st)
+        has_b3 = cv.bias is not None
+
+        def compose(eng):
+            wn = eng.f32(co8, cin + 1, 27)
+            b3n = eng.f32(co8) if has_b3 else None
+            call("ctu_upfuse_compose", ct.weight.data_ptr(), ct.bias.data_ptr() if ct.bias is not None else None,
+                 cv.weight.data_ptr(), cv.bias.data_ptr() if has_b3 else None, wn.data_ptr(),
+                 b3n.data_ptr() if has_b3 else None, cin, cout, k, stream_ptr())
+            return wn, b3n
+
         all_srcs = list(srcs) + [self._ones(srcs[0])]
-        y = self._conv_fwd(all_srcs, wn, b3n, 3, co8, cout, bn_stats)
+        need = [bool(n) and self.record for n in need_src_grad] + [False]
+        wk, tc, wkd, tc_d, wn, extra = self._conv_weights("up_conv", all_srcs, need, None, 3, co8, compose)
+        b3n = extra[0]
+        y = self._conv_fwd(all_srcs, wk, tc, b3n, 3, co8, cout, bn_stats)
         y.c_nat = cout
         if self.record:
-            need = list(need_src_grad) + [False]
-
             def bwd():
                 st = stream_ptr()
                 dwn = torch.empty_like(wn)
-                dbn = self.f32(co8) if b3n is not None else None
-                self._conv_bwd(all_srcs, need, wn, y, 3, co8, dwn, dbn)
+                dbn = self.f32(co8) if has_b3 else None
+                self._conv_bwd(all_srcs, need, wkd, tc_d, y, 3, co8, dwn, dbn)
                 dwt, dw3 = self._grad_buffer(ct.weight), self._grad_buffer(cv.weight)
                 dbt = self._grad_buffer(ct.bias) if ct.bias is not None else None
-                db3 = self._grad_buffer(cv.bias) if cv.bias is not None else None
+                db3 = self._grad_buffer(cv.bias) if has_b3 else None
                 call("ctu_upfuse_decompose", dwn.data_ptr(), dbn.data_ptr() if dbn is not None else None,
                      ct.weight.data_ptr(), ct.bias.data_ptr() if ct.bias is not None else None, cv.weight.data_ptr(),
                      dwt.data_ptr(), dbt.data_ptr() if dbt is not None else None, dw3.data_ptr(),

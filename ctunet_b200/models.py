@@ -145,8 +145,20 @@ class _FusedNet(nn.Module):
         record = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
         if not record:
             eng = Engine(x.device, self.compute_dtype, record=False)
-            return self._run(eng, x, self.training)
+            return _run_planned(self, eng, x, False)
         return _NetFn.apply(self, x, *params)
+
+
+def _run_planned(net, eng: Engine, x, record: bool):
+    """Run the network with the weight-preparation plan of this (shape, mode) configuration (Engine.begin)."""
+    from . import engine as E
+    store = net.__dict__.setdefault("_prep_plans", {})
+    key = (id(net), tuple(x.shape), str(x.device), net.compute_dtype, bool(net.training), record, eng.want_input_grad,
+           E.UP_FUSION, E.CONV_PATH)
+    eng.begin(store, key)
+    out = net._run(eng, x, net.training)
+    eng.end_forward()
+    return out
 
 
 class _NetFn(torch.autograd.Function):
@@ -157,7 +169,7 @@ class _NetFn(torch.autograd.Function):
         eng = Engine(x.device, net.compute_dtype, record=True)
         eng.grad_sink = getattr(net, "_grad_sink", None)
         eng.want_input_grad = bool(ctx.needs_input_grad[1])
-        out = net._run(eng, x, net.training)
+        out = _run_planned(net, eng, x, True)
         ctx.eng = eng
         ctx.params = params
         ctx.two = isinstance(out, tuple)
