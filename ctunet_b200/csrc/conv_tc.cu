@@ -428,10 +428,7 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
         const int nob = (p.cob_n - ob0) < COB ? (p.cob_n - ob0) : COB;
         float part[K][CP];                             // partial sums of the K output planes in flight
         float s1[NSLOT * 8], s2[NSLOT * 8];
-        float bv[CP];
-#pragma unroll
-        for (int c = 0; c < CP; ++c)
-            bv[c] = (p.bias != nullptr && ob0 * 8 + c < p.cout) ? __ldg(p.bias + ob0 * 8 + c) : 0.f;
+        const bool has_bias = p.bias != nullptr;       // only the legacy 5^3 family: read on use, not held in registers
 #pragma unroll
         for (int i = 0; i < NSLOT * 8; ++i) s1[i] = s2[i] = 0.f;
         uint32_t step = 0;
@@ -475,7 +472,11 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
                     for (int ob = 0; ob < COB; ++ob) {
                         V8 o;
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) o.v[c] = round_to<__nv_bfloat16>(part[0][ob * 8 + c] + bv[ob * 8 + c]);
+                        for (int c = 0; c < 8; ++c) {
+                            float v = part[0][ob * 8 + c];
+                            if (has_bias && (ob0 + ob) * 8 + c < p.cout) v += __ldg(p.bias + (ob0 + ob) * 8 + c);
+                            o.v[c] = round_to<__nv_bfloat16>(v);
+                        }
                         if (inb && ob < nob) {
                             Vec8<__nv_bfloat16>::store(ycol + ((long long)ob * plane + (long long)gz * p.h * p.w) * 8, o);
                             if (want_stats) {

@@ -102,22 +102,34 @@ __device__ __forceinline__ int head_block_source(const HeadParams& p, int c) {
     return q;
 }
 
-template <typename T, int CO, int CBT>
-__device__ __forceinline__ void head_logits(const HeadParams& p, const float* wsm, const float* bsm, int n, long long s,
-                                            HeadVals<CO>& h, V8 (&xs)[CBT]) {
-#pragma unroll
-    for (int o = 0; o < CO; ++o) h.lc[o] = bsm[o];
+template <typename T, int CBT>
+__device__ __forceinline__ void head_load(const HeadParams& p, int n, long long s, V8 (&xs)[CBT]) {
 #pragma unroll
     for (int c = 0; c < CBT; ++c) {
         const int q = head_block_source(p, c);
         const int b = c - p.m.cboff[q];
         const T* sp = reinterpret_cast<const T*>(p.src[q]);
         xs[c] = Vec8<T>::load(sp + (((long long)n * p.src_cb[q] + b) * p.spatial + s) * 8);
+    }
+}
+
+template <int CO, int CBT>
+__device__ __forceinline__ void head_logits_of(const float* wsm, const float* bsm, HeadVals<CO>& h, const V8 (&xs)[CBT]) {
+#pragma unroll
+    for (int o = 0; o < CO; ++o) h.lc[o] = bsm[o];
+#pragma unroll
+    for (int c = 0; c < CBT; ++c)
 #pragma unroll
         for (int o = 0; o < CO; ++o)
 #pragma unroll
             for (int j = 0; j < 8; ++j) h.lc[o] = fmaf(xs[c].v[j], wsm[o * CBT * 8 + c * 8 + j], h.lc[o]);
-    }
+}
+
+template <typename T, int CO, int CBT>
+__device__ __forceinline__ void head_logits(const HeadParams& p, const float* wsm, const float* bsm, int n, long long s,
+                                            HeadVals<CO>& h, V8 (&xs)[CBT]) {
+    head_load<T, CBT>(p, n, s, xs);
+    head_logits_of<CO, CBT>(wsm, bsm, h, xs);
 }
 
 template <typename T, int CO, int CBT>
@@ -165,19 +177,42 @@ __global__ void __launch_bounds__(kHeadThreads) head_bwd_kernel(HeadParams p) {
 #pragma unroll
         for (int l = 0; l < CBT * 8; ++l) gw[o][l] = 0.f;
     }
-    for (long long i = (long long)blockIdx.x * kHeadThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kHeadThreads) {
+    // software pipeline: the inputs of the next voxel are in flight while the current one is processed
+    const long long stride = (long long)gridDim.x * kHeadThreads;
+    long long i = (long long)blockIdx.x * kHeadThreads + threadIdx.x;
+    V8 xn[CBT];
+    float gn[4] = {0.f, 0.f, 0.f, 0.f};
+    auto fetch = [&](long long idx, V8 (&xo)[CBT], float (&go)[4]) {
+        const int n = (int)(idx / p.spatial);
+        const long long s = idx % p.spatial;
+        head_load<T, CBT>(p, n, s, xo);
+        if (sp) {
+            go[0] = p.dout0 ? p.dout0[((long long)n * 2 + 0) * p.spatial + s] : 0.f;
+            go[1] = p.dout0 ? p.dout0[((long long)n * 2 + 1) * p.spatial + s] : 0.f;
+            go[2] = p.dout1 ? p.dout1[((long long)n * 2 + 0) * p.spatial + s] : 0.f;
+            go[3] = p.dout1 ? p.dout1[((long long)n * 2 + 1) * p.spatial + s] : 0.f;
+        } else {
+#pragma unroll
+            for (int o = 0; o < CO; ++o) go[o] = p.dout0[((long long)n * CO + o) * p.spatial + s];
+        }
+    };
+    if (i < total) fetch(i, xn, gn);
+    for (; i < total; i += stride) {
         const int n = (int)(i / p.spatial);
         const long long s = i % p.spatial;
-        HeadVals<CO> h;
         V8 xs[CBT];
-        head_logits<T, CO, CBT>(p, wsm, bsm, n, s, h, xs);
+        float gc[4];
+#pragma unroll
+        for (int c = 0; c < CBT; ++c) xs[c] = xn[c];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) gc[o] = gn[o];
+        if (i + stride < total) fetch(i + stride, xn, gn);
+        HeadVals<CO> h;
+        head_logits_of<CO, CBT>(wsm, bsm, h, xs);
         head_forward_chain<CO>(h, p.flags);
         float dsg[CO];
         if (sp) {
-            float g00 = p.dout0 ? p.dout0[((long long)n * 2 + 0) * p.spatial + s] : 0.f;
-            float g01 = p.dout0 ? p.dout0[((long long)n * 2 + 1) * p.spatial + s] : 0.f;
-            float g10 = p.dout1 ? p.dout1[((long long)n * 2 + 0) * p.spatial + s] : 0.f;
-            float g11 = p.dout1 ? p.dout1[((long long)n * 2 + 1) * p.spatial + s] : 0.f;
+            float g00 = gc[0], g01 = gc[1], g10 = gc[2], g11 = gc[3];
             if (p.flags & CTU_HEAD_SP_SOFTMAX) {
                 // out = softmax(pair): d(pair_j) = out_j * (g_j - sum_i g_i out_i)
                 float d0 = g00 * h.o0[0] + g01 * h.o0[1];
@@ -193,7 +228,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_bwd_kernel(HeadParams p) {
             dsg[CO - 1] = g01;
         } else {
 #pragma unroll
-            for (int o = 0; o < CO; ++o) dsg[o] = p.dout0[((long long)n * CO + o) * p.spatial + s];
+            for (int o = 0; o < CO; ++o) dsg[o] = gc[o];
         }
         float dsm[CO], dlc[CO];
 #pragma unroll
