@@ -683,6 +683,7 @@ int conv3d_fprop_tc(const void* const* h_srcs, const int* h_src_channels, int ns
         // to one per SM); one grid row per group of COB output blocks -- all rows stream the same input planes, so
         // their re-reads hit L2
         int occ = 1;
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, g.smem) != cudaSuccess || occ < 1) occ = 1;
         if (occ > ctas_per_sm) occ = ctas_per_sm;
         // d-chunk: about three work items per resident CTA (load balance), but at least 8 planes per chunk

@@ -36,11 +36,13 @@ _ONES = {}
 
 # Re-pack all weights of a pass up front on a side stream (Engine.begin) instead of inline in the layer chain.
 WEIGHT_PREP_ASYNC = True
+# Weight gradients run on a second stream, overlapping the rest of the backward chain (Engine._conv_bwd).
+WGRAD_ASYNC = True
 _SIDE = {}
 
 
-def _side_stream(device):
-    key = str(device)
+def _side_stream(device, which=0):
+    key = (str(device), which)
     if key not in _SIDE:
         _SIDE[key] = torch.cuda.Stream(device=device)
     return _SIDE[key]
@@ -92,6 +94,7 @@ class Engine:
         self._results = []
         self._pi = 0
         self._side = None
+        self._wgrad_stream = None
 
     # ------------------------------------------------------------------ weight preparation on a side stream
     def begin(self, store: dict, key) -> None:
@@ -253,26 +256,50 @@ class Engine:
         self._conv_launch(srcs, wk, tc, bias, y, cout, k, y.sums, stat_cout)
         return y
 
-    def _conv_bwd(self, srcs, need, wkd, tc_d, y, k, cout, dw_out, db_out):
+    def _conv_bwd(self, srcs, need, wkd, tc_d, y, k, cout, dw_out, db_out, after_wgrad=None):
         """Weight gradient into ``dw_out`` (native layout, nullable) / ``db_out`` and the data gradient of every
-        source with ``need[i]`` (prepared weights ``wkd[i]``)."""
+        source with ``need[i]`` (prepared weights ``wkd[i]``).
+
+        The weight gradient is a leaf of the backward graph (only the optimizer reads it), so it is enqueued on a
+        second stream (``WGRAD_ASYNC``): it overlaps the BatchNorm / head kernels of the layers below while the data
+        gradient stays on the critical path.  ``after_wgrad()`` runs behind it on the same stream."""
         lib = _lib.load()
         s0 = srcs[0]
         dy = self.agrads.pop(id(y))
         pa, ca, ns = self._src_args(srcs)
         if dw_out is not None:
-            dwp = self.f32(lib.ctu_conv_wpack_floats(cout, k, ns, ca))
-            tc = self.use_tc and bool(lib.ctu_conv_tc_wgrad_supported(k, ns, ca, cout, s0.d, s0.h, s0.w))
-            call("ctu_conv3d_wgrad", self.dtype, pa, ca, ns, dy.ptr, dwp.data_ptr(),
-                 db_out.data_ptr() if db_out is not None else None, cout, k, s0.n, s0.d, s0.h, s0.w, int(tc),
-                 stream_ptr())
-            call("ctu_conv_unpack_wgrad", dwp.data_ptr(), dw_out.data_ptr(), cout, k, ns, ca, stream_ptr())
+            def wgrad():
+                dwp = self.f32(lib.ctu_conv_wpack_floats(cout, k, ns, ca))
+                tc = self.use_tc and bool(lib.ctu_conv_tc_wgrad_supported(k, ns, ca, cout, s0.d, s0.h, s0.w))
+                call("ctu_conv3d_wgrad", self.dtype, pa, ca, ns, dy.ptr, dwp.data_ptr(),
+                     db_out.data_ptr() if db_out is not None else None, cout, k, s0.n, s0.d, s0.h, s0.w, int(tc),
+                     stream_ptr())
+                call("ctu_conv_unpack_wgrad", dwp.data_ptr(), dw_out.data_ptr(), cout, k, ns, ca, stream_ptr())
+                if after_wgrad is not None:
+                    after_wgrad()
+
+            if WGRAD_ASYNC:
+                main = torch.cuda.current_stream()
+                side = _side_stream(self.device, 1)
+                side.wait_stream(main)                      # dy (and everything before it) is ready
+                with torch.cuda.stream(side):
+                    wgrad()
+                dy.buf.record_stream(side)
+                self._wgrad_stream = side
+            else:
+                wgrad()
         for i, s in enumerate(srcs):
             if not need[i]:
                 continue
             dx = self.new_act(s.c, s.n, s.d, s.h, s.w)
             self._conv_launch([dy], wkd[i], tc_d[i], None, dx, s.c, k, None)
             self._set_agrad(s, dx)
+
+    def _pgrad_done(self, pairs):
+        """Register parameter gradients produced on the current stream (see _add_pgrad)."""
+        for prm, g in pairs:
+            if g is not None:
+                self._add_pgrad(prm, g)
 
     def conv(self, srcs: Sequence[Act], weight, bias, k: int, need_src_grad: Sequence[bool],
              bn_stats: bool = False) -> Act:
@@ -286,11 +313,8 @@ class Engine:
             def bwd():
                 dw = self._grad_buffer(weight) if weight.requires_grad else None
                 db = self._grad_buffer(bias) if (dw is not None and bias is not None and bias.requires_grad) else None
-                self._conv_bwd(srcs, need, wkd, tc_d, y, k, cout, dw, db)
-                if dw is not None:
-                    self._add_pgrad(weight, dw)
-                if db is not None:
-                    self._add_pgrad(bias, db)
+                self._conv_bwd(srcs, need, wkd, tc_d, y, k, cout, dw, db,
+                               lambda: self._pgrad_done(((weight, dw), (bias, db))))
 
             self.tape.append(bwd)
         return y
@@ -349,20 +373,23 @@ class Engine:
         y.c_nat = cout
         if self.record:
             def bwd():
-                st = stream_ptr()
                 dwn = torch.empty_like(wn)
                 dbn = self.f32(co8) if has_b3 else None
-                self._conv_bwd(all_srcs, need, wkd, tc_d, y, 3, co8, dwn, dbn)
                 dwt, dw3 = self._grad_buffer(ct.weight), self._grad_buffer(cv.weight)
                 dbt = self._grad_buffer(ct.bias) if ct.bias is not None else None
                 db3 = self._grad_buffer(cv.bias) if has_b3 else None
-                call("ctu_upfuse_decompose", dwn.data_ptr(), dbn.data_ptr() if dbn is not None else None,
-                     ct.weight.data_ptr(), ct.bias.data_ptr() if ct.bias is not None else None, cv.weight.data_ptr(),
-                     dwt.data_ptr(), dbt.data_ptr() if dbt is not None else None, dw3.data_ptr(),
-                     db3.data_ptr() if db3 is not None else None, cin, cout, k, st)
-                for prm, g in ((ct.weight, dwt), (ct.bias, dbt), (cv.weight, dw3), (cv.bias, db3)):
-                    if g is not None:
-                        self._add_pgrad(prm, g)
+
+                def decompose():
+                    call("ctu_upfuse_decompose", dwn.data_ptr(), dbn.data_ptr() if dbn is not None else None,
+                         ct.weight.data_ptr(), ct.bias.data_ptr() if ct.bias is not None else None,
+                         cv.weight.data_ptr(), dwt.data_ptr(), dbt.data_ptr() if dbt is not None else None,
+                         dw3.data_ptr(), db3.data_ptr() if db3 is not None else None, cin, cout, k, stream_ptr())
+                    for t in (dwn, dbn):
+                        if t is not None:
+                            t.record_stream(torch.cuda.current_stream())
+                    self._pgrad_done(((ct.weight, dwt), (ct.bias, dbt), (cv.weight, dw3), (cv.bias, db3)))
+
+                self._conv_bwd(all_srcs, need, wkd, tc_d, y, 3, co8, dwn, dbn, decompose)
 
             self.tape.append(bwd)
         return y
@@ -505,11 +532,18 @@ class Engine:
         return (out0, out1) if sp else out0
 
     # ------------------------------------------------------------------ backward driver
-    def backward(self, g0, g1):
-        self.head_bwd(g0, g1)
+    def run_tape(self):
+        """Run the recorded backward closures (last stage first) and join the weight-gradient stream."""
         for fn in reversed(self.tape):
             fn()
         self.tape = []
+        if self._wgrad_stream is not None:                   # weight gradients -> visible to the optimizer's stream
+            torch.cuda.current_stream().wait_stream(self._wgrad_stream)
+            self._wgrad_stream = None
+
+    def backward(self, g0, g1):
+        self.head_bwd(g0, g1)
+        self.run_tape()
 
 
 def tc_supported(k, src_channels, cout, d, h, w) -> bool:

@@ -70,6 +70,8 @@ class GradSync:
         bi = self.bucket_of.get(id(param))
         if bi is None:
             return
+        if self.cuda:                                      # gradients of one bucket may come from several streams
+            self._producers[bi].add(torch.cuda.current_stream())
         self._remaining[bi] -= 1
         if self._remaining[bi] == 0:
             self._launch(bi)
@@ -78,6 +80,7 @@ class GradSync:
     def begin_step(self) -> None:
         self._remaining = list(self.n_in_bucket)
         self._handles = []
+        self._producers = [set() for _ in self.n_in_bucket]
 
     def _launch(self, bi: int) -> None:
         lo, hi = self.bucket_ranges[bi]
@@ -85,7 +88,8 @@ class GradSync:
         if self.world == 1:
             return
         if self.cuda:
-            self.comm_stream.wait_stream(torch.cuda.current_stream())
+            for st in self._producers[bi] | {torch.cuda.current_stream()}:
+                self.comm_stream.wait_stream(st)
             with torch.cuda.stream(self.comm_stream):
                 dist.all_reduce(view, op=dist.ReduceOp.AVG, group=self.group)
         else:  # gloo (CPU tests): no AVG, no streams

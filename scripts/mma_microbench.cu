@@ -1,0 +1,116 @@
+// Micro-benchmark of tcgen05.mma issue behaviour on sm_100a for the SMALL shapes the U-Net convolutions use
+// (M in {64,128}, N in {24..256}, K = 16, bf16, no-swizzle K-major operands in shared memory).
+// Question it answers: how many cycles does one MMA cost as a function of
+//   W = number of issuing warps, A = independent TMEM accumulators each warp cycles through, and the shape,
+// i.e. are back-to-back MMAs limited by the tensor pipe, by the shared-memory operand fetch, or by a per-MMA latency
+// that only independent chains can hide.
+//   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o scripts/mma_microbench scripts/mma_microbench.cu
+//   ./scripts/mma_microbench
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred;
+}
+__device__ __forceinline__ void mma(uint32_t leader, uint32_t d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi,
+                                    uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %7, 0;\n\tsetp.ne.b32 q, %0, 0;\n\t"
+        "mov.b64 da, {%2, %3};\n\tmov.b64 db, {%4, %5};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%1], da, db, %6, p;\n\t}"
+        ::"r"(leader), "r"(d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void commit(uint32_t leader, uint32_t bar) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %0, 0;\n\t"
+                 "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%1];\n\t}" ::"r"(leader), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    }
+}
+
+// W issuing warps; warp w cycles through A accumulators; L MMAs per warp.  mn_major: both operands MN-major (wgrad).
+__global__ void bench(int M, int N, int W, int A, int L, int mn_major, long long* out) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ uint64_t bars[8];
+    __shared__ uint32_t tmem_slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 64 * 1024 / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 8; ++i)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[i])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+    if (warp < W) {
+        const uint32_t leader = elect_one();
+        uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+        if (mn_major) idesc |= (1u << 15) | (1u << 16);
+        const uint32_t base = smem_u32(smem) >> 4;
+        // K-major: SBO = 256 B between 8-row groups, LBO = 128 B; MN-major: SBO = 16 B (lag groups), LBO = 128 B
+        const uint32_t ahi = (mn_major ? 1u : 16u) | (1u << 14), bhi = 16u | (1u << 14);
+        const uint32_t alo = (base + warp * 64) | (8u << 16), blo = (base + 2048) | (8u << 16);
+        long long t0 = clock64();
+        for (int i = 0; i < L; ++i) {
+            const uint32_t d = tmem + (uint32_t)((warp * A + (i % A)) * N);
+            mma(leader, d, alo + (i & 7) * 2, ahi, blo + (i & 3) * 2, bhi, idesc, i >= A ? 1u : 0u);
+        }
+        commit(leader, smem_u32(&bars[warp]));
+        mbar_wait(smem_u32(&bars[warp]), 0);
+        long long t1 = clock64();
+        if (lane == 0 && blockIdx.x == 0) out[warp] = t1 - t0;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+int main() {
+    long long* d_out;
+    cudaMalloc(&d_out, 8 * sizeof(long long));
+    cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    const int L = 4096;
+    printf("%-4s %-4s %-3s %-3s %-3s | cycles per MMA per warp | aggregate cycles per MMA | tensor floor max(M,128)*N/256\n", "M", "N",
+           "W", "A", "MN");
+    const int Ms[] = {128, 64};
+    const int Ns[] = {32, 48, 96, 128, 256};
+    for (int mn = 0; mn < 2; ++mn)
+        for (int M : Ms)
+            for (int N : Ns)
+                for (int W = 1; W <= 4; W *= 2)
+                    for (int A = 1; A <= 4; A *= 2) {
+                        if (W * A * N > 512) continue;
+                        if (mn && M != 64) continue;
+                        bench<<<1, 32 * 4, 64 * 1024>>>(M, N, W, A, L, mn, d_out);
+                        cudaError_t e = cudaDeviceSynchronize();
+                        if (e != cudaSuccess) {
+                            printf("M=%d N=%d W=%d A=%d mn=%d: %s\n", M, N, W, A, mn, cudaGetErrorString(e));
+                            return 1;
+                        }
+                        long long h[8];
+                        cudaMemcpy(h, d_out, sizeof(h), cudaMemcpyDeviceToHost);
+                        long long mx = 0;
+                        for (int w = 0; w < W; ++w) mx = h[w] > mx ? h[w] : mx;
+                        printf("%-4d %-4d %-3d %-3d %-3d | %8.1f | %8.1f | %d\n", M, N, W, A, mn, (double)mx / L, (double)mx / (L * W),
+                               (M > 128 ? M : 128) * N / 256);
+                    }
+    return 0;
+}

@@ -70,8 +70,7 @@ def test_tc_conv_matches_reference(case):
     assert torch.allclose(sums[cpad:cpad + cout], ref_sq, rtol=1e-4, atol=1e-3)
     # data gradient through the same kernel (flipped / transposed weights)
     eng.agrads[id(y)] = eng.pack(dy.to(DEV))
-    for fn in reversed(eng.tape):
-        fn()
+    eng.run_tape()
     dx = eng.unpack(eng.agrads[id(xa)]).cpu()
     gs = xr.grad.abs().max().item()
     gerr = (dx - xr.grad).abs().max().item()
@@ -140,8 +139,7 @@ def test_tc_conv_concatenated_sources(chans, cout):
     assert torch.allclose(y.sums.cpu()[:cout], yo.double().sum((0, 2, 3, 4)), rtol=1e-4, atol=1e-2 * yr.abs().max().item())
     assert torch.allclose(y.sums.cpu()[cpad:cpad + cout], (yo.double() ** 2).sum((0, 2, 3, 4)), rtol=1e-4, atol=1e-3)
     eng.agrads[id(y)] = eng.pack(dy.to(DEV))
-    for fn in reversed(eng.tape):
-        fn()
+    eng.run_tape()
     for a, r in zip(acts, xr):
         dx = eng.unpack(eng.agrads[id(a)]).cpu()
         assert (dx - r.grad).abs().max().item() <= 1.2e-2 * r.grad.abs().max().item()

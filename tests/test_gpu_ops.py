@@ -87,8 +87,7 @@ def test_conv3d_fwd_bwd(mode, case):
     y = eng.conv(acts, wg, bg, k, [True] * len(acts))
     _close(eng.unpack(y), yr, mode, what="fprop")
     eng.agrads[id(y)] = eng.pack(dy.to(DEV))
-    for fn in reversed(eng.tape):
-        fn()
+    eng.run_tape()
     for a, x in zip(acts, xr):
         _close(eng.unpack(eng.agrads[id(a)]), x.grad, mode, what="dgrad")
     _close(eng.pgrads[id(wg)], wr.grad, mode, what="wgrad")
@@ -117,8 +116,7 @@ def test_convt_fwd_bwd(mode, case):
     y = eng.convt(acts, wg, bg, [True] * len(acts))
     _close(eng.unpack(y), yr, mode, what="convT fprop")
     eng.agrads[id(y)] = eng.pack(dy.to(DEV))
-    for fn in reversed(eng.tape):
-        fn()
+    eng.run_tape()
     for a, x in zip(acts, xr):
         _close(eng.unpack(eng.agrads[id(a)]), x.grad, mode, what="convT dgrad")
     _close(eng.pgrads[id(wg)], wr.grad, mode, what="convT wgrad")
@@ -159,8 +157,7 @@ def test_bn_relu_pool_fwd_bwd(mode, pool, shape):
     assert int(bn_gpu.num_batches_tracked) == 1
     for o, gg in zip(res, gr):
         eng.agrads[id(o)] = eng.pack(gg.to(DEV))
-    for fn in reversed(eng.tape):
-        fn()
+    eng.run_tape()
     if mode == "bf16" and pool:
         # two window entries that round to the same bf16 value may elect a different arg-max than fp32:
         # the routed gradient then lands on the neighbouring voxel (isolated elements, sums unaffected)

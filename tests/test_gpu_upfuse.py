@@ -119,8 +119,7 @@ def _run_stage(mode, case, force):
         assert (a.d, a.h, a.w) == (2 * d, 2 * h, 2 * w)
         ao = eng.unpack(a).cpu()
         eng.agrads[id(a)] = eng.pack(dA.to(DEV))
-        for fn in reversed(eng.tape):
-            fn()
+        eng.run_tape()
         dxs = [eng.unpack(eng.agrads[id(s)]).cpu() for s in acts]
         got = {"ct.w": eng.pgrads[id(ctg.weight)], "ct.b": eng.pgrads[id(ctg.bias)], "cv.w": eng.pgrads[id(cvg.weight)],
                "bn.w": eng.pgrads[id(bng.weight)], "bn.b": eng.pgrads[id(bng.bias)]}
