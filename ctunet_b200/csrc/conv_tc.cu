@@ -151,6 +151,19 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Batched TMEM reads: issue several tcgen05.ld, wait ONCE, then pin the registers behind the wait (an empty volatile
+// asm that "rewrites" them, so no consumer can be scheduled above the wait).  A wait after every load serialises
+// the ~hundreds of cycles of TMEM latency -- measured as the bound of the small-channel epilogues.
+__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld8_pin(uint32_t (&r)[8]) {
+    asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]));
+}
+
 // K-major, no-swizzle shared-memory matrix descriptor (sm_100 version bit set).
 __device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     uint64_t d = (uint64_t)((addr & 0x3FFFFu) >> 4);
@@ -452,15 +465,26 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (stage * TC_WB + te) * p.nt;
                 // P[kd] of input plane pl feeds output plane pl - kd, kept in part[K-1-kd]
+                // all loads of up to two output blocks in flight, one wait
+                constexpr int OBB = COB < 2 ? COB : 2;
 #pragma unroll
-                for (int kd = 0; kd < K; ++kd)
+                for (int ob0b = 0; ob0b < COB; ob0b += OBB) {
+                    uint32_t raw[K][OBB][8];
 #pragma unroll
-                    for (int ob = 0; ob < COB; ++ob) {
-                        float v[8];
-                        tmem_ld8(taddr + kd * CP + ob * 8, v);
+                    for (int kd = 0; kd < K; ++kd)
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) part[K - 1 - kd][ob * 8 + c] += v[c];
-                    }
+                        for (int ob = 0; ob < OBB; ++ob) tmem_ld8_issue(taddr + kd * CP + (ob0b + ob) * 8, raw[kd][ob]);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int kd = 0; kd < K; ++kd)
+#pragma unroll
+                        for (int ob = 0; ob < OBB; ++ob) {
+                            tmem_ld8_pin(raw[kd][ob]);
+#pragma unroll
+                            for (int c = 0; c < 8; ++c)
+                                part[K - 1 - kd][(ob0b + ob) * 8 + c] += __uint_as_float(raw[kd][ob][c]);
+                        }
+                }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(b_aempty + 8 * (stage * TC_WB + te));
@@ -540,8 +564,7 @@ struct TcGeom {
 };
 
 // Ring depth: as deep as a ~100 KB budget allows (two CTAs per SM), at least `min_slots`, at most TC_MAX_SLOTS.
-static uint32_t pick_slots(int min_slots, size_t fixed_bytes, size_t slot_bytes) {
-    const size_t budget = 100 * 1024;
+static uint32_t pick_slots(int min_slots, size_t fixed_bytes, size_t slot_bytes, size_t budget = 100 * 1024) {
     long long ns = fixed_bytes < budget ? (long long)((budget - fixed_bytes) / slot_bytes) : 0;
     if (ns < min_slots) ns = min_slots;
     if (ns > TC_MAX_SLOTS) ns = TC_MAX_SLOTS;
@@ -570,7 +593,8 @@ static bool tc_geometry(int k, int cb, int cout, int h, int w, TcGeom& g) {
         g.wimg_bytes = (uint32_t)g.nm * g.nt * 32;
         const size_t fixed = ((g.wimg_bytes + 1023u) & ~1023u) + ((g.nm * 8 + 15) & ~15) +
                              8 * (2 * TC_MAX_SLOTS + 4 * TC_WB + 2) + 16 + 1024;
-        g.ns = pick_slots(g.ncg > 1 ? 4 : 3, fixed, g.slot_bytes);
+        // the wide-output variants are limited to one CTA per SM by registers: give their ring the whole SM
+        g.ns = pick_slots(g.ncg > 1 ? 4 : 3, fixed, g.slot_bytes, cobg >= 2 ? 200 * 1024 : 100 * 1024);
         g.smem = fixed + (size_t)g.ns * g.slot_bytes;
         if (g.smem > 220 * 1024 && g.ns > 3) {
             g.ns = 3;
@@ -970,7 +994,8 @@ static bool wg_geometry(int k, int cb, int cout, int h, int w, WgGeom& g) {
     // deepen both rings while a ~100 KB budget (two CTAs per SM) allows: more TMA loads in flight
     g.ns = k + 1;
     g.nds = 2;
-    while (g.ns < TC_MAX_SLOTS && g.smem + g.xslot_bytes + g.dyslot_bytes <= 100 * 1024) {
+    const size_t wg_budget = (uint32_t)k2 * g.cbg * g.ng > 256 ? 200 * 1024 : 100 * 1024;   // > 256 TMEM columns: one CTA per SM
+    while (g.ns < TC_MAX_SLOTS && g.smem + g.xslot_bytes + g.dyslot_bytes <= wg_budget) {
         ++g.ns;
         if (g.nds < TC_MAX_SLOTS) ++g.nds;
         g.smem += g.xslot_bytes + g.dyslot_bytes;
