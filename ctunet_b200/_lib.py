@@ -13,7 +13,7 @@ from ctypes import c_char_p, c_double, c_float, c_int, c_longlong, c_void_p
 import torch  # noqa: F401  (loads libcudart / libcuda into the process before our library)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libctunet_b200.so")
+LIB_PATH = os.environ.get("CTUNET_B200_LIB") or os.path.join(_HERE, "libctunet_b200.so")   # override: A/B builds
 
 CTU_F32, CTU_BF16 = 0, 1
 CTU_MAX_SRC = 4

@@ -41,16 +41,18 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const T* __restric
     float acc[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-    const long long s0 = (long long)blockIdx.x * kBnThreads * kStatVoxPerThread;
+    for (long long s0 = (long long)blockIdx.x * kBnThreads * kStatVoxPerThread; s0 < spatial;
+         s0 += (long long)gridDim.x * kBnThreads * kStatVoxPerThread) {
 #pragma unroll 4
-    for (int it = 0; it < kStatVoxPerThread; ++it) {
-        long long s = s0 + (long long)it * kBnThreads + threadIdx.x;
-        if (s < spatial) {
-            V8 v = Vec8<T>::load(base + s * 8);
+        for (int it = 0; it < kStatVoxPerThread; ++it) {
+            long long s = s0 + (long long)it * kBnThreads + threadIdx.x;
+            if (s < spatial) {
+                V8 v = Vec8<T>::load(base + s * 8);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                acc[j] += v.v[j];
-                acc[8 + j] = fmaf(v.v[j], v.v[j], acc[8 + j]);
+                for (int j = 0; j < 8; ++j) {
+                    acc[j] += v.v[j];
+                    acc[8 + j] = fmaf(v.v[j], v.v[j], acc[8 + j]);
+                }
             }
         }
     }
@@ -223,6 +225,7 @@ struct BwdArgs {
     float* dgamma;
     float* dbeta;
     int c, cb, d, h, w;
+    long long nblk;       // chunks of kBnThreads (x kVoxPerThread in mode 0) voxels per (n, block) plane
 };
 
 template <typename T, int MODE, bool APPLY>
@@ -264,8 +267,11 @@ __global__ void __launch_bounds__(kBnThreads) bn_relu_bwd_kernel(BwdArgs p) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) acc[i] = 0.f;
 
+    // (the reduce pass walks several chunks per block: its 16 double atomics per block all hit the same
+    // addresses and serialise at ~1 ns each, so fewer, fatter blocks)
+    for (long long blk = blockIdx.x; blk < p.nblk; blk += gridDim.x) {
     if (MODE == 0) {
-        const long long s0 = (long long)blockIdx.x * kBnThreads * kVoxPerThread + threadIdx.x;
+        const long long s0 = blk * kBnThreads * kVoxPerThread + threadIdx.x;
         V8 yv[kVoxPerThread], g[kVoxPerThread];
 #pragma unroll
         for (int it = 0; it < kVoxPerThread; ++it) {
@@ -298,7 +304,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_relu_bwd_kernel(BwdArgs p) {
     } else {
         const int pd = p.d / 2, ph = p.h / 2, pw = p.w / 2;
         const long long pspatial = (long long)pd * ph * pw;
-        const long long ps = (long long)blockIdx.x * kBnThreads + threadIdx.x;
+        const long long ps = blk * kBnThreads + threadIdx.x;
         if (ps < pspatial) {
             const int px = (int)(ps % pw);
             const int py = (int)((ps / pw) % ph);
@@ -365,6 +371,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_relu_bwd_kernel(BwdArgs p) {
             }
         }
     }
+    }
     if (!APPLY) {
         int cvalid = p.c - b * 8;
         if (cvalid > 8) cvalid = 8;
@@ -386,7 +393,10 @@ int ctu_bn_stats(int dtype, const void* y, int c, int phases, int n, long long s
         set_error("ctu_bn_stats: memset: %s", cudaGetErrorString(e));
         return (int)e;
     }
-    dim3 grid(cdiv(spatial, (long long)kBnThreads * kStatVoxPerThread), phases * cb, n);
+    long long gx = cdiv(spatial, (long long)kBnThreads * kStatVoxPerThread);
+    const long long want = (148 * 4 + (long long)phases * cb * n - 1) / ((long long)phases * cb * n);
+    if (gx > want) gx = want;
+    dim3 grid((unsigned)gx, phases * cb, n);
     CTU_DISPATCH_DTYPE(dtype, (bn_stats_kernel<T><<<grid, kBnThreads, 0, (cudaStream_t)stream>>>((const T*)y, sums, c, cb, spatial)));
     return check_launch("ctu_bn_stats");
 }
@@ -445,7 +455,13 @@ static int bn_bwd(int dtype, BwdArgs& p, int n, bool apply, int y_phase_major, c
         return CTU_ERR_INVALID;
     }
     const int mode = pool ? 1 : (y_phase_major ? 2 : 0);
-    dim3 grid(mode ? cdiv(spatial / 8, kBnThreads) : cdiv(spatial, kBnThreads * kVoxPerThread), p.cb, n);
+    p.nblk = mode ? cdiv(spatial / 8, kBnThreads) : cdiv(spatial, kBnThreads * kVoxPerThread);
+    long long gx = p.nblk;
+    if (!apply) {                                   // reduce pass: about four blocks per SM in total
+        const long long want = (148 * 4 + (long long)p.cb * n - 1) / ((long long)p.cb * n);
+        if (gx > want) gx = want;
+    }
+    dim3 grid((unsigned)gx, p.cb, n);
     CTU_DISPATCH_DTYPE(dtype, {
         if (mode == 1 && apply) bn_relu_bwd_kernel<T, 1, true><<<grid, kBnThreads, 0, stream>>>(p);
         else if (mode == 1) bn_relu_bwd_kernel<T, 1, false><<<grid, kBnThreads, 0, stream>>>(p);

@@ -47,7 +47,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
+#ifdef CTU_DBG_TESTWAIT
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+#else
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+#endif
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
         : "r"(bar), "r"(parity)
@@ -62,8 +66,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+#ifdef CTU_DBG_NOFENCE
+__device__ __forceinline__ void tc_fence_before() {}
+__device__ __forceinline__ void tc_fence_after() {}
+#else
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+#endif
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
                                             uint32_t bar) {
@@ -134,6 +143,10 @@ __device__ __forceinline__ void umma_bf16_lead(uint32_t leader, uint32_t d_tmem,
         : "memory");
 }
 __device__ __forceinline__ void umma_commit_lead(uint32_t leader, uint32_t bar) {
+#ifdef CTU_DBG_NOCOMMIT
+    if (leader) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+    return;
+#endif
     asm volatile(
         "{\n\t.reg .pred q;\n\t"
         "setp.ne.b32 q, %0, 0;\n\t"
@@ -300,6 +313,7 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
     const uint32_t b_full = s_bar, b_empty = s_bar + 8 * TC_MAX_SLOTS, b_afull = s_bar + 16 * TC_MAX_SLOTS,
                    b_aempty = b_afull + 8 * 2 * TC_WB, b_w = b_aempty + 8 * 2 * TC_WB;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (b_w + 8 - s_base));
+    float* st_red = reinterpret_cast<float*>(smem + (b_w + 32 - s_base));   // [4*TC_WB epilogue warps][NSLOT*16]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -349,8 +363,13 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
                         const int b0 = g * p.cbg;
                         const int gb = (p.cb - b0) < p.cbg ? (p.cb - b0) : p.cbg;
                         mbar_wait(b_empty + 8 * pr.slot, pr.phase ^ 1);
+#ifdef CTU_DBG_NOTMA
+                        mbar_arrive(b_full + 8 * pr.slot);
+                        for (int b = 0; b < 0; ++b) {
+#else
                         mbar_expect_tx(b_full + 8 * pr.slot, (uint32_t)gb * HH * WW * 16);
                         for (int b = 0; b < gb; ++b) {
+#endif
                             int s = 0;
 #pragma unroll
                             for (int q = 1; q < CTU_MAX_SRC; ++q)
@@ -403,6 +422,9 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
                             for (int tp = 0; tp < K2; ++tp) {
                                 const uint32_t a_tap = a16 + (tp / K) * (ROW >> 4) + (tp % K);
                                 for (int pr = 0; pr < pairs; ++pr) {
+#ifdef CTU_DBG_NOMMA
+                                    if (p.cb == 12345)
+#endif
                                     umma_bf16_lead(leader, d_tmem, (a_tap + 2u * pr * plane16) | lbo_pair, a_hi, b_lo, b_hi,
                                                    idesc, acc);
                                     acc = 1;
@@ -418,6 +440,9 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
                                 constexpr uint32_t R16 = ROW >> 4;
                                 const int t0 = 2 * j, t1 = (2 * j + 1 < K2) ? 2 * j + 1 : 2 * j;
                                 const uint32_t o0 = (t0 / K) * R16 + (t0 % K), o1 = (t1 / K) * R16 + (t1 % K);
+#ifdef CTU_DBG_NOMMA
+                                if (p.cb == 12345)
+#endif
                                 umma_bf16_lead(leader, d_tmem, (a_blk + o0) | ((o1 - o0) << 16), a_hi, b_lo, b_hi, idesc, acc);
                                 acc = 1;
                                 b_lo += bstep;
@@ -467,8 +492,13 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
                 // P[kd] of input plane pl feeds output plane pl - kd, kept in part[K-1-kd]
                 // all loads of up to two output blocks in flight, one wait
                 constexpr int OBB = COB < 2 ? COB : 2;
+#ifdef CTU_DBG_NOEPI
+                if (taddr == 0xffffffffu) part[0][0] += 1.f;
+                for (int ob0b = 0; ob0b < 0; ob0b += OBB) {
+#else
 #pragma unroll
                 for (int ob0b = 0; ob0b < COB; ob0b += OBB) {
+#endif
                     uint32_t raw[K][OBB][8];
 #pragma unroll
                     for (int kd = 0; kd < K; ++kd)
@@ -502,7 +532,11 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
                             o.v[c] = round_to<__nv_bfloat16>(v);
                         }
                         if (inb && ob < nob) {
+#ifndef CTU_DBG_NOSTORE
                             Vec8<__nv_bfloat16>::store(ycol + ((long long)ob * plane + (long long)gz * p.h * p.w) * 8, o);
+#else
+                            if (o.v[0] == 1234.567f) Vec8<__nv_bfloat16>::store(ycol, o);
+#endif
                             if (want_stats) {
 #pragma unroll
                                 for (int c = 0; c < 8; ++c) {
@@ -522,16 +556,15 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
             }
         }
         if (want_stats) {
-            // accumulator slot s holds the output blocks ob0 + s, ob0 + s + NSLOT, ...: all the same natural block
-            // (the host only fuses the statistics when that holds)
-            const int cpn = p.cobo * 8;
+            // warp totals -> shared memory; one atomic per channel and CTA after the teardown barrier (same-address
+            // double atomics from every warp of every CTA serialise at ~1 ns each: tens of microseconds of tail)
+            float* red = st_red + (warp - 1 - TC_WB) * (NSLOT * 16);
 #pragma unroll
             for (int i = 0; i < NSLOT * 8; ++i) {
                 const float a1 = warp_sum(s1[i]), a2 = warp_sum(s2[i]);
-                const int ch = ((ob0 + (i >> 3)) % p.cobo) * 8 + (i & 7);
-                if (lane == 0 && (i >> 3) < nob && ch < p.cstat) {
-                    atomicAdd(p.stats + ch, (double)a1);
-                    atomicAdd(p.stats + cpn + ch, (double)a2);
+                if (lane == 0) {
+                    red[i] = a1;
+                    red[NSLOT * 8 + i] = a2;
                 }
             }
         }
@@ -539,6 +572,20 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
     // ------------------------------------------------------------------------- teardown
     tc_fence_before();
     __syncthreads();
+    if (p.stats != nullptr && threadIdx.x < NSLOT * 16) {
+        // accumulator slot s holds the output blocks ob0 + s, ob0 + s + NSLOT, ...: all the same natural block
+        // (the host only fuses the statistics when that holds)
+        const int i = threadIdx.x % (NSLOT * 8), q = threadIdx.x / (NSLOT * 8);     // q: 0 = sum, 1 = sum of squares
+        const int ob0 = blockIdx.y * COB;
+        const int nob = (p.cob_n - ob0) < COB ? (p.cob_n - ob0) : COB;
+        const int ch = ((ob0 + (i >> 3)) % p.cobo) * 8 + (i & 7);
+        if ((i >> 3) < nob && ch < p.cstat) {
+            double tot = 0.0;
+#pragma unroll
+            for (int wq = 0; wq < 4 * TC_WB; ++wq) tot += (double)st_red[wq * (NSLOT * 16) + q * (NSLOT * 8) + i];
+            atomicAdd(p.stats + q * (p.cobo * 8) + ch, tot);
+        }
+    }
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
     }
@@ -592,7 +639,7 @@ static bool tc_geometry(int k, int cb, int cout, int h, int w, TcGeom& g) {
         g.nt = (k * cobg * 8 + 15) / 16 * 16;
         g.wimg_bytes = (uint32_t)g.nm * g.nt * 32;
         const size_t fixed = ((g.wimg_bytes + 1023u) & ~1023u) + ((g.nm * 8 + 15) & ~15) +
-                             8 * (2 * TC_MAX_SLOTS + 4 * TC_WB + 2) + 16 + 1024;
+                             8 * (2 * TC_MAX_SLOTS + 4 * TC_WB + 2) + 32 + 4 * TC_WB * 32 * 4 + 1024;
         // the wide-output variants are limited to one CTA per SM by registers: give their ring the whole SM
         g.ns = pick_slots(g.ncg > 1 ? 4 : 3, fixed, g.slot_bytes, cobg >= 2 ? 200 * 1024 : 100 * 1024);
         g.smem = fixed + (size_t)g.ns * g.slot_bytes;
@@ -706,10 +753,17 @@ int conv3d_fprop_tc(const void* const* h_srcs, const int* h_src_channels, int ns
         // persistent grid = exactly the CTAs that are resident at once (registers limit the wide-output variants
         // to one per SM); one grid row per group of COB output blocks -- all rows stream the same input planes, so
         // their re-reads hit L2
-        int occ = 1;
+        // (shared memory and TMEM give ctas_per_sm; the register file is accounted for here -- the occupancy API
+        // was observed to answer 1 where two CTAs do become resident)
+        int occ = ctas_per_sm;
+        cudaFuncAttributes fa;
+        if (cudaFuncGetAttributes(&fa, kern) == cudaSuccess && fa.numRegs > 0) {
+            const int regs_per_warp = (fa.numRegs * 32 + 255) / 256 * 256;
+            const int by_regs = 65536 / (regs_per_warp * (threads / 32));
+            if (occ > by_regs) occ = by_regs;
+        }
+        if (occ < 1) occ = 1;
         cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, g.smem) != cudaSuccess || occ < 1) occ = 1;
-        if (occ > ctas_per_sm) occ = ctas_per_sm;
         // d-chunk: about three work items per resident CTA (load balance), but at least 8 planes per chunk
         // (every chunk re-reads K-1 halo planes)
         int dc = d;

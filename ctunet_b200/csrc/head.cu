@@ -338,7 +338,8 @@ static int head_bwd_launch(const HeadParams& p, cudaStream_t stream) {
     const int cbt = p.m.cb_total;
     const int nv = CO * cbt * 8 + CO;
     const size_t smem = (size_t)(CO * cbt * 8 + 8 + (kHeadThreads / 32) * nv) * sizeof(float);
-    const int grid = head_grid((long long)p.n * p.spatial);
+    int grid = head_grid((long long)p.n * p.spatial);
+    if (grid > 148 * 2) grid = 148 * 2;     // every block ends with CO*(Cin+1) same-address atomics: keep the tail short
     switch (cbt) {
         case 1: head_bwd_kernel<T, CO, 1><<<grid, kHeadThreads, smem, stream>>>(p); break;
         case 2: head_bwd_kernel<T, CO, 2><<<grid, kHeadThreads, smem, stream>>>(p); break;

@@ -83,7 +83,68 @@ __global__ void bench(int M, int N, int W, int A, int L, int mn_major, long long
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
+// Commit cost: every iteration issues `nm` MMAs (M=128, N=32) and `nc` tcgen05.commit onto mbarriers with a huge
+// arrival count (never waited on inside the loop).
+__global__ void bench_commit(int W, int nm, int nc, int L, long long* out) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ uint64_t bars[8];
+    __shared__ uint32_t tmem_slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 64 * 1024 / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 8; ++i)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bars[i])), "r"(i < 4 ? 1 : 1000000) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+    if (warp < W) {
+        const uint32_t leader = elect_one();
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t base = smem_u32(smem) >> 4;
+        const uint32_t ahi = 16u | (1u << 14), bhi = 16u | (1u << 14);
+        const uint32_t alo = (base + warp * 64) | (8u << 16), blo = (base + 2048) | (8u << 16);
+        long long t0 = clock64();
+        for (int i = 0; i < L; ++i) {
+            for (int m = 0; m < nm; ++m) mma(leader, tmem + warp * 32, alo + m * 2, ahi, blo, bhi, idesc, (i | m) ? 1u : 0u);
+            for (int c = 0; c < nc; ++c) commit(leader, smem_u32(&bars[4 + ((warp + c) & 3)]));
+        }
+        commit(leader, smem_u32(&bars[warp]));
+        mbar_wait(smem_u32(&bars[warp]), 0);
+        long long t1 = clock64();
+        if (lane == 0 && blockIdx.x == 0) out[warp] = t1 - t0;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
 int main() {
+    {
+        long long* d_o;
+        cudaMalloc(&d_o, 8 * sizeof(long long));
+        cudaFuncSetAttribute(bench_commit, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        printf("commit cost: W warps, nm MMAs (M=128,N=32) + nc commits per iteration -> cycles per iteration (max over warps)\n");
+        for (int W = 1; W <= 4; W *= 2)
+            for (int nm = 0; nm <= 5; nm += 5)
+                for (int nc = 0; nc <= 2; ++nc) {
+                    if (nm == 0 && nc == 0) continue;
+                    bench_commit<<<1, 128, 64 * 1024>>>(W, nm, nc, 2000, d_o);
+                    if (cudaDeviceSynchronize() != cudaSuccess) { printf("commit bench failed\n"); return 1; }
+                    long long h[8];
+                    cudaMemcpy(h, d_o, sizeof(h), cudaMemcpyDeviceToHost);
+                    long long mx = 0;
+                    for (int w = 0; w < W; ++w) mx = h[w] > mx ? h[w] : mx;
+                    printf("W=%d nm=%d nc=%d : %8.1f cycles/iter\n", W, nm, nc, (double)mx / 2000);
+                }
+    }
     long long* d_out;
     cudaMalloc(&d_out, 8 * sizeof(long long));
     cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
