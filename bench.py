@@ -40,7 +40,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
-                    help="capture the training step in a CUDA graph (auto: on for a single GPU)")
+                    help="capture the training step in CUDA graphs (auto = on; data parallel: two graphs around one eager "
+                         "NCCL all-reduce of the flat gradient buffer)")
     return ap.parse_args()
 
 
@@ -265,6 +266,16 @@ def describe(name, args, esize):
     return name, 0.0, 0.0
 
 
+def ncu_traffic():
+    """{kernel key: dram__bytes_read.sum + dram__bytes_write.sum per launch} from profiles/ncu_traffic.json (written by
+    hand from the ncu --set full captures under profiles/; a kernel that was not captured reports null)."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        return json.load(open(path))
+    except (OSError, ValueError):
+        return {}
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(path):
@@ -300,8 +311,8 @@ def run_b200_arm(a):
     C.set_compute_dtype(a.dtype)
     torch.manual_seed(0)
     net = getattr(C, a.model)().to(dev)
-    sync = GradSync(net) if world > 1 else None
-    use_graph = a.graph == "on" or (a.graph == "auto" and world == 1)
+    use_graph = a.graph != "off"
+    sync = GradSync(net, deferred=use_graph) if world > 1 else None
     step = TrainStep(net, HANDLER[a.model], 1.0, 1.0, lr=1e-4, grad_sync=sync, graph=use_graph)
     cin = in_channels(a.model)
     img, (sk_t, fl_t) = make_training_batch(a.batch, cin, a.size, seed=1234 + 1000 * rank, device=dev)
@@ -351,10 +362,15 @@ def run_b200_arm(a):
     import ctunet_b200.losses as LS
     E.call = LS.call = timed_call
     eager_step = TrainStep(net, HANDLER[a.model], 1.0, 1.0, lr=1e-4, grad_sync=sync) if use_graph else step
+    # one stream for this pass: with the weight-gradient / weight-preparation side streams the kernels overlap and an
+    # event pair would time the overlap, not the kernel
+    flags = (E.WGRAD_ASYNC, E.WEIGHT_PREP_ASYNC)
+    E.WGRAD_ASYNC = E.WEIGHT_PREP_ASYNC = False
     try:
         timed(lambda: eager_step(img, target), a.steps)
     finally:
         E.call = LS.call = orig
+        E.WGRAD_ASYNC, E.WEIGHT_PREP_ASYNC = flags
         net._grad_sink = sync
 
     # ---- end-to-end steps: pinned host -> device every iteration, loss read back ----------------
@@ -417,7 +433,7 @@ def run_b200_arm(a):
         else:
             roof = {"bound": "hbm", "achieved": by / avg_s / 1e9, "peak": peaks["hbm"], "unit": "GB/s"}
         roof["frac"] = roof["achieved"] / roof["peak"]
-        roof["traffic"] = None
+        roof["traffic"] = ncu_traffic().get(key)          # dram bytes per launch from the committed ncu --set full capture
         roof["kernel"] = key
         roof["avg_launch_ms"] = ms / cnt
         roof["launches_per_step"] = cnt / a.steps

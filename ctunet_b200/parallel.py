@@ -21,11 +21,16 @@ import torch.distributed as dist
 
 
 class GradSync:
-    def __init__(self, module: torch.nn.Module, process_group=None, n_buckets: int = 3, skip_prefixes=("cblock.",)):
+    def __init__(self, module: torch.nn.Module, process_group=None, n_buckets: int = 3, skip_prefixes=("cblock.",),
+                 deferred: bool = False):
         """``skip_prefixes``: parameters that never receive a gradient (the generic UNet's discarded
         center block, models.py:241) -- they are left with ``grad = None`` exactly like the reference."""
         self.module = module
         self.group = process_group
+        # deferred: no bucket is reduced while the backward pass runs; finish() reduces the whole flat buffer in one
+        # call.  Used by the CUDA-graph step (trainer.py): forward+backward and the optimizer are two captured graphs
+        # with ONE eager NCCL all-reduce (4.6 MB for UNetSP) between them.
+        self.deferred = bool(deferred)
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         named = [(n, p) for n, p in module.named_parameters() if p.requires_grad]
         if type(module).__name__ in ("recAE_v2_fixed", "UNet4_2IC"):
@@ -73,7 +78,7 @@ class GradSync:
         if self.cuda:                                      # gradients of one bucket may come from several streams
             self._producers[bi].add(torch.cuda.current_stream())
         self._remaining[bi] -= 1
-        if self._remaining[bi] == 0:
+        if self._remaining[bi] == 0 and not self.deferred:
             self._launch(bi)
 
     # -- step protocol ---------------------------------------------------------------------------
@@ -96,12 +101,34 @@ class GradSync:
             h = dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
             self._handles.append((h, view))
 
-    def finish(self) -> None:
-        """Make the averaged gradients visible to the optimizer (current stream) and publish them as
-        ``param.grad`` views of the flat buffer."""
+    def check_complete(self) -> None:
         if any(r != 0 for r in self._remaining):
             missing = [n for n, p in zip(self.names, self.params) if self._remaining[self.bucket_of[id(p)]] != 0]
             raise RuntimeError("gradient sync: some gradients were never produced, e.g. %s" % missing[:3])
+
+    def reduce_all(self) -> None:
+        """One all-reduce (average) of the whole flat buffer on the current stream (deferred mode)."""
+        if self.world > 1:
+            if self.cuda:
+                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
+            else:
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+                self.flat.div_(self.world)
+
+    def publish(self) -> None:
+        """``param.grad`` = view of the flat buffer."""
+        for p in self.params:
+            p.grad = self.slices[id(p)]
+
+    def finish(self) -> None:
+        """Make the averaged gradients visible to the optimizer (current stream) and publish them as
+        ``param.grad`` views of the flat buffer."""
+        self.check_complete()
+        if self.deferred:
+            self.reduce_all()
+            self.publish()
+            self.begin_step()
+            return
         if self.cuda:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
         for h, view in self._handles:

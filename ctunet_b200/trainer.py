@@ -40,6 +40,7 @@ class TrainStep:
         params = list(model.parameters())
         self.graph = bool(graph)
         self._graph = None
+        self._graph_opt = None
         self._static = None
         self._static_out = None
         self._calls = 0
@@ -95,12 +96,41 @@ class TrainStep:
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             l0 = _lib.launches
-            with torch.cuda.graph(g):                         # records the launches; nothing executes here
-                self._static_out = self._eager(st_img, st_tgt)
+            if self.grad_sync is None:
+                with torch.cuda.graph(g):                     # records the launches; nothing executes here
+                    self._static_out = self._eager(st_img, st_tgt)
+            else:
+                # data parallel: graph 1 = forward + loss + backward (gradients land in the flat buffer), ONE eager
+                # NCCL all-reduce of that buffer, graph 2 = optimizer step on views of the flat buffer
+                if not self.grad_sync.deferred:
+                    raise RuntimeError("graph mode needs GradSync(deferred=True)")
+                with torch.cuda.graph(g):
+                    self._static_out = self._forward_backward(st_img, st_tgt)
+                self.grad_sync.check_complete()
+                self.grad_sync.begin_step()
+                self.grad_sync.publish()
+                g2 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g2, pool=g.pool()):
+                    self.optimizer.step()
+                self._graph_opt = g2
+                for p in self.model.parameters():
+                    p.grad = None
             self.launches_per_step = _lib.launches - l0
             self._graph = g
         self._graph.replay()
+        if self.grad_sync is not None:
+            self.grad_sync.reduce_all()
+            self._graph_opt.replay()
         return self._static_out
+
+    def _forward_backward(self, image: torch.Tensor, target):
+        self.model.train()
+        if self.input_requires_grad:
+            image = image.detach().requires_grad_()
+        out = self.model(image)
+        total, comps = self.loss(out, target)
+        total.backward()
+        return comps
 
     def _eager(self, image: torch.Tensor, target):
         self.model.train()

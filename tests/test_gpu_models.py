@@ -359,3 +359,31 @@ def test_cuda_graph_step_matches_eager_step(mode, size):
             # differences of up to lr per step on near-zero gradients: 5 steps x 1e-3
             assert float((sa[k] - sb[k]).abs().max()) <= (5e-3 if mode == "fp32" else 1e-2), k
             assert float((sa[k] - sb[k]).abs().mean()) <= (2e-4 if mode == "fp32" else 1.5e-3), k
+
+
+def test_data_parallel_graph_step_world1_matches_plain_step(tmp_path):
+    """The data-parallel CUDA-graph step (graph 1: forward+backward into the flat gradient buffer, one eager NCCL
+    all-reduce, graph 2: optimizer) on a single-rank NCCL group reproduces the plain eager step."""
+    import torch.distributed as dist
+    from ctunet_b200.parallel import GradSync
+    from ctunet_b200.trainer import TrainStep
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", init_method="file://%s" % (tmp_path / "rdv"), rank=0, world_size=1,
+                                device_id=torch.device(DEV, 0))
+    try:
+        torch.manual_seed(0)
+        ref = _build("UNetSP", "fp32").to(DEV).train()
+        torch.manual_seed(0)
+        net = _build("UNetSP", "fp32").to(DEV).train()
+        s_ref = TrainStep(ref, "double", 1.0, 1.0, lr=1e-3)
+        s_ddp = TrainStep(net, "double", 1.0, 1.0, lr=1e-3, grad_sync=GradSync(net, deferred=True), graph=True)
+        for it in range(4):
+            x = _x(2, 16, 40 + it, 2).to(DEV)
+            sk_t, fl_t = _targets(2, 16, 50 + it)
+            a = s_ref(x, (sk_t.to(DEV), fl_t.to(DEV))).tolist()
+            b = s_ddp(x, (sk_t.to(DEV), fl_t.to(DEV))).tolist()
+            assert a == pytest.approx(b, rel=2e-4, abs=2e-4), it
+        assert s_ddp._graph is not None and s_ddp._graph_opt is not None
+        assert net.cblock.block[0].weight.grad is None
+    finally:
+        dist.destroy_process_group()

@@ -64,6 +64,15 @@ def _worker(rank, world, port, q):
             results.append(False)
         except RuntimeError:
             results.append(True)
+        # deferred mode (the CUDA-graph step): nothing is reduced while gradients arrive, finish() reduces once
+        dsync = GradSync(net, n_buckets=2, deferred=True)
+        for i, p in enumerate(reversed(live)):
+            dsync.buffer_for(p).copy_(torch.full_like(p, float(10 * rank + i)))
+            dsync.delivered(p)
+        assert not dsync._handles
+        dsync.finish()
+        results.append(all(torch.allclose(p.grad, torch.full_like(p, sum(10.0 * r + i for r in range(world)) / world))
+                           for i, p in enumerate(reversed(live))))
         lo, hi = shard_range(7, rank, world)
         q.put((rank, results, (lo, hi)))
     finally:
