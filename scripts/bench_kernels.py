@@ -83,3 +83,28 @@ for name, chans, cout, n, d, h, w in SHAPES:
         else:
             line += " dgrad %8.1f us" % fprop([cout], chans[0], n, d, h, w)
     print(line, flush=True)
+
+
+def bn_bwd(c, n, d, h, w, pool=False, pm=False):
+    y = act(n, c * (8 if pm else 1) if pm else c, d // (2 if pm else 1), h // (2 if pm else 1), w // (2 if pm else 1)) if pm else act(n, c, d, h, w)
+    dA = act(n, c, d, h, w)
+    dP = act(n, c, d // 2, h // 2, w // 2) if pool else None
+    dy = torch.empty_like(y)
+    cpad = (c + 7) // 8 * 8
+    ss = torch.rand(4 * cpad, device=dev)
+    gamma = torch.rand(cpad, device=dev)
+    sums2 = torch.zeros(2 * cpad, dtype=torch.float64, device=dev)
+    dg, db = torch.empty(cpad, device=dev), torch.empty(cpad, device=dev)
+    pA, pP = dA.data_ptr(), (dP.data_ptr() if pool else None)
+    r = timeit(lambda: call("ctu_bn_relu_bwd_reduce", 1, y.data_ptr(), ss.data_ptr(), pA, pP, sums2.data_ptr(), c, n, d, h, w,
+                            int(pm), stream_ptr()))
+    a = timeit(lambda: call("ctu_bn_relu_bwd_apply", 1, y.data_ptr(), ss.data_ptr(), gamma.data_ptr(), pA, pP, sums2.data_ptr(),
+                            float(n * d * h * w), dy.data_ptr(), dg.data_ptr(), db.data_ptr(), c, n, d, h, w, int(pm),
+                            stream_ptr()))
+    return r, a
+
+
+if which in ("bn", "both"):
+    for name, kw in (("plain", {}), ("pool", {"pool": True}), ("phase-major", {"pm": True})):
+        r, a = bn_bwd(7, 4, 128, 128, 128, **kw)
+        print("BN bwd c7 @4x128^3 %-12s reduce %7.1f us  apply %7.1f us" % (name, r, a), flush=True)

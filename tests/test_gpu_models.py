@@ -353,7 +353,8 @@ def test_cuda_graph_step_matches_eager_step(mode, size):
         if k.endswith("num_batches_tracked"):
             assert int(sa[k]) == int(sb[k]), k
         elif "running" in k:
-            assert torch.allclose(sa[k], sb[k], rtol=50 * tol, atol=50 * tol * float(sa[k].abs().max()) + 1e-6), k
+            # (the two runs follow slightly different Adam trajectories, see below: statistics agree to a few percent)
+            assert torch.allclose(sa[k], sb[k], rtol=5e-2, atol=2e-2 * float(sa[k].abs().max()) + 1e-6), k
         elif not k.startswith("cblock"):
             # Adam's normalised update turns rounding-level gradient differences (atomic accumulation order) into
             # differences of up to lr per step on near-zero gradients: 5 steps x 1e-3
