@@ -364,13 +364,13 @@ def run_b200_arm(a):
     eager_step = TrainStep(net, HANDLER[a.model], 1.0, 1.0, lr=1e-4, grad_sync=sync) if use_graph else step
     # one stream for this pass: with the weight-gradient / weight-preparation side streams the kernels overlap and an
     # event pair would time the overlap, not the kernel
-    flags = (E.WGRAD_ASYNC, E.WEIGHT_PREP_ASYNC)
-    E.WGRAD_ASYNC = E.WEIGHT_PREP_ASYNC = False
+    flags = (E.WGRAD_ASYNC, E.WEIGHT_PREP_ASYNC, E.DEAD_BRANCH_ASYNC)
+    E.WGRAD_ASYNC = E.WEIGHT_PREP_ASYNC = E.DEAD_BRANCH_ASYNC = False
     try:
         timed(lambda: eager_step(img, target), a.steps)
     finally:
         E.call = LS.call = orig
-        E.WGRAD_ASYNC, E.WEIGHT_PREP_ASYNC = flags
+        E.WGRAD_ASYNC, E.WEIGHT_PREP_ASYNC, E.DEAD_BRANCH_ASYNC = flags
         net._grad_sink = sync
 
     # ---- end-to-end steps: pinned host -> device every iteration, loss read back ----------------

@@ -38,6 +38,8 @@ _ONES = {}
 WEIGHT_PREP_ASYNC = True
 # Weight gradients run on a second stream, overlapping the rest of the backward chain (Engine._conv_bwd).
 WGRAD_ASYNC = True
+# The discarded center block of the generic UNet runs on a third stream (Engine.off_critical_path).
+DEAD_BRANCH_ASYNC = True
 _SIDE = {}
 
 
@@ -95,6 +97,7 @@ class Engine:
         self._pi = 0
         self._side = None
         self._wgrad_stream = None
+        self._dead_stream = None
 
     # ------------------------------------------------------------------ weight preparation on a side stream
     def begin(self, store: dict, key) -> None:
@@ -126,12 +129,29 @@ class Engine:
                 self._results.append((tag, out, ev))
 
     def end_forward(self) -> None:
-        """Publish a freshly recorded plan / join the side stream (required before a graph capture ends)."""
+        """Publish a freshly recorded plan / join the side streams (required before a graph capture ends)."""
         if self._recording:
             self._store[self._key] = self._plan
             self._recording = False
         elif self._side is not None:
             torch.cuda.current_stream().wait_stream(self._side)
+        if self._dead_stream is not None:
+            torch.cuda.current_stream().wait_stream(self._dead_stream)
+            self._dead_stream = None
+
+    def off_critical_path(self, *inputs: "Act"):
+        """Context: run stages whose OUTPUT nobody consumes (the generic UNet's discarded center block,
+        models.py:238-241 -- only its BatchNorm buffers matter) on their own stream, beside the decoder."""
+        import contextlib
+        if not DEAD_BRANCH_ASYNC:
+            return contextlib.nullcontext()
+        main = torch.cuda.current_stream()
+        side = _side_stream(self.device, 2)
+        side.wait_stream(main)
+        for a in inputs:
+            a.buf.record_stream(side)
+        self._dead_stream = side
+        return torch.cuda.stream(side)
 
     def _prepared(self, tag: str, fn):
         """``fn(engine) -> tuple of tensors`` computed from parameters and static shapes only."""

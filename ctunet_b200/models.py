@@ -282,10 +282,11 @@ class UNet(_FusedNet):
             # discarded: no gradient ever reaches it.
             rec, eng.record = eng.record, False
             seq = self.cblock.block
-            y = eng.conv([cur], seq[0].weight, seq[0].bias, k, [False], True)
-            a = eng.bn_relu(y, seq[1], True)
-            y = eng.conv([a], seq[3].weight, seq[3].bias, k, [False], True)
-            eng.bn_relu(y, seq[4], True)
+            with eng.off_critical_path(cur):
+                y = eng.conv([cur], seq[0].weight, seq[0].bias, k, [False], True)
+                a = eng.bn_relu(y, seq[1], True)
+                y = eng.conv([a], seq[3].weight, seq[3].bias, k, [False], True)
+                eng.bn_relu(y, seq[4], True)
             eng.record = rec
         srcs = [cur]
         for i, blk in enumerate(self.u_blocks):
