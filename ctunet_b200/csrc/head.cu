@@ -160,7 +160,10 @@ __global__ void __launch_bounds__(kHeadThreads) head_fwd_kernel(HeadParams p) {
     }
 }
 
-template <typename T, int CO, int CBT>
+// PART 0: source gradients and parameter gradients; 1: source gradients only (the critical path of the backward
+// pass); 2: parameter gradients only (a leaf: the engine runs it beside the weight gradients).  The 48+ per-thread
+// dW accumulators are what limits occupancy, so the split halves the latency of the part the decoder waits for.
+template <typename T, int CO, int CBT, int PART>
 __global__ void __launch_bounds__(kHeadThreads) head_bwd_kernel(HeadParams p) {
     extern __shared__ float hsm[];
     float* wsm = hsm;
@@ -244,6 +247,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_bwd_kernel(HeadParams p) {
             for (int o = 0; o < CO; ++o) dlc[o] = dsm[o];
         }
         // parameter gradients (per-thread partials) and source gradients
+        if (PART != 2) {
 #pragma unroll
         for (int c = 0; c < CBT; ++c) {
             const int q = head_block_source(p, c);
@@ -259,6 +263,8 @@ __global__ void __launch_bounds__(kHeadThreads) head_bwd_kernel(HeadParams p) {
             }
             if (dp != nullptr) Vec8<T>::store(dp + (((long long)n * p.src_cb[q] + b) * p.spatial + s) * 8, g);
         }
+        }
+        if (PART != 1) {
 #pragma unroll
         for (int o = 0; o < CO; ++o) {
             gb[o] += dlc[o];
@@ -267,7 +273,9 @@ __global__ void __launch_bounds__(kHeadThreads) head_bwd_kernel(HeadParams p) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) gw[o][c * 8 + j] = fmaf(dlc[o], xs[c].v[j], gw[o][c * 8 + j]);
         }
+        }
     }
+    if (PART == 1) return;
     // block reduction of the CO*(CBT*8+1) partials, then one atomic each
     constexpr int NV = CO * CBT * 8 + CO;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -333,20 +341,27 @@ static int head_fwd_launch(const HeadParams& p, int grid, size_t smem, cudaStrea
     return check_launch("ctu_head_fwd");
 }
 
-template <typename T, int CO>
-static int head_bwd_launch(const HeadParams& p, cudaStream_t stream) {
+template <typename T, int CO, int PART>
+static int head_bwd_launch_part(const HeadParams& p, cudaStream_t stream) {
     const int cbt = p.m.cb_total;
     const int nv = CO * cbt * 8 + CO;
     const size_t smem = (size_t)(CO * cbt * 8 + 8 + (kHeadThreads / 32) * nv) * sizeof(float);
     int grid = head_grid((long long)p.n * p.spatial);
-    if (grid > 148 * 2) grid = 148 * 2;     // every block ends with CO*(Cin+1) same-address atomics: keep the tail short
+    if (PART != 1 && grid > 148 * 2) grid = 148 * 2;   // every block ends with CO*(Cin+1) same-address atomics
     switch (cbt) {
-        case 1: head_bwd_kernel<T, CO, 1><<<grid, kHeadThreads, smem, stream>>>(p); break;
-        case 2: head_bwd_kernel<T, CO, 2><<<grid, kHeadThreads, smem, stream>>>(p); break;
-        case 3: head_bwd_kernel<T, CO, 3><<<grid, kHeadThreads, smem, stream>>>(p); break;
-        default: head_bwd_kernel<T, CO, 4><<<grid, kHeadThreads, smem, stream>>>(p); break;
+        case 1: head_bwd_kernel<T, CO, 1, PART><<<grid, kHeadThreads, smem, stream>>>(p); break;
+        case 2: head_bwd_kernel<T, CO, 2, PART><<<grid, kHeadThreads, smem, stream>>>(p); break;
+        case 3: head_bwd_kernel<T, CO, 3, PART><<<grid, kHeadThreads, smem, stream>>>(p); break;
+        default: head_bwd_kernel<T, CO, 4, PART><<<grid, kHeadThreads, smem, stream>>>(p); break;
     }
     return check_launch("ctu_head_bwd");
+}
+
+template <typename T, int CO>
+static int head_bwd_launch(const HeadParams& p, int part, cudaStream_t stream) {
+    if (part == 1) return head_bwd_launch_part<T, CO, 1>(p, stream);
+    if (part == 2) return head_bwd_launch_part<T, CO, 2>(p, stream);
+    return head_bwd_launch_part<T, CO, 0>(p, stream);
 }
 
 }  // namespace ctu
@@ -386,21 +401,30 @@ int ctu_head_bwd(int dtype, const void* const* h_srcs, const int* h_src_channels
     int rc = head_setup(p, h_srcs, h_src_channels, nsrc, w, bias, cout, flags, n, spatial, "ctu_head_bwd");
     if (rc != CTU_OK) return rc;
     const bool sp = (flags & (CTU_HEAD_SP | CTU_HEAD_SP_SOFTMAX)) != 0;
-    CTU_REQUIRE(dw && db && (sp ? (dout0 || dout1) : dout0 != nullptr), "ctu_head_bwd: missing gradient buffers");
-    for (int i = 0; i < nsrc; ++i) p.dsrc[i] = h_dsrcs ? h_dsrcs[i] : nullptr;
+    CTU_REQUIRE((dw != nullptr) == (db != nullptr) && (sp ? (dout0 || dout1) : dout0 != nullptr),
+                "ctu_head_bwd: missing gradient buffers");
+    bool any_dsrc = false;
+    for (int i = 0; i < nsrc; ++i) {
+        p.dsrc[i] = h_dsrcs ? h_dsrcs[i] : nullptr;
+        any_dsrc = any_dsrc || p.dsrc[i] != nullptr;
+    }
+    CTU_REQUIRE(dw != nullptr || any_dsrc, "ctu_head_bwd: nothing to compute");
+    const int part = dw == nullptr ? 1 : (any_dsrc ? 0 : 2);
     p.dout0 = dout0; p.dout1 = dout1; p.dw = dw; p.db = db;
-    cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * cout * p.m.c_total, (cudaStream_t)stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(db, 0, sizeof(float) * cout, (cudaStream_t)stream);
-    if (e != cudaSuccess) {
-        set_error("ctu_head_bwd: memset: %s", cudaGetErrorString(e));
-        return (int)e;
+    if (dw != nullptr) {
+        cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * cout * p.m.c_total, (cudaStream_t)stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(db, 0, sizeof(float) * cout, (cudaStream_t)stream);
+        if (e != cudaSuccess) {
+            set_error("ctu_head_bwd: memset: %s", cudaGetErrorString(e));
+            return (int)e;
+        }
     }
     CTU_DISPATCH_DTYPE(dtype, {
         switch (cout) {
-            case 1: return head_bwd_launch<T, 1>(p, (cudaStream_t)stream);
-            case 2: return head_bwd_launch<T, 2>(p, (cudaStream_t)stream);
-            case 3: return head_bwd_launch<T, 3>(p, (cudaStream_t)stream);
-            default: return head_bwd_launch<T, 4>(p, (cudaStream_t)stream);
+            case 1: return head_bwd_launch<T, 1>(p, part, (cudaStream_t)stream);
+            case 2: return head_bwd_launch<T, 2>(p, part, (cudaStream_t)stream);
+            case 3: return head_bwd_launch<T, 3>(p, part, (cudaStream_t)stream);
+            default: return head_bwd_launch<T, 4>(p, part, (cudaStream_t)stream);
         }
     });
     return CTU_OK;

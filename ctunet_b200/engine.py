@@ -540,11 +540,29 @@ class Engine:
                 pa, ca, ns = self._src_args(srcs)
                 dsrcs = [self.new_act(s.c, s.n, s.d, s.h, s.w) for s in srcs]
                 dw, db = self._grad_buffer(weight), self._grad_buffer(bias)
-                call("ctu_head_bwd", self.dtype, pa, ca, ns, weight.data_ptr(), bias.data_ptr(), cout, flags,
-                     g0.data_ptr() if g0 is not None else None, g1.data_ptr() if g1 is not None else None,
-                     ptr_array([d.ptr for d in dsrcs]), dw.data_ptr(), db.data_ptr(), s0.n, s0.spatial, stream_ptr())
-                self._add_pgrad(weight, dw)
-                self._add_pgrad(bias, db)
+                p0 = g0.data_ptr() if g0 is not None else None
+                p1 = g1.data_ptr() if g1 is not None else None
+
+                def params():      # parameter gradients: a leaf, beside the weight gradients (second stream)
+                    call("ctu_head_bwd", self.dtype, pa, ca, ns, weight.data_ptr(), bias.data_ptr(), cout, flags, p0, p1,
+                         None, dw.data_ptr(), db.data_ptr(), s0.n, s0.spatial, stream_ptr())
+                    self._pgrad_done(((weight, dw), (bias, db)))
+
+                if WGRAD_ASYNC:
+                    main = torch.cuda.current_stream()
+                    side = _side_stream(self.device, 1)
+                    side.wait_stream(main)
+                    with torch.cuda.stream(side):
+                        params()
+                    for g in (g0, g1):
+                        if g is not None:
+                            g.record_stream(side)
+                    self._wgrad_stream = side
+                else:
+                    params()
+                # source gradients: the critical path
+                call("ctu_head_bwd", self.dtype, pa, ca, ns, weight.data_ptr(), bias.data_ptr(), cout, flags, p0, p1,
+                     ptr_array([d.ptr for d in dsrcs]), None, None, s0.n, s0.spatial, stream_ptr())
                 for s, d in zip(srcs, dsrcs):
                     self._set_agrad(s, d)
 

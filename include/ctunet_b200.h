@@ -152,7 +152,8 @@ int ctu_bn_relu_bwd_apply(int dtype, const void* y, const float* ss, const float
 int ctu_head_fwd(int dtype, const void* const* h_srcs, const int* h_src_channels, int nsrc, const float* w,
                  const float* bias, int cout, int flags, float* out0, float* out1, int n, long long spatial,
                  ctu_stream stream);
-/* dsrcs[i] nullable; dw [cout][cin_total] and db [cout] are zeroed by the call */
+/* dsrcs[i] nullable; dw [cout][cin_total] and db [cout] are zeroed by the call.  dw = db = NULL: source gradients only;
+ * every dsrcs[i] NULL: parameter gradients only (two launches that can run on different streams) */
 int ctu_head_bwd(int dtype, const void* const* h_srcs, const int* h_src_channels, int nsrc, const float* w,
                  const float* bias, int cout, int flags, const float* dout0, const float* dout1, void* const* h_dsrcs,
                  float* dw, float* db, int n, long long spatial, ctu_stream stream);
