@@ -206,7 +206,7 @@ def describe(name, args, esize):
         if name in ("ctu_conv3d_fprop", "ctu_conv3d_wgrad"):
             ca, ns = args[2], args[3]
             cin = sum(ca[i] for i in range(ns))
-            o = 9 if name == "ctu_conv3d_fprop" else 7
+            o = 9 if name == "ctu_conv3d_fprop" else 8
             cout, k, n, d, h, w = args[o], args[o + 1], args[o + 2], args[o + 3], args[o + 4], args[o + 5]
             name = name + ("[tcgen05]" if args[o + 6] else "[cuda-core]")
             vox = n * d * h * w

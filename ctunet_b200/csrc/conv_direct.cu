@@ -329,7 +329,7 @@ static int launch_wgrad(const WgradParams& p, int k, cudaStream_t stream) {
 int conv3d_fprop_tc(const void* const* h_srcs, const int* h_src_channels, int nsrc, const float* wp, const float* bias,
                     void* y, double* stats, int stat_cout, int cout, int k, int n, int d, int h, int w, cudaStream_t stream);
 int conv3d_wgrad_tc(const void* const* h_srcs, const int* h_src_channels, int nsrc, const void* dy, float* dwp,
-                    float* dbias, int cout, int k, int n, int d, int h, int w, cudaStream_t stream);
+                    float* dbias, int phase_cout, int cout, int k, int n, int d, int h, int w, cudaStream_t stream);
 
 }  // namespace ctu
 
@@ -373,8 +373,8 @@ int ctu_conv3d_fprop(int dtype, const void* const* h_srcs, const int* h_src_chan
 }
 
 int ctu_conv3d_wgrad(int dtype, const void* const* h_srcs, const int* h_src_channels, int nsrc, const void* dy,
-                     float* dwp, float* dbias, int cout, int k, int n, int d, int h, int w, int use_tensor_path,
-                     ctu_stream stream) {
+                     float* dwp, float* dbias, int phase_cout, int cout, int k, int n, int d, int h, int w,
+                     int use_tensor_path, ctu_stream stream) {
     SrcMap m;
     int rc = make_srcmap(m, nsrc, h_src_channels);
     if (rc != CTU_OK) return rc;
@@ -392,7 +392,8 @@ int ctu_conv3d_wgrad(int dtype, const void* const* h_srcs, const int* h_src_chan
             set_error("ctu_conv3d_wgrad: the tensor path is bf16 only");
             return CTU_ERR_UNSUPPORTED;
         }
-        return conv3d_wgrad_tc(h_srcs, h_src_channels, nsrc, dy, dwp, dbias, cout, k, n, d, h, w, (cudaStream_t)stream);
+        return conv3d_wgrad_tc(h_srcs, h_src_channels, nsrc, dy, dwp, dbias, phase_cout, cout, k, n, d, h, w,
+                               (cudaStream_t)stream);
     }
     WgradParams p;
     for (int i = 0; i < CTU_MAX_SRC; ++i) {

@@ -810,6 +810,11 @@ struct WgParams {
     uint32_t plane_bytes, xslot_bytes, dyslot_bytes, tmem_cols;
     uint32_t ns, nds;           // x-plane / dy-plane ring depths
     int nsrc, src_cb[CTU_MAX_SRC], src_cboff[CTU_MAX_SRC];   // concatenated sources of x
+    // phase-sparse mode (weight gradient of the fused up-sampling stage, K = 3, output channel = q*8P*... phase-major):
+    // a group of output channels = the phases with one qd (sparse == 1, 4P blocks) or one (qd, qh) (sparse == 2, 2P
+    // blocks); only the taps kd in {qd, qd+1} and kh in {qh, qh+1} of the composed weights are structurally non-zero,
+    // so every (kd, input block) accumulator covers 2 of 3 kd and a contiguous run of 8P (4P) n-groups.  0 = dense.
+    int sparse, pblk;           // pblk = P = channel blocks per phase
 };
 
 template <int K>
@@ -909,14 +914,21 @@ __global__ void __launch_bounds__(WG_THREADS) conv3d_wgrad_tc_kernel(const __gri
     } else {
         // ===================================================================== MMA issuers + flush (warps 1..4)
         // D=f32, A=B=bf16, both MN-major (bits 15, 16), N at [17,23), M=64 at [24,29)
-        const int ncol = K * nn;                                  // MMA N: kh taps x output channels
+        // dense: N = kh taps x output channels, K accumulators (kd) per input block.  phase-sparse: see WgParams
+        const int P = p.pblk;
+        const int qd = p.sparse == 1 ? ng_i : (ng_i >> 1), qh = ng_i & 1;
+        const int nkd = p.sparse ? 2 : K, kd0 = p.sparse ? qd : 0;
+        const int ncol = p.sparse == 1 ? 64 * P : (p.sparse == 2 ? 32 * P : K * nn);
+        // first n-group of the MMA inside the (row r) window of the dy slot, in 16-byte units
+        const uint32_t b_off16 = p.sparse == 1 ? (uint32_t)(2 * P) * (DYBLK >> 4)
+                                               : (p.sparse == 2 ? (uint32_t)(1 - qh) * (dyrow >> 4) : 0u);
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                                ((uint32_t)(ncol >> 3) << 17) | (4u << 24);
         const uint32_t a_hi = 1u | (1u << 14);                    // SBO = 16 B: m-group g = lag g
         const uint32_t b_hi = (DYBLK >> 4) | (1u << 14);          // SBO = 256 B: next (row, channel block) n-group
         const uint32_t lbo = 8u << 16;                            // second 8-voxel core matrix: +128 B
         const int q = warp - 1;
-        const int nacc = K * ncb;                                 // one accumulator per (kd, input block)
+        const int nacc = nkd * ncb;                               // one accumulator per (kd, input block)
         // All 32 lanes walk the schedule (warp-uniform, branch-free descriptor arithmetic); only the elected lane's
         // MMAs / commits issue.  Per accumulator e = (kd, input block): HH back-to-back MMAs, A and B descriptors
         // advancing by one halo row / one dy row.
@@ -935,10 +947,10 @@ __global__ void __launch_bounds__(WG_THREADS) conv3d_wgrad_tc_kernel(const __gri
                 }
                 mbar_wait(b_dyfull + 8 * dyr.slot, dyr.phase);
                 tc_fence_after();
-                const uint32_t dy16 = ((s_dy + dyr.slot * p.dyslot_bytes) >> 4) | lbo;
+                const uint32_t dy16 = (((s_dy + dyr.slot * p.dyslot_bytes) >> 4) + b_off16) | lbo;
                 int b = q % ncb, kd = q / ncb;                // accumulator e = q, q + WG_ISSUERS, ...
                 for (int e = q; e < nacc; e += WG_ISSUERS) {
-                    uint32_t slot = head.slot + kd;
+                    uint32_t slot = head.slot + kd0 + kd;
                     if (slot >= NS) slot -= NS;
                     const uint32_t x16 = ((s_x + slot * p.xslot_bytes + b * p.plane_bytes) >> 4) | lbo;
                     const uint32_t tcol = tmem_base + (uint32_t)e * ncol;
@@ -972,18 +984,29 @@ __global__ void __launch_bounds__(WG_THREADS) conv3d_wgrad_tc_kernel(const __gri
         const bool useful = lane < 16 && lag < K;
         const int taps = K * K * K;
         for (int a = 0; a < nacc; ++a) {
-            const int b = a % ncb, kd = a / ncb;
-            for (int g = 0; g < K; ++g) {                  // n-group g holds kh = K-1-g
-                const int tap = (kd * K + (K - 1 - g)) * K + lag;
-                for (int ob = 0; ob < nob; ++ob) {
-                    float v[8];
-                    tmem_ld8(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)a * ncol + g * nn + ob * 8, v);
-                    if (useful) {
-                        float* dst = p.dwp + ((((long long)(ob0 + ob) * p.cb + cb0 + b) * taps + tap) * 64 + ci * 8);
+            const int b = a % ncb, kd = kd0 + a / ncb;
+            for (int g = 0; g < ncol / 8; ++g) {           // n-group g of the accumulator -> (kh, output block)
+                int kh, ob;
+                if (p.sparse == 1) {                       // [kh=2: blocks 2P..4P) | kh=1: all 4P | kh=0: blocks 0..2P)
+                    if (g < 2 * P) { kh = 2; ob = 2 * P + g; }
+                    else if (g < 6 * P) { kh = 1; ob = g - 2 * P; }
+                    else { kh = 0; ob = g - 6 * P; }
+                } else if (p.sparse == 2) {                // [kh = qh+1: 2P blocks | kh = qh: 2P blocks]
+                    kh = g < 2 * P ? qh + 1 : qh;
+                    ob = g < 2 * P ? g : g - 2 * P;
+                } else {                                   // n-group row g / nob holds kh = K-1-row
+                    kh = K - 1 - g / nob;
+                    ob = g % nob;
+                }
+                if (ob >= nob) continue;
+                const int tap = (kd * K + kh) * K + lag;
+                float v[8];
+                tmem_ld8(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)a * ncol + g * 8, v);
+                if (useful) {
+                    float* dst = p.dwp + ((((long long)(ob0 + ob) * p.cb + cb0 + b) * taps + tap) * 64 + ci * 8);
 #pragma unroll
-                        for (int c = 0; c < 8; ++c)
-                            if (v[c] != 0.f) atomicAdd(dst + c, v[c]);
-                    }
+                    for (int c = 0; c < 8; ++c)
+                        if (v[c] != 0.f) atomicAdd(dst + c, v[c]);
                 }
             }
         }
@@ -1017,12 +1040,13 @@ __global__ void tc_channel_sum_kernel(const __nv_bfloat16* __restrict__ dy, floa
 }
 
 struct WgGeom {
-    int cb, cob_n, cbg, ng, n_cbgroups, n_ngroups;
+    int cb, cob_n, cbg, ng, n_cbgroups, n_ngroups, sparse, pblk;
     uint32_t plane_bytes, xslot_bytes, dyslot_bytes, tmem_cols, ns, nds;
     size_t smem;
 };
 
-static bool wg_geometry(int k, int cb, int cout, int h, int w, WgGeom& g) {
+// phase_cout: 0, or the natural channel count of a phase-major dy (fused up-sampling stage: cout = 8 phases x 8P)
+static bool wg_geometry(int k, int cb, int cout, int h, int w, WgGeom& g, int phase_cout = 0) {
     if (k != 3 && k != 5) return false;
     if (h % TC_TH || w % TC_TW || cb < 1 || cout < 1) return false;
     g.cb = cb;
@@ -1030,11 +1054,25 @@ static bool wg_geometry(int k, int cb, int cout, int h, int w, WgGeom& g) {
     const int k2 = k * k;
     const int hh = TC_TH + k - 1, ww = TC_TW + k - 1;
     g.plane_bytes = ((uint32_t)hh * ww * 16 + 127u) & ~127u;
-    // choose (cbg, ng): k2*cbg*ng <= 512 TMEM columns; prefer all output channels, then as many input blocks as fit
-    g.ng = g.cob_n * 8;
-    while (k2 * g.ng > 512 || k * g.ng > 256) g.ng = ((g.ng / 8 + 1) / 2) * 8;
-    g.cbg = 512 / (k2 * g.ng);
+    g.sparse = 0;
+    g.pblk = 0;
+    int cols_per_block;       // TMEM columns per input block
+    if (phase_cout > 0 && k == 3 && cout == 8 * ((phase_cout + 7) / 8 * 8)) {
+        // phase-sparse: group = one qd (N = 64P) while that fits 128 columns, else one (qd, qh) (N = 32P)
+        g.pblk = (phase_cout + 7) / 8;
+        g.sparse = 64 * g.pblk <= 128 ? 1 : 2;
+        if (g.sparse == 2 && 32 * g.pblk > 256) return false;
+        g.ng = (g.sparse == 1 ? 4 : 2) * g.pblk * 8;
+        cols_per_block = 2 * (g.sparse == 1 ? 64 : 32) * g.pblk;
+    } else {
+        // choose (cbg, ng): k2*cbg*ng <= 512 TMEM columns; prefer all output channels, then as many input blocks as fit
+        g.ng = g.cob_n * 8;
+        while (k2 * g.ng > 512 || k * g.ng > 256) g.ng = ((g.ng / 8 + 1) / 2) * 8;
+        cols_per_block = k2 * g.ng;
+    }
+    g.cbg = 512 / cols_per_block;
     if (g.cbg > g.cb) g.cbg = g.cb;
+    if (g.cbg * (g.sparse ? 2 : k) > WG_ISSUERS * WG_MAX_OWN) g.cbg = WG_ISSUERS * WG_MAX_OWN / (g.sparse ? 2 : k);
     // shared memory: x ring (k+1 slots x cbg planes) + dy ring
     const size_t fixed = 8 * (4 * TC_MAX_SLOTS + 3) + 16 + WG_ISSUERS * WG_MAX_OWN * 8 + 1024;
     for (;;) {
@@ -1048,7 +1086,7 @@ static bool wg_geometry(int k, int cb, int cout, int h, int w, WgGeom& g) {
     // deepen both rings while a ~100 KB budget (two CTAs per SM) allows: more TMA loads in flight
     g.ns = k + 1;
     g.nds = 2;
-    const size_t wg_budget = (uint32_t)k2 * g.cbg * g.ng > 256 ? 200 * 1024 : 100 * 1024;   // > 256 TMEM columns: one CTA per SM
+    const size_t wg_budget = (uint32_t)cols_per_block * g.cbg > 256 ? 200 * 1024 : 100 * 1024;   // > 256 TMEM columns: one CTA per SM
     while (g.ns < TC_MAX_SLOTS && g.smem + g.xslot_bytes + g.dyslot_bytes <= wg_budget) {
         ++g.ns;
         if (g.nds < TC_MAX_SLOTS) ++g.nds;
@@ -1056,17 +1094,17 @@ static bool wg_geometry(int k, int cb, int cout, int h, int w, WgGeom& g) {
     }
     g.n_cbgroups = (g.cb + g.cbg - 1) / g.cbg;
     g.n_ngroups = (g.cob_n * 8 + g.ng - 1) / g.ng;
-    uint32_t cols = (uint32_t)k2 * g.cbg * g.ng;
+    uint32_t cols = (uint32_t)cols_per_block * g.cbg;
     g.tmem_cols = 32;
     while (g.tmem_cols < cols) g.tmem_cols *= 2;
     return g.tmem_cols <= 512;
 }
 
 int conv3d_wgrad_tc(const void* const* h_srcs, const int* h_src_channels, int nsrc, const void* dy, float* dwp,
-                    float* dbias, int cout, int k, int n, int d, int h, int w, cudaStream_t stream) {
+                    float* dbias, int phase_cout, int cout, int k, int n, int d, int h, int w, cudaStream_t stream) {
     WgGeom g;
     const int cbt = total_blocks(nsrc, h_src_channels);
-    if (cbt < 0 || !wg_geometry(k, cbt, cout, h, w, g)) {
+    if (cbt < 0 || !wg_geometry(k, cbt, cout, h, w, g, phase_cout)) {
         set_error("conv3d wgrad tensor path: shape k=%d blocks=%d cout=%d %dx%dx%d not covered", k, cbt, cout, d, h, w);
         return CTU_ERR_UNSUPPORTED;
     }
@@ -1104,6 +1142,7 @@ int conv3d_wgrad_tc(const void* const* h_srcs, const int* h_src_channels, int ns
     p.total_items = tiles * p.dchunks;
     p.plane_bytes = g.plane_bytes; p.xslot_bytes = g.xslot_bytes; p.dyslot_bytes = g.dyslot_bytes; p.tmem_cols = g.tmem_cols;
     p.ns = g.ns; p.nds = g.nds;
+    p.sparse = g.sparse; p.pblk = g.pblk;
     p.nsrc = nsrc;
     for (int i = 0, off = 0; i < CTU_MAX_SRC; ++i) {
         p.src_cb[i] = i < nsrc ? (h_src_channels[i] + 7) / 8 : 0;
@@ -1155,7 +1194,7 @@ int ctu_conv_tc_wgrad_supported(int k, int nsrc, const int* h_src_channels, int 
     (void)d;
     WgGeom g;
     const int cb = total_blocks(nsrc, h_src_channels);
-    return (cb > 0 && wg_geometry(k, cb, cout, h, w, g)) ? 1 : 0;
+    return (cb > 0 && wg_geometry(k, cb, cout, h, w, g)) ? 1 : 0;     // (the phase-sparse mode covers a superset)
 }
 
 long long ctu_conv_tc_wimg_bytes(int k, int nsrc, const int* h_src_channels, int cout) {

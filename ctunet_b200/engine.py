@@ -276,7 +276,7 @@ class Engine:
         self._conv_launch(srcs, wk, tc, bias, y, cout, k, y.sums, stat_cout)
         return y
 
-    def _conv_bwd(self, srcs, need, wkd, tc_d, y, k, cout, dw_out, db_out, after_wgrad=None):
+    def _conv_bwd(self, srcs, need, wkd, tc_d, y, k, cout, dw_out, db_out, after_wgrad=None, phase_cout=0):
         """Weight gradient into ``dw_out`` (native layout, nullable) / ``db_out`` and the data gradient of every
         source with ``need[i]`` (prepared weights ``wkd[i]``).
 
@@ -292,8 +292,8 @@ class Engine:
                 dwp = self.f32(lib.ctu_conv_wpack_floats(cout, k, ns, ca))
                 tc = self.use_tc and bool(lib.ctu_conv_tc_wgrad_supported(k, ns, ca, cout, s0.d, s0.h, s0.w))
                 call("ctu_conv3d_wgrad", self.dtype, pa, ca, ns, dy.ptr, dwp.data_ptr(),
-                     db_out.data_ptr() if db_out is not None else None, cout, k, s0.n, s0.d, s0.h, s0.w, int(tc),
-                     stream_ptr())
+                     db_out.data_ptr() if db_out is not None else None, phase_cout, cout, k, s0.n, s0.d, s0.h, s0.w,
+                     int(tc), stream_ptr())
                 call("ctu_conv_unpack_wgrad", dwp.data_ptr(), dw_out.data_ptr(), cout, k, ns, ca, stream_ptr())
                 if after_wgrad is not None:
                     after_wgrad()
@@ -409,7 +409,10 @@ class Engine:
                             t.record_stream(torch.cuda.current_stream())
                     self._pgrad_done(((ct.weight, dwt), (ct.bias, dbt), (cv.weight, dw3), (cv.bias, db3)))
 
-                self._conv_bwd(all_srcs, need, wkd, tc_d, y, 3, co8, dwn, dbn, decompose)
+                # a composed 3^3 stage has structurally zero taps (each phase sees 2 of 3 per dimension) that the weight
+                # gradient skips; composed from 5^3 every low-resolution tap is populated
+                self._conv_bwd(all_srcs, need, wkd, tc_d, y, 3, co8, dwn, dbn, decompose,
+                               phase_cout=cout if k == 3 else 0)
 
             self.tape.append(bwd)
         return y

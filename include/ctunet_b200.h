@@ -87,10 +87,13 @@ int ctu_conv_tc_wgrad_supported(int k, int nsrc, const int* h_src_channels, int 
 long long ctu_conv_tc_wimg_bytes(int k, int nsrc, const int* h_src_channels, int cout);
 int ctu_conv_tc_pack_weight(const float* wp, void* wimg, int k, int nsrc, const int* h_src_channels, int cout,
                             ctu_stream stream);
-/* dwp (packed layout, fp32) and dbias (nullable, [cout]) are zeroed by the call, then accumulated */
+/* dwp (packed layout, fp32) and dbias (nullable, [cout]) are zeroed by the call, then accumulated.
+ * phase_cout: 0, or the natural channel count when dy is the phase-major gradient of the fused up-sampling stage
+ * COMPOSED FROM A 3x3x3 CONVOLUTION (cout = 8 phases x 8*ceil(phase_cout/8)): the tensor path then skips the taps that are
+ * structurally zero (their entries of dwp stay 0 or hold unspecified values that ctu_upfuse_decompose never reads). */
 int ctu_conv3d_wgrad(int dtype, const void* const* h_srcs, const int* h_src_channels, int nsrc, const void* dy,
-                     float* dwp, float* dbias, int cout, int k, int n, int d, int h, int w, int use_tensor_path,
-                     ctu_stream stream);
+                     float* dwp, float* dbias, int phase_cout, int cout, int k, int n, int d, int h, int w,
+                     int use_tensor_path, ctu_stream stream);
 
 /* ---- ConvTranspose3d k=2, stride 2, with bias (models.py:37, :427).  Native weight
  *      [Cin][Cout][2][2][2]; packed [cob][cib][abc][ci8][co8].  n,d,h,w are the INPUT dims. --- */

@@ -36,13 +36,13 @@ def timeit(fn, reps=20):
     return s.elapsed_time(e) / reps * 1e3
 
 
-def wgrad(chans, cout, n, d, h, w, k=3):
+def wgrad(chans, cout, n, d, h, w, k=3, phase=0):
     srcs = [act(n, c, d, h, w) for c in chans]
     dy = act(n, cout, d, h, w)
     ca = int_array(chans)
     dwp = torch.empty(lib.ctu_conv_wpack_floats(cout, k, len(chans), ca), device=dev)
     pa = ptr_array([s.data_ptr() for s in srcs])
-    fn = lambda: call("ctu_conv3d_wgrad", 1, pa, ca, len(chans), dy.data_ptr(), dwp.data_ptr(), None, cout, k, n, d, h, w, 1,
+    fn = lambda: call("ctu_conv3d_wgrad", 1, pa, ca, len(chans), dy.data_ptr(), dwp.data_ptr(), None, phase, cout, k, n, d, h, w, 1,
                       stream_ptr())
     return timeit(fn)
 
@@ -74,7 +74,7 @@ which = sys.argv[1] if len(sys.argv) > 1 else "both"
 for name, chans, cout, n, d, h, w in SHAPES:
     line = "%-36s" % name
     if which in ("wgrad", "both"):
-        line += " wgrad %8.1f us" % wgrad(chans, cout, n, d, h, w)
+        line += " wgrad %8.1f us" % wgrad(chans, cout, n, d, h, w, 3, cout // 8 - 1 if len(chans) == 3 else 0)
     if which in ("fprop", "both"):
         sc = cout // 8 if len(chans) == 3 else 0
         line += " fprop %8.1f us" % fprop(chans, cout, n, d, h, w, 3, sc)
