@@ -841,9 +841,12 @@ __global__ void __launch_bounds__(WG_THREADS) conv3d_wgrad_tc_kernel(const __gri
     const int cb0 = cbg_i * p.cbg;
     const int ncb = (p.cb - cb0) < p.cbg ? (p.cb - cb0) : p.cbg;         // input blocks of this group
     const int ob0 = ng_i * (p.ng / 8);
+    // valid output blocks of this group; the LAYOUT (TMA box, row pitch, MMA N) always spans the full group of ng/8
+    // blocks -- a partial last group is zero-filled by TMA (out-of-range coordinates) and skipped at the flush
     const int nob = (p.cob_n - ob0) < (p.ng / 8) ? (p.cob_n - ob0) : (p.ng / 8);
-    const int nn = nob * 8;                                              // output channels of this group
-    const uint32_t dyrow = (uint32_t)nob * DYBLK;                        // one dy row, all channel blocks
+    const int nobx = p.ng / 8;
+    const int nn = nobx * 8;                                             // output channels of this group
+    const uint32_t dyrow = (uint32_t)nobx * DYBLK;                       // one dy row, all channel blocks
 
     // zero rows above / below every dy slot (never written by TMA), visible to the async proxy before any MMA
     for (uint32_t sl = 0; sl < NDS; ++sl) {
@@ -995,8 +998,8 @@ __global__ void __launch_bounds__(WG_THREADS) conv3d_wgrad_tc_kernel(const __gri
                     kh = g < 2 * P ? qh + 1 : qh;
                     ob = g < 2 * P ? g : g - 2 * P;
                 } else {                                   // n-group row g / nob holds kh = K-1-row
-                    kh = K - 1 - g / nob;
-                    ob = g % nob;
+                    kh = K - 1 - g / nobx;
+                    ob = g % nobx;
                 }
                 if (ob >= nob) continue;
                 const int tap = (kd * K + kh) * K + lag;

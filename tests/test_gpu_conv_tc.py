@@ -27,6 +27,7 @@ CASES = [
     (3, 112, 28, False, (1, 2, 16, 16)),
     (3, 28, 112, False, (1, 2, 16, 16)),     # wgrad: output channels split over TMEM
     (5, 14, 28, True, (1, 3, 16, 16)),
+    (5, 56, 56, True, (1, 3, 16, 16)),       # wgrad: partial last output-channel group (16,16,16,8); fprop on CUDA cores
 ]
 
 
@@ -41,7 +42,7 @@ def test_tc_conv_matches_reference(case):
     k, cin, cout, use_bias, (n, d, h, w) = case
     assert _lib.load().ctu_has_tensor_path() == 1
     fprop_on_tc = tc_supported(k, [cin], cout, d, h, w)     # wide inputs are staged in groups of four channel blocks
-    assert fprop_on_tc
+    assert fprop_on_tc or (k == 5 and cin >= 56)            # 5^3 weights of wide layers do not fit shared memory yet
     g = torch.Generator().manual_seed(k * 100 + cin)
     x = _bf(torch.randn(n, cin, d, h, w, generator=g))
     wt = torch.randn(cout, cin, k, k, k, generator=g) / (cin * k ** 3) ** 0.5
