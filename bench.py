@@ -251,7 +251,7 @@ def describe(name, args, esize):
         if name in ("ctu_head_fwd", "ctu_head_bwd"):
             ca, ns = args[2], args[3]
             cin = sum(ca[i] for i in range(ns))
-            n, sp = (args[10], args[11]) if name == "ctu_head_fwd" else (args[13], args[14])
+            n, sp = (args[10], args[11]) if name == "ctu_head_fwd" else (args[15], args[16])
             outs = 4 if (args[7] & 12) else args[6]
             by = n * sp * (esize * cin * (1 if name == "ctu_head_fwd" else 2) + 4 * outs)
             return "%s %d->%d @%dx%d" % (name, cin, args[6], n, sp), 2.0 * n * sp * cin * args[6], by

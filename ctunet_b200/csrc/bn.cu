@@ -321,28 +321,26 @@ __global__ void __launch_bounds__(kBnThreads, 2) bn_relu_bwd_kernel(BwdArgs p) {
             if (POOL) gp = Vec8<T>::load(dP + (((long long)n * p.cb + b) * pspatial + ps) * 8);
             // av: the activation BEFORE rounding to the storage type.  Rounding is monotone, so the maximum of
             // the rounded values is the rounded maximum (forward/backward stay consistent) while values that
-            // collide in bf16 still elect the arg-max an fp32 evaluation would.
-            V8 yv[8], av[8];
+            // collide in bf16 still elect the arg-max an fp32 evaluation would.  The children stay in their storage
+            // form (Raw8) and av is recomputed on use: the pooled variant fits 128 registers without spilling.
+            Raw8<T> yr[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                yv[q] = Vec8<T>::load(y + offy[q]);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) av[q].v[j] = fmaxf(fmaf(yv[q].v[j], sc[j], sh[j]), 0.f);
-            }
+            for (int q = 0; q < 8; ++q) yr[q].load(y + offy[q]);
             int win[8];
             if (POOL) {
                 // first maximum in (d, h, w) scan order, strict '>' like torch's max_pool3d
+                float best[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float best = av[0].v[j];
-                    int bi = 0;
+                for (int q = 0; q < 8; ++q) {
+                    const V8 yq = yr[q].get();
 #pragma unroll
-                    for (int q = 1; q < 8; ++q)
-                        if (av[q].v[j] > best) {
-                            best = av[q].v[j];
-                            bi = q;
+                    for (int j = 0; j < 8; ++j) {
+                        const float a = fmaxf(fmaf(yq.v[j], sc[j], sh[j]), 0.f);
+                        if (q == 0 || a > best[j]) {
+                            best[j] = a;
+                            win[j] = q;
                         }
-                    win[j] = bi;
+                    }
                 }
             }
 #pragma unroll
@@ -354,13 +352,14 @@ __global__ void __launch_bounds__(kBnThreads, 2) bn_relu_bwd_kernel(BwdArgs p) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) g.v[j] = 0.f;
                 }
+                const V8 yq = yr[q].get();
                 V8 o;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     float dz = g.v[j];
                     if (POOL) dz += (win[j] == q) ? gp.v[j] : 0.f;
-                    dz = av[q].v[j] > 0.f ? dz : 0.f;
-                    const float xhat = (yv[q].v[j] - mean[j]) * invstd[j];
+                    dz = fmaf(yq.v[j], sc[j], sh[j]) > 0.f ? dz : 0.f;
+                    const float xhat = (yq.v[j] - mean[j]) * invstd[j];
                     if (APPLY) {
                         o.v[j] = sc[j] * (dz - k1[j] - xhat * k2[j]);
                     } else {

@@ -71,6 +71,28 @@ template <> struct Vec8<__nv_bfloat16> {
     }
 };
 
+// Register-frugal staging: keep the 8 channels of a voxel in their STORAGE form (4 registers in bf16) and unpack on use.
+template <typename T> struct Raw8;
+template <> struct Raw8<float> {
+    V8 v;
+    __device__ __forceinline__ void load(const float* p) { v = Vec8<float>::load(p); }
+    __device__ __forceinline__ V8 get() const { return v; }
+};
+template <> struct Raw8<__nv_bfloat16> {
+    uint4 u;
+    __device__ __forceinline__ void load(const __nv_bfloat16* p) { u = *reinterpret_cast<const uint4*>(p); }
+    __device__ __forceinline__ V8 get() const {
+        V8 r;
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            r.v[2 * i] = __uint_as_float(w[i] << 16);
+            r.v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        }
+        return r;
+    }
+};
+
 // Value as it will be read back after a store in storage type T (so statistics are taken on what
 // the next kernel really sees).
 template <typename T> __device__ __forceinline__ float round_to(float x);

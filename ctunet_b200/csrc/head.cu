@@ -25,6 +25,8 @@ struct HeadParams {
     float* out1;
     const float* dout0;
     const float* dout1;
+    const float* fo0;     // forward outputs (nullable): head_bwd recovers the sigmoid values from them
+    const float* fo1;
     float* dw;
     float* db;
     int n;
@@ -163,7 +165,10 @@ __global__ void __launch_bounds__(kHeadThreads) head_fwd_kernel(HeadParams p) {
 // PART 0: source gradients and parameter gradients; 1: source gradients only (the critical path of the backward
 // pass); 2: parameter gradients only (a leaf: the engine runs it beside the weight gradients).  The 48+ per-thread
 // dW accumulators are what limits occupancy, so the split halves the latency of the part the decoder waits for.
-template <typename T, int CO, int CBT, int PART>
+// FROMOUT (plain-sigmoid SP head, CO == 3): the sigmoid values are recovered from the forward OUTPUTS
+// (skull = [s0, s1+s2], flap = [1-s1, s1]) instead of being recomputed from the inputs: the source-gradient launch then
+// reads 28 B and writes 32 B per voxel, with no logits and no exponentials.
+template <typename T, int CO, int CBT, int PART, bool FROMOUT>
 __global__ void __launch_bounds__(kHeadThreads) head_bwd_kernel(HeadParams p) {
     extern __shared__ float hsm[];
     float* wsm = hsm;
@@ -184,11 +189,17 @@ __global__ void __launch_bounds__(kHeadThreads) head_bwd_kernel(HeadParams p) {
     const long long stride = (long long)gridDim.x * kHeadThreads;
     long long i = (long long)blockIdx.x * kHeadThreads + threadIdx.x;
     V8 xn[CBT];
-    float gn[4] = {0.f, 0.f, 0.f, 0.f};
-    auto fetch = [&](long long idx, V8 (&xo)[CBT], float (&go)[4]) {
+    float gn[4] = {0.f, 0.f, 0.f, 0.f}, on[3] = {0.f, 0.f, 0.f};
+    constexpr bool NEEDX = !FROMOUT || PART != 1;
+    auto fetch = [&](long long idx, V8 (&xo)[CBT], float (&go)[4], float (&oo)[3]) {
         const int n = (int)(idx / p.spatial);
         const long long s = idx % p.spatial;
-        head_load<T, CBT>(p, n, s, xo);
+        if (NEEDX) head_load<T, CBT>(p, n, s, xo);
+        if (FROMOUT) {
+            oo[0] = p.fo0[((long long)n * 2 + 0) * p.spatial + s];
+            oo[1] = p.fo0[((long long)n * 2 + 1) * p.spatial + s];
+            oo[2] = p.fo1[((long long)n * 2 + 1) * p.spatial + s];
+        }
         if (sp) {
             go[0] = p.dout0 ? p.dout0[((long long)n * 2 + 0) * p.spatial + s] : 0.f;
             go[1] = p.dout0 ? p.dout0[((long long)n * 2 + 1) * p.spatial + s] : 0.f;
@@ -199,20 +210,28 @@ __global__ void __launch_bounds__(kHeadThreads) head_bwd_kernel(HeadParams p) {
             for (int o = 0; o < CO; ++o) go[o] = p.dout0[((long long)n * CO + o) * p.spatial + s];
         }
     };
-    if (i < total) fetch(i, xn, gn);
+    if (i < total) fetch(i, xn, gn, on);
     for (; i < total; i += stride) {
         const int n = (int)(i / p.spatial);
         const long long s = i % p.spatial;
         V8 xs[CBT];
-        float gc[4];
+        float gc[4], oc[3];
 #pragma unroll
         for (int c = 0; c < CBT; ++c) xs[c] = xn[c];
 #pragma unroll
         for (int o = 0; o < 4; ++o) gc[o] = gn[o];
-        if (i + stride < total) fetch(i + stride, xn, gn);
+#pragma unroll
+        for (int o = 0; o < 3; ++o) oc[o] = on[o];
+        if (i + stride < total) fetch(i + stride, xn, gn, on);
         HeadVals<CO> h;
-        head_logits_of<CO, CBT>(wsm, bsm, h, xs);
-        head_forward_chain<CO>(h, p.flags);
+        if (FROMOUT) {
+            h.sg[0] = oc[0];
+            h.sg[1] = oc[2];
+            h.sg[CO - 1] = oc[1] - oc[2];
+        } else {
+            head_logits_of<CO, CBT>(wsm, bsm, h, xs);
+            head_forward_chain<CO>(h, p.flags);
+        }
         float dsg[CO];
         if (sp) {
             float g00 = gc[0], g01 = gc[1], g10 = gc[2], g11 = gc[3];
@@ -348,11 +367,25 @@ static int head_bwd_launch_part(const HeadParams& p, cudaStream_t stream) {
     const size_t smem = (size_t)(CO * cbt * 8 + 8 + (kHeadThreads / 32) * nv) * sizeof(float);
     int grid = head_grid((long long)p.n * p.spatial);
     if (PART != 1 && grid > 148 * 2) grid = 148 * 2;   // every block ends with CO*(Cin+1) same-address atomics
+    const bool fromout = CO == 3 && p.fo0 != nullptr && p.fo1 != nullptr &&
+                         p.flags == (CTU_HEAD_SIGMOID | CTU_HEAD_SP);
+    if (fromout) {
+        if (CO == 3) {       // (compile-time guard: the fast path is only instantiated for the 3-channel SP head)
+            constexpr int C3 = CO == 3 ? 3 : 1;
+            switch (cbt) {
+                case 1: head_bwd_kernel<T, C3, 1, PART, CO == 3><<<grid, kHeadThreads, smem, stream>>>(p); break;
+                case 2: head_bwd_kernel<T, C3, 2, PART, CO == 3><<<grid, kHeadThreads, smem, stream>>>(p); break;
+                case 3: head_bwd_kernel<T, C3, 3, PART, CO == 3><<<grid, kHeadThreads, smem, stream>>>(p); break;
+                default: head_bwd_kernel<T, C3, 4, PART, CO == 3><<<grid, kHeadThreads, smem, stream>>>(p); break;
+            }
+        }
+        return check_launch("ctu_head_bwd");
+    }
     switch (cbt) {
-        case 1: head_bwd_kernel<T, CO, 1, PART><<<grid, kHeadThreads, smem, stream>>>(p); break;
-        case 2: head_bwd_kernel<T, CO, 2, PART><<<grid, kHeadThreads, smem, stream>>>(p); break;
-        case 3: head_bwd_kernel<T, CO, 3, PART><<<grid, kHeadThreads, smem, stream>>>(p); break;
-        default: head_bwd_kernel<T, CO, 4, PART><<<grid, kHeadThreads, smem, stream>>>(p); break;
+        case 1: head_bwd_kernel<T, CO, 1, PART, false><<<grid, kHeadThreads, smem, stream>>>(p); break;
+        case 2: head_bwd_kernel<T, CO, 2, PART, false><<<grid, kHeadThreads, smem, stream>>>(p); break;
+        case 3: head_bwd_kernel<T, CO, 3, PART, false><<<grid, kHeadThreads, smem, stream>>>(p); break;
+        default: head_bwd_kernel<T, CO, 4, PART, false><<<grid, kHeadThreads, smem, stream>>>(p); break;
     }
     return check_launch("ctu_head_bwd");
 }
@@ -395,7 +428,7 @@ int ctu_head_fwd(int dtype, const void* const* h_srcs, const int* h_src_channels
 }
 
 int ctu_head_bwd(int dtype, const void* const* h_srcs, const int* h_src_channels, int nsrc, const float* w,
-                 const float* bias, int cout, int flags, const float* dout0, const float* dout1, void* const* h_dsrcs,
+                 const float* bias, int cout, int flags, const float* dout0, const float* dout1, const float* out0, const float* out1, void* const* h_dsrcs,
                  float* dw, float* db, int n, long long spatial, ctu_stream stream) {
     HeadParams p = {};
     int rc = head_setup(p, h_srcs, h_src_channels, nsrc, w, bias, cout, flags, n, spatial, "ctu_head_bwd");
@@ -411,6 +444,7 @@ int ctu_head_bwd(int dtype, const void* const* h_srcs, const int* h_src_channels
     CTU_REQUIRE(dw != nullptr || any_dsrc, "ctu_head_bwd: nothing to compute");
     const int part = dw == nullptr ? 1 : (any_dsrc ? 0 : 2);
     p.dout0 = dout0; p.dout1 = dout1; p.dw = dw; p.db = db;
+    p.fo0 = out0; p.fo1 = out1;
     if (dw != nullptr) {
         cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * cout * p.m.c_total, (cudaStream_t)stream);
         if (e == cudaSuccess) e = cudaMemsetAsync(db, 0, sizeof(float) * cout, (cudaStream_t)stream);

@@ -546,9 +546,14 @@ class Engine:
                 p0 = g0.data_ptr() if g0 is not None else None
                 p1 = g1.data_ptr() if g1 is not None else None
 
+                # product mode: the SP head's backward pass reads the forward outputs instead of recomputing the
+                # sigmoids (fp32 check mode keeps the recomputation: s2 = (s1+s2) - s1 loses a few ulps)
+                o0 = out0.data_ptr() if self.dtype == CTU_BF16 else None
+                o1 = out1.data_ptr() if (out1 is not None and self.dtype == CTU_BF16) else None
+
                 def params():      # parameter gradients: a leaf, beside the weight gradients (second stream)
                     call("ctu_head_bwd", self.dtype, pa, ca, ns, weight.data_ptr(), bias.data_ptr(), cout, flags, p0, p1,
-                         None, dw.data_ptr(), db.data_ptr(), s0.n, s0.spatial, stream_ptr())
+                         o0, o1, None, dw.data_ptr(), db.data_ptr(), s0.n, s0.spatial, stream_ptr())
                     self._pgrad_done(((weight, dw), (bias, db)))
 
                 if WGRAD_ASYNC:
@@ -565,7 +570,7 @@ class Engine:
                     params()
                 # source gradients: the critical path
                 call("ctu_head_bwd", self.dtype, pa, ca, ns, weight.data_ptr(), bias.data_ptr(), cout, flags, p0, p1,
-                     ptr_array([d.ptr for d in dsrcs]), None, None, s0.n, s0.spatial, stream_ptr())
+                     o0, o1, ptr_array([d.ptr for d in dsrcs]), None, None, s0.n, s0.spatial, stream_ptr())
                 for s, d in zip(srcs, dsrcs):
                     self._set_agrad(s, d)
 
@@ -583,7 +588,10 @@ class Engine:
             self._wgrad_stream = None
 
     def backward(self, g0, g1):
-        self.head_bwd(g0, g1)
+        # (drop the closure first: it references the engine AND the forward outputs, i.e. the autograd graph -- a cycle
+        # that would keep this pass's AccumulateGrad nodes alive until the next garbage collection)
+        fn, self.head_bwd = self.head_bwd, None
+        fn(g0, g1)
         self.run_tape()
 
 

@@ -157,8 +157,10 @@ int ctu_head_fwd(int dtype, const void* const* h_srcs, const int* h_src_channels
                  ctu_stream stream);
 /* dsrcs[i] nullable; dw [cout][cin_total] and db [cout] are zeroed by the call.  dw = db = NULL: source gradients only;
  * every dsrcs[i] NULL: parameter gradients only (two launches that can run on different streams) */
+/* out0 / out1 (nullable): the outputs ctu_head_fwd produced; with them the plain-sigmoid SP head skips the logits */
 int ctu_head_bwd(int dtype, const void* const* h_srcs, const int* h_src_channels, int nsrc, const float* w,
-                 const float* bias, int cout, int flags, const float* dout0, const float* dout1, void* const* h_dsrcs,
+                 const float* bias, int cout, int flags, const float* dout0, const float* dout1, const float* out0,
+                 const float* out1, void* const* h_dsrcs,
                  float* dw, float* db, int n, long long spatial, ctu_stream stream);
 
 /* ---- loss: soft Dice (utilities.py:39-50) + CrossEntropy (ProblemHandler.py:67-70, 247-257) on
