@@ -330,6 +330,9 @@ int conv3d_fprop_tc(const void* const* h_srcs, const int* h_src_channels, int ns
                     void* y, double* stats, int stat_cout, int cout, int k, int n, int d, int h, int w, cudaStream_t stream);
 int conv3d_wgrad_tc(const void* const* h_srcs, const int* h_src_channels, int nsrc, const void* dy, float* dwp,
                     float* dbias, int phase_cout, int cout, int k, int n, int d, int h, int w, cudaStream_t stream);
+// implemented in conv_wide.cu
+int conv3d_fprop_wide(const void* x, int cin, const void* wimg, const float* bias, void* y, int cout, int k, int n, int d,
+                      int h, int w, cudaStream_t stream);
 
 }  // namespace ctu
 
@@ -353,6 +356,13 @@ int ctu_conv3d_fprop(int dtype, const void* const* h_srcs, const int* h_src_chan
         if (dtype != CTU_BF16) {
             set_error("ctu_conv3d_fprop: the tensor path is bf16 only");
             return CTU_ERR_UNSUPPORTED;
+        }
+        if (use_tensor_path == 2) {      // weight-streaming kernel for wide, low-resolution layers (conv_wide.cu)
+            CTU_REQUIRE(nsrc == 1, "ctu_conv3d_fprop: the wide tensor path takes one source");
+            rc = conv3d_fprop_wide(h_srcs[0], h_src_channels[0], wp, bias, y, cout, k, n, d, h, w, (cudaStream_t)stream);
+            if (rc == CTU_OK && bn_sums != nullptr)
+                rc = ctu_bn_stats(dtype, y, stat_cout, ((cout + 7) / 8) / cob_nat, n, (long long)d * h * w, bn_sums, stream);
+            return rc;
         }
         return conv3d_fprop_tc(h_srcs, h_src_channels, nsrc, (const float*)wp, bias, y, bn_sums, stat_cout, cout, k, n, d,
                                h, w, (cudaStream_t)stream);

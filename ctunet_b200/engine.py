@@ -199,9 +199,11 @@ class Engine:
         return ptr_array([s.ptr for s in srcs]), int_array([s.c for s in srcs]), len(srcs)
 
     def _tc_ok(self, k, srcs, cout):
-        return self.use_tc and tc_supported(k, [s.c for s in srcs], cout, srcs[0].d, srcs[0].h, srcs[0].w)
+        """0 = CUDA-core kernel, 1 = conv_tc.cu (weights resident in shared memory), 2 = conv_wide.cu (weights streamed)."""
+        s0 = srcs[0]
+        return tc_variant(k, [s.c for s in srcs], cout, s0.n, s0.d, s0.h, s0.w) if self.use_tc else 0
 
-    def _kernel_weights(self, native, cout, k, chans, tc, dgrad_of=None):
+    def _kernel_weights(self, native, cout, k, chans, tc, dgrad_of=None, dims=None):
         """Kernel-ready weights of conv(cat(srcs with ``chans`` channels)) -> cout: the packed fp32 tensor (CUDA-core
         kernel) or the bf16 UMMA image (tcgen05 kernel).  ``dgrad_of = (i, cs)``: instead the weights of the data
         gradient dy (cout channels) -> d(src i) (cs channels)."""
@@ -218,6 +220,11 @@ class Engine:
             kin, kout = (1, int_array([cout])), cs
         if not tc:
             return wp
+        if tc == 2:      # weight-streaming kernel: the image depends on the launch geometry (dims = n, d, h, w)
+            cin1 = kin[1][0]
+            wimg = torch.empty(lib.ctu_conv_wide_wimg_bytes(k, cin1, kout, *dims), dtype=torch.uint8, device=self.device)
+            call("ctu_conv_wide_pack_weight", wp.data_ptr(), wimg.data_ptr(), k, cin1, kout, *dims, st)
+            return wimg
         wimg = torch.empty(lib.ctu_conv_tc_wimg_bytes(k, kin[0], kin[1], kout), dtype=torch.uint8, device=self.device)
         call("ctu_conv_tc_pack_weight", wp.data_ptr(), wimg.data_ptr(), k, kin[0], kin[1], kout, st)
         return wimg
@@ -249,7 +256,8 @@ class Engine:
         chans = [s.c for s in srcs]
         s0 = srcs[0]
         tc_f = self._tc_ok(k, srcs, cout)
-        tc_d = [bool(nd) and self.use_tc and tc_supported(k, [cout], s.c, s0.d, s0.h, s0.w) for s, nd in zip(srcs, need)]
+        dims = (s0.n, s0.d, s0.h, s0.w)
+        tc_d = [tc_variant(k, [cout], s.c, *dims) if (nd and self.use_tc) else 0 for s, nd in zip(srcs, need)]
         need = list(need)
 
         def prep(eng):
@@ -258,9 +266,9 @@ class Engine:
             if compose is not None:
                 res = compose(eng)
                 wn, extra = res[0], tuple(res[1:])
-            out = [eng._kernel_weights(wn, cout, k, chans, tc_f)]
+            out = [eng._kernel_weights(wn, cout, k, chans, tc_f, dims=dims)]
             for i, nd in enumerate(need):
-                out.append(eng._kernel_weights(wn, cout, k, chans, tc_d[i], (i, chans[i])) if nd else None)
+                out.append(eng._kernel_weights(wn, cout, k, chans, tc_d[i], (i, chans[i]), dims=dims) if nd else None)
             return tuple(out) + (wn,) + extra
 
         res = self._prepared(tag, prep)
@@ -593,6 +601,24 @@ class Engine:
         fn, self.head_bwd = self.head_bwd, None
         fn(g0, g1)
         self.run_tape()
+
+
+# The weight-streaming kernel (conv_wide.cu) is preferred over the resident-weights kernel where both cover a layer
+# and the grid is small (h and w at most WIDE_MAX_HW): measured on B200 (scripts/bench_wide.py, batch 4) 56->56 3^3 at
+# 16^3 takes 10.9 us streamed vs 32.0 us resident, while at 32^3 the resident kernel wins (28->28: 24.8 vs 29.3 us).
+WIDE_MIN_CH = 9
+WIDE_MAX_HW = 16
+
+
+def tc_variant(k, src_channels, cout, n, d, h, w) -> int:
+    """Which tcgen05 kernel runs conv(cat(srcs)) -> cout: 0 none (CUDA cores), 1 conv_tc.cu, 2 conv_wide.cu."""
+    lib = _lib.load()
+    chans = list(src_channels)
+    narrow = bool(lib.ctu_conv_tc_supported(k, len(chans), int_array(chans), cout, d, h, w))
+    if len(chans) == 1 and lib.ctu_conv_wide_supported(k, chans[0], cout, n, d, h, w):
+        if not narrow or (min(chans[0], cout) >= WIDE_MIN_CH and max(h, w) <= WIDE_MAX_HW):
+            return 2
+    return 1 if narrow else 0
 
 
 def tc_supported(k, src_channels, cout, d, h, w) -> bool:

@@ -77,7 +77,9 @@ int ctu_conv_unpack_wgrad(const float* dwp, float* dw, int cout, int k, int nsrc
  * fused up-sampling stage (cout = 8 phases x 8*ceil(stat_cout/8); statistics are summed over phases).
  * use_tensor_path: 0 = CUDA-core direct kernel (both dtypes; wp = fp32 packed weights),
  * 1 = tcgen05/TMA implicit GEMM (bf16, shapes accepted by ctu_conv_tc_supported;
- * wp = the bf16 B-tile image written by ctu_conv_tc_pack_weight). */
+ * wp = the bf16 B-tile image written by ctu_conv_tc_pack_weight),
+ * 2 = tcgen05/TMA weight-streaming implicit GEMM for wide low-resolution layers (bf16, one source, shapes accepted
+ * by ctu_conv_wide_supported; wp = the image written by ctu_conv_wide_pack_weight). */
 int ctu_conv3d_fprop(int dtype, const void* const* h_srcs, const int* h_src_channels, int nsrc, const void* wp,
                      const float* bias, void* y, double* bn_sums, int stat_cout, int cout, int k, int n, int d, int h,
                      int w, int use_tensor_path, ctu_stream stream);
@@ -87,6 +89,13 @@ int ctu_conv_tc_wgrad_supported(int k, int nsrc, const int* h_src_channels, int 
 long long ctu_conv_tc_wimg_bytes(int k, int nsrc, const int* h_src_channels, int cout);
 int ctu_conv_tc_pack_weight(const float* wp, void* wimg, int k, int nsrc, const int* h_src_channels, int cout,
                             ctu_stream stream);
+/* wide tensor path (many channels on a 16^3 / 8^3 grid -- models.py:71,76 center block, :483,487 and the 56..128-channel
+ * 5^3 layers of the legacy family): weights streamed tap by tap, h and w multiples of 8.  The image depends on the
+ * launch geometry, so the batch and grid sizes are arguments of all three. */
+int ctu_conv_wide_supported(int k, int cin, int cout, int n, int d, int h, int w);
+long long ctu_conv_wide_wimg_bytes(int k, int cin, int cout, int n, int d, int h, int w);
+int ctu_conv_wide_pack_weight(const float* wp, void* wimg, int k, int cin, int cout, int n, int d, int h, int w,
+                              ctu_stream stream);
 /* dwp (packed layout, fp32) and dbias (nullable, [cout]) are zeroed by the call, then accumulated.
  * phase_cout: 0, or the natural channel count when dy is the phase-major gradient of the fused up-sampling stage
  * COMPOSED FROM A 3x3x3 CONVOLUTION (cout = 8 phases x 8*ceil(phase_cout/8)): the tensor path then skips the taps that are

@@ -27,7 +27,22 @@ CASES = [
     (3, 112, 28, False, (1, 2, 16, 16)),
     (3, 28, 112, False, (1, 2, 16, 16)),     # wgrad: output channels split over TMEM
     (5, 14, 28, True, (1, 3, 16, 16)),
-    (5, 56, 56, True, (1, 3, 16, 16)),       # wgrad: partial last output-channel group (16,16,16,8); fprop on CUDA cores
+    (5, 56, 56, True, (1, 3, 16, 16)),       # wgrad: partial last output-channel group (16,16,16,8); fprop: wide kernel
+]
+
+# wide, low-resolution layers: the weight-streaming kernel (conv_wide.cu), M = 128 tiles at 16^3, M = 64 at 8^3
+WIDE_CASES = [
+    (5, 64, 64, True, (2, 4, 16, 16)),
+    (5, 128, 64, True, (1, 3, 16, 16)),      # two channel groups of 8 blocks
+    (5, 112, 56, True, (1, 4, 16, 16)),      # groups of 8 + 6 blocks, 7 output blocks
+    (5, 64, 128, True, (2, 8, 8, 8)),        # 8 x 8 planes: M = 64
+    (5, 128, 128, True, (1, 8, 8, 8)),
+    (5, 56, 112, True, (1, 5, 8, 8)),        # odd block count: dummy K chunk
+    (3, 56, 112, False, (2, 8, 8, 8)),       # generic UNet center block (dead branch)
+    (3, 112, 112, False, (1, 8, 8, 8)),
+    (3, 56, 56, False, (4, 16, 16, 16)),     # both kernels cover it: the wide one is preferred
+    (3, 7, 7, False, (1, 2, 8, 8)),          # below the preference threshold, but the only tensor kernel for 8 x 8
+    (3, 40, 48, False, (1, 3, 32, 32)),      # the resident-weights kernel (preferred above 16 x 16)
 ]
 
 
@@ -35,14 +50,18 @@ def _bf(t):
     return t.to(torch.bfloat16).to(torch.float32)
 
 
-@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("case", CASES + WIDE_CASES)
 def test_tc_conv_matches_reference(case):
-    from ctunet_b200.engine import Engine, tc_supported
+    from ctunet_b200.engine import Engine, tc_variant
     from ctunet_b200 import _lib
     k, cin, cout, use_bias, (n, d, h, w) = case
     assert _lib.load().ctu_has_tensor_path() == 1
-    fprop_on_tc = tc_supported(k, [cin], cout, d, h, w)     # wide inputs are staged in groups of four channel blocks
-    assert fprop_on_tc or (k == 5 and cin >= 56)            # 5^3 weights of wide layers do not fit shared memory yet
+    fprop_on_tc = tc_variant(k, [cin], cout, n, d, h, w)
+    from ctunet_b200.engine import WIDE_MAX_HW, WIDE_MIN_CH, tc_supported
+    wide = (not tc_supported(k, [cin], cout, d, h, w)) or (min(cin, cout) >= WIDE_MIN_CH and max(h, w) <= WIDE_MAX_HW)
+    assert fprop_on_tc == (2 if wide else 1)
+    assert wide or case not in WIDE_CASES[:-2]
+    assert tc_variant(k, [cout], cin, n, d, h, w) > 0        # the data gradient runs on the tensor cores too
     g = torch.Generator().manual_seed(k * 100 + cin)
     x = _bf(torch.randn(n, cin, d, h, w, generator=g))
     wt = torch.randn(cout, cin, k, k, k, generator=g) / (cin * k ** 3) ** 0.5
@@ -77,7 +96,7 @@ def test_tc_conv_matches_reference(case):
     gerr = (dx - xr.grad).abs().max().item()
     assert gerr <= 1.2e-2 * gs, "dgrad err %.3e (scale %.3e)" % (gerr, gs)
     # weight gradient on the tensor cores (voxels as the K dimension): bf16 products, fp32 accumulation
-    assert _lib.load().ctu_conv_tc_wgrad_supported(k, 1, _lib.int_array([cin]), cout, d, h, w) == 1
+    assert _lib.load().ctu_conv_tc_wgrad_supported(k, 1, _lib.int_array([cin]), cout, d, h, w) == (1 if h % 16 == 0 else 0)
     wr = wt.clone().requires_grad_()
     br = bs.clone().requires_grad_() if use_bias else None
     F.conv3d(x, wr, br, 1, k // 2).backward(dy)
@@ -110,6 +129,9 @@ def test_tc_and_direct_agree_on_network_layer():
 def test_unsupported_shapes_fall_back_to_direct():
     from ctunet_b200.engine import tc_supported
     assert not tc_supported(3, [7], 7, 8, 8, 8)          # h, w not multiples of 16
+    from ctunet_b200.engine import tc_variant
+    assert tc_variant(3, [7], 7, 1, 8, 8, 8) == 2        # ... the weight-streaming kernel takes 8 x 8 planes
+    assert tc_variant(3, [7], 7, 1, 12, 12, 12) == 0
     assert not tc_supported(1, [7], 7, 16, 16, 16)       # 1x1x1 is the head kernel's job
     assert tc_supported(3, [7, 7], 7, 16, 16, 16)        # concatenated sources: one tensor map per source
     assert not tc_supported(3, [7] * 5, 7, 16, 16, 16)   # at most CTU_MAX_SRC sources
