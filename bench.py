@@ -38,6 +38,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=4)
     ap.add_argument("--size", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-workloads", action="store_true",
+                    help="skip the short device-resident runs of the legacy 5^3 models reported under other_workloads")
+    ap.add_argument("--kernels-out", default=None, help="write the full per-kernel timing table to this file")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="capture the training step in CUDA graphs (auto = on; data parallel: two graphs around one eager "
@@ -49,9 +52,15 @@ HANDLER = {"UNetSP": "double", "UNetDO": "double", "UNetSPSmall": "double", "UNe
            "recAE_v2_fixed": "single", "UNet": "single"}
 
 
+EXAMPLE_INI = {"UNetSP": "examples/autoimplant2020/UNetSPDO/FlapRecSP2O.ini",
+               "recAE_v2_fixed": "examples/autoimplant2020/UNet/AutoImplant2020_woShapePrior.ini",
+               "UNet4_2IC": "examples/autoimplant2020/UNetSP/AutoImplant2020_wShapePrior.ini"}
+
+
 def workload_name(a):
-    return ("%s + %s loss (dice_lambda=1, ce_lambda=1) + Adam(amsgrad) lr 1e-4, batch %d/GPU, %dx%d^3 synthetic "
-            "skull CT" % (a.model, "FlapRecWithShapePriorDoubleOut" if HANDLER[a.model] == "double" else "ProblemHandler",
+    return ("%s%s + %s loss (dice_lambda=1, ce_lambda=1) + Adam(amsgrad) lr 1e-4, batch %d/GPU, %dx%d^3 synthetic "
+            "skull CT" % (a.model, " (%s)" % EXAMPLE_INI[a.model] if a.model in EXAMPLE_INI else "",
+                          "FlapRecWithShapePriorDoubleOut" if HANDLER[a.model] == "double" else "ProblemHandler",
                           a.batch, 2 if a.model in ("UNetSP", "UNetSPSmall", "UNet4_2IC") else 1, a.size))
 
 
@@ -327,12 +336,14 @@ def run_b200_arm(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, after=None):
         barrier()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         for _ in range(steps):
             fn()
+        if after is not None:
+            after()                       # e.g. read the last step's loss back: still inside the timed region
         e.record()
         barrier()
         ms = torch.tensor([s.elapsed_time(e)], device=dev)
@@ -352,7 +363,6 @@ def run_b200_arm(a):
     l0 = _lib.launches
     ms_resident = timed(resident, a.steps)
     launches = (a.steps * step.launches_per_step) if use_graph else (_lib.launches - l0)
-    clk = clocks.stop() if rank == 0 else None
     # the same K steps again with a CUDA-event pair around every C-ABI call (on the launching stream): the
     # per-kernel durations behind `roofline`.  Kept out of the `value` loop: creating ~1500 events per step in
     # Python costs more host time than the step itself.
@@ -374,39 +384,65 @@ def run_b200_arm(a):
         net._grad_sink = sync
 
     # ---- end-to-end steps: pinned host -> device every iteration, loss read back ----------------
+    # e2e      : the reference-facing call -- float32 image + one-hot float32 targets exactly as the reference's
+    #            DataLoader hands them to Model.forward_pass (Model.py:343-349), from pinned host memory
+    # e2e_u8   : the device-side batch encoding (ctu_encode_flaprec_u8, datasets.py:195-235): the host ships the three
+    #            uint8 masks (3 B/voxel instead of 24) and the atlas channel stays resident
+    # Both double-buffer the H2D copy on a copy stream and read every step's loss components back through
+    # LossReadback (one step of latency, so the host never idles the GPU).
+    from ctunet_b200.trainer import LossReadback
     copy_stream = torch.cuda.Stream(device=dev)
-    dbuf = [[torch.empty_like(t, device=dev) for t in host] for _ in range(2)]
-    state = {"i": 0, "ready": None}
+    double = HANDLER[a.model] == "double"
 
-    def prefetch(slot):
-        with torch.cuda.stream(copy_stream):
-            for dst, src in zip(dbuf[slot], host):
-                dst.copy_(src, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(copy_stream)
-        return ev
+    def make_e2e(host_bufs, run_step):
+        dbuf = [[torch.empty_like(t, device=dev) for t in host_bufs] for _ in range(2)]
+        state = {"i": 0, "ready": None}
+        rb = LossReadback(5 if double else 3)
 
-    d2h_bytes = 0
+        def prefetch(slot):
+            with torch.cuda.stream(copy_stream):
+                for dst, src in zip(dbuf[slot], host_bufs):
+                    dst.copy_(src, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return ev
 
-    def e2e_step():
-        nonlocal d2h_bytes
-        slot = state["i"] & 1
-        if state["ready"] is None:
-            state["ready"] = prefetch(slot)
-        torch.cuda.current_stream().wait_event(state["ready"])
-        bufs = dbuf[slot]
-        copy_stream.wait_stream(torch.cuda.current_stream())      # the other slot's consumer has been enqueued
-        state["ready"] = prefetch(slot ^ 1)                        # overlap next batch's H2D with this step
-        comps = step(bufs[0], (bufs[1], bufs[2]) if len(bufs) == 3 else bufs[1])
-        vals = comps.tolist()                                      # the D2H of the step's result (one sync)
-        d2h_bytes = 4 * len(vals)
-        state["i"] += 1
-        return vals
+        def one():
+            slot = state["i"] & 1
+            if state["ready"] is None:
+                state["ready"] = prefetch(slot)
+            torch.cuda.current_stream().wait_event(state["ready"])
+            copy_stream.wait_stream(torch.cuda.current_stream())      # the other slot's consumer has been enqueued
+            state["ready"] = prefetch(slot ^ 1)                        # overlap next batch's H2D with this step
+            comps = run_step(dbuf[slot])
+            state["i"] += 1
+            return rb.push(comps)                                      # D2H of this step's result; returns step i-1's
 
-    for _ in range(2):
+        return one, rb
+
+    e2e_step, rb = make_e2e(host, lambda b: step(b[0], (b[1], b[2]) if len(b) == 3 else b[1]))
+    for _ in range(3):
         e2e_step()
-    ms_e2e = timed(e2e_step, a.steps)
+    ms_e2e = timed(e2e_step, a.steps, after=rb.drain)
+    d2h_bytes = rb.bytes_per_step
 
+    e2e_u8 = None
+    if double:
+        # uint8 masks: broken skull = image channel 0, full skull = target 0 class 1, flap = target 1 class 1
+        host_u8 = [t.to(torch.uint8).cpu().pin_memory() for t in (img[:, 0], sk_t[:, 1], fl_t[:, 1])]
+        atlas_dev = img[0, 1].contiguous() if cin > 1 else None
+
+        u8_step, rb8 = make_e2e(host_u8, lambda b: step.step_from_masks(b[0], b[1], b[2], atlas_dev))
+        for _ in range(3):
+            u8_step()
+        ms_u8 = timed(u8_step, a.steps, after=rb8.drain)
+        e2e_u8 = {"value": a.batch * a.size ** 3 * world / (ms_u8 * 1e-3), "unit": UNIT, "ms_per_step": ms_u8,
+                  "h2d_bytes_per_step": sum(t.numel() for t in host_u8), "d2h_bytes_per_step": rb8.bytes_per_step,
+                  "note": "TrainStep.step_from_masks: uint8 masks from pinned host memory, batch encoded on the device "
+                          "(ctu_encode_flaprec_u8) into the captured step's inputs"}
+
+    # nvidia-smi was sampling (every 50 ms) from the start of the timed `value` loop to the end of the e2e loops
+    clk = clocks.stop() if rank == 0 else None
     vox_per_step = a.batch * a.size ** 3 * world
     value = vox_per_step / (ms_resident * 1e-3)
     e2e_value = vox_per_step / (ms_e2e * 1e-3)
@@ -446,6 +482,12 @@ def run_b200_arm(a):
         e = k.split(" ")[0]
         by_entry[e] = by_entry.get(e, 0.0) + v[0] / a.steps
     by_entry = dict(sorted(by_entry.items(), key=lambda kv: -kv[1]))
+    if a.kernels_out:            # the full per-kernel table (launch count, mean us, algorithmic TFLOP/s and GB/s)
+        with open(a.kernels_out, "w") as f:
+            f.write("%-64s %5s %10s %9s %9s\n" % ("kernel", "n/st", "us/launch", "TFLOP/s", "GB/s"))
+            for k, (ms, cnt, fl, by) in ranked:
+                us = ms / cnt * 1e3
+                f.write("%-64s %5.1f %10.1f %9.1f %9.1f\n" % (k, cnt / a.steps, us, fl / us / 1e6, by / us / 1e3))
 
     cpu = None
     if world == 1 and not a.no_cpu_baseline:
@@ -453,6 +495,24 @@ def run_b200_arm(a):
         sec, used = cpu_reference_step_time(a.model, cb, cs, steps=3, warmup=1, threads=os.cpu_count())
         cpu = {"value": cb * cs ** 3 / sec, "unit": UNIT, "cores": used, "kind": "port",
                "sample": "batch %d x %d^3 (BASELINE config 0 shape), fp32, 3 steps after 1 warm-up, %.2f s/step" % (cb, cs, sec)}
+
+    # the other BASELINE configs[1] models (the 5^3 autoimplant2020 family): short device-resident runs, same batch and size
+    others = None
+    if world == 1 and not a.no_other_workloads and a.model == "UNetSP":
+        others = []
+        torch.cuda.empty_cache()
+        for other in ("recAE_v2_fixed", "UNet4_2IC"):
+            torch.manual_seed(0)
+            onet = getattr(C, other)().to(dev)
+            ostep = TrainStep(onet, HANDLER[other], 1.0, 1.0, lr=1e-4, graph=use_graph)
+            oimg, (osk, _) = make_training_batch(a.batch, in_channels(other), a.size, seed=1234, device=dev)
+            for _ in range(4):
+                ostep(oimg, osk)
+            oms = timed(lambda: ostep(oimg, osk), 10)
+            others.append({"workload": workload_name(argparse.Namespace(model=other, batch=a.batch, size=a.size)),
+                           "value": a.batch * a.size ** 3 / (oms * 1e-3), "unit": UNIT, "ms_per_step": oms, "steps": 10})
+            del ostep, onet
+            torch.cuda.empty_cache()
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
@@ -462,13 +522,17 @@ def run_b200_arm(a):
                    "l2": flush_note, "conv_path": "tcgen05" if _lib.load().ctu_has_tensor_path() else "cuda-core",
                    "cuda_graph": use_graph},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes,
-                "d2h_bytes_per_step": d2h_bytes},
+                "d2h_bytes_per_step": d2h_bytes,
+                "note": "float32 image + one-hot float32 targets from pinned host memory (the reference DataLoader's "
+                        "format), double-buffered H2D, loss components read back every step one step late"},
+        "e2e_u8_masks": e2e_u8,
         "gpu_launches": launches,
         "gpu_launches_note": "C-ABI entry points in the timed region (each enqueues >= 1 kernel of this library)"
                              + ("; the step is replayed from a CUDA graph captured once" if use_graph else ""),
         "clocks": clk,
         "roofline": roof,
         "cpu_baseline": cpu,
+        "other_workloads": others,
         "top_kernels": top,
         "ms_per_step_by_entry_point": by_entry,
         "profiled_ms_per_step": total_ms / a.steps,

@@ -10,7 +10,7 @@ from .models import (UNet, UNet4b1i3o, UNet4b2i3o, UNet5b2i3o, UNetDO, UNetSP, U
                      set_compute_dtype, get_compute_dtype)
 from .losses import (dice_loss, dice_ce, ProblemHandler, FlapRec, FlapRecWithShapePrior,  # noqa: F401
                      FlapRecWithShapePriorDoubleOut, FlapRecDoubleOut)
-from .utilities import (hard_segm_from_tensor, shape_3d, blank_patch, random_blank_patch,  # noqa: F401
+from .utilities import (hard_segm_from_tensor, shape_3d, blank_patch, random_blank_patch, encode_flaprec_batch,  # noqa: F401
                         SkullRandomHole, kth_nonzero, count_nonzero)
 from . import preprocess  # noqa: F401
 from .dropin import install, MODEL_CLASSES, HANDLER_CLASSES  # noqa: F401

@@ -70,7 +70,8 @@ SIGNATURES = {
     "ctu_argmax_channels": (I, [P, P, I, I, LL, P]),
     "ctu_count_nonzero_u8": (I, [P, LL, P, P]),
     "ctu_kth_nonzero_u8": (I, [P, I, I, I, LL, P, P, P]),
-    "ctu_flap_mask_u8": (I, [P, P, P, I, I, I, P, D, I, P]),
+    "ctu_flap_mask_u8": (I, [P, P, P, I, I, I, P, D, I, D, P]),
+    "ctu_encode_flaprec_u8": (I, [P, P, P, P, P, P, P, I, I, LL, P]),
     "ctu_hu_window": (I, [P, P, LL, F, F, P]),
     "ctu_hu_threshold": (I, [P, P, LL, I, P]),
     "ctu_resample_nearest_f32": (I, [P, P, I, I, I, I, I, I, P]),

@@ -74,6 +74,72 @@ __global__ void flap_mask_kernel(const unsigned char* __restrict__ img, unsigned
     extracted[v] = (on && inside) ? 1 : 0;                              // transforms.py:294
 }
 
+// shape_3d(shape="flap") (utilities.py:145-166): union of two cylinders along d (raster_geometry.cylinder, axis 0) and
+// a cube (raster_geometry.cube).  raster_geometry is an un-vendored, unpinned dependency of the reference and is not
+// installed here, so its published algorithm is RESTATED -- parity unpinned: relative positions become absolute grid
+// origins x0 = round((dim - 1) * rel) (round half to even), a cylinder is {(y-y0)^2 + (x-x0)^2 <= radius^2 and
+// |z-z0| <= height/2}, a cube is {|c - c0| <= side/2 on every axis}, all in float64.
+__global__ void flap_shape_mask_kernel(const unsigned char* __restrict__ img, unsigned char* __restrict__ masked,
+                                       unsigned char* __restrict__ extracted, int d, int h, int w,
+                                       const int* __restrict__ center, double size, double c_diam, long long nvox) {
+    const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nvox) return;
+    const int x = (int)(v % w);
+    const int y = (int)((v / w) % h);
+    const int z = (int)(v / ((long long)w * h));
+    const double c0 = (double)center[0], c1 = (double)center[1], c2 = (double)center[2];
+    // center_relative, z_edge_1, z_edge_2 (utilities.py:148-158) -> absolute origins
+    const double z0 = rint((d - 1) * (c0 / d));
+    const double ey = rint((h - 1) * ((c1 - size / 2) / h));
+    const double ex1 = rint((w - 1) * ((c2 - size / 2) / w)), ex2 = rint((w - 1) * ((c2 + size / 2) / w));
+    const double qy = rint((h - 1) * (c1 / h)), qx = rint((w - 1) * (c2 / w));
+    const double dz = z - z0;
+    const bool in_height = fabs(dz) <= size / 2;
+    const double r2 = c_diam * c_diam, dy = y - ey;
+    const bool cyl1 = in_height && (dy * dy + (x - ex1) * (x - ex1) <= r2);
+    const bool cyl2 = in_height && (dy * dy + (x - ex2) * (x - ex2) <= r2);
+    const bool cub = in_height && fabs(y - qy) <= size / 2 && fabs(x - qx) <= size / 2;
+    const bool inside = cyl1 || cyl2 || cub;                            // mask; shape_np = 1 - mask (utilities.py:165-166)
+    const bool on = img[v] != 0;
+    masked[v] = (on && !inside) ? 1 : 0;
+    extracted[v] = (on && inside) ? 1 : 0;
+}
+
+// datasets.py:195-235 on the device: image channel 0 = the broken skull as float, channel 1 = the atlas
+// (load_atlas_and_append_at_axis, datasets.py:30-47); targets = one_hot(label, 2) as float32 (datasets.py:209-214).
+// 16 voxels per thread: one 16-byte load per mask, 16-byte stores.
+__global__ void encode_flaprec_kernel(const unsigned char* __restrict__ broken, const unsigned char* __restrict__ full,
+                                      const unsigned char* __restrict__ flap, const float* __restrict__ atlas,
+                                      float* __restrict__ image, float* __restrict__ skull_t, float* __restrict__ flap_t,
+                                      int cin, long long spatial) {
+    const int b = blockIdx.y;
+    const long long v0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (v0 >= spatial) return;
+    const uint4 ub = *reinterpret_cast<const uint4*>(broken + b * spatial + v0);
+    const uint4 uf = *reinterpret_cast<const uint4*>(full + b * spatial + v0);
+    const uint4 ul = *reinterpret_cast<const uint4*>(flap + b * spatial + v0);
+    const uint32_t wb[4] = {ub.x, ub.y, ub.z, ub.w}, wf[4] = {uf.x, uf.y, uf.z, uf.w}, wl[4] = {ul.x, ul.y, ul.z, ul.w};
+    float* img0 = image + (long long)b * cin * spatial + v0;
+    float* sk0 = skull_t + (long long)b * 2 * spatial + v0;
+    float* fl0 = flap_t + (long long)b * 2 * spatial + v0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float vb[4], vf[4], vl[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            vb[j] = (float)((wb[i] >> (8 * j)) & 0xffu);                 // tensor.float(): the value itself
+            vf[j] = ((wf[i] >> (8 * j)) & 0xffu) ? 1.f : 0.f;            // one_hot class of a {0,1} label
+            vl[j] = ((wl[i] >> (8 * j)) & 0xffu) ? 1.f : 0.f;
+        }
+        *reinterpret_cast<float4*>(img0 + 4 * i) = make_float4(vb[0], vb[1], vb[2], vb[3]);
+        *reinterpret_cast<float4*>(sk0 + 4 * i) = make_float4(1.f - vf[0], 1.f - vf[1], 1.f - vf[2], 1.f - vf[3]);
+        *reinterpret_cast<float4*>(sk0 + spatial + 4 * i) = make_float4(vf[0], vf[1], vf[2], vf[3]);
+        *reinterpret_cast<float4*>(fl0 + 4 * i) = make_float4(1.f - vl[0], 1.f - vl[1], 1.f - vl[2], 1.f - vl[3]);
+        *reinterpret_cast<float4*>(fl0 + spatial + 4 * i) = make_float4(vl[0], vl[1], vl[2], vl[3]);
+        if (cin > 1) *reinterpret_cast<float4*>(img0 + spatial + 4 * i) = *reinterpret_cast<const float4*>(atlas + v0 + 4 * i);
+    }
+}
+
 __global__ void hu_window_kernel(const short* __restrict__ hu, float* __restrict__ out, long long nvox, float lo,
                                  float hi) {
     const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -171,12 +237,28 @@ int ctu_kth_nonzero_u8(const unsigned char* img, int d, int h, int w, long long 
 }
 
 int ctu_flap_mask_u8(const unsigned char* img, unsigned char* masked, unsigned char* extracted, int d, int h, int w,
-                     const int* center, double size, int shape, ctu_stream stream) {
-    CTU_REQUIRE(img && masked && extracted && center && d > 0 && h > 0 && w > 0 && (shape == 0 || shape == 1),
-                "ctu_flap_mask_u8: bad arguments (shape 0 sphere / 1 box; 'flap' needs raster_geometry: parity unpinned)");
+                     const int* center, double size, int shape, double c_diam, ctu_stream stream) {
+    CTU_REQUIRE(img && masked && extracted && center && d > 0 && h > 0 && w > 0 && shape >= 0 && shape <= 2,
+                "ctu_flap_mask_u8: bad arguments (shape 0 sphere / 1 box / 2 flap)");
     const long long nvox = (long long)d * h * w;
-    flap_mask_kernel<<<cdiv(nvox, 256), 256, 0, (cudaStream_t)stream>>>(img, masked, extracted, d, h, w, center, size, shape, nvox);
+    if (shape == 2)
+        flap_shape_mask_kernel<<<cdiv(nvox, 256), 256, 0, (cudaStream_t)stream>>>(img, masked, extracted, d, h, w, center, size, c_diam, nvox);
+    else
+        flap_mask_kernel<<<cdiv(nvox, 256), 256, 0, (cudaStream_t)stream>>>(img, masked, extracted, d, h, w, center, size, shape, nvox);
     return check_launch("ctu_flap_mask_u8");
+}
+
+int ctu_encode_flaprec_u8(const unsigned char* broken, const unsigned char* full, const unsigned char* flap,
+                          const float* atlas, float* image, float* skull_target, float* flap_target, int batch,
+                          int in_channels, long long spatial, ctu_stream stream) {
+    CTU_REQUIRE(broken && full && flap && image && skull_target && flap_target && batch > 0 && spatial > 0,
+                "ctu_encode_flaprec_u8: bad arguments");
+    CTU_REQUIRE(in_channels == 1 || (in_channels == 2 && atlas), "ctu_encode_flaprec_u8: 1 input channel, or 2 with an atlas");
+    CTU_REQUIRE(spatial % 16 == 0, "ctu_encode_flaprec_u8: the volume size must be a multiple of 16 voxels");
+    dim3 grid(cdiv(spatial / 16, 256), batch);
+    encode_flaprec_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(broken, full, flap, atlas, image, skull_target, flap_target,
+                                                                  in_channels, spatial);
+    return check_launch("ctu_encode_flaprec_u8");
 }
 
 int ctu_hu_window(const short* hu, float* out, long long nvox, float lo, float hi, ctu_stream stream) {

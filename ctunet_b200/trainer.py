@@ -117,11 +117,28 @@ class TrainStep:
                     p.grad = None
             self.launches_per_step = _lib.launches - l0
             self._graph = g
+        return self._replay()
+
+    def _replay(self):
         self._graph.replay()
         if self.grad_sync is not None:
             self.grad_sync.reduce_all()
             self._graph_opt.replay()
         return self._static_out
+
+    def step_from_masks(self, broken: torch.Tensor, full: torch.Tensor, flap: torch.Tensor, atlas=None):
+        """One iteration from the uint8 masks of a batch ([B,D,H,W] each, on the device): the float image (+ atlas
+        channel) and the two one-hot targets of datasets.py:195-235 are produced by ``ctu_encode_flaprec_u8`` --
+        straight into the captured graph's static inputs once the step is captured -- so a training loop ships
+        3 bytes per voxel over PCIe instead of 24."""
+        from .utilities import encode_flaprec_batch
+        if self.handler != "double":
+            raise ValueError("step_from_masks feeds the double-output handler (full skull + flap targets)")
+        if self._graph is not None:
+            encode_flaprec_batch(broken, full, flap, atlas, out=(self._static[0], (self._static[1], self._static[2])))
+            return self._replay()
+        image, target = encode_flaprec_batch(broken, full, flap, atlas)
+        return self(image, target)
 
     def _forward_backward(self, image: torch.Tensor, target):
         self.model.train()
@@ -145,3 +162,34 @@ class TrainStep:
         for p in self.model.parameters():                     # Model.py:373-374
             p.grad = None
         return comps
+
+
+class LossReadback:
+    """Deferred read-back of the loss components.
+
+    The reference reads every component with ``float(...)`` as soon as it exists (ProblemHandler.py:253-302): five host
+    syncs per batch, each idling the GPU until the host has enqueued the next kernels.  Here every step's component
+    tensor is copied asynchronously into pinned host memory on the step's stream; ``push`` returns the values of the
+    PREVIOUS step (already complete, or waited for while the current step runs), ``drain`` the last one.  The
+    ``losses_and_metrics`` lists (Model.py:363, ProblemHandler.py:71-102) receive the same floats, one step later."""
+
+    def __init__(self, n_values: int, depth: int = 2):
+        self.host = [torch.empty(n_values, dtype=torch.float32).pin_memory() for _ in range(depth)]
+        self.events = [torch.cuda.Event() for _ in range(depth)]
+        self.count = 0
+        self.bytes_per_step = 4 * n_values
+
+    def push(self, comps: torch.Tensor):
+        slot = self.count % len(self.host)
+        self.host[slot].copy_(comps, non_blocking=True)
+        self.events[slot].record()
+        self.count += 1
+        return self._read(self.count - 2) if self.count >= 2 else None
+
+    def drain(self):
+        return self._read(self.count - 1) if self.count else None
+
+    def _read(self, index: int):
+        slot = index % len(self.host)
+        self.events[slot].synchronize()
+        return self.host[slot].tolist()

@@ -1,13 +1,15 @@
 """GPU versions of the hot-path helpers of ``ctunet.utilities`` / ``ctunet.pytorch.transforms``.
 
   hard_segm_from_tensor   ctunet/utilities.py:103-124
-  shape_3d (sphere, box)  ctunet/utilities.py:127-178
+  shape_3d                ctunet/utilities.py:127-178
   random_blank_patch      ctunet/pytorch/transforms.py:241-300
   SkullRandomHole         ctunet/pytorch/transforms.py:52-94
+  encode_flaprec_batch    ctunet/pytorch/datasets.py:195-235, :30-47 (one-hot targets, atlas channel)
 
-The 'flap' shape of shape_3d calls the un-vendored ``raster_geometry`` package in the reference
-(utilities.py:145-166): its exact voxelisation cannot be verified here (parity unpinned), so it is not
-offered; ``random_blank_patch`` draws its shape from ("sphere", "box").
+The 'flap' shape of shape_3d calls the un-vendored, unpinned ``raster_geometry`` package in the reference
+(utilities.py:145-166); it is not installed here, so ``cylinder`` / ``cube`` are RESTATED from the package's published
+algorithm (oracle/unet_oracle.py: ``rg_cylinder``, ``rg_cube``) -- sphere and box are pinned to the reference,
+the flap shape is parity unpinned.
 """
 from __future__ import annotations
 
@@ -19,7 +21,7 @@ import torch
 from ._lib import call, stream_ptr
 from .losses import dice_loss  # noqa: F401  (re-export: utils.dice_loss)
 
-_SHAPES = {"circle": 0, "sphere": 0, "square": 1, "box": 1, "cube": 1}
+_SHAPES = {"circle": 0, "sphere": 0, "square": 1, "box": 1, "cube": 1, "flap": 2, "autoimplant": 2}
 
 
 def _need_cuda(t, what):
@@ -44,12 +46,15 @@ def hard_segm_from_tensor(prob_map: torch.Tensor, keep_dims: bool = False) -> to
     return out.unsqueeze(0) if keep_dims else out
 
 
-def blank_patch(image: torch.Tensor, center, size, shape: str):
+def blank_patch(image: torch.Tensor, center, size, shape: str, c_diam=None):
     """``masked = image AND outside``, ``extracted = image AND inside`` (uint8), the arithmetic of
-    transforms.py:286-296 for a given centre / radius / shape.  ``center`` is a host triple or a device int32[3]."""
+    transforms.py:286-296 for a given centre / radius / shape.  ``center`` is a host triple or a device int32[3].
+    The 'flap' shape draws its cylinder radius ``c_diam`` from the numpy RNG as utilities.py:146-148 unless given."""
     _need_cuda(image, "blank_patch")
     if shape not in _SHAPES:
-        raise NotImplementedError("shape %r is not available (the 'flap' shape needs raster_geometry)" % (shape,))
+        raise ValueError("shape %r is not supported (sphere, box, flap)" % (shape,))
+    if _SHAPES[shape] == 2 and c_diam is None:
+        c_diam = np.random.uniform(0.25, 1) * size / 4
     img = image.to(torch.uint8).contiguous()
     if img.dim() != 3:
         raise ValueError("expected a [D, H, W] volume")
@@ -58,15 +63,16 @@ def blank_patch(image: torch.Tensor, center, size, shape: str):
     masked, extracted = torch.empty_like(img), torch.empty_like(img)
     d, h, w = img.shape
     call("ctu_flap_mask_u8", img.data_ptr(), masked.data_ptr(), extracted.data_ptr(), d, h, w, center.data_ptr(),
-         float(size), _SHAPES[shape], stream_ptr())
+         float(size), _SHAPES[shape], float(c_diam or 0.0), stream_ptr())
     return masked, extracted
 
 
-def shape_3d(center, size, image_size, shape="sphere", device="cuda") -> torch.Tensor:
-    """utilities.py:127-178 for 'sphere' / 'box': float64 volume, 0 inside (bound inclusive), 1 outside."""
+def shape_3d(center, size, image_size, shape="flap", device="cuda", c_diam=None) -> torch.Tensor:
+    """utilities.py:127-178: 0 inside the shape (bounds inclusive), 1 outside; float64 for sphere / box, uint8 for
+    the flap shape, as the reference returns them."""
     ones = torch.ones(tuple(image_size), dtype=torch.uint8, device=device)
-    masked, _ = blank_patch(ones, center, size, shape)
-    return masked.to(torch.float64)
+    masked, _ = blank_patch(ones, center, size, shape, c_diam)
+    return masked if _SHAPES[shape] == 2 else masked.to(torch.float64)
 
 
 def count_nonzero(image: torch.Tensor) -> int:
@@ -94,10 +100,11 @@ def radius_bounds(image_size):
 
 
 def random_blank_patch(image: torch.Tensor, prob=1, return_extracted=False, p_type="random",
-                       valid_shapes=("sphere", "box")):
+                       valid_shapes=("sphere", "box", "flap")):
     """transforms.py:241-300 on a CUDA volume.  Consumes the host RNGs in the reference's order
-    (random.uniform, np.random.choice, np.random.randint, np.random.randint) so a seeded run picks the
-    same voxel index, radius and shape index as the reference would for the same nonzero count."""
+    (random.uniform, np.random.choice, np.random.randint, np.random.randint, and np.random.uniform for the flap
+    shape) so a seeded run picks the same voxel index, radius, shape index and cylinder radius as the reference would
+    for the same nonzero count."""
     _need_cuda(image, "random_blank_patch")
     img = image.to(torch.uint8).contiguous()
     r = random.uniform(0, 1)
@@ -138,3 +145,35 @@ class SkullRandomHole(object):
         if self.double_output:
             return {"image": brk, "target": (full, flap)}
         return {"image": brk, "target": flap}
+
+
+def encode_flaprec_batch(broken: torch.Tensor, full: torch.Tensor, flap: torch.Tensor, atlas=None, out=None):
+    """What ``FlapRecWShapePrior2OTrainDataset.__getitem__`` + the default collate hand the model
+    (datasets.py:195-235), computed on the device from uint8 masks [B,D,H,W]:
+    image [B,Cin,D,H,W] float32 (channel 0 = the broken skull, channel 1 = ``atlas`` [D,H,W] float32 as
+    ``load_atlas_and_append_at_axis`` appends it, datasets.py:30-47) and the two targets
+    ``one_hot(label, 2).movedim(-1, 1).float()`` [B,2,D,H,W] (datasets.py:209-214).  The host then ships 3 bytes per
+    voxel instead of 24.  ``out = (image, (skull_target, flap_target))`` writes into existing tensors."""
+    for t in (broken, full, flap):
+        _need_cuda(t, "encode_flaprec_batch")
+        if t.dtype != torch.uint8 or t.dim() != 4 or t.shape != broken.shape:
+            raise TypeError("encode_flaprec_batch expects three uint8 [B, D, H, W] masks of one shape")
+    b = broken.shape[0]
+    vol = tuple(broken.shape[1:])
+    spatial = broken[0].numel()
+    cin = 1 if atlas is None else 2
+    if atlas is not None and (atlas.dtype != torch.float32 or tuple(atlas.shape) != vol or not atlas.is_cuda):
+        raise TypeError("atlas: float32 CUDA volume of the mask shape")
+    if out is None:
+        image = torch.empty((b, cin) + vol, dtype=torch.float32, device=broken.device)
+        sk = torch.empty((b, 2) + vol, dtype=torch.float32, device=broken.device)
+        fl = torch.empty_like(sk)
+    else:
+        image, (sk, fl) = out
+        for t, c in ((image, cin), (sk, 2), (fl, 2)):
+            if t.dtype != torch.float32 or tuple(t.shape) != (b, c) + vol or not t.is_contiguous() or not t.is_cuda:
+                raise TypeError("encode_flaprec_batch: out tensors must be contiguous float32 CUDA [B, C, D, H, W]")
+    call("ctu_encode_flaprec_u8", broken.contiguous().data_ptr(), full.contiguous().data_ptr(),
+         flap.contiguous().data_ptr(), atlas.contiguous().data_ptr() if atlas is not None else None, image.data_ptr(),
+         sk.data_ptr(), fl.data_ptr(), b, cin, spatial, stream_ptr())
+    return image, (sk, fl)

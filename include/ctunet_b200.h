@@ -192,10 +192,19 @@ int ctu_count_nonzero_u8(const unsigned char* img, long long nvox, long long* co
 /* coords[0..2] = np.argwhere(img > 0)[k] in C order; block_counts is scratch: long long[ceil(nvox/4096)+1] */
 int ctu_kth_nonzero_u8(const unsigned char* img, int d, int h, int w, long long k, long long* block_counts, int* coords,
                        ctu_stream stream);
-/* shape: 0 sphere (2-norm), 1 box (inf-norm); centre read from DEVICE int[3];
- * masked = img AND outside, extracted = img AND inside (distance <= size, float64 like numpy) */
+/* shape: 0 sphere (2-norm), 1 box (inf-norm), 2 flap (two cylinders of radius c_diam + a cube, utilities.py:145-166;
+ * restates raster_geometry.cylinder / cube, which the reference imports un-vendored: parity unpinned);
+ * centre read from DEVICE int[3]; masked = img AND outside, extracted = img AND inside (distance <= size, float64
+ * like numpy).  c_diam is only read for shape 2. */
 int ctu_flap_mask_u8(const unsigned char* img, unsigned char* masked, unsigned char* extracted, int d, int h, int w,
-                     const int* center, double size, int shape, ctu_stream stream);
+                     const int* center, double size, int shape, double c_diam, ctu_stream stream);
+
+/* ---- batch encoding on the device (datasets.py:195-235, :30-47): uint8 masks [batch][spatial] ->
+ *      image [batch][in_channels][spatial] float32 (channel 0 = broken skull, channel 1 = atlas [spatial], nullable for
+ *      1-channel models) and the two one-hot float32 targets [batch][2][spatial] (datasets.py:209-214). ---------- */
+int ctu_encode_flaprec_u8(const unsigned char* broken, const unsigned char* full, const unsigned char* flap,
+                          const float* atlas, float* image, float* skull_target, float* flap_target, int batch,
+                          int in_channels, long long spatial, ctu_stream stream);
 
 /* ---- CT preprocessing (no reference implementation: oracle/unet_oracle.py defines it) -------- */
 int ctu_hu_window(const short* hu, float* out, long long nvox, float lo, float hi, ctu_stream stream);

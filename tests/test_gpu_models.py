@@ -362,6 +362,34 @@ def test_cuda_graph_step_matches_eager_step(mode, size):
             assert float((sa[k] - sb[k]).abs().max()) <= 1e-4, k          # at most 5 steps x lr 1e-5 x 2
 
 
+@pytest.mark.parametrize("graph", [False, True])
+def test_step_from_masks_equals_step_from_float_batch(graph):
+    """TrainStep.step_from_masks (uint8 masks, batch encoded on the device -- datasets.py:195-235) feeds the step the
+    same tensors as the float batch the reference DataLoader would deliver: identical loss components."""
+    from ctunet_b200.synthetic import make_training_batch
+    from ctunet_b200.trainer import LossReadback, TrainStep
+    img, (sk_t, fl_t) = make_training_batch(2, 2, 32, seed=77, device=DEV)
+    masks = [t.to(torch.uint8).contiguous() for t in (img[:, 0], sk_t[:, 1], fl_t[:, 1])]
+    atlas = img[0, 1].contiguous()
+    hist = []
+    for use_masks in (False, True):
+        torch.manual_seed(0)
+        net = _build("UNetSP", "bf16").to(DEV).train()
+        step = TrainStep(net, "double", 1.0, 1.0, lr=1e-5, graph=graph)
+        rb, vals = LossReadback(5), []
+        for _ in range(4):
+            comps = step.step_from_masks(*masks, atlas) if use_masks else step(img, (sk_t, fl_t))
+            prev = rb.push(comps)
+            if prev is not None:
+                vals.append(prev)
+        vals.append(rb.drain())
+        assert len(vals) == 4 and all(len(v) == 5 for v in vals)
+        hist.append(vals)
+    for a, b in zip(hist[0], hist[1]):
+        assert a == pytest.approx(b, rel=2e-3, abs=2e-3)      # same inputs; only atomic accumulation order differs
+    assert hist[0][0][-1] == pytest.approx(sum(hist[0][0][:-1]), rel=1e-5)
+
+
 def test_data_parallel_graph_step_world1_matches_plain_step(tmp_path):
     """The data-parallel CUDA-graph step (graph 1: forward+backward into the flat gradient buffer, one eager NCCL
     all-reduce, graph 2: optimizer) on a single-rank NCCL group reproduces the plain eager step."""

@@ -313,6 +313,56 @@ def test_flap_mask_bit_exact(golden):
     assert int((C.shape_3d((8, 8, 8), 4, (16, 16, 16), "box") == 0).sum()) == s["box_zeros"]
 
 
+def test_flap_shape_bit_exact():
+    """The 'flap' shape (two cylinders + cube) against the golden vectors made by the reference's own shape_3d /
+    random_blank_patch over the restated raster_geometry functions, and against the oracle on random cases."""
+    import os
+    import random
+    import ctunet_b200 as C
+    from oracle import unet_oracle as O
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "flap_shape_golden.pt"))
+    for c in gold["cases"]:
+        shp = C.shape_3d(c["center"], c["size"], c["image_size"], "flap", c_diam=c["c_diam"])
+        assert shp.dtype == torch.uint8 and int((shp == 0).sum()) == c["zeros"]
+        assert np.array_equal(np.packbits(shp.cpu().numpy()), c["packed"].numpy())
+    r = gold["random_blank_patch"]
+    random.seed(r["seed"])
+    np.random.seed(r["seed"])
+    m, e = C.random_blank_patch(r["img"].to(DEV), 1, True, p_type="flap")
+    assert torch.equal(m.cpu(), r["masked"]) and torch.equal(e.cpu(), r["extracted"])
+    ra = gold["random_blank_patch_any"]                    # p_type="random": shape index drawn from all three shapes
+    random.seed(ra["seed"])
+    np.random.seed(ra["seed"])
+    m, e = C.random_blank_patch(r["img"].to(DEV), 1, True)
+    assert torch.equal(m.cpu(), ra["masked"]) and torch.equal(e.cpu(), ra["extracted"])
+    rng = np.random.RandomState(3)
+    for _ in range(6):
+        dims = tuple(int(v) for v in rng.randint(6, 48, 3))
+        vol = (rng.rand(*dims) > 0.5).astype(np.uint8)
+        center = [int(rng.randint(0, s)) for s in dims]
+        size, c_diam = int(rng.randint(2, 20)), float(rng.uniform(0.3, 5.0))
+        mo, eo = O.blank_patch(vol, center, size, "flap", c_diam)
+        m, e = C.blank_patch(torch.from_numpy(vol).to(DEV), center, size, "flap", c_diam)
+        assert np.array_equal(m.cpu().numpy(), mo) and np.array_equal(e.cpu().numpy(), eo)
+
+
+def test_encode_flaprec_batch_bit_exact():
+    import ctunet_b200 as C
+    from oracle import unet_oracle as O
+    g = torch.Generator().manual_seed(5)
+    for shape, with_atlas in [((2, 16, 16, 16), True), ((3, 8, 24, 32), False), ((1, 32, 32, 32), True)]:
+        full = (torch.rand(shape, generator=g) > 0.6).to(torch.uint8)
+        flap = full * (torch.rand(shape, generator=g) > 0.5).to(torch.uint8)
+        broken = full - flap
+        atlas = torch.rand(shape[1:], generator=g) if with_atlas else None
+        ref_img, (ref_sk, ref_fl) = O.encode_flaprec_batch(broken, full, flap, atlas)
+        img, (sk, fl) = C.encode_flaprec_batch(broken.to(DEV), full.to(DEV), flap.to(DEV),
+                                               atlas.to(DEV) if with_atlas else None)
+        assert torch.equal(img.cpu(), ref_img) and torch.equal(sk.cpu(), ref_sk) and torch.equal(fl.cpu(), ref_fl)
+    with pytest.raises(RuntimeError):
+        C.encode_flaprec_batch(full, full, full)           # CPU tensors: no fallback
+
+
 def test_kth_nonzero_and_count():
     import ctunet_b200 as C
     rng = np.random.RandomState(1)

@@ -123,6 +123,44 @@ def test_shape_3d_and_blank_patch(golden):
     assert list(O.kth_nonzero(img, 0)) == [int(v) for v in np.argwhere(img > 0)[0]]
 
 
+def test_flap_shape_matches_reference_code_over_restated_raster_geometry():
+    """tests/golden/flap_shape_golden.pt comes from the reference's own shape_3d / random_blank_patch (make_golden_flap.py)
+    with only raster_geometry.cylinder / cube restated: the oracle must reproduce it bit for bit."""
+    import os
+    import random
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "flap_shape_golden.pt"))
+    for c in gold["cases"]:
+        shp = O.shape_3d(c["center"], c["size"], c["image_size"], "flap", c["c_diam"])
+        assert str(shp.dtype) == c["dtype"] == "uint8" and int((shp == 0).sum()) == c["zeros"]
+        assert np.array_equal(np.packbits(shp), c["packed"].numpy())
+        np.random.seed(c["seed"])                          # the radius draw happens inside shape_3d when not supplied
+        assert np.array_equal(O.shape_3d(c["center"], c["size"], c["image_size"], "flap"), shp)
+    r = gold["random_blank_patch"]
+    img = r["img"].numpy()
+    random.seed(r["seed"])
+    np.random.seed(r["seed"])
+    random.uniform(0, 1)                                   # transforms.py:243
+    center = O.kth_nonzero(img, int(np.random.choice(int((img > 0).sum()))))   # :252
+    lo, hi = O.radius_bounds(img.shape)
+    size = np.random.randint(lo, hi)                       # :268
+    masked, extracted = O.blank_patch(img, center, size, "flap")                # draws c_diam (utilities.py:146)
+    assert np.array_equal(masked, r["masked"].numpy()) and np.array_equal(extracted, r["extracted"].numpy())
+    assert np.array_equal(masked + extracted, img) and extracted.sum() > 0
+
+
+def test_encode_flaprec_batch_is_one_hot_plus_atlas():
+    g = torch.Generator().manual_seed(2)
+    full = (torch.rand(2, 4, 6, 8, generator=g) > 0.5).to(torch.uint8)
+    flap = full * (torch.rand(2, 4, 6, 8, generator=g) > 0.5).to(torch.uint8)
+    atlas = torch.rand(4, 6, 8, generator=g)
+    img, (sk, fl) = O.encode_flaprec_batch(full - flap, full, flap, atlas)
+    assert img.shape == (2, 2, 4, 6, 8) and sk.shape == fl.shape == (2, 2, 4, 6, 8) and sk.dtype == torch.float32
+    assert torch.equal(img[:, 0], (full - flap).float()) and torch.equal(img[1, 1], atlas)
+    assert torch.equal(sk[:, 1], full.float()) and torch.equal(sk[:, 0], 1 - full.float())
+    assert torch.equal(fl.argmax(1), flap.long())
+    assert O.encode_flaprec_batch(full - flap, full, flap)[0].shape == (2, 1, 4, 6, 8)
+
+
 def test_nearest_index_matches_torch():
     for n_in, n_out in [(512, 128), (256, 128), (100, 37), (37, 100), (128, 128), (7, 3)]:
         v = torch.arange(n_in, dtype=torch.float32)[None, None, :, None, None].expand(1, 1, n_in, 1, 1)
