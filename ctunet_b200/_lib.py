@@ -45,6 +45,7 @@ SIGNATURES = {
     "ctu_conv_wide_supported": (I, [I, I, I, I, I, I, I]),
     "ctu_conv_wide_wimg_bytes": (LL, [I, I, I, I, I, I, I]),
     "ctu_conv_wide_pack_weight": (I, [P, P, I, I, I, I, I, I, I, P]),
+    "ctu_conv_wide_wgrad_supported": (I, [I, I, I, I, I, I]),
     "ctu_upfuse_cout": (I, [I]),
     "ctu_upfuse_compose": (I, [P, P, P, P, P, P, I, I, I, P]),
     "ctu_upfuse_decompose": (I, [P, P, P, P, P, P, P, P, P, I, I, I, P]),

@@ -331,6 +331,8 @@ int conv3d_fprop_tc(const void* const* h_srcs, const int* h_src_channels, int ns
 int conv3d_wgrad_tc(const void* const* h_srcs, const int* h_src_channels, int nsrc, const void* dy, float* dwp,
                     float* dbias, int phase_cout, int cout, int k, int n, int d, int h, int w, cudaStream_t stream);
 // implemented in conv_wide.cu
+int conv3d_wgrad_small(const void* x, int cin, const void* dy, float* dwp, float* dbias, int cout, int k, int n, int d, int h,
+                       int w, cudaStream_t stream);
 int conv3d_fprop_wide(const void* x, int cin, const void* wimg, const float* bias, void* y, int cout, int k, int n, int d,
                       int h, int w, cudaStream_t stream);
 
@@ -401,6 +403,10 @@ int ctu_conv3d_wgrad(int dtype, const void* const* h_srcs, const int* h_src_chan
         if (dtype != CTU_BF16) {
             set_error("ctu_conv3d_wgrad: the tensor path is bf16 only");
             return CTU_ERR_UNSUPPORTED;
+        }
+        if (use_tensor_path == 2) {      // tap-stationary kernel for 8 x 8 plane tiles (conv_wide.cu)
+            CTU_REQUIRE(nsrc == 1, "ctu_conv3d_wgrad: the small-grid tensor path takes one source");
+            return conv3d_wgrad_small(h_srcs[0], h_src_channels[0], dy, dwp, dbias, cout, k, n, d, h, w, (cudaStream_t)stream);
         }
         return conv3d_wgrad_tc(h_srcs, h_src_channels, nsrc, dy, dwp, dbias, phase_cout, cout, k, n, d, h, w,
                                (cudaStream_t)stream);

@@ -1000,13 +1000,14 @@ int conv3d_wgrad_tc(const void* const* h_srcs, const int* h_src_channels, int ns
         return check_launch("ctu_conv3d_wgrad(tcgen05)");
     };
     rc = k == 3 ? go(conv3d_wgrad_tc_kernel<3>) : go(conv3d_wgrad_tc_kernel<5>);
-    if (rc == CTU_OK && dbias != nullptr) {
-        const long long spatial = (long long)d * h * w;
-        dim3 bgrid((unsigned)((spatial + 256 * 32 - 1) / (256 * 32)), g.cob_n, n);
-        tc_channel_sum_kernel<<<bgrid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dy), dbias, cout, g.cob_n, spatial);
-        rc = check_launch("ctu_conv3d_wgrad(dbias)");
-    }
+    if (rc == CTU_OK && dbias != nullptr) rc = channel_sum_bias(dy, dbias, cout, g.cob_n, n, (long long)d * h * w, stream);
     return rc;
+}
+
+int channel_sum_bias(const void* dy, float* dbias, int cout, int cob_n, int n, long long spatial, cudaStream_t stream) {
+    dim3 bgrid((unsigned)((spatial + 256 * 32 - 1) / (256 * 32)), cob_n, n);
+    tc_channel_sum_kernel<<<bgrid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dy), dbias, cout, cob_n, spatial);
+    return check_launch("ctu_conv3d_wgrad(dbias)");
 }
 
 }  // namespace ctu

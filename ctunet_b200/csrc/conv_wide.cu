@@ -371,6 +371,213 @@ int conv3d_fprop_wide(const void* x, int cin, const void* wimg, const float* bia
     return go(conv3d_wide_kernel<5, 8, 1>, 32 * 6);
 }
 
+
+// ================================================================================================ wgrad, small grids
+// dW[co][ci][kd][kh][kw] = sum_{n,z,y,x} dy[n][co][z][y][x] * x[n][ci][z+kd-P][y+kh-P][x+kw-P] on 8 x 8 plane tiles
+// (the 8^3 level: conv3d_wgrad_tc_kernel needs 16-wide rows).  TAP-STATIONARY: a CTA owns up to 512/N taps of one kd
+// (one TMEM accumulator [M = input channels] x [N = output channels] per tap) and one sample, and walks the d-planes:
+//   A = x halo plane, MN-major: M-groups = channel blocks (SBO = plane pitch), K = 16 voxels = two 8-voxel rows
+//       (LBO = halo row pitch); start address = the tap's (kh, kw) shift;
+//   B = dy plane [cob][8][8][8], MN-major: N-groups = channel blocks (SBO = 1 KB), K = the same two rows (LBO = 128 B).
+// Four MMAs (row pairs) per (plane, tap).  Partial sums are flushed with fp32 atomics (dwp zeroed by the caller).
+struct WsParams {
+    float* dwp;
+    int cb, cob_n, mblk, nblk;       // real blocks; blocks spanned by the MMA (M / 8, N / 8)
+    int tpc, chunks;                 // taps per CTA, tap chunks per kd
+    int n, d, h, w, tiles_h, tiles_w;
+    uint32_t plane_bytes, xslot_bytes, dyslot_bytes, tmem_cols, ns;
+};
+
+template <int K>
+__global__ void __launch_bounds__(32 * 6) conv3d_wgrad_small_kernel(const __grid_constant__ CUtensorMap xmap,
+                                                                    const __grid_constant__ CUtensorMap dymap, WsParams p) {
+    constexpr int PAD = K / 2, K2 = K * K, K3 = K2 * K;
+    constexpr int WW = 8 + K - 1, HH = 8 + K - 1;
+    constexpr uint32_t ROW = WW * 16;
+    const uint32_t NS = p.ns;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const uint32_t s_base = smem_u32(smem);
+    const uint32_t s_x = s_base, s_dy = s_x + NS * p.xslot_bytes, s_bar = s_dy + NS * p.dyslot_bytes;
+    const uint32_t b_full = s_bar, b_empty = s_bar + 8 * TC_MAX_SLOTS, b_done = s_bar + 16 * TC_MAX_SLOTS;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (b_done + 8 - s_base));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kd = blockIdx.x / p.chunks, chunk = blockIdx.x % p.chunks;
+    const int tap0 = chunk * p.tpc;                                   // first (kh, kw) tap of this CTA
+    const int ntap = (K2 - tap0) < p.tpc ? (K2 - tap0) : p.tpc;
+    const int n = blockIdx.y;
+    const int ncol = p.nblk * 8, M = p.mblk * 8;
+
+    if (threadIdx.x == 0) {
+        for (uint32_t i = 0; i < NS; ++i) {
+            mbar_init(b_full + 8 * i, 1);
+            mbar_init(b_empty + 8 * i, 1);
+        }
+        mbar_init(b_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(p.tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int tiles = p.tiles_h * p.tiles_w;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            Ring pr = {0, 0};
+            for (int z = 0; z < p.d; ++z) {
+                const int zi = z + kd - PAD;
+                if (zi < 0 || zi >= p.d) continue;
+                for (int t = 0; t < tiles; ++t, pr.next(NS)) {
+                    const int h0 = (t / p.tiles_w) * 8, w0 = (t % p.tiles_w) * 8;
+                    mbar_wait(b_empty + 8 * pr.slot, pr.phase ^ 1);
+                    mbar_expect_tx(b_full + 8 * pr.slot, (uint32_t)p.mblk * HH * WW * 16 + (uint32_t)p.nblk * 1024u);
+                    // blocks past the real channel count read the neighbouring sample (or zero fill past the tensor):
+                    // they only feed accumulator rows / columns that are never flushed
+                    for (int b = 0; b < p.mblk; ++b)
+                        tma_load_4d(s_x + pr.slot * p.xslot_bytes + b * p.plane_bytes, &xmap, (w0 - PAD) * 8, h0 - PAD, zi,
+                                    n * p.cb + b, b_full + 8 * pr.slot);
+                    for (int b = 0; b < p.nblk; ++b)
+                        tma_load_4d(s_dy + pr.slot * p.dyslot_bytes + b * 1024u, &dymap, w0 * 8, h0, z, n * p.cob_n + b,
+                                    b_full + 8 * pr.slot);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t leader = elect_one();
+        // D=f32, A=B=bf16, both MN-major (bits 15, 16), N at [17,23), M at [24,29)
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(ncol >> 3) << 17) |
+                               ((uint32_t)(M >> 4) << 24);
+        const uint32_t a_hi = (p.plane_bytes >> 4) | (1u << 14);      // SBO: next channel block (M group)
+        const uint32_t b_hi = (1024u >> 4) | (1u << 14);              // SBO: next output channel block (N group)
+        const uint32_t a_lbo = (ROW >> 4) << 16, b_lbo = 8u << 16;    // LBO: the second row of the K = 16 voxels
+        Ring cons = {0, 0};
+        uint32_t first = 1;
+        for (int z = 0; z < p.d; ++z) {
+            const int zi = z + kd - PAD;
+            if (zi < 0 || zi >= p.d) continue;
+            for (int t = 0; t < tiles; ++t, cons.next(NS)) {
+                mbar_wait(b_full + 8 * cons.slot, cons.phase);
+                tc_fence_after();
+                const uint32_t x16 = (s_x + cons.slot * p.xslot_bytes) >> 4, dy16 = (s_dy + cons.slot * p.dyslot_bytes) >> 4;
+                for (int tp = 0; tp < ntap; ++tp) {
+                    const int kh = (tap0 + tp) / K, kw = (tap0 + tp) % K;
+                    const uint32_t a_tap = x16 + (uint32_t)kh * (ROW >> 4) + (uint32_t)kw;
+                    const uint32_t d_tmem = tmem_base + (uint32_t)tp * ncol;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)      // output rows 2j, 2j+1
+                        umma_bf16_lead(leader, d_tmem, (a_tap + 2u * j * (ROW >> 4)) | a_lbo, a_hi, (dy16 + 16u * j) | b_lbo, b_hi,
+                                       idesc, (j == 0) ? (first ^ 1u) : 1u);
+                }
+                first = 0;
+                umma_commit_lead(leader, b_empty + 8 * cons.slot);
+            }
+        }
+        umma_commit_lead(leader, b_done);
+    } else {
+        // ===================================================================== flush (4 warps = 4 TMEM lane quarters)
+        const int quarter = warp & 3;
+        mbar_wait(b_done, 0);
+        tc_fence_after();
+        const int row = (M == 128) ? quarter * 32 + lane : quarter * 16 + (lane & 15);   // input channel
+        const bool useful = ((M == 128) || lane < 16) && row < p.cb * 8;
+        bool any = false;                                   // a CTA whose kd never meets the volume has nothing to flush
+        for (int z = 0; z < p.d; ++z) any = any || (z + kd - PAD >= 0 && z + kd - PAD < p.d);
+        if (any) {
+            for (int tp = 0; tp < ntap; ++tp) {
+                const int tap = kd * K2 + tap0 + tp;
+                for (int ob = 0; ob < p.cob_n; ++ob) {
+                    float v[8];
+                    tmem_ld8(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)tp * ncol + ob * 8, v);
+                    if (useful) {
+                        float* dst = p.dwp + ((((long long)ob * p.cb + (row >> 3)) * K3 + tap) * 64 + (row & 7) * 8);
+#pragma unroll
+                        for (int c = 0; c < 8; ++c)
+                            if (v[c] != 0.f) atomicAdd(dst + c, v[c]);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    }
+}
+
+struct WsGeom {
+    int cb, cob_n, mblk, nblk, tpc, chunks;
+    uint32_t plane_bytes, xslot_bytes, dyslot_bytes, tmem_cols, ns;
+    size_t smem;
+};
+
+static bool wgrad_small_geometry(int k, int cin, int cout, int h, int w, WsGeom& g) {
+    if ((k != 3 && k != 5) || cin < 1 || cout < 1 || h % 8 || w % 8) return false;
+    g.cb = (cin + 7) / 8;
+    g.cob_n = (cout + 7) / 8;
+    if (g.cb > 16 || g.cob_n > 16) return false;
+    g.mblk = g.cb <= 8 ? 8 : 16;                       // M = 64 or 128
+    g.nblk = (g.cob_n + 1) / 2 * 2;                    // N a multiple of 16
+    const int ncol = g.nblk * 8;
+    g.tpc = 512 / ncol;
+    if (g.tpc > 8) g.tpc = 8;
+    g.chunks = (k * k + g.tpc - 1) / g.tpc;
+    g.tpc = (k * k + g.chunks - 1) / g.chunks;         // even out the chunks
+    g.plane_bytes = ((uint32_t)(8 + k - 1) * (8 + k - 1) * 16 + 127u) & ~127u;
+    g.xslot_bytes = g.plane_bytes * g.mblk;
+    g.dyslot_bytes = 1024u * g.nblk;
+    const size_t fixed = 8 * (2 * TC_MAX_SLOTS + 1) + 64 + 1024;
+    g.ns = 4;
+    while (g.ns > 2 && fixed + (size_t)g.ns * (g.xslot_bytes + g.dyslot_bytes) > 200 * 1024) --g.ns;
+    g.smem = fixed + (size_t)g.ns * (g.xslot_bytes + g.dyslot_bytes);
+    if (g.smem > 220 * 1024) return false;
+    g.tmem_cols = 32;
+    while (g.tmem_cols < (uint32_t)(g.tpc * ncol)) g.tmem_cols *= 2;
+    return g.tmem_cols <= 512;
+}
+
+bool conv3d_wgrad_small_supported(int k, int cin, int cout, int h, int w) {
+    WsGeom g;
+    return wgrad_small_geometry(k, cin, cout, h, w, g);
+}
+
+int conv3d_wgrad_small(const void* x, int cin, const void* dy, float* dwp, float* dbias, int cout, int k, int n, int d, int h,
+                       int w, cudaStream_t stream) {
+    WsGeom g;
+    if (!wgrad_small_geometry(k, cin, cout, h, w, g)) {
+        set_error("conv3d wgrad small-grid path: shape k=%d cin=%d cout=%d %dx%dx%d not covered", k, cin, cout, d, h, w);
+        return CTU_ERR_UNSUPPORTED;
+    }
+    CUtensorMap xmap, dymap;
+    int rc = make_map(&xmap, x, n * g.cb, d, h, w, 8 + k - 1, 8 + k - 1);
+    if (rc == CTU_OK) rc = make_map(&dymap, dy, n * g.cob_n, d, h, w, 8, 8);
+    if (rc != CTU_OK) return rc;
+    WsParams p = {};
+    p.dwp = dwp;
+    p.cb = g.cb; p.cob_n = g.cob_n; p.mblk = g.mblk; p.nblk = g.nblk; p.tpc = g.tpc; p.chunks = g.chunks;
+    p.n = n; p.d = d; p.h = h; p.w = w; p.tiles_h = h / 8; p.tiles_w = w / 8;
+    p.plane_bytes = g.plane_bytes; p.xslot_bytes = g.xslot_bytes; p.dyslot_bytes = g.dyslot_bytes;
+    p.tmem_cols = g.tmem_cols; p.ns = g.ns;
+    auto go = [&](auto kern) -> int {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+        if (e != cudaSuccess) {
+            set_error("conv3d wgrad small-grid path: smem %zu: %s", g.smem, cudaGetErrorString(e));
+            return (int)e;
+        }
+        kern<<<dim3(k * g.chunks, n), 32 * 6, g.smem, stream>>>(xmap, dymap, p);
+        return check_launch("ctu_conv3d_wgrad(tcgen05 small grid)");
+    };
+    rc = k == 3 ? go(conv3d_wgrad_small_kernel<3>) : go(conv3d_wgrad_small_kernel<5>);
+    if (rc == CTU_OK && dbias != nullptr) rc = channel_sum_bias(dy, dbias, cout, g.cob_n, n, (long long)d * h * w, stream);
+    return rc;
+}
+
 }  // namespace ctu
 
 using namespace ctu;
@@ -389,6 +596,11 @@ int ctu_conv_wide_pack_weight(const float* wp, void* wimg, int k, int cin, int c
                               ctu_stream stream) {
     CTU_REQUIRE(wp && wimg && cin > 0, "ctu_conv_wide_pack_weight: bad arguments");
     return conv3d_wide_pack_weight(wp, wimg, k, (cin + 7) / 8, cout, n, d, h, w, (cudaStream_t)stream);
+}
+
+int ctu_conv_wide_wgrad_supported(int k, int cin, int cout, int d, int h, int w) {
+    (void)d;
+    return conv3d_wgrad_small_supported(k, cin, cout, h, w) ? 1 : 0;
 }
 
 }  // extern "C"

@@ -177,5 +177,7 @@ constexpr int TC_MAX_SLOTS = 16;
 // host: 4-D tensor map [N*Cb][D][H][W*8] of a blocked bf16 activation with a (box_w voxels x box_h rows) halo box
 int make_map(CUtensorMap* map, const void* ptr, int nblocks, int d, int h, int w, int box_w, int box_h);
 PFN_cuTensorMapEncodeTiled_v12000 get_encode();
+// host: dbias[co] += sum over voxels of dy (blocked bf16), the bias gradient of convolutions that carry a bias
+int channel_sum_bias(const void* dy, float* dbias, int cout, int cob_n, int n, long long spatial, cudaStream_t stream);
 
 }  // namespace ctu

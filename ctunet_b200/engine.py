@@ -298,7 +298,11 @@ class Engine:
         if dw_out is not None:
             def wgrad():
                 dwp = self.f32(lib.ctu_conv_wpack_floats(cout, k, ns, ca))
-                tc = self.use_tc and bool(lib.ctu_conv_tc_wgrad_supported(k, ns, ca, cout, s0.d, s0.h, s0.w))
+                tc = 0
+                if self.use_tc and lib.ctu_conv_tc_wgrad_supported(k, ns, ca, cout, s0.d, s0.h, s0.w):
+                    tc = 1
+                elif self.use_tc and ns == 1 and lib.ctu_conv_wide_wgrad_supported(k, srcs[0].c, cout, s0.d, s0.h, s0.w):
+                    tc = 2      # 8 x 8 plane tiles: the tap-stationary kernel
                 call("ctu_conv3d_wgrad", self.dtype, pa, ca, ns, dy.ptr, dwp.data_ptr(),
                      db_out.data_ptr() if db_out is not None else None, phase_cout, cout, k, s0.n, s0.d, s0.h, s0.w,
                      int(tc), stream_ptr())

@@ -96,10 +96,15 @@ int ctu_conv_wide_supported(int k, int cin, int cout, int n, int d, int h, int w
 long long ctu_conv_wide_wimg_bytes(int k, int cin, int cout, int n, int d, int h, int w);
 int ctu_conv_wide_pack_weight(const float* wp, void* wimg, int k, int cin, int cout, int n, int d, int h, int w,
                               ctu_stream stream);
+/* weight gradient on 8 x 8 plane tiles (the 8^3 level; h, w multiples of 8, at most 128 input and output channels,
+ * one source): ctu_conv3d_wgrad with use_tensor_path = 2 */
+int ctu_conv_wide_wgrad_supported(int k, int cin, int cout, int d, int h, int w);
 /* dwp (packed layout, fp32) and dbias (nullable, [cout]) are zeroed by the call, then accumulated.
  * phase_cout: 0, or the natural channel count when dy is the phase-major gradient of the fused up-sampling stage
  * COMPOSED FROM A 3x3x3 CONVOLUTION (cout = 8 phases x 8*ceil(phase_cout/8)): the tensor path then skips the taps that are
  * structurally zero (their entries of dwp stay 0 or hold unspecified values that ctu_upfuse_decompose never reads). */
+/* use_tensor_path: 0 CUDA cores, 1 conv_tc.cu (16-wide rows, ctu_conv_tc_wgrad_supported), 2 the tap-stationary
+ * small-grid kernel (ctu_conv_wide_wgrad_supported). */
 int ctu_conv3d_wgrad(int dtype, const void* const* h_srcs, const int* h_src_channels, int nsrc, const void* dy,
                      float* dwp, float* dbias, int phase_cout, int cout, int k, int n, int d, int h, int w,
                      int use_tensor_path, ctu_stream stream);

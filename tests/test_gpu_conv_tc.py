@@ -97,6 +97,7 @@ def test_tc_conv_matches_reference(case):
     assert gerr <= 1.2e-2 * gs, "dgrad err %.3e (scale %.3e)" % (gerr, gs)
     # weight gradient on the tensor cores (voxels as the K dimension): bf16 products, fp32 accumulation
     assert _lib.load().ctu_conv_tc_wgrad_supported(k, 1, _lib.int_array([cin]), cout, d, h, w) == (1 if h % 16 == 0 else 0)
+    assert h % 16 == 0 or _lib.load().ctu_conv_wide_wgrad_supported(k, cin, cout, d, h, w) == 1   # 8 x 8: tap-stationary kernel
     wr = wt.clone().requires_grad_()
     br = bs.clone().requires_grad_() if use_bias else None
     F.conv3d(x, wr, br, 1, k // 2).backward(dy)
