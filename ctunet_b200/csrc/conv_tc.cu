@@ -145,6 +145,7 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
                    b_aempty = b_afull + 8 * 2 * TC_WB, b_w = b_aempty + 8 * 2 * TC_WB;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (b_w + 8 - s_base));
     float* st_red = reinterpret_cast<float*>(smem + (b_w + 32 - s_base));   // [4*TC_WB epilogue warps][NSLOT*16]
+    float* st_bias = st_red + 4 * TC_WB * 32;                               // [CP] bias of this CTA's output blocks
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -165,6 +166,10 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
                      "r"(p.tmem_cols)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + CP) {   // bias -> shared memory (read per plane by every epilogue thread)
+        const int ch = blockIdx.y * CP + (int)threadIdx.x - 64;
+        st_bias[threadIdx.x - 64] = (p.bias != nullptr && ch < p.cout) ? p.bias[ch] : 0.f;
     }
     tc_fence_before();
     __syncthreads();
@@ -359,7 +364,7 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
                             float v = part[0][ob * 8 + c];
-                            if (has_bias && (ob0 + ob) * 8 + c < p.cout) v += __ldg(p.bias + (ob0 + ob) * 8 + c);
+                            if (has_bias) v += st_bias[ob * 8 + c];
                             o.v[c] = round_to<__nv_bfloat16>(v);
                         }
                         if (inb && ob < nob) {
@@ -470,7 +475,7 @@ static bool tc_geometry(int k, int cb, int cout, int h, int w, TcGeom& g) {
         g.nt = (k * cobg * 8 + 15) / 16 * 16;
         g.wimg_bytes = (uint32_t)g.nm * g.nt * 32;
         const size_t fixed = ((g.wimg_bytes + 1023u) & ~1023u) + ((g.nm * 8 + 15) & ~15) +
-                             8 * (2 * TC_MAX_SLOTS + 4 * TC_WB + 2) + 32 + 4 * TC_WB * 32 * 4 + 1024;
+                             8 * (2 * TC_MAX_SLOTS + 4 * TC_WB + 2) + 32 + 4 * TC_WB * 32 * 4 + 128 + 1024;
         // the wide-output variants are limited to one CTA per SM by registers: give their ring the whole SM
         g.ns = pick_slots(g.ncg > 1 ? 4 : 3, fixed, g.slot_bytes, cobg >= 2 ? 200 * 1024 : 100 * 1024);
         g.smem = fixed + (size_t)g.ns * g.slot_bytes;
@@ -595,10 +600,22 @@ int conv3d_fprop_tc(const void* const* h_srcs, const int* h_src_channels, int ns
         }
         if (occ < 1) occ = 1;
         cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        // d-chunk: about three work items per resident CTA (load balance), but at least 8 planes per chunk
-        // (every chunk re-reads K-1 halo planes)
+        // d-chunk: every chunk walks dc + K - 1 input planes (K - 1 of them halo re-reads AND re-computed MMAs), and the
+        // resident CTAs take the items in rounds: minimise rounds x planes per item (ties: the smaller chunk, for balance)
         int dc = d;
-        while (dc > 8 && (long long)tiles * ((d + dc - 1) / dc) * g.ngroups < 148 * occ * 3) dc = (dc + 1) / 2;
+        {
+            const long long slots = (148LL * occ) / g.ngroups > 0 ? (148LL * occ) / g.ngroups : 1;
+            long long best = -1;
+            for (int c = d; c >= 1; --c) {
+                const long long items = (long long)tiles * ((d + c - 1) / c);
+                const long long rounds = (items + slots - 1) / slots;
+                const long long cost = rounds * (c + k - 1);
+                if (best < 0 || cost <= best) {
+                    best = cost;
+                    dc = c;
+                }
+            }
+        }
         p.dc = dc;
         p.dchunks = (d + dc - 1) / dc;
         p.total_items = tiles * p.dchunks;
@@ -860,16 +877,37 @@ __global__ void tc_channel_sum_kernel(const __nv_bfloat16* __restrict__ dy, floa
     float acc[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) acc[c] = 0.f;
-    for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < spatial; s += (long long)gridDim.x * blockDim.x) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; s + 7 * stride < spatial; s += 8 * stride) {          // eight 16-byte loads in flight per thread
+        Raw8<__nv_bfloat16> r[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) r[u].load(base + (s + u * stride) * 8);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const V8 v = r[u].get();
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[c] += v.v[c];
+        }
+    }
+    for (; s < spatial; s += stride) {
         V8 v = Vec8<__nv_bfloat16>::load(base + s * 8);
 #pragma unroll
         for (int c = 0; c < 8; ++c) acc[c] += v.v[c];
     }
+    // one atomic per channel and BLOCK (same-address atomics serialise at ~1 ns each)
+    __shared__ float red[8][8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
         const float t = warp_sum(acc[c]);
-        const int ch = ob * 8 + c;
-        if ((threadIdx.x & 31) == 0 && ch < cout && t != 0.f) atomicAdd(dbias + ch, t);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][c] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        float t = 0.f;
+        for (int wq = 0; wq < (int)(blockDim.x >> 5); ++wq) t += red[wq][threadIdx.x];
+        const int ch = ob * 8 + threadIdx.x;
+        if (ch < cout && t != 0.f) atomicAdd(dbias + ch, t);
     }
 }
 
