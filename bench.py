@@ -357,6 +357,17 @@ def run_b200_arm(a):
 
     for _ in range(max(a.warmup, 3)):
         resident()
+    if use_graph and step.static_inputs() is not None:
+        # the batch is resident IN the captured step's input buffers (what a device-side pipeline fills in place)
+        s_img, s_tgt = step.static_inputs()
+        s_img.copy_(img)
+        for d_, s_ in zip(s_tgt if isinstance(s_tgt, tuple) else (s_tgt,), target if isinstance(target, tuple) else (target,)):
+            d_.copy_(s_)
+        img_r, target_r = s_img, s_tgt
+
+        def resident():           # noqa: F811
+            step(img_r, target_r)
+        resident()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()

@@ -89,7 +89,8 @@ class TrainStep:
         elif any(a.shape != b.shape or a.dtype != b.dtype for a, b in zip(flat, self._static)):
             raise RuntimeError("graph mode: the batch shape changed after the step was captured")
         for dst, src in zip(self._static, flat):
-            dst.copy_(src, non_blocking=True)
+            if dst.data_ptr() != src.data_ptr():              # a pipeline may fill static_inputs() in place
+                dst.copy_(src, non_blocking=True)
         if self._graph is None:
             st_img = self._static[0]
             st_tgt = tuple(self._static[1:]) if isinstance(target, (tuple, list)) else self._static[1]
@@ -118,6 +119,14 @@ class TrainStep:
             self.launches_per_step = _lib.launches - l0
             self._graph = g
         return self._replay()
+
+    def static_inputs(self):
+        """(image, target) buffers the captured graph reads, or None before the capture: a data pipeline that writes
+        the next batch straight into them (and passes them to ``__call__``) saves the per-step device copy."""
+        if self._graph is None:
+            return None
+        tgt = tuple(self._static[1:]) if len(self._static) > 2 else self._static[1]
+        return self._static[0], tgt
 
     def _replay(self):
         self._graph.replay()
