@@ -384,12 +384,13 @@ struct WsParams {
     float* dwp;
     int cb, cob_n, mblk, nblk;       // real blocks; blocks spanned by the MMA (M / 8, N / 8)
     int tpc, chunks;                 // taps per CTA, tap chunks per kd
+    int zsplit;                      // CTAs sharing the d-planes of one (kd, chunk, sample)
     int n, d, h, w, tiles_h, tiles_w;
     uint32_t plane_bytes, xslot_bytes, dyslot_bytes, tmem_cols, ns;
 };
 
 template <int K>
-__global__ void __launch_bounds__(32 * 6) conv3d_wgrad_small_kernel(const __grid_constant__ CUtensorMap xmap,
+__global__ void __launch_bounds__(32 * 5) conv3d_wgrad_small_kernel(const __grid_constant__ CUtensorMap xmap,
                                                                     const __grid_constant__ CUtensorMap dymap, WsParams p) {
     constexpr int PAD = K / 2, K2 = K * K, K3 = K2 * K;
     constexpr int WW = 8 + K - 1, HH = 8 + K - 1;
@@ -406,13 +407,14 @@ __global__ void __launch_bounds__(32 * 6) conv3d_wgrad_small_kernel(const __grid
     const int ntap = (K2 - tap0) < p.tpc ? (K2 - tap0) : p.tpc;
     const int n = blockIdx.y;
     const int ncol = p.nblk * 8, M = p.mblk * 8;
+    const int zb = (int)(((long long)p.d * blockIdx.z) / p.zsplit), ze = (int)(((long long)p.d * (blockIdx.z + 1)) / p.zsplit);
 
     if (threadIdx.x == 0) {
         for (uint32_t i = 0; i < NS; ++i) {
             mbar_init(b_full + 8 * i, 1);
-            mbar_init(b_empty + 8 * i, 1);
+            mbar_init(b_empty + 8 * i, 4);          // every issuer warp releases the slot
         }
-        mbar_init(b_done, 1);
+        mbar_init(b_done, 4);
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -430,7 +432,7 @@ __global__ void __launch_bounds__(32 * 6) conv3d_wgrad_small_kernel(const __grid
     if (warp == 0) {
         if (lane == 0) {
             Ring pr = {0, 0};
-            for (int z = 0; z < p.d; ++z) {
+            for (int z = zb; z < ze; ++z) {
                 const int zi = z + kd - PAD;
                 if (zi < 0 || zi >= p.d) continue;
                 for (int t = 0; t < tiles; ++t, pr.next(NS)) {
@@ -448,7 +450,10 @@ __global__ void __launch_bounds__(32 * 6) conv3d_wgrad_small_kernel(const __grid
                 }
             }
         }
-    } else if (warp == 1) {
+    } else {
+        // ===================================================================== 4 issuer warps (taps dealt round-robin: one
+        // issuing thread sustains one MMA per ~76 cycles, four reach the shared-memory operand limit), then the flush
+        const int q4 = warp - 1;
         const uint32_t leader = elect_one();
         // D=f32, A=B=bf16, both MN-major (bits 15, 16), N at [17,23), M at [24,29)
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(ncol >> 3) << 17) |
@@ -458,14 +463,14 @@ __global__ void __launch_bounds__(32 * 6) conv3d_wgrad_small_kernel(const __grid
         const uint32_t a_lbo = (ROW >> 4) << 16, b_lbo = 8u << 16;    // LBO: the second row of the K = 16 voxels
         Ring cons = {0, 0};
         uint32_t first = 1;
-        for (int z = 0; z < p.d; ++z) {
+        for (int z = zb; z < ze; ++z) {
             const int zi = z + kd - PAD;
             if (zi < 0 || zi >= p.d) continue;
             for (int t = 0; t < tiles; ++t, cons.next(NS)) {
                 mbar_wait(b_full + 8 * cons.slot, cons.phase);
                 tc_fence_after();
                 const uint32_t x16 = (s_x + cons.slot * p.xslot_bytes) >> 4, dy16 = (s_dy + cons.slot * p.dyslot_bytes) >> 4;
-                for (int tp = 0; tp < ntap; ++tp) {
+                for (int tp = q4; tp < ntap; tp += 4) {
                     const int kh = (tap0 + tp) / K, kw = (tap0 + tp) % K;
                     const uint32_t a_tap = x16 + (uint32_t)kh * (ROW >> 4) + (uint32_t)kw;
                     const uint32_t d_tmem = tmem_base + (uint32_t)tp * ncol;
@@ -479,7 +484,7 @@ __global__ void __launch_bounds__(32 * 6) conv3d_wgrad_small_kernel(const __grid
             }
         }
         umma_commit_lead(leader, b_done);
-    } else {
+        __syncwarp();
         // ===================================================================== flush (4 warps = 4 TMEM lane quarters)
         const int quarter = warp & 3;
         mbar_wait(b_done, 0);
@@ -487,7 +492,7 @@ __global__ void __launch_bounds__(32 * 6) conv3d_wgrad_small_kernel(const __grid
         const int row = (M == 128) ? quarter * 32 + lane : quarter * 16 + (lane & 15);   // input channel
         const bool useful = ((M == 128) || lane < 16) && row < p.cb * 8;
         bool any = false;                                   // a CTA whose kd never meets the volume has nothing to flush
-        for (int z = 0; z < p.d; ++z) any = any || (z + kd - PAD >= 0 && z + kd - PAD < p.d);
+        for (int z = zb; z < ze; ++z) any = any || (z + kd - PAD >= 0 && z + kd - PAD < p.d);
         if (any) {
             for (int tp = 0; tp < ntap; ++tp) {
                 const int tap = kd * K2 + tap0 + tp;
@@ -564,13 +569,17 @@ int conv3d_wgrad_small(const void* x, int cin, const void* dy, float* dwp, float
     p.n = n; p.d = d; p.h = h; p.w = w; p.tiles_h = h / 8; p.tiles_w = w / 8;
     p.plane_bytes = g.plane_bytes; p.xslot_bytes = g.xslot_bytes; p.dyslot_bytes = g.dyslot_bytes;
     p.tmem_cols = g.tmem_cols; p.ns = g.ns;
+    // split the d-planes until about one CTA per SM (every CTA flushes its taps with atomics)
+    p.zsplit = 148 / (k * g.chunks * n);
+    if (p.zsplit > d) p.zsplit = d;
+    if (p.zsplit < 1) p.zsplit = 1;
     auto go = [&](auto kern) -> int {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
         if (e != cudaSuccess) {
             set_error("conv3d wgrad small-grid path: smem %zu: %s", g.smem, cudaGetErrorString(e));
             return (int)e;
         }
-        kern<<<dim3(k * g.chunks, n), 32 * 6, g.smem, stream>>>(xmap, dymap, p);
+        kern<<<dim3(k * g.chunks, n, p.zsplit), 32 * 5, g.smem, stream>>>(xmap, dymap, p);
         return check_launch("ctu_conv3d_wgrad(tcgen05 small grid)");
     };
     rc = k == 3 ? go(conv3d_wgrad_small_kernel<3>) : go(conv3d_wgrad_small_kernel<5>);

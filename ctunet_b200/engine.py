@@ -299,10 +299,14 @@ class Engine:
             def wgrad():
                 dwp = self.f32(lib.ctu_conv_wpack_floats(cout, k, ns, ca))
                 tc = 0
-                if self.use_tc and lib.ctu_conv_tc_wgrad_supported(k, ns, ca, cout, s0.d, s0.h, s0.w):
+                small = (self.use_tc and ns == 1 and not phase_cout
+                         and lib.ctu_conv_wide_wgrad_supported(k, srcs[0].c, cout, s0.d, s0.h, s0.w))
+                if small and max(s0.h, s0.w) <= WIDE_MAX_HW:
+                    tc = 2      # small grids: the tap-stationary kernel (8 x 8 plane tiles, d-planes split over CTAs)
+                elif self.use_tc and lib.ctu_conv_tc_wgrad_supported(k, ns, ca, cout, s0.d, s0.h, s0.w):
                     tc = 1
-                elif self.use_tc and ns == 1 and lib.ctu_conv_wide_wgrad_supported(k, srcs[0].c, cout, s0.d, s0.h, s0.w):
-                    tc = 2      # 8 x 8 plane tiles: the tap-stationary kernel
+                elif small:
+                    tc = 2
                 call("ctu_conv3d_wgrad", self.dtype, pa, ca, ns, dy.ptr, dwp.data_ptr(),
                      db_out.data_ptr() if db_out is not None else None, phase_cout, cout, k, s0.n, s0.d, s0.h, s0.w,
                      int(tc), stream_ptr())

@@ -55,3 +55,27 @@ for k, cin, cout, n, d, h, w in SHAPES:
     best = min(t for t in ts if t is not None)
     print("k%d %3d->%-3d @%dx%d^3 %-6s %10s %10s %10s   %.0f" % (
         k, cin, cout, n, d, "", *["%.1f" % t if t is not None else "-" for t in ts], fl / best / 1e6))
+
+
+def wgrad(variant, cin, cout, n, d, h, w, k):
+    x, dy = act(n, cin, d, h, w), act(n, cout, d, h, w)
+    ca = int_array([cin])
+    if variant == 1 and not lib.ctu_conv_tc_wgrad_supported(k, 1, ca, cout, d, h, w):
+        return None
+    if variant == 2 and not lib.ctu_conv_wide_wgrad_supported(k, cin, cout, d, h, w):
+        return None
+    dwp = torch.empty(lib.ctu_conv_wpack_floats(cout, k, 1, ca), device=dev)
+    pa = ptr_array([x.data_ptr()])
+    fn = lambda: call("ctu_conv3d_wgrad", 1, pa, ca, 1, dy.data_ptr(), dwp.data_ptr(), None, 0, cout, k, n, d, h, w, variant,
+                      stream_ptr())
+    return timeit(fn)
+
+
+print("\nweight gradient: %-12s %10s %10s %10s" % ("layer", "cuda-core", "16-wide", "tap-stat."))
+for k, cin, cout, n, d, h, w in [(3, 28, 56, 4, 16, 16, 16), (3, 56, 56, 4, 16, 16, 16), (3, 56, 112, 4, 8, 8, 8),
+                                 (5, 32, 64, 4, 16, 16, 16), (5, 64, 64, 4, 16, 16, 16), (5, 128, 64, 4, 16, 16, 16),
+                                 (5, 56, 56, 4, 16, 16, 16), (5, 112, 56, 4, 16, 16, 16),
+                                 (5, 64, 128, 4, 8, 8, 8), (5, 128, 128, 4, 8, 8, 8),
+                                 (3, 28, 28, 4, 32, 32, 32), (5, 32, 32, 4, 32, 32, 32), (5, 16, 32, 4, 32, 32, 32)]:
+    ts = [wgrad(v, cin, cout, n, d, h, w, k) for v in (0, 1, 2)]
+    print("k%d %3d->%-3d @%dx%d^3 %-6s %10s %10s %10s" % (k, cin, cout, n, d, "", *["%.1f" % t if t is not None else "-" for t in ts]))

@@ -110,6 +110,35 @@ def test_tc_conv_matches_reference(case):
         assert (db - br.grad).abs().max().item() <= 2e-3 * br.grad.abs().max().item()
 
 
+@pytest.mark.parametrize("case", [(3, 56, 56, (4, 16, 16, 16)), (5, 64, 64, (2, 16, 16, 16)), (5, 128, 64, (1, 6, 16, 16)),
+                                  (3, 28, 56, (2, 16, 16, 16)), (5, 56, 112, (3, 8, 8, 8)), (3, 24, 40, (1, 5, 16, 24))])
+def test_tap_stationary_wgrad_matches_reference(case):
+    """conv3d_wgrad_small_kernel (use_tensor_path = 2) called directly: 8x8 tiles of 16-wide planes, d-planes split over CTAs."""
+    from ctunet_b200 import _lib
+    from ctunet_b200._lib import call, int_array, ptr_array, stream_ptr
+    from ctunet_b200.engine import Engine
+    k, cin, cout, (n, d, h, w) = case
+    lib = _lib.load()
+    assert lib.ctu_conv_wide_wgrad_supported(k, cin, cout, d, h, w) == 1
+    g = torch.Generator().manual_seed(cin + cout)
+    x = _bf(torch.randn(n, cin, d, h, w, generator=g))
+    dy = _bf(torch.randn(n, cout, d, h, w, generator=g))
+    wr = torch.zeros(cout, cin, k, k, k, requires_grad=True)
+    br = torch.zeros(cout, requires_grad=True)
+    F.conv3d(x, wr, br, 1, k // 2).backward(dy)
+    eng = Engine(torch.device(DEV), "bf16", record=False)
+    xa, dya = eng.pack(x.to(DEV)), eng.pack(dy.to(DEV))
+    ca = int_array([cin])
+    dwp = torch.empty(lib.ctu_conv_wpack_floats(cout, k, 1, ca), device=DEV)
+    db = torch.empty(cout, device=DEV)
+    dw = torch.empty(cout, cin, k, k, k, device=DEV)
+    call("ctu_conv3d_wgrad", 1, ptr_array([xa.ptr]), ca, 1, dya.ptr, dwp.data_ptr(), db.data_ptr(), 0, cout, k, n, d, h, w, 2,
+         stream_ptr())
+    call("ctu_conv_unpack_wgrad", dwp.data_ptr(), dw.data_ptr(), cout, k, 1, ca, stream_ptr())
+    assert (dw.cpu() - wr.grad).abs().max().item() <= 2e-3 * wr.grad.abs().max().item()
+    assert (db.cpu() - br.grad).abs().max().item() <= 2e-3 * br.grad.abs().max().item()
+
+
 def test_tc_and_direct_agree_on_network_layer():
     """Same bf16 inputs through both kernels: only weight rounding and accumulation order differ."""
     import ctunet_b200.engine as E
