@@ -47,8 +47,9 @@ SIGNATURES = {
     "ctu_conv_wide_pack_weight": (I, [P, P, I, I, I, I, I, I, I, P]),
     "ctu_conv_wide_wgrad_supported": (I, [I, I, I, I, I, I]),
     "ctu_upfuse_cout": (I, [I]),
-    "ctu_upfuse_compose": (I, [P, P, P, P, P, P, I, I, I, P]),
-    "ctu_upfuse_decompose": (I, [P, P, P, P, P, P, P, P, P, I, I, I, P]),
+    "ctu_upfuse_workspace_floats": (LL, [I, I, I]),
+    "ctu_upfuse_compose": (I, [P, P, P, P, P, P, I, I, I, P, P]),
+    "ctu_upfuse_decompose": (I, [P, P, P, P, P, P, P, P, P, I, I, I, P, P]),
     "ctu_conv3d_wgrad": (I, [I, P, P, I, P, P, P, I, I, I, I, I, I, I, I, P]),
     "ctu_convt_wpack_floats": (LL, [I, I, P]),
     "ctu_convt_pack_weight": (I, [P, P, I, I, P, P]),

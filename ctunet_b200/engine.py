@@ -396,9 +396,11 @@ class Engine:
         def compose(eng):
             wn = eng.f32(co8, cin + 1, 27)
             b3n = eng.f32(co8) if has_b3 else None
+            ws = eng.f32(lib.ctu_upfuse_workspace_floats(cin, cout, k))
             call("ctu_upfuse_compose", ct.weight.data_ptr(), ct.bias.data_ptr() if ct.bias is not None else None,
                  cv.weight.data_ptr(), cv.bias.data_ptr() if has_b3 else None, wn.data_ptr(),
-                 b3n.data_ptr() if has_b3 else None, cin, cout, k, stream_ptr())
+                 b3n.data_ptr() if has_b3 else None, cin, cout, k, ws.data_ptr(), stream_ptr())
+            ws.record_stream(torch.cuda.current_stream())
             return wn, b3n
 
         all_srcs = list(srcs) + [self._ones(srcs[0])]
@@ -416,11 +418,13 @@ class Engine:
                 db3 = self._grad_buffer(cv.bias) if has_b3 else None
 
                 def decompose():
+                    ws = self.f32(lib.ctu_upfuse_workspace_floats(cin, cout, k))
                     call("ctu_upfuse_decompose", dwn.data_ptr(), dbn.data_ptr() if dbn is not None else None,
                          ct.weight.data_ptr(), ct.bias.data_ptr() if ct.bias is not None else None,
                          cv.weight.data_ptr(), dwt.data_ptr(), dbt.data_ptr() if dbt is not None else None,
-                         dw3.data_ptr(), db3.data_ptr() if db3 is not None else None, cin, cout, k, stream_ptr())
-                    for t in (dwn, dbn):
+                         dw3.data_ptr(), db3.data_ptr() if db3 is not None else None, cin, cout, k, ws.data_ptr(),
+                         stream_ptr())
+                    for t in (dwn, dbn, ws):
                         if t is not None:
                             t.record_stream(torch.cuda.current_stream())
                     self._pgrad_done(((ct.weight, dwt), (ct.bias, dbt), (cv.weight, dw3), (cv.bias, db3)))

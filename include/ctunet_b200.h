@@ -131,11 +131,13 @@ int ctu_convt2_wgrad(int dtype, const void* const* h_srcs, const int* h_src_chan
  *      all-ones input channel (index cin).  wt [cin][cin][2][2][2], bt [cin] (nullable), w3 [cout][cin][k][k][k],
  *      b3 [cout] (nullable, with b3n [8*cop]);  wn: native [8*cop][cin+1][3][3][3] for ctu_conv_pack_weight. ---- */
 int ctu_upfuse_cout(int cout);
+/* workspace (caller-owned fp32 scratch of ctu_upfuse_workspace_floats elements): transposed operand copies */
+long long ctu_upfuse_workspace_floats(int cin, int cout, int k);
 int ctu_upfuse_compose(const float* wt, const float* bt, const float* w3, const float* b3, float* wn, float* b3n, int cin,
-                       int cout, int k, ctu_stream stream);
+                       int cout, int k, float* workspace, ctu_stream stream);
 /* chain rule of the composition: dwn [8*cop][cin+1][27] (+ dbn [8*cop]) -> dwt, dbt, dw3 (+ db3) */
 int ctu_upfuse_decompose(const float* dwn, const float* dbn, const float* wt, const float* bt, const float* w3, float* dwt,
-                         float* dbt, float* dw3, float* db3, int cin, int cout, int k, ctu_stream stream);
+                         float* dbt, float* dw3, float* db3, int cin, int cout, int k, float* workspace, ctu_stream stream);
 
 /* ---- BatchNorm3d (+ReLU, + MaxPool3d(2,2)) (models.py:27-28,31-32,39-40,43-44,190-191,233) ---
  * sums: double[2*cpad] = per-channel sum and sum of squares (zeroed by ctu_bn_stats).

@@ -32,9 +32,10 @@ def test_compose_decompose_kernels_match_oracle(k, cin, cout, bias3):
     wn = torch.empty(co8, cin + 1, 27, device=DEV)
     b3n = torch.empty(co8, device=DEV) if bias3 else None
     wtd, btd, w3d = d(wt), d(bt), d(w3)              # keep the device copies alive across the call
+    wsp = torch.empty(lib.ctu_upfuse_workspace_floats(cin, cout, k), device=DEV)
     b3d = d(b3) if bias3 else None
     call("ctu_upfuse_compose", wtd.data_ptr(), btd.data_ptr(), w3d.data_ptr(), b3d.data_ptr() if bias3 else None,
-         wn.data_ptr(), b3n.data_ptr() if bias3 else None, cin, cout, k, stream_ptr())
+         wn.data_ptr(), b3n.data_ptr() if bias3 else None, cin, cout, k, wsp.data_ptr(), stream_ptr())
     torch.cuda.synchronize()
     scale = ref.abs().max().item()
     assert (wn.cpu().view_as(ref) - ref.detach()).abs().max().item() <= 1e-5 * scale
@@ -54,7 +55,7 @@ def test_compose_decompose_kernels_match_oracle(k, cin, cout, bias3):
     dbnd = dbn.to(DEV) if bias3 else None
     call("ctu_upfuse_decompose", dwnd.data_ptr(), dbnd.data_ptr() if bias3 else None, wtd.data_ptr(), btd.data_ptr(),
          w3d.data_ptr(), dwt.data_ptr(), dbt.data_ptr(), dw3.data_ptr(), db3.data_ptr() if bias3 else None, cin, cout, k,
-         stream_ptr())
+         wsp.data_ptr(), stream_ptr())
     torch.cuda.synchronize()
     for got, exp, what in ((dwt, gwt, "dWT"), (dbt, gbt, "dbT"), (dw3, gw3, "dW3")):
         err = (got.cpu() - exp).abs().max().item()
