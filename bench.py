@@ -395,10 +395,12 @@ def run_b200_arm(a):
         net._grad_sink = sync
 
     # ---- end-to-end steps: pinned host -> device every iteration, loss read back ----------------
-    # e2e      : the reference-facing call -- float32 image + one-hot float32 targets exactly as the reference's
-    #            DataLoader hands them to Model.forward_pass (Model.py:343-349), from pinned host memory
-    # e2e_u8   : the device-side batch encoding (ctu_encode_flaprec_u8, datasets.py:195-235): the host ships the three
-    #            uint8 masks (3 B/voxel instead of 24) and the atlas channel stays resident
+    # f32 batch: float32 image + one-hot float32 targets exactly as the reference's DataLoader hands them to
+    #            Model.forward_pass (Model.py:343-349), from pinned host memory (24 B/voxel: at 8 GPUs the eight ranks
+    #            together pull ~300 GB/s out of host memory and the copy, not the GPU, sets the pace: 8.6 vs 5.3 ms)
+    # u8 masks : TrainStep.step_from_masks -- the device-side batch encoding (ctu_encode_flaprec_u8, datasets.py:195-235):
+    #            the host ships the three uint8 masks (3 B/voxel) and the atlas channel stays resident.  This is the
+    #            pipeline the package is built around and the one reported as `e2e` for the double-output models.
     # Both double-buffer the H2D copy on a copy stream and read every step's loss components back through
     # LossReadback (one step of latency, so the host never idles the GPU).
     from ctunet_b200.trainer import LossReadback
@@ -449,8 +451,10 @@ def run_b200_arm(a):
         ms_u8 = timed(u8_step, a.steps, after=rb8.drain)
         e2e_u8 = {"value": a.batch * a.size ** 3 * world / (ms_u8 * 1e-3), "unit": UNIT, "ms_per_step": ms_u8,
                   "h2d_bytes_per_step": sum(t.numel() for t in host_u8), "d2h_bytes_per_step": rb8.bytes_per_step,
-                  "note": "TrainStep.step_from_masks: uint8 masks from pinned host memory, batch encoded on the device "
-                          "(ctu_encode_flaprec_u8) into the captured step's inputs"}
+                  "note": "TrainStep.step_from_masks: the batch's three uint8 masks (broken skull, full skull, flap) from "
+                          "pinned host memory, double-buffered H2D, encoded on the device (ctu_encode_flaprec_u8: float "
+                          "image + atlas channel + one-hot float targets, datasets.py:195-235) into the captured step's "
+                          "inputs; loss components read back every step, one step late"}
 
     # nvidia-smi was sampling (every 50 ms) from the start of the timed `value` loop to the end of the e2e loops
     clk = clocks.stop() if rank == 0 else None
@@ -502,10 +506,11 @@ def run_b200_arm(a):
 
     cpu = None
     if world == 1 and not a.no_cpu_baseline:
-        cs, cb = 64, 1
+        cs, cb = a.size, 1
         sec, used = cpu_reference_step_time(a.model, cb, cs, steps=3, warmup=1, threads=os.cpu_count())
         cpu = {"value": cb * cs ** 3 / sec, "unit": UNIT, "cores": used, "kind": "port",
-               "sample": "batch %d x %d^3 (BASELINE config 0 shape), fp32, 3 steps after 1 warm-up, %.2f s/step" % (cb, cs, sec)}
+               "sample": "one volume of the %d-volume batch (batch %d x %d^3), fp32, 3 steps after 1 warm-up, %.2f s/step"
+                         % (a.batch, cb, cs, sec)}
 
     # the other BASELINE configs[1] models (the 5^3 autoimplant2020 family): short device-resident runs, same batch and size
     others = None
@@ -525,6 +530,11 @@ def run_b200_arm(a):
             del ostep, onet
             torch.cuda.empty_cache()
 
+    e2e_f32 = {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes,
+               "d2h_bytes_per_step": d2h_bytes,
+               "note": "TrainStep.__call__: float32 image + one-hot float32 targets from pinned host memory (the reference "
+                       "DataLoader's format), double-buffered H2D, loss components read back every step one step late"}
+    e2e_main = e2e_u8 if e2e_u8 is not None else e2e_f32
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
         "ms_per_step": ms_resident, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -532,11 +542,8 @@ def run_b200_arm(a):
         "config": {"workload": workload_name(a), "global_batch": a.batch * world, "parallelism": "dp%d" % world,
                    "l2": flush_note, "conv_path": "tcgen05" if _lib.load().ctu_has_tensor_path() else "cuda-core",
                    "cuda_graph": use_graph},
-        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes,
-                "d2h_bytes_per_step": d2h_bytes,
-                "note": "float32 image + one-hot float32 targets from pinned host memory (the reference DataLoader's "
-                        "format), double-buffered H2D, loss components read back every step one step late"},
-        "e2e_u8_masks": e2e_u8,
+        "e2e": e2e_main,
+        "e2e_f32_batch": e2e_f32 if e2e_main is not e2e_f32 else None,
         "gpu_launches": launches,
         "gpu_launches_note": "C-ABI entry points in the timed region (each enqueues >= 1 kernel of this library)"
                              + ("; the step is replayed from a CUDA graph captured once" if use_graph else ""),
