@@ -130,7 +130,6 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
     constexpr uint32_t ROW = WW * 16;              // bytes per halo row of one channel block
     constexpr int CP = COB * 8;                    // padded output channels
     constexpr int NSLOT = COB < 2 ? COB : 2;       // statistics accumulators (blocks) per thread
-    constexpr int NTHREADS = 32 * (1 + TC_WB + 4 * TC_WB);
     const uint32_t NS = p.ns;
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t s_base = smem_u32(smem);
@@ -138,7 +137,6 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
     const uint32_t s_planes = s_base + ((p.wimg_bytes + 1023u) & ~1023u);   // NS slots
     const uint32_t s_tab = s_planes + NS * p.slot_bytes;                    // per-MMA descriptor low words (A, B)
     const int nm = tc_mmas_per_kd(K, p.cb, p.cbg);
-    uint2* tab = reinterpret_cast<uint2*>(smem + (s_tab - s_base));
     const uint32_t s_bar = s_tab + ((nm * 8u + 15u) & ~15u);
     // barriers: plane_full[NS], plane_empty[NS], acc_full[2 stages][TC_WB tiles], acc_empty[2][TC_WB], w_full
     const uint32_t b_full = s_bar, b_empty = s_bar + 8 * TC_MAX_SLOTS, b_afull = s_bar + 16 * TC_MAX_SLOTS,
@@ -682,7 +680,6 @@ __global__ void __launch_bounds__(WG_THREADS) conv3d_wgrad_tc_kernel(const __gri
     const uint32_t b_xfull = s_bar, b_xempty = s_bar + 8 * TC_MAX_SLOTS, b_dyfull = s_bar + 16 * TC_MAX_SLOTS,
                    b_dyempty = s_bar + 24 * TC_MAX_SLOTS, b_done = s_bar + 32 * TC_MAX_SLOTS;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (b_done + 8 - s_base));
-    uint2* wtab = reinterpret_cast<uint2*>(smem + (b_done + 16 - s_base));   // [WG_ISSUERS][WG_MAX_OWN]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = blockIdx.y;
     const int cbg_i = grp % p.n_cbgroups, ng_i = grp / p.n_cbgroups;

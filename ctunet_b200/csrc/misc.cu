@@ -12,9 +12,18 @@ __global__ void count_blocks_kernel(const unsigned char* __restrict__ img, long 
                                     long long* __restrict__ block_counts, long long* __restrict__ total) {
     const long long base = (long long)blockIdx.x * kVoxPerBlock;
     int cnt = 0;
-    for (int i = threadIdx.x; i < kVoxPerBlock; i += blockDim.x) {
-        long long v = base + i;
-        if (v < nvox && img[v] > 0) ++cnt;
+    if (base + kVoxPerBlock <= nvox && (reinterpret_cast<uintptr_t>(img) & 15u) == 0) {
+        // 256 threads x one 16-byte load = the block's 4096 voxels
+        const uint4 u = reinterpret_cast<const uint4*>(img + base)[threadIdx.x];
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)      // a byte is non-zero <=> its low 7 bits carry into bit 7, or bit 7 is set
+            cnt += __popc((((w[j] & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w[j]) & 0x80808080u);
+    } else {
+        for (int i = threadIdx.x; i < kVoxPerBlock; i += blockDim.x) {
+            long long v = base + i;
+            if (v < nvox && img[v] > 0) ++cnt;
+        }
     }
     __shared__ int red[8];
     int s = cnt;
@@ -30,28 +39,80 @@ __global__ void count_blocks_kernel(const unsigned char* __restrict__ img, long 
     }
 }
 
-// np.argwhere(img > 0)[k] in C order: walk the per-block counts, then the block's voxels.
-__global__ void kth_nonzero_kernel(const unsigned char* __restrict__ img, int d, int h, int w, long long k,
-                                   const long long* __restrict__ block_counts, int nblocks, int* __restrict__ coords) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const long long nvox = (long long)d * h * w;
-    long long seen = 0;
-    int blk = 0;
-    for (; blk < nblocks; ++blk) {
-        if (seen + block_counts[blk] > k) break;
-        seen += block_counts[blk];
+// np.argwhere(img > 0)[k] in C order: a block-wide prefix over the per-block counts finds the 4096-voxel block, a second
+// prefix over its voxels (4 per thread) finds the voxel.  One block of 1024 threads.
+__device__ __forceinline__ long long block_exclusive_scan(long long v, long long* warp_tot, long long& total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    long long inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
     }
-    coords[0] = coords[1] = coords[2] = -1;
-    if (blk == nblocks) return;
-    for (long long v = (long long)blk * kVoxPerBlock; v < nvox; ++v) {
-        if (img[v] > 0) {
-            if (seen == k) {
-                coords[2] = (int)(v % w);
-                coords[1] = (int)((v / w) % h);
-                coords[0] = (int)(v / ((long long)w * h));
-                return;
+    __syncthreads();                      // warp_tot may still be read from a previous scan
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    long long off = 0;
+    total = 0;
+    for (int i = 0; i < 32; ++i) {
+        const long long t = warp_tot[i];
+        if (i < wid) off += t;
+        total += t;
+    }
+    return off + inc - v;
+}
+
+__global__ void __launch_bounds__(1024) kth_nonzero_kernel(const unsigned char* __restrict__ img, int d, int h, int w,
+                                                           long long k, const long long* __restrict__ block_counts,
+                                                           int nblocks, int* __restrict__ coords) {
+    __shared__ long long warp_tot[32];
+    __shared__ long long sel[2];          // chosen block, rank of the voxel inside it
+    const long long nvox = (long long)d * h * w;
+    if (threadIdx.x < 3) coords[threadIdx.x] = -1;
+    if (threadIdx.x == 0) sel[0] = -1;
+    // phase 1: every thread owns a contiguous chunk of the per-block counts
+    const int per = (nblocks + 1023) / 1024;
+    const int b0 = threadIdx.x * per, b1 = min(nblocks, b0 + per);
+    long long mine = 0;
+    for (int b = b0; b < b1; ++b) mine += block_counts[b];
+    long long total;
+    const long long before = block_exclusive_scan(mine, warp_tot, total);
+    if (k >= total) return;               // fewer than k+1 non-zero voxels: coords stay -1 (uniform exit)
+    if (k >= before && k < before + mine) {
+        long long seen = before;
+        for (int b = b0; b < b1; ++b) {
+            if (seen + block_counts[b] > k) {
+                sel[0] = b;
+                sel[1] = k - seen;
+                break;
             }
-            ++seen;
+            seen += block_counts[b];
+        }
+    }
+    __syncthreads();
+    const long long blk = sel[0], rank = sel[1];
+    // phase 2: 4096 voxels of the block, 4 consecutive voxels per thread
+    const long long v0 = blk * kVoxPerBlock + 4LL * threadIdx.x;
+    int nz[4], cnt = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        nz[j] = (v0 + j < nvox && img[v0 + j] > 0) ? 1 : 0;
+        cnt += nz[j];
+    }
+    long long tot2;
+    long long seen = block_exclusive_scan(cnt, warp_tot, tot2);
+    if (rank >= seen && rank < seen + cnt) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (nz[j]) {
+                if (seen == rank) {
+                    const long long v = v0 + j;
+                    coords[2] = (int)(v % w);
+                    coords[1] = (int)((v / w) % h);
+                    coords[0] = (int)(v / ((long long)w * h));
+                }
+                ++seen;
+            }
         }
     }
 }
@@ -156,6 +217,108 @@ __global__ void hu_threshold_kernel(const short* __restrict__ hu, unsigned char*
     out[v] = hu[v] >= thr ? 1 : 0;
 }
 
+// ---- 16-byte vector variants (the byte-per-thread kernels above reach 4-25 % of the HBM roofline: too few bytes in
+// flight per thread).  The host uses them for the 16-aligned bulk of a volume and the scalar kernels for the tail.
+__global__ void hu_window_vec_kernel(const short* __restrict__ hu, float* __restrict__ out, long long ngroups, float lo,
+                                     float hi) {   // 16 voxels per thread: two 16-byte loads, four 16-byte stores
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ngroups) return;
+    const uint4 a = reinterpret_cast<const uint4*>(hu)[2 * i], b = reinterpret_cast<const uint4*>(hu)[2 * i + 1];
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    const float den = __fsub_rn(hi, lo);
+    float o[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const short sv = (short)((w[j >> 1] >> (16 * (j & 1))) & 0xffffu);
+        float x = (float)sv;
+        x = fminf(fmaxf(x, lo), hi);
+        o[j] = __fdiv_rn(__fsub_rn(x, lo), den);
+    }
+    float4* dst = reinterpret_cast<float4*>(out) + 4 * i;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dst[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+}
+
+__global__ void hu_threshold_vec_kernel(const short* __restrict__ hu, unsigned char* __restrict__ out, long long ngroups,
+                                        int thr) {   // 16 voxels per thread
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ngroups) return;
+    const uint4 a = reinterpret_cast<const uint4*>(hu)[2 * i], b = reinterpret_cast<const uint4*>(hu)[2 * i + 1];
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t o[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const short sv = (short)((w[j >> 1] >> (16 * (j & 1))) & 0xffffu);
+        if ((int)sv >= thr) o[j >> 2] |= 1u << (8 * (j & 3));
+    }
+    reinterpret_cast<uint4*>(out)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// sphere / box with an INTEGER radius (np.random.randint, transforms.py:268): squared distances of integer offsets are
+// exact in int64 and sqrt is monotone, so  norm <= size  <=>  d2 <= size^2  bit for bit; 16 voxels of one row per thread
+template <typename I>   // I = int when every squared distance fits 31 bits (volumes up to 16384 voxels a side), else long long
+__global__ void flap_mask_vec_kernel(const unsigned char* __restrict__ img, unsigned char* __restrict__ masked,
+                                     unsigned char* __restrict__ extracted, int d, int h, int w, const int* __restrict__ center,
+                                     long long size_ll, int shape, long long ngroups) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ngroups) return;
+    const int wg = w >> 4;
+    const int x0 = (int)(i % wg) << 4;
+    const int y = (int)((i / wg) % h);
+    const int z = (int)(i / ((long long)wg * h));
+    const I size = (I)size_ll;
+    const I dz = z - center[0], dy = y - center[1], cx = center[2];
+    const I base2 = dz * dz + dy * dy, size2 = size * size;
+    const bool row_in_box = (dz < 0 ? -dz : dz) <= size && (dy < 0 ? -dy : dy) <= size;
+    const uint4 u = reinterpret_cast<const uint4*>(img)[i];
+    const uint32_t wv[4] = {u.x, u.y, u.z, u.w};
+    uint32_t m[4] = {0, 0, 0, 0}, e[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const I dx = x0 + j - cx;
+        const bool inside = shape == 0 ? (base2 + dx * dx <= size2) : (row_in_box && (dx < 0 ? -dx : dx) <= size);
+        const bool on = ((wv[j >> 2] >> (8 * (j & 3))) & 0xffu) != 0;
+        if (on && !inside) m[j >> 2] |= 1u << (8 * (j & 3));
+        if (on && inside) e[j >> 2] |= 1u << (8 * (j & 3));
+    }
+    reinterpret_cast<uint4*>(masked)[i] = make_uint4(m[0], m[1], m[2], m[3]);
+    reinterpret_cast<uint4*>(extracted)[i] = make_uint4(e[0], e[1], e[2], e[3]);
+}
+
+// the flap shape, 16 voxels of one row per thread (same float64 arithmetic as flap_shape_mask_kernel, row terms hoisted)
+__global__ void flap_shape_mask_vec_kernel(const unsigned char* __restrict__ img, unsigned char* __restrict__ masked,
+                                           unsigned char* __restrict__ extracted, int d, int h, int w,
+                                           const int* __restrict__ center, double size, double c_diam, long long ngroups) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ngroups) return;
+    const int wg = w >> 4;
+    const int x0 = (int)(i % wg) << 4;
+    const int y = (int)((i / wg) % h);
+    const int z = (int)(i / ((long long)wg * h));
+    const double c0 = (double)center[0], c1 = (double)center[1], c2 = (double)center[2];
+    const double z0 = rint((d - 1) * (c0 / d));
+    const double ey = rint((h - 1) * ((c1 - size / 2) / h));
+    const double ex1 = rint((w - 1) * ((c2 - size / 2) / w)), ex2 = rint((w - 1) * ((c2 + size / 2) / w));
+    const double qy = rint((h - 1) * (c1 / h)), qx = rint((w - 1) * (c2 / w));
+    const bool in_height = fabs(z - z0) <= size / 2;
+    const double r2 = c_diam * c_diam, dy = y - ey, dy2 = dy * dy;
+    const bool cube_row = in_height && fabs(y - qy) <= size / 2;
+    const uint4 u = reinterpret_cast<const uint4*>(img)[i];
+    const uint32_t wv[4] = {u.x, u.y, u.z, u.w};
+    uint32_t m[4] = {0, 0, 0, 0}, e[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const double x = x0 + j;
+        const bool inside = in_height && ((dy2 + (x - ex1) * (x - ex1) <= r2) || (dy2 + (x - ex2) * (x - ex2) <= r2)) ||
+                            (cube_row && fabs(x - qx) <= size / 2);
+        const bool on = ((wv[j >> 2] >> (8 * (j & 3))) & 0xffu) != 0;
+        if (on && !inside) m[j >> 2] |= 1u << (8 * (j & 3));
+        if (on && inside) e[j >> 2] |= 1u << (8 * (j & 3));
+    }
+    reinterpret_cast<uint4*>(masked)[i] = make_uint4(m[0], m[1], m[2], m[3]);
+    reinterpret_cast<uint4*>(extracted)[i] = make_uint4(e[0], e[1], e[2], e[3]);
+}
+
 __device__ __forceinline__ int nearest_src(int dst, int in_size, float scale) {
     int i = (int)floorf(__fmul_rn((float)dst, scale));
     return i < in_size - 1 ? i : in_size - 1;
@@ -211,6 +374,8 @@ __global__ void resample_trilinear_kernel(const float* __restrict__ src, float* 
 
 using namespace ctu;
 
+static inline bool aligned16_host(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
 extern "C" {
 
 int ctu_count_nonzero_u8(const unsigned char* img, long long nvox, long long* count, ctu_stream stream) {
@@ -232,7 +397,7 @@ int ctu_kth_nonzero_u8(const unsigned char* img, int d, int h, int w, long long 
     const long long nvox = (long long)d * h * w;
     const int nblocks = cdiv(nvox, kVoxPerBlock);
     count_blocks_kernel<<<nblocks, 256, 0, st>>>(img, nvox, block_counts, nullptr);
-    kth_nonzero_kernel<<<1, 32, 0, st>>>(img, d, h, w, k, block_counts, nblocks, coords);
+    kth_nonzero_kernel<<<1, 1024, 0, st>>>(img, d, h, w, k, block_counts, nblocks, coords);
     return check_launch("ctu_kth_nonzero_u8");
 }
 
@@ -241,10 +406,22 @@ int ctu_flap_mask_u8(const unsigned char* img, unsigned char* masked, unsigned c
     CTU_REQUIRE(img && masked && extracted && center && d > 0 && h > 0 && w > 0 && shape >= 0 && shape <= 2,
                 "ctu_flap_mask_u8: bad arguments (shape 0 sphere / 1 box / 2 flap)");
     const long long nvox = (long long)d * h * w;
-    if (shape == 2)
-        flap_shape_mask_kernel<<<cdiv(nvox, 256), 256, 0, (cudaStream_t)stream>>>(img, masked, extracted, d, h, w, center, size, c_diam, nvox);
-    else
-        flap_mask_kernel<<<cdiv(nvox, 256), 256, 0, (cudaStream_t)stream>>>(img, masked, extracted, d, h, w, center, size, shape, nvox);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool vec = (w % 16 == 0) && aligned16_host(img) && aligned16_host(masked) && aligned16_host(extracted);
+    const long long ngroups = nvox / 16;
+    if (shape == 2) {
+        if (vec) flap_shape_mask_vec_kernel<<<cdiv(ngroups, 256), 256, 0, st>>>(img, masked, extracted, d, h, w, center, size, c_diam, ngroups);
+        else flap_shape_mask_kernel<<<cdiv(nvox, 256), 256, 0, st>>>(img, masked, extracted, d, h, w, center, size, c_diam, nvox);
+    } else if (vec && size >= 0 && size < 1048576.0 && size == (double)(long long)size) {
+        // int32: 3 * 16384^2 < 2^31; a radius beyond the volume diagonal is clamped (everything is inside either way)
+        if (d <= 16384 && h <= 16384 && w <= 16384)
+            flap_mask_vec_kernel<int><<<cdiv(ngroups, 256), 256, 0, st>>>(img, masked, extracted, d, h, w, center,
+                                                                         size > 28378.0 ? 28378LL : (long long)size, shape, ngroups);
+        else
+            flap_mask_vec_kernel<long long><<<cdiv(ngroups, 256), 256, 0, st>>>(img, masked, extracted, d, h, w, center, (long long)size, shape, ngroups);
+    } else {
+        flap_mask_kernel<<<cdiv(nvox, 256), 256, 0, st>>>(img, masked, extracted, d, h, w, center, size, shape, nvox);
+    }
     return check_launch("ctu_flap_mask_u8");
 }
 
@@ -263,13 +440,27 @@ int ctu_encode_flaprec_u8(const unsigned char* broken, const unsigned char* full
 
 int ctu_hu_window(const short* hu, float* out, long long nvox, float lo, float hi, ctu_stream stream) {
     CTU_REQUIRE(hu && out && nvox > 0 && hi > lo, "ctu_hu_window: bad arguments");
-    hu_window_kernel<<<cdiv(nvox, 256), 256, 0, (cudaStream_t)stream>>>(hu, out, nvox, lo, hi);
+    cudaStream_t st = (cudaStream_t)stream;
+    long long done = 0;
+    if (aligned16_host(hu) && aligned16_host(out) && nvox >= 16) {
+        const long long ngroups = nvox / 16;
+        hu_window_vec_kernel<<<cdiv(ngroups, 256), 256, 0, st>>>(hu, out, ngroups, lo, hi);
+        done = ngroups * 16;
+    }
+    if (done < nvox) hu_window_kernel<<<cdiv(nvox - done, 256), 256, 0, st>>>(hu + done, out + done, nvox - done, lo, hi);
     return check_launch("ctu_hu_window");
 }
 
 int ctu_hu_threshold(const short* hu, unsigned char* out, long long nvox, int thr, ctu_stream stream) {
     CTU_REQUIRE(hu && out && nvox > 0, "ctu_hu_threshold: bad arguments");
-    hu_threshold_kernel<<<cdiv(nvox, 256), 256, 0, (cudaStream_t)stream>>>(hu, out, nvox, thr);
+    cudaStream_t st = (cudaStream_t)stream;
+    long long done = 0;
+    if (aligned16_host(hu) && aligned16_host(out) && nvox >= 16) {
+        const long long ngroups = nvox / 16;
+        hu_threshold_vec_kernel<<<cdiv(ngroups, 256), 256, 0, st>>>(hu, out, ngroups, thr);
+        done = ngroups * 16;
+    }
+    if (done < nvox) hu_threshold_kernel<<<cdiv(nvox - done, 256), 256, 0, st>>>(hu + done, out + done, nvox - done, thr);
     return check_launch("ctu_hu_threshold");
 }
 

@@ -298,8 +298,10 @@ def test_flap_mask_bit_exact(golden):
     assert torch.equal(m.cpu(), b["masked"]) and torch.equal(e.cpu(), b["extracted"])
     rng = np.random.RandomState(0)
     for shape in ["sphere", "box"]:
-        for _ in range(4):
+        for it in range(6):
             dims = tuple(int(v) for v in rng.randint(5, 40, 3))
+            if it >= 3:                       # rows that are a multiple of 16 voxels take the 16-byte vector kernel
+                dims = dims[:2] + (16 * int(rng.randint(1, 4)),)
             vol = (rng.rand(*dims) > 0.6).astype(np.uint8)
             center = [int(rng.randint(0, s)) for s in dims]
             size = int(rng.randint(1, 12))
@@ -336,8 +338,10 @@ def test_flap_shape_bit_exact():
     m, e = C.random_blank_patch(r["img"].to(DEV), 1, True)
     assert torch.equal(m.cpu(), ra["masked"]) and torch.equal(e.cpu(), ra["extracted"])
     rng = np.random.RandomState(3)
-    for _ in range(6):
+    for it in range(8):
         dims = tuple(int(v) for v in rng.randint(6, 48, 3))
+        if it >= 4:                           # vector kernel
+            dims = dims[:2] + (16 * int(rng.randint(1, 4)),)
         vol = (rng.rand(*dims) > 0.5).astype(np.uint8)
         center = [int(rng.randint(0, s)) for s in dims]
         size, c_diam = int(rng.randint(2, 20)), float(rng.uniform(0.3, 5.0))
@@ -366,7 +370,7 @@ def test_encode_flaprec_batch_bit_exact():
 def test_kth_nonzero_and_count():
     import ctunet_b200 as C
     rng = np.random.RandomState(1)
-    for dims in [(16, 20, 24), (33, 17, 65), (4, 4, 4)]:
+    for dims in [(16, 20, 24), (33, 17, 65), (4, 4, 4), (64, 64, 64), (40, 128, 96)]:
         vol = (rng.rand(*dims) > 0.8).astype(np.uint8)
         vol[0, 0, 0] = 1
         t = torch.from_numpy(vol).to(DEV)
@@ -408,6 +412,9 @@ def test_preprocess_matches_oracle():
     hg = hu.to(DEV)
     assert torch.equal(P.hu_window(hg, -100.0, 1500.0).cpu(), O.hu_window(hu, -100.0, 1500.0))
     assert torch.equal(P.hu_threshold(hg, 300).cpu(), O.hu_threshold(hu, 300))
+    odd = O.skull_phantom_hu((7, 9, 11), 4)       # 693 voxels: vector bulk + scalar tail
+    assert torch.equal(P.hu_window(odd.to(DEV), 0.0, 800.0).cpu(), O.hu_window(odd, 0.0, 800.0))
+    assert torch.equal(P.hu_threshold(odd.to(DEV), 150).cpu(), O.hu_threshold(odd, 150))
     for out in [(20, 24, 28), (32, 32, 32), (50, 61, 70), (40, 48, 56)]:
         bone = O.hu_threshold(hu, 300)
         assert torch.equal(P.resample_nearest(bone.to(DEV), out).cpu(), O.resample_nearest(bone, out))
