@@ -45,13 +45,15 @@ class TrainStep:
         self._static_out = None
         self._calls = 0
         self.launches_per_step = None                         # C-ABI calls recorded in the captured step
-        cap = dict(capturable=True) if self.graph else {}
+        # fused=True: one multi-tensor kernel per step instead of the ~12 foreach launches (0.25 ms at the END of the step,
+        # where nothing overlaps them); same update rule, fp32 math
+        cap = dict(capturable=True, fused=True) if self.graph else dict(fused=True)
         if optimizer == "adam":                               # Model.py:514-520
             self.optimizer = torch.optim.Adam(params, lr=lr, weight_decay=weight_decay, amsgrad=True, **cap)
         elif optimizer == "adamw":                            # Model.py:521-527
             self.optimizer = torch.optim.AdamW(params, lr=lr, weight_decay=weight_decay, amsgrad=True, **cap)
         elif optimizer == "sgd":                              # Model.py:535-541
-            self.optimizer = torch.optim.SGD(params, lr=lr, momentum=0.99, weight_decay=weight_decay)
+            self.optimizer = torch.optim.SGD(params, lr=lr, momentum=0.99, weight_decay=weight_decay, fused=True)
         else:
             raise ValueError("optimizer %r" % optimizer)
 
