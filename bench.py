@@ -246,9 +246,11 @@ def describe(name, args, esize):
         if name == "ctu_bn_stats":
             c, ph, n, sp = args[2], args[3], args[4], args[5]
             return "%s c%d @%dx%d" % (name, c, n, sp * ph), 0.0, esize * c * n * sp * ph
-        if name == "ctu_bn_relu_fwd":
-            c, n, d, h, w = args[5], args[6], args[7], args[8], args[9]
-            pooled = args[4] is not None
+        if name in ("ctu_bn_relu_fwd", "ctu_bn_relu_fwd_train"):
+            o = 5 if name == "ctu_bn_relu_fwd" else 15
+            c, n, d, h, w = args[o], args[o + 1], args[o + 2], args[o + 3], args[o + 4]
+            pooled = args[o - 1] is not None
+            name = "ctu_bn_relu_fwd"
             return ("%s c%d @%dx%dx%dx%d%s" % (name, c, n, d, h, w, " +pool" if pooled else ""), 0.0,
                     esize * c * n * d * h * w * (2 + (0.125 if pooled else 0)))
         if name in ("ctu_bn_relu_bwd_reduce", "ctu_bn_relu_bwd_apply"):

@@ -63,6 +63,7 @@ SIGNATURES = {
     "ctu_bn_finalize": (I, [P, D, P, P, P, P, P, F, F, I, I, I, P, P]),
     "ctu_bn_running_update": (I, [P, D, P, P, P, F, I, I, P]),
     "ctu_bn_relu_fwd": (I, [I, P, P, P, P, I, I, I, I, I, I, P]),
+    "ctu_bn_relu_fwd_train": (I, [I, P, P, D, P, P, P, P, P, F, F, I, P, P, P, I, I, I, I, I, I, P]),
     "ctu_bn_relu_bwd_reduce": (I, [I, P, P, P, P, P, I, I, I, I, I, I, P]),
     "ctu_bn_relu_bwd_apply": (I, [I, P, P, P, P, P, P, D, P, P, P, I, I, I, I, I, I, P]),
     "ctu_head_fwd": (I, [I, P, P, I, P, P, I, I, P, P, I, LL, P]),

@@ -134,17 +134,80 @@ __device__ __forceinline__ V8 bn_relu_apply(const V8& y, const float (&sc)[8], c
 constexpr int kVoxPerThread = 4;   // plain (unpooled) kernels: voxels per thread, strided by the block size
 
 // a = relu(scale*y + shift); grid = (chunks, cb, n)
+// Training-mode finalisation folded into the forward kernels (ctu_bn_relu_fwd_train): every block derives scale / shift of
+// its 8 channels from the batch sums (what bn_finalize_kernel computes); the first block of each channel block also
+// writes ss for the backward pass and moves the running statistics.  One launch less per BatchNorm on the critical path.
+struct BnFin {
+    const double* sums;      // nullptr: read ss (the separate ctu_bn_finalize path, e.g. eval mode)
+    double count;
+    const float* gamma;
+    const float* beta;
+    float* running_mean;
+    float* running_var;
+    long long* nbt;
+    float momentum, eps;
+    int c, n_updates;
+    float* ss_out;
+};
+
+__device__ __forceinline__ void bn_scale_shift(const BnFin& f, const float* __restrict__ ss, int b, int cpad, bool writer,
+                                               float (&sc)[8], float (&sh)[8]) {
+    if (f.sums == nullptr) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            sc[j] = __ldg(ss + b * 8 + j);
+            sh[j] = __ldg(ss + cpad + b * 8 + j);
+        }
+        return;
+    }
+    __shared__ float s_sc[8], s_sh[8];
+    if (threadIdx.x < 8) {
+        const int ch = b * 8 + threadIdx.x;
+        float scale = 0.f, shift = 0.f, meanf = 0.f, invstd = 0.f;
+        if (ch < f.c) {
+            const double mean = f.sums[ch] / f.count;
+            double var = f.sums[cpad + ch] / f.count - mean * mean;
+            if (var < 0.0) var = 0.0;
+            if (writer && f.running_mean != nullptr && f.running_var != nullptr) {
+                const double unbiased = f.count > 1.0 ? var * f.count / (f.count - 1.0) : var;
+                float rm = f.running_mean[ch], rv = f.running_var[ch];
+                for (int u = 0; u < f.n_updates; ++u) {
+                    rm = (1.f - f.momentum) * rm + f.momentum * (float)mean;
+                    rv = (1.f - f.momentum) * rv + f.momentum * (float)unbiased;
+                }
+                f.running_mean[ch] = rm;
+                f.running_var[ch] = rv;
+            }
+            invstd = (float)(1.0 / sqrt(var + (double)f.eps));
+            meanf = (float)mean;
+            scale = f.gamma[ch] * invstd;
+            shift = f.beta[ch] - meanf * scale;
+        }
+        s_sc[threadIdx.x] = scale;
+        s_sh[threadIdx.x] = shift;
+        if (writer) {
+            f.ss_out[ch] = scale;
+            f.ss_out[cpad + ch] = shift;
+            f.ss_out[2 * cpad + ch] = meanf;
+            f.ss_out[3 * cpad + ch] = invstd;
+            if (ch == 0 && f.nbt != nullptr) *f.nbt += f.n_updates;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        sc[j] = s_sc[j];
+        sh[j] = s_sh[j];
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kBnThreads) bn_relu_fwd_kernel(const T* __restrict__ y, const float* __restrict__ ss,
-                                                                 T* __restrict__ a, int cb, long long spatial) {
+                                                                 T* __restrict__ a, int cb, long long spatial, BnFin fin) {
     const int b = blockIdx.y, n = blockIdx.z;
     const int cpad = cb * 8;
     float sc[8], sh[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        sc[j] = __ldg(ss + b * 8 + j);
-        sh[j] = __ldg(ss + cpad + b * 8 + j);
-    }
+    bn_scale_shift(fin, ss, b, cpad, blockIdx.x == 0 && n == 0, sc, sh);
     const long long base = ((long long)n * cb + b) * spatial;
     const long long s0 = (long long)blockIdx.x * kBnThreads * kVoxPerThread + threadIdx.x;
     V8 v[kVoxPerThread];
@@ -168,15 +231,11 @@ template <typename T, bool S2D>
 __global__ void __launch_bounds__(kBnThreads) bn_relu_child_fwd_kernel(const T* __restrict__ y,
                                                                        const float* __restrict__ ss, T* __restrict__ a,
                                                                        T* __restrict__ pooled, int cb, int d, int h,
-                                                                       int w) {
+                                                                       int w, BnFin fin) {
     const int b = blockIdx.y, n = blockIdx.z;
     const int cpad = cb * 8;
     float sc[8], sh[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        sc[j] = __ldg(ss + b * 8 + j);
-        sh[j] = __ldg(ss + cpad + b * 8 + j);
-    }
+    bn_scale_shift(fin, ss, b, cpad, blockIdx.x == 0 && n == 0, sc, sh);
     const int pd = d / 2, ph = h / 2, pw = w / 2;
     const long long pspatial = (long long)pd * ph * pw;
     const long long ps = (long long)blockIdx.x * kBnThreads + threadIdx.x;
@@ -417,24 +476,39 @@ int ctu_bn_running_update(const double* sums, double count, float* running_mean,
     return check_launch("ctu_bn_running_update");
 }
 
-int ctu_bn_relu_fwd(int dtype, const void* y, const float* ss, void* a, void* pooled, int c, int n, int d, int h, int w,
-                    int y_phase_major, ctu_stream stream) {
-    CTU_REQUIRE(y && ss && a && c > 0 && n > 0 && d > 0 && h > 0 && w > 0, "ctu_bn_relu_fwd: bad arguments");
-    CTU_REQUIRE(!(y_phase_major && pooled), "ctu_bn_relu_fwd: a phase-major input is never pooled");
+static int bn_relu_fwd_launch(int dtype, const void* y, const float* ss, void* a, void* pooled, int c, int n, int d, int h,
+                              int w, int y_phase_major, const BnFin& fin, ctu_stream stream, const char* what) {
+    CTU_REQUIRE(y && (ss || fin.sums) && a && c > 0 && n > 0 && d > 0 && h > 0 && w > 0, "%s: bad arguments", what);
+    CTU_REQUIRE(!(y_phase_major && pooled), "%s: a phase-major input is never pooled", what);
     const int cb = (c + 7) / 8;
     const long long spatial = (long long)d * h * w;
     if (pooled != nullptr || y_phase_major) {
-        CTU_REQUIRE(d % 2 == 0 && h % 2 == 0 && w % 2 == 0, "ctu_bn_relu_fwd: needs even dims (%d,%d,%d)", d, h, w);
+        CTU_REQUIRE(d % 2 == 0 && h % 2 == 0 && w % 2 == 0, "%s: needs even dims (%d,%d,%d)", what, d, h, w);
         dim3 grid(cdiv(spatial / 8, kBnThreads), cb, n);
         if (y_phase_major)
-            CTU_DISPATCH_DTYPE(dtype, (bn_relu_child_fwd_kernel<T, true><<<grid, kBnThreads, 0, (cudaStream_t)stream>>>((const T*)y, ss, (T*)a, nullptr, cb, d, h, w)));
+            CTU_DISPATCH_DTYPE(dtype, (bn_relu_child_fwd_kernel<T, true><<<grid, kBnThreads, 0, (cudaStream_t)stream>>>((const T*)y, ss, (T*)a, nullptr, cb, d, h, w, fin)));
         else
-            CTU_DISPATCH_DTYPE(dtype, (bn_relu_child_fwd_kernel<T, false><<<grid, kBnThreads, 0, (cudaStream_t)stream>>>((const T*)y, ss, (T*)a, (T*)pooled, cb, d, h, w)));
+            CTU_DISPATCH_DTYPE(dtype, (bn_relu_child_fwd_kernel<T, false><<<grid, kBnThreads, 0, (cudaStream_t)stream>>>((const T*)y, ss, (T*)a, (T*)pooled, cb, d, h, w, fin)));
     } else {
         dim3 grid(cdiv(spatial, kBnThreads * kVoxPerThread), cb, n);
-        CTU_DISPATCH_DTYPE(dtype, (bn_relu_fwd_kernel<T><<<grid, kBnThreads, 0, (cudaStream_t)stream>>>((const T*)y, ss, (T*)a, cb, spatial)));
+        CTU_DISPATCH_DTYPE(dtype, (bn_relu_fwd_kernel<T><<<grid, kBnThreads, 0, (cudaStream_t)stream>>>((const T*)y, ss, (T*)a, cb, spatial, fin)));
     }
-    return check_launch("ctu_bn_relu_fwd");
+    return check_launch(what);
+}
+
+int ctu_bn_relu_fwd(int dtype, const void* y, const float* ss, void* a, void* pooled, int c, int n, int d, int h, int w,
+                    int y_phase_major, ctu_stream stream) {
+    BnFin fin = {};
+    return bn_relu_fwd_launch(dtype, y, ss, a, pooled, c, n, d, h, w, y_phase_major, fin, stream, "ctu_bn_relu_fwd");
+}
+
+int ctu_bn_relu_fwd_train(int dtype, const void* y, const double* sums, double count, const float* gamma, const float* beta,
+                          float* running_mean, float* running_var, long long* num_batches_tracked, float momentum, float eps,
+                          int n_updates, float* ss, void* a, void* pooled, int c, int n, int d, int h, int w,
+                          int y_phase_major, ctu_stream stream) {
+    CTU_REQUIRE(sums && gamma && beta && ss && count > 0, "ctu_bn_relu_fwd_train: bad arguments");
+    BnFin fin = {sums, count, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, c, n_updates, ss};
+    return bn_relu_fwd_launch(dtype, y, ss, a, pooled, c, n, d, h, w, y_phase_major, fin, stream, "ctu_bn_relu_fwd_train");
 }
 
 static int bn_bwd(int dtype, BwdArgs& p, int n, bool apply, int y_phase_major, cudaStream_t stream, const char* what) {

@@ -502,16 +502,19 @@ class Engine:
                 call("ctu_bn_stats", self.dtype, y.ptr, c, 8 if pm else 1, y.n, y.spatial, sums.data_ptr(), st)
             track = bn.track_running_stats and bn.running_mean is not None
             mom = BN_MOMENTUM if bn.momentum is None else float(bn.momentum)
-            call("ctu_bn_finalize", sums.data_ptr(), count, bn.weight.data_ptr(), bn.bias.data_ptr(),
-                 bn.running_mean.data_ptr() if track else None, bn.running_var.data_ptr() if track else None,
-                 bn.num_batches_tracked.data_ptr() if track else None, mom, float(bn.eps), c, 1, 1, ss.data_ptr(), st)
         else:
             call("ctu_bn_finalize", None, count, bn.weight.data_ptr(), bn.bias.data_ptr(), bn.running_mean.data_ptr(),
                  bn.running_var.data_ptr(), None, 0.0, float(bn.eps), c, 0, 0, ss.data_ptr(), st)
         a = self.new_act(c, yn, yd, yh, yw)
         pooled = self.new_act(c, yn, yd // 2, yh // 2, yw // 2) if pool else None
-        call("ctu_bn_relu_fwd", self.dtype, y.ptr, ss.data_ptr(), a.ptr, pooled.ptr if pool else None,
-             c, yn, yd, yh, yw, pm, st)
+        if training:        # finalisation (scale / shift, ss for the backward pass, running statistics) inside the kernel
+            call("ctu_bn_relu_fwd_train", self.dtype, y.ptr, sums.data_ptr(), count, bn.weight.data_ptr(), bn.bias.data_ptr(),
+                 bn.running_mean.data_ptr() if track else None, bn.running_var.data_ptr() if track else None,
+                 bn.num_batches_tracked.data_ptr() if track else None, mom, float(bn.eps), 1, ss.data_ptr(), a.ptr,
+                 pooled.ptr if pool else None, c, yn, yd, yh, yw, pm, st)
+        else:
+            call("ctu_bn_relu_fwd", self.dtype, y.ptr, ss.data_ptr(), a.ptr, pooled.ptr if pool else None,
+                 c, yn, yd, yh, yw, pm, st)
         if self.record:
             if not training:
                 raise RuntimeError("backward through eval-mode BatchNorm is not supported by the fused path")
@@ -523,9 +526,23 @@ class Engine:
                     raise RuntimeError("internal: BatchNorm stage received no gradient")
                 st = stream_ptr()
                 if extra_updates > 0 and bn.track_running_stats and bn.running_mean is not None:
+                    # buffers only (nothing in this step reads them): beside the weight gradients, off the critical path
                     mom = BN_MOMENTUM if bn.momentum is None else float(bn.momentum)
-                    call("ctu_bn_running_update", sums.data_ptr(), count, bn.running_mean.data_ptr(),
-                         bn.running_var.data_ptr(), bn.num_batches_tracked.data_ptr(), mom, c, extra_updates, st)
+
+                    def update():
+                        call("ctu_bn_running_update", sums.data_ptr(), count, bn.running_mean.data_ptr(),
+                             bn.running_var.data_ptr(), bn.num_batches_tracked.data_ptr(), mom, c, extra_updates,
+                             stream_ptr())
+
+                    if WGRAD_ASYNC:
+                        side = _side_stream(self.device, 1)
+                        side.wait_stream(torch.cuda.current_stream())
+                        with torch.cuda.stream(side):
+                            update()
+                        sums.record_stream(side)
+                        self._wgrad_stream = side
+                    else:
+                        update()
                 sums2 = self.f64(2 * cpad)
                 pA = dA.ptr if dA is not None else None
                 pP = dP.ptr if dP is not None else None

@@ -156,6 +156,12 @@ int ctu_bn_running_update(const double* sums, double count, float* running_mean,
  * up-sampling stage; a / dA stay natural [n][cb][d][h][w][8]; d,h,w are always the natural (high-res) dims. */
 int ctu_bn_relu_fwd(int dtype, const void* y, const float* ss, void* a, void* pooled, int c, int n, int d, int h, int w,
                     int y_phase_major, ctu_stream stream);
+/* training mode, ctu_bn_finalize folded in: scale / shift come from the batch sums inside the kernel, which also writes
+ * ss [4*cpad] for the backward pass and moves running_mean / running_var / num_batches_tracked (nullable) n_updates times */
+int ctu_bn_relu_fwd_train(int dtype, const void* y, const double* sums, double count, const float* gamma, const float* beta,
+                          float* running_mean, float* running_var, long long* num_batches_tracked, float momentum, float eps,
+                          int n_updates, float* ss, void* a, void* pooled, int c, int n, int d, int h, int w,
+                          int y_phase_major, ctu_stream stream);
 /* backward, pass 1: sums2 = double[2*cpad] = sum(dz), sum(dz*xhat) with
  * dz = (dA + unpool(dP)) * [a > 0]; dA and dP are nullable (not both) */
 int ctu_bn_relu_bwd_reduce(int dtype, const void* y, const float* ss, const void* dA, const void* dP, double* sums2,
