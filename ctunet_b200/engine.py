@@ -23,6 +23,7 @@ from ._lib import CTU_BF16, CTU_F32, call, int_array, ptr_array, stream_ptr
 
 BN_MOMENTUM = 0.1
 BN_EPS = 1e-5
+BN_FOLD_MAX_VOXELS = 4 * 64 ** 3      # see Engine.bn_relu
 
 # "auto": tcgen05 implicit GEMM where the kernel covers the shape, CUDA-core direct kernel elsewhere;
 # "direct": CUDA-core kernels only (always the case in fp32 accumulate-check mode).
@@ -507,7 +508,15 @@ class Engine:
                  bn.running_var.data_ptr(), None, 0.0, float(bn.eps), c, 0, 0, ss.data_ptr(), st)
         a = self.new_act(c, yn, yd, yh, yw)
         pooled = self.new_act(c, yn, yd // 2, yh // 2, yw // 2) if pool else None
-        if training:        # finalisation (scale / shift, ss for the backward pass, running statistics) inside the kernel
+        # Small tensors: finalisation (scale / shift, ss for the backward pass, running statistics) inside the forward kernel,
+        # one launch less on the critical path.  Large ones keep the separate 1-block finalize: the per-block prologue
+        # (double-precision divide / sqrt + a barrier) costs the short-lived blocks of a 128^3 launch 17 us (ncu: 38 -> 56 us).
+        fold = training and yn * yd * yh * yw <= BN_FOLD_MAX_VOXELS
+        if training and not fold:
+            call("ctu_bn_finalize", sums.data_ptr(), count, bn.weight.data_ptr(), bn.bias.data_ptr(),
+                 bn.running_mean.data_ptr() if track else None, bn.running_var.data_ptr() if track else None,
+                 bn.num_batches_tracked.data_ptr() if track else None, mom, float(bn.eps), c, 1, 1, ss.data_ptr(), st)
+        if fold:
             call("ctu_bn_relu_fwd_train", self.dtype, y.ptr, sums.data_ptr(), count, bn.weight.data_ptr(), bn.bias.data_ptr(),
                  bn.running_mean.data_ptr() if track else None, bn.running_var.data_ptr() if track else None,
                  bn.num_batches_tracked.data_ptr() if track else None, mom, float(bn.eps), 1, ss.data_ptr(), a.ptr,
