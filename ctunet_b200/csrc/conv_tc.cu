@@ -952,6 +952,14 @@ static bool wg_geometry(int k, int cb, int cout, int h, int w, WgGeom& g, int ph
         --g.cbg;
     }
     if (g.smem > 220 * 1024) return false;
+    // balance the input-block groups (5 blocks as 3 + 2, not 4 + 1): every group gets the same number of CTAs, so the
+    // largest group sets the kernel's duration
+    {
+        const int ngr = (g.cb + g.cbg - 1) / g.cbg;
+        g.cbg = (g.cb + ngr - 1) / ngr;
+        g.xslot_bytes = g.plane_bytes * g.cbg;
+        g.smem = fixed + (size_t)(k + 1) * g.xslot_bytes + 2 * (size_t)g.dyslot_bytes;
+    }
     // deepen both rings while a ~100 KB budget (two CTAs per SM) allows: more TMA loads in flight
     g.ns = k + 1;
     g.nds = 2;
