@@ -89,6 +89,7 @@ class Engine:
         self.agrads: Dict[int, Act] = {}            # id(Act) -> gradient Act
         self.pgrads: Dict[int, torch.Tensor] = {}   # id(param) -> gradient tensor
         self.want_input_grad = False
+        self.input_grad = None                      # NCDHW fp32 gradient of the network input (leaf_input convolution)
         self.grad_sink = None                       # parallel.GradSync: gradients land in its flat buffer
         self.use_tc = (CONV_PATH == "auto" and compute_dtype == "bf16" and bool(_lib.load().ctu_has_tensor_path()))
         # weight preparation plan (see begin()): None = not in use, every preparation runs inline
@@ -285,7 +286,8 @@ class Engine:
         self._conv_launch(srcs, wk, tc, bias, y, cout, k, y.sums, stat_cout)
         return y
 
-    def _conv_bwd(self, srcs, need, wkd, tc_d, y, k, cout, dw_out, db_out, after_wgrad=None, phase_cout=0):
+    def _conv_bwd(self, srcs, need, wkd, tc_d, y, k, cout, dw_out, db_out, after_wgrad=None, phase_cout=0,
+                  leaf_input=False):
         """Weight gradient into ``dw_out`` (native layout, nullable) / ``db_out`` and the data gradient of every
         source with ``need[i]`` (prepared weights ``wkd[i]``).
 
@@ -325,12 +327,29 @@ class Engine:
                 self._wgrad_stream = side
             else:
                 wgrad()
-        for i, s in enumerate(srcs):
-            if not need[i]:
-                continue
-            dx = self.new_act(s.c, s.n, s.d, s.h, s.w)
-            self._conv_launch([dy], wkd[i], tc_d[i], None, dx, s.c, k, None)
-            self._set_agrad(s, dx)
+        def dgrads():
+            for i, s in enumerate(srcs):
+                if not need[i]:
+                    continue
+                dx = self.new_act(s.c, s.n, s.d, s.h, s.w)
+                self._conv_launch([dy], wkd[i], tc_d[i], None, dx, s.c, k, None)
+                self._set_agrad(s, dx)
+
+        if leaf_input and WGRAD_ASYNC and any(need):
+            # The gradient of the NETWORK INPUT (the reference asks for it only because reentrant checkpointing needs an
+            # input that requires grad, Model.py:351-352; nothing consumes it): a leaf like the weight gradients, so it is
+            # computed and converted to NCDHW on the second stream, off the critical path; run_tape() joins that stream.
+            main = torch.cuda.current_stream()
+            side = _side_stream(self.device, 1)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                dgrads()
+                self.input_grad = self.unpack(self.agrads.pop(id(srcs[0])))
+            self.input_grad.record_stream(main)
+            dy.buf.record_stream(side)
+            self._wgrad_stream = side
+        else:
+            dgrads()
 
     def _pgrad_done(self, pairs):
         """Register parameter gradients produced on the current stream (see _add_pgrad)."""
@@ -339,8 +358,9 @@ class Engine:
                 self._add_pgrad(prm, g)
 
     def conv(self, srcs: Sequence[Act], weight, bias, k: int, need_src_grad: Sequence[bool],
-             bn_stats: bool = False) -> Act:
-        """``bn_stats``: also produce the batch statistics of the output (``y.sums``) for the BatchNorm that follows."""
+             bn_stats: bool = False, leaf_input: bool = False) -> Act:
+        """``bn_stats``: also produce the batch statistics of the output (``y.sums``) for the BatchNorm that follows.
+        ``leaf_input``: ``srcs[0]`` is the network input (its gradient is a leaf of the backward pass)."""
         cout = weight.shape[0]
         srcs = list(srcs)
         need = [bool(n) and self.record for n in need_src_grad]
@@ -351,7 +371,7 @@ class Engine:
                 dw = self._grad_buffer(weight) if weight.requires_grad else None
                 db = self._grad_buffer(bias) if (dw is not None and bias is not None and bias.requires_grad) else None
                 self._conv_bwd(srcs, need, wkd, tc_d, y, k, cout, dw, db,
-                               lambda: self._pgrad_done(((weight, dw), (bias, db))))
+                               lambda: self._pgrad_done(((weight, dw), (bias, db))), leaf_input=leaf_input)
 
             self.tape.append(bwd)
         return y

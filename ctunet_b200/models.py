@@ -184,7 +184,7 @@ class _NetFn(torch.autograd.Function):
         eng.backward(g[0], g[1] if ctx.two else None)
         dx = None
         if eng.want_input_grad:
-            dx = eng.unpack(eng.agrads.pop(id(eng.input_act)))
+            dx = eng.input_grad if eng.input_grad is not None else eng.unpack(eng.agrads.pop(id(eng.input_act)))
         if eng.grad_sink is not None:
             # gradients were written into the data-parallel flat buffer; GradSync.finish() publishes them
             grads = tuple(None if eng.grad_sink.buffer_for(p) is not None else
@@ -272,7 +272,8 @@ class UNet(_FusedNet):
         skips = []
         for i, blk in enumerate(self.d_blocks):
             seq = blk.block
-            y = eng.conv([cur], seq[0].weight, seq[0].bias, k, [eng.want_input_grad if i == 0 else True], training)
+            y = eng.conv([cur], seq[0].weight, seq[0].bias, k, [eng.want_input_grad if i == 0 else True], training,
+                         leaf_input=(i == 0))
             a = eng.bn_relu(y, seq[1], training, extra)
             y = eng.conv([a], seq[3].weight, seq[3].bias, k, [True], training)
             s, cur = eng.bn_relu(y, seq[4], training, extra, pool=True)        # skip tensor + MaxPool (models.py:233)
@@ -414,7 +415,8 @@ class recAE_v2_fixed(_FusedNet):
         eng.input_act = cur
         skips = []
         for i, seq in enumerate([self.dblock1, self.dblock2, self.dblock3, self.dblock4]):
-            y = eng.conv([cur], seq[0].weight, seq[0].bias, k, [eng.want_input_grad if i == 0 else True], training)
+            y = eng.conv([cur], seq[0].weight, seq[0].bias, k, [eng.want_input_grad if i == 0 else True], training,
+                         leaf_input=(i == 0))
             a = eng.bn_relu(y, seq[1], training, extra)
             y = eng.conv([a], seq[3].weight, seq[3].bias, k, [True], training)
             s, cur = eng.bn_relu(y, seq[4], training, extra, pool=True)
