@@ -493,7 +493,17 @@ def run_b200_arm(a):
         roof["share_of_step"] = ms / total_ms
         roof["peak_source"] = peaks["source"]
         break
-    top = [{"kernel": k, "ms_per_step": v[0] / a.steps, "share": v[0] / total_ms} for k, v in ranked[:8]]
+    top = []
+    for k, (ms, cnt, fl, by) in ranked[:8]:
+        ent = {"kernel": k, "ms_per_step": ms / a.steps, "share": ms / total_ms}
+        if fl or by:      # the same roofline arithmetic as above for every top kernel
+            avg_s = ms / cnt * 1e-3
+            t_tc, t_hbm = fl / (peaks["tensor"] * 1e12), by / (peaks["hbm"] * 1e9)
+            if fl > 0 and t_tc >= t_hbm:
+                ent.update(bound="tensor", frac=fl / avg_s / 1e12 / peaks["tensor"])
+            else:
+                ent.update(bound="hbm", frac=by / avg_s / 1e9 / peaks["hbm"])
+        top.append(ent)
     by_entry = {}
     for k, v in agg.items():
         e = k.split(" ")[0]
