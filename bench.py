@@ -547,6 +547,40 @@ def run_b200_arm(a):
                "note": "TrainStep.__call__: float32 image + one-hot float32 targets from pinned host memory (the reference "
                        "DataLoader's format), double-buffered H2D, loss components read back every step one step late"}
     e2e_main = e2e_u8 if e2e_u8 is not None else e2e_f32
+    # BASELINE configs 4 and 5 (secondary numbers, same GPU): sliding-window inference over a synthetic 512x512x256 volume
+    # (32 patches of 128^3, 8 per batch, eval-mode model + argmax) and the preprocessing chain on the int16 HU volume
+    extra = None
+    if world == 1 and not a.no_other_workloads and a.model == "UNetSP" and a.size == 128:
+        from ctunet_b200 import preprocess as P
+        from ctunet_b200.utilities import blank_patch, kth_nonzero
+        torch.manual_seed(0)
+        inet = C.UNetSP().to(dev).eval()
+        D_, H_, W_ = 256, 512, 512
+        hu = (torch.randn(D_, H_, W_, device=dev) * 400).to(torch.int16)
+        vol = torch.stack((P.hu_threshold(hu, 300).float(), (torch.rand(D_, H_, W_, device=dev) > 0.8).float()))
+
+        def infer():
+            P.sliding_window_argmax(inet, vol, patch=128, batch=8)
+
+        def prep():
+            b = P.hu_threshold(hu, 300)
+            w_ = P.hu_window(hu, -100.0, 1500.0)
+            P.resample_trilinear(w_, (128, 256, 256))
+            sm = P.resample_nearest(b, (128, 256, 256))
+            blank_patch(sm, kth_nonzero(sm, 1000), 40, "sphere")
+
+        infer()
+        prep()
+        ms_inf, ms_prep = timed(infer, 3), timed(prep, 10)
+        nv = D_ * H_ * W_
+        extra = {"inference_config4": {"workload": "512x512x256 volume, 32 patches of 128^3 (8 per batch), UNetSP eval + argmax",
+                                       "ms_per_volume": ms_inf, "value": nv / (ms_inf * 1e-3), "unit": UNIT},
+                 "preprocessing_config5": {"workload": "512x512x256 int16 HU: threshold + window + trilinear and nearest resample "
+                                                       "to 256x256x128 + voxel pick + sphere mask",
+                                           "ms_per_volume": ms_prep, "value": nv / (ms_prep * 1e-3), "unit": UNIT}}
+        del inet, hu, vol
+        torch.cuda.empty_cache()
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
         "ms_per_step": ms_resident, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -563,6 +597,7 @@ def run_b200_arm(a):
         "roofline": roof,
         "cpu_baseline": cpu,
         "other_workloads": others,
+        "other_configs": extra,
         "top_kernels": top,
         "ms_per_step_by_entry_point": by_entry,
         "profiled_ms_per_step": total_ms / a.steps,
