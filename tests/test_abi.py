@@ -60,3 +60,24 @@ def test_sass_is_sm100a(lib_path):
         pytest.skip("cuobjdump unavailable")
     archs = set(re.findall(r"sm_(\d+a?)", out.stdout))
     assert archs == {"100a"}, archs
+
+
+def test_kernel_selection_is_host_logic_and_needs_no_gpu():
+    """Coverage predicates / geometry of the three tensor-path convolution kernels answer on the CPU (no launch):
+    resident-weights kernel for h, w multiples of 16 above 16x16, weight-streaming kernel on small grids and for the
+    wide 5^3 layers, tap-stationary weight gradient on 8x8 planes."""
+    from ctunet_b200 import _lib
+    from ctunet_b200.engine import tc_variant
+    lib = _lib.load()
+    assert tc_variant(3, [7], 7, 4, 128, 128, 128) == 1          # level 0 of UNetSP
+    assert tc_variant(3, [14, 14, 1], 64, 4, 64, 64, 64) == 1    # fused up stage: concatenated sources
+    assert tc_variant(3, [56], 56, 4, 16, 16, 16) == 2           # small grid: streamed weights preferred
+    assert tc_variant(5, [64], 64, 4, 16, 16, 16) == 2           # 5^3 weights do not fit shared memory
+    assert tc_variant(5, [128], 128, 4, 8, 8, 8) == 2            # 8 x 8 planes (M = 64 tiles)
+    assert tc_variant(3, [7], 7, 1, 12, 12, 12) == 0             # neither: CUDA cores
+    assert tc_variant(1, [14], 3, 4, 128, 128, 128) == 0         # 1^3 is the head kernel's job
+    assert lib.ctu_conv_wide_wimg_bytes(5, 64, 64, 4, 16, 16, 16) == 64 * 64 * 125 * 2
+    assert lib.ctu_conv_wide_wgrad_supported(5, 128, 128, 8, 8, 8) == 1
+    assert lib.ctu_conv_wide_wgrad_supported(5, 136, 128, 8, 8, 8) == 0     # more than 128 input channels
+    assert lib.ctu_conv_tc_wgrad_supported(3, 1, _lib.int_array([7]), 7, 8, 8, 8) == 0
+    assert lib.ctu_upfuse_workspace_floats(28, 7, 3) > 0
