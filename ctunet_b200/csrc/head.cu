@@ -143,6 +143,41 @@ __global__ void __launch_bounds__(kHeadThreads) head_fwd_kernel(HeadParams p) {
     __syncthreads();
     const long long total = (long long)p.n * p.spatial;
     const bool sp = (p.flags & (CTU_HEAD_SP | CTU_HEAD_SP_SOFTMAX)) != 0;
+    if ((p.spatial & 3) == 0) {
+        // four consecutive voxels per thread: 4 x CBT 16-byte loads in flight, one 16-byte store per output plane
+        const long long groups = total >> 2, sg = p.spatial >> 2;
+        for (long long i = (long long)blockIdx.x * kHeadThreads + threadIdx.x; i < groups; i += (long long)gridDim.x * kHeadThreads) {
+            const int n = (int)(i / sg);
+            const long long s = (i - (long long)n * sg) << 2;
+            V8 xs[4][CBT];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) head_load<T, CBT>(p, n, s + v, xs[v]);
+            float o[4][CO > 4 ? CO : 4];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                HeadVals<CO> h;
+                head_logits_of<CO, CBT>(wsm, bsm, h, xs[v]);
+                head_forward_chain<CO>(h, p.flags);
+                if (sp) {
+                    o[v][0] = h.o0[0]; o[v][1] = h.o0[1]; o[v][2] = h.o1[0]; o[v][3] = h.o1[1];
+                } else {
+#pragma unroll
+                    for (int c = 0; c < CO; ++c) o[v][c] = h.sg[c];
+                }
+            }
+            if (sp) {
+                *reinterpret_cast<float4*>(p.out0 + ((long long)n * 2 + 0) * p.spatial + s) = make_float4(o[0][0], o[1][0], o[2][0], o[3][0]);
+                *reinterpret_cast<float4*>(p.out0 + ((long long)n * 2 + 1) * p.spatial + s) = make_float4(o[0][1], o[1][1], o[2][1], o[3][1]);
+                *reinterpret_cast<float4*>(p.out1 + ((long long)n * 2 + 0) * p.spatial + s) = make_float4(o[0][2], o[1][2], o[2][2], o[3][2]);
+                *reinterpret_cast<float4*>(p.out1 + ((long long)n * 2 + 1) * p.spatial + s) = make_float4(o[0][3], o[1][3], o[2][3], o[3][3]);
+            } else {
+#pragma unroll
+                for (int c = 0; c < CO; ++c)
+                    *reinterpret_cast<float4*>(p.out0 + ((long long)n * CO + c) * p.spatial + s) = make_float4(o[0][c], o[1][c], o[2][c], o[3][c]);
+            }
+        }
+        return;
+    }
     for (long long i = (long long)blockIdx.x * kHeadThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kHeadThreads) {
         const int n = (int)(i / p.spatial);
         const long long s = i % p.spatial;
