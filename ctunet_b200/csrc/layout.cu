@@ -42,6 +42,38 @@ __global__ void pack_kernel(const float* __restrict__ src, T* __restrict__ dst, 
     Vec8<T>::store(dst + i * 8, r);
 }
 
+// four consecutive voxels per thread (spatial % 4 == 0): one 16-byte load per real channel, four group stores
+template <typename T>
+__global__ void pack4_kernel(const float* __restrict__ src, T* __restrict__ dst, int c, int cb, long long spatial4,
+                             long long total4) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total4) return;
+    const long long s4 = i % spatial4;
+    const long long ncb = i / spatial4;
+    const int b = (int)(ncb % cb);
+    const long long n = ncb / cb, spatial = spatial4 * 4;
+    float4 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int ch = b * 8 + j;
+        v[j] = ch < c ? __ldg(reinterpret_cast<const float4*>(src + (n * c + ch) * spatial) + s4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    T* out = dst + (ncb * spatial + s4 * 4) * 8;
+    V8 r;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r.v[j] = v[j].x;
+    Vec8<T>::store(out, r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r.v[j] = v[j].y;
+    Vec8<T>::store(out + 8, r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r.v[j] = v[j].z;
+    Vec8<T>::store(out + 16, r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r.v[j] = v[j].w;
+    Vec8<T>::store(out + 24, r);
+}
+
 template <typename T>
 __global__ void unpack_kernel(const T* __restrict__ src, float* __restrict__ dst, int c, int cb, long long spatial,
                               long long total) {
@@ -133,7 +165,11 @@ int ctu_pack_ncdhw(const float* src, void* dst, int dtype, int n, int c, long lo
     CTU_REQUIRE(src && dst && n > 0 && c > 0 && spatial > 0, "ctu_pack_ncdhw: bad arguments");
     int cb = (c + 7) / 8;
     long long total = (long long)n * cb * spatial;
-    CTU_DISPATCH_DTYPE(dtype, (pack_kernel<T><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(src, (T*)dst, c, cb, spatial, total)));
+    if (spatial % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+        CTU_DISPATCH_DTYPE(dtype, (pack4_kernel<T><<<cdiv(total / 4, 256), 256, 0, (cudaStream_t)stream>>>(src, (T*)dst, c, cb, spatial / 4, total / 4)));
+    } else {
+        CTU_DISPATCH_DTYPE(dtype, (pack_kernel<T><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(src, (T*)dst, c, cb, spatial, total)));
+    }
     return check_launch("ctu_pack_ncdhw");
 }
 
