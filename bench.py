@@ -412,7 +412,7 @@ def run_b200_arm(a):
     def make_e2e(host_bufs, run_step):
         dbuf = [[torch.empty_like(t, device=dev) for t in host_bufs] for _ in range(2)]
         state = {"i": 0, "ready": None}
-        rb = LossReadback(5 if double else 3)
+        rb = LossReadback(5 if double else 3, depth=int(os.environ.get("CTU_READBACK_DEPTH", "2")))
 
         def prefetch(slot):
             with torch.cuda.stream(copy_stream):

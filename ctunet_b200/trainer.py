@@ -195,10 +195,14 @@ class LossReadback:
         self.host[slot].copy_(comps, non_blocking=True)
         self.events[slot].record()
         self.count += 1
-        return self._read(self.count - 2) if self.count >= 2 else None
+        lag = len(self.host) - 1                # depth 2: the previous step; depth 3: two steps back, ...
+        return self._read(self.count - 1 - lag) if self.count > lag else None
 
     def drain(self):
-        return self._read(self.count - 1) if self.count else None
+        """Values of every step not yet returned by ``push`` (oldest first); the last entry is the final step's."""
+        lag = len(self.host) - 1
+        out = [self._read(i) for i in range(max(0, self.count - lag), self.count)]
+        return out[-1] if out else None
 
     def _read(self, index: int):
         slot = index % len(self.host)
