@@ -23,6 +23,7 @@
 namespace ctu {
 
 constexpr int WD_MAX_CGB = 8;     // input channel blocks per plane-ring slot
+constexpr int WD_NISS_SMALL = 4;  // issuer warps of the single M = 64 tile (8 x 8 planes)
 
 struct WdParams {
     const __nv_bfloat16* wimg;   // [ngroup][pair-unit order of use][NC/8][2][8][8] bf16 (wd_pack_wimg_kernel)
@@ -64,9 +65,11 @@ __global__ void wd_pack_wimg_kernel(const float* __restrict__ wp, __nv_bfloat16*
     wimg[i] = __float2bfloat16_rn(v);
 }
 
-template <int K, int TH, int NTILE>
-__global__ void __launch_bounds__(32 * (1 + 5 * NTILE)) conv3d_wide_kernel(const __grid_constant__ CUtensorMap xmap,
-                                                                           WdParams p) {
+// NISS issuer warps per tile: the taps are dealt round-robin, every issuer accumulates into its own TMEM columns and the
+// epilogue adds them up (one issuing thread sustains one MMA per ~76 cycles; an M = 64 MMA is worth ~24).
+template <int K, int TH, int NTILE, int NISS>
+__global__ void __launch_bounds__(32 * (1 + NTILE * NISS + 4 * NTILE)) conv3d_wide_kernel(const __grid_constant__ CUtensorMap xmap,
+                                                                                          WdParams p) {
     constexpr int PAD = K / 2, K2 = K * K, K3 = K2 * K;
     constexpr int TWID = 8 * NTILE;
     constexpr int HH = TH + K - 1, WW = TWID + K - 1;
@@ -87,14 +90,14 @@ __global__ void __launch_bounds__(32 * (1 + 5 * NTILE)) conv3d_wide_kernel(const
     if (threadIdx.x == 0) {
         for (uint32_t i = 0; i < NP; ++i) {
             mbar_init(b_pfull + 8 * i, 1);
-            mbar_init(b_pempty + 8 * i, NTILE);
+            mbar_init(b_pempty + 8 * i, NTILE * NISS);   // every issuer warp releases the plane
         }
         for (uint32_t i = 0; i < NW; ++i) {
             mbar_init(b_wfull + 8 * i, 1);
-            mbar_init(b_wempty + 8 * i, NTILE);
+            mbar_init(b_wempty + 8 * i, NTILE);          // a tap is consumed by one issuer per tile
         }
         for (int i = 0; i < NTILE; ++i) {
-            mbar_init(b_afull + 8 * i, 1);
+            mbar_init(b_afull + 8 * i, NISS);
             mbar_init(b_aempty + 8 * i, 4);
         }
         fence_barrier_init();
@@ -148,17 +151,17 @@ __global__ void __launch_bounds__(32 * (1 + 5 * NTILE)) conv3d_wide_kernel(const
                 }
             }
         }
-    } else if (warp <= NTILE) {
-        // ===================================================================== MMA issuer of tile t
+    } else if (warp <= NTILE * NISS) {
+        // ===================================================================== MMA issuer q of tile t
         const uint32_t leader = elect_one();
-        const uint32_t t = warp - 1;
+        const uint32_t t = (warp - 1) / NISS, q_iss = (warp - 1) % NISS;
         // D=f32, A=B=bf16, both K-major, N at [17,23), M at [24,29)
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.nc >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
         const uint32_t a_hi = (ROW >> 4) | (1u << 14);            // SBO = halo row pitch (next h)
         const uint32_t b_hi = 16u | (1u << 14);                   // SBO = 256 B between n-groups
         const uint32_t plane16 = p.plane_bytes >> 4;
         const uint32_t bstep = mma_bytes >> 4;
-        const uint32_t d_tmem = tmem_base + t * (uint32_t)p.nc;
+        const uint32_t d_tmem = tmem_base + (t * NISS + q_iss) * (uint32_t)p.nc;
         Ring pc = {0, 0}, wc = {0, 0};
         uint32_t it = 0;
         for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
@@ -175,6 +178,7 @@ __global__ void __launch_bounds__(32 * (1 + 5 * NTILE)) conv3d_wide_kernel(const
                     const uint32_t a16 = (s_planes + pc.slot * p.pslot_bytes + t * 128u) >> 4;
 #pragma unroll 1
                     for (int tap = 0; tap < K2; ++tap, wc.next(NW)) {
+                        if (NISS > 1 && (uint32_t)(tap % NISS) != q_iss) continue;   // (the for-increment still advances the ring)
                         mbar_wait(b_wfull + 8 * wc.slot, wc.phase);
                         tc_fence_after();
                         uint32_t b_lo = ((s_w + wc.slot * p.wslot_bytes) >> 4) | (8u << 16);   // LBO = 128 B (second K chunk)
@@ -195,7 +199,7 @@ __global__ void __launch_bounds__(32 * (1 + 5 * NTILE)) conv3d_wide_kernel(const
         }
     } else {
         // ===================================================================== epilogue: 4 warps per tile
-        const int te = (warp - 1 - NTILE) >> 2;
+        const int te = (warp - 1 - NTILE * NISS) >> 2;
         const int quarter = warp & 3;
         const int row = (M == 128) ? quarter * 32 + lane : quarter * 16 + (lane & 15);
         const bool active = (M == 128) || lane < 16;
@@ -213,20 +217,26 @@ __global__ void __launch_bounds__(32 * (1 + 5 * NTILE)) conv3d_wide_kernel(const
             __nv_bfloat16* ycol = p.y + (((long long)n * p.cob_n + ob0) * plane + ((long long)z * p.h + gy) * p.w + gx) * 8;
             mbar_wait(b_afull + 8 * te, it & 1);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)te * p.nc;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(te * NISS) * p.nc;
             for (int ob = 0; ob < nobc; ob += 2) {
-                uint32_t raw[2][8];
-                tmem_ld8_issue(taddr + ob * 8, raw[0]);
-                tmem_ld8_issue(taddr + ob * 8 + 8, raw[1]);      // nc is a multiple of 16
+                uint32_t raw[NISS][2][8];
+#pragma unroll
+                for (int qi = 0; qi < NISS; ++qi) {
+                    tmem_ld8_issue(taddr + qi * p.nc + ob * 8, raw[qi][0]);
+                    tmem_ld8_issue(taddr + qi * p.nc + ob * 8 + 8, raw[qi][1]);      // nc is a multiple of 16
+                }
                 tmem_ld_wait();
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
-                    tmem_ld8_pin(raw[u]);
+#pragma unroll
+                    for (int qi = 0; qi < NISS; ++qi) tmem_ld8_pin(raw[qi][u]);
                     if (!active || ob0 + ob + u >= p.cob_n) continue;
                     V8 o;
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
-                        float v = __uint_as_float(raw[u][c]);
+                        float v = __uint_as_float(raw[0][u][c]);
+#pragma unroll
+                        for (int qi = 1; qi < NISS; ++qi) v += __uint_as_float(raw[qi][u][c]);
                         const int ch = (ob0 + ob + u) * 8 + c;
                         if (has_bias && ch < p.cout) v += __ldg(p.bias + ch);
                         o.v[c] = v;
@@ -302,7 +312,7 @@ static bool wide_geometry(int k, int cb, int cout, int n, int d, int h, int w, W
     while (g.np < 4 && fixed + (size_t)(g.np + 1) * g.pslot_bytes + (size_t)g.nw * g.wslot_bytes <= 216 * 1024) ++g.np;
     g.smem = fixed + (size_t)g.np * g.pslot_bytes + (size_t)g.nw * g.wslot_bytes;
     if (g.smem > 220 * 1024) return false;
-    uint32_t cols = (uint32_t)g.ntile * g.nc;
+    uint32_t cols = (uint32_t)g.ntile * (g.ntile == 1 ? WD_NISS_SMALL : 1) * g.nc;
     g.tmem_cols = 32;
     while (g.tmem_cols < cols) g.tmem_cols *= 2;
     return g.tmem_cols <= 512;
@@ -365,10 +375,10 @@ int conv3d_fprop_wide(const void* x, int cin, const void* wimg, const float* bia
         kern<<<dim3(gx, g.ngroups), threads, g.smem, stream>>>(xmap, p);
         return check_launch("ctu_conv3d_fprop(tcgen05 wide)");
     };
-    if (k == 3 && g.ntile == 2) return go(conv3d_wide_kernel<3, 16, 2>, 32 * 11);
-    if (k == 3) return go(conv3d_wide_kernel<3, 8, 1>, 32 * 6);
-    if (g.ntile == 2) return go(conv3d_wide_kernel<5, 16, 2>, 32 * 11);
-    return go(conv3d_wide_kernel<5, 8, 1>, 32 * 6);
+    if (k == 3 && g.ntile == 2) return go(conv3d_wide_kernel<3, 16, 2, 1>, 32 * 11);
+    if (k == 3) return go(conv3d_wide_kernel<3, 8, 1, WD_NISS_SMALL>, 32 * (1 + WD_NISS_SMALL + 4));
+    if (g.ntile == 2) return go(conv3d_wide_kernel<5, 16, 2, 1>, 32 * 11);
+    return go(conv3d_wide_kernel<5, 8, 1, WD_NISS_SMALL>, 32 * (1 + WD_NISS_SMALL + 4));
 }
 
 
