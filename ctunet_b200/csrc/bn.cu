@@ -150,9 +150,10 @@ struct BnFin {
     float* ss_out;
 };
 
+template <bool FOLD>
 __device__ __forceinline__ void bn_scale_shift(const BnFin& f, const float* __restrict__ ss, int b, int cpad, bool writer,
                                                float (&sc)[8], float (&sh)[8]) {
-    if (f.sums == nullptr) {
+    if constexpr (!FOLD) {     // (compile-time: the plain kernels stay exactly what they were before the fold existed)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             sc[j] = __ldg(ss + b * 8 + j);
@@ -201,13 +202,13 @@ __device__ __forceinline__ void bn_scale_shift(const BnFin& f, const float* __re
     }
 }
 
-template <typename T>
+template <typename T, bool FOLD>
 __global__ void __launch_bounds__(kBnThreads) bn_relu_fwd_kernel(const T* __restrict__ y, const float* __restrict__ ss,
                                                                  T* __restrict__ a, int cb, long long spatial, BnFin fin) {
     const int b = blockIdx.y, n = blockIdx.z;
     const int cpad = cb * 8;
     float sc[8], sh[8];
-    bn_scale_shift(fin, ss, b, cpad, blockIdx.x == 0 && n == 0, sc, sh);
+    bn_scale_shift<FOLD>(fin, ss, b, cpad, blockIdx.x == 0 && n == 0, sc, sh);
     const long long base = ((long long)n * cb + b) * spatial;
     const long long s0 = (long long)blockIdx.x * kBnThreads * kVoxPerThread + threadIdx.x;
     V8 v[kVoxPerThread];
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_relu_fwd_kernel(const T* __rest
 //   POOL:  y, a natural [n][cb][d][h][w][8]; pooled = maxpool 2x2x2 of a.
 //   S2D:   y phase-major [n][8*cb][d/2][h/2][w/2][8] (output of the fused up-sampling stage, block = q*cb + b,
 //          q = qd*4 + qh*2 + qw), a natural.
-template <typename T, bool S2D>
+template <typename T, bool S2D, bool FOLD>
 __global__ void __launch_bounds__(kBnThreads) bn_relu_child_fwd_kernel(const T* __restrict__ y,
                                                                        const float* __restrict__ ss, T* __restrict__ a,
                                                                        T* __restrict__ pooled, int cb, int d, int h,
@@ -235,7 +236,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_relu_child_fwd_kernel(const T* 
     const int b = blockIdx.y, n = blockIdx.z;
     const int cpad = cb * 8;
     float sc[8], sh[8];
-    bn_scale_shift(fin, ss, b, cpad, blockIdx.x == 0 && n == 0, sc, sh);
+    bn_scale_shift<FOLD>(fin, ss, b, cpad, blockIdx.x == 0 && n == 0, sc, sh);
     const int pd = d / 2, ph = h / 2, pw = w / 2;
     const long long pspatial = (long long)pd * ph * pw;
     const long long ps = (long long)blockIdx.x * kBnThreads + threadIdx.x;
@@ -509,16 +510,23 @@ static int bn_relu_fwd_launch(int dtype, const void* y, const float* ss, void* a
     CTU_REQUIRE(!(y_phase_major && pooled), "%s: a phase-major input is never pooled", what);
     const int cb = (c + 7) / 8;
     const long long spatial = (long long)d * h * w;
+    const bool fold = fin.sums != nullptr;
+    cudaStream_t st = (cudaStream_t)stream;
     if (pooled != nullptr || y_phase_major) {
         CTU_REQUIRE(d % 2 == 0 && h % 2 == 0 && w % 2 == 0, "%s: needs even dims (%d,%d,%d)", what, d, h, w);
         dim3 grid(cdiv(spatial / 8, kBnThreads), cb, n);
-        if (y_phase_major)
-            CTU_DISPATCH_DTYPE(dtype, (bn_relu_child_fwd_kernel<T, true><<<grid, kBnThreads, 0, (cudaStream_t)stream>>>((const T*)y, ss, (T*)a, nullptr, cb, d, h, w, fin)));
-        else
-            CTU_DISPATCH_DTYPE(dtype, (bn_relu_child_fwd_kernel<T, false><<<grid, kBnThreads, 0, (cudaStream_t)stream>>>((const T*)y, ss, (T*)a, (T*)pooled, cb, d, h, w, fin)));
+        CTU_DISPATCH_DTYPE(dtype, {
+            if (y_phase_major && fold) bn_relu_child_fwd_kernel<T, true, true><<<grid, kBnThreads, 0, st>>>((const T*)y, ss, (T*)a, nullptr, cb, d, h, w, fin);
+            else if (y_phase_major) bn_relu_child_fwd_kernel<T, true, false><<<grid, kBnThreads, 0, st>>>((const T*)y, ss, (T*)a, nullptr, cb, d, h, w, fin);
+            else if (fold) bn_relu_child_fwd_kernel<T, false, true><<<grid, kBnThreads, 0, st>>>((const T*)y, ss, (T*)a, (T*)pooled, cb, d, h, w, fin);
+            else bn_relu_child_fwd_kernel<T, false, false><<<grid, kBnThreads, 0, st>>>((const T*)y, ss, (T*)a, (T*)pooled, cb, d, h, w, fin);
+        });
     } else {
         dim3 grid(cdiv(spatial, kBnThreads * kVoxPerThread), cb, n);
-        CTU_DISPATCH_DTYPE(dtype, (bn_relu_fwd_kernel<T><<<grid, kBnThreads, 0, (cudaStream_t)stream>>>((const T*)y, ss, (T*)a, cb, spatial, fin)));
+        CTU_DISPATCH_DTYPE(dtype, {
+            if (fold) bn_relu_fwd_kernel<T, true><<<grid, kBnThreads, 0, st>>>((const T*)y, ss, (T*)a, cb, spatial, fin);
+            else bn_relu_fwd_kernel<T, false><<<grid, kBnThreads, 0, st>>>((const T*)y, ss, (T*)a, cb, spatial, fin);
+        });
     }
     return check_launch(what);
 }
