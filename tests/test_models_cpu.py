@@ -130,3 +130,21 @@ def test_install_into_real_reference_when_present():
         trainer.FlapRecWithShapePriorDoubleOut.comp_losses_metrics = staticmethod(ph)
         trainer.ProblemHandler.comp_losses_metrics = staticmethod(base)
         torch.autograd.set_detect_anomaly(False)
+
+
+def test_bench_reference_arm_prints_contract_line():
+    """`bench.py --impl reference` (the CPU port of the reference's path, the one place besides tests / smoke that may run
+    oracle/) needs no GPU and prints one JSON line with the keys the driver reads."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--size", "16", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "voxels/s" and line["value"] > 0
+    assert line["higher_is_better"] is True and line["gpu_launches"] == 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
