@@ -140,7 +140,7 @@ def test_bench_reference_arm_prints_contract_line():
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--size", "16", "--steps", "1",
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--size", "32", "--steps", "1",
                           "--warmup", "0"], capture_output=True, text=True, timeout=300, cwd=root)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
