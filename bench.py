@@ -8,10 +8,13 @@ One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
   value  : whole-job voxels/s with the batch resident in HBM (max-over-ranks device time)
   e2e    : the same step fed from pinned HOST buffers each iteration (H2D of image + targets inside the
            timed region, D2H of the loss components), through the public TrainStep API
-  roofline / cpu_baseline : the dominant kernel against the measured B200 peaks; the CPU oracle
-           (a port of the reference's PyTorch path, oracle/unet_oracle.py) timed on the host cores
---impl reference times that CPU port alone (the reference itself is pure Python and cannot travel to
-the GPU box; the port is pinned to it by tests/test_oracle_pinned.py).
+  roofline / cpu_baseline : the dominant kernel against the measured B200 peaks; the reference's own CPU path timed
+           on the host cores -- the UNMODIFIED reference (ctunet.pytorch.Model.forward_pass with its model, handler and
+           torch.optim.Adam) from oracle/_ref when that pip-installed copy is present (kind "reference"), else the oracle
+           port oracle/unet_oracle.py (kind "port", pinned to the reference by tests/test_oracle_pinned.py)
+  stock_gpu / dropin : (N = 1, oracle/_ref present) the unmodified reference on the same B200 through stock PyTorch/cuDNN
+           -- what its `device = cuda` dispatches -- and the reference's own forward_pass with ctunet_b200.install()
+--impl reference times that CPU path alone.  Both arms consume the SAME synthetic tensors (synthetic_batch below).
 """
 import argparse
 import json
@@ -58,8 +61,8 @@ EXAMPLE_INI = {"UNetSP": "examples/autoimplant2020/UNetSPDO/FlapRecSP2O.ini",
 
 
 def workload_name(a):
-    return ("%s%s + %s loss (dice_lambda=1, ce_lambda=1) + Adam(amsgrad) lr 1e-4, batch %d/GPU, %dx%d^3 synthetic "
-            "skull CT" % (a.model, " (%s)" % EXAMPLE_INI[a.model] if a.model in EXAMPLE_INI else "",
+    return ("%s%s + %s loss (dice_lambda=1, ce_lambda=1) + Adam(amsgrad) lr 1e-4 + ReduceLROnPlateau per iteration, "
+            "batch %d/GPU, %dx%d^3 synthetic skull CT" % (a.model, " (%s)" % EXAMPLE_INI[a.model] if a.model in EXAMPLE_INI else "",
                           "FlapRecWithShapePriorDoubleOut" if HANDLER[a.model] == "double" else "ProblemHandler",
                           a.batch, 2 if a.model in ("UNetSP", "UNetSPSmall", "UNet4_2IC") else 1, a.size))
 
@@ -119,22 +122,130 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ------------------------------------------------------------------------------------------ CPU arm
-def cpu_reference_step_time(model, batch, size, steps, warmup, threads=None):
-    """The CPU oracle (port of the reference's PyTorch path): fwd + loss + bwd + Adam(amsgrad), fp32,
-    checkpoint semantics as shipped, anomaly mode off.  Returns (seconds per step, threads)."""
+# ------------------------------------------------------------------------------------------ synthetic data
+def synthetic_batch(batch, in_channels, size, seed):
+    """The workload's input, generated on the host with plain torch / numpy so that BOTH arms consume identical tensors
+    (SURVEY.md section 8d): an ellipsoidal bone-shell phantom per sample, a seeded spherical or box virtual craniectomy
+    (transforms.py:241-300: centre = a random bone voxel, radius in [min//5 - 1, max//3.5)), channel 1 = an intact phantom
+    standing in for the atlas (datasets.py:30-47), one-hot float32 targets (datasets.py:209-214).
+    Returns (image [B,Cin,S,S,S] float32, (skull_onehot, flap_onehot) [B,2,S,S,S] float32)."""
+    import numpy as np
     import torch
-    from oracle import unet_oracle as O
+
+    def phantom(sd):
+        g = torch.Generator().manual_seed(sd)
+        jit = (0.03 * torch.rand(3, generator=g)).tolist()
+        lin = torch.linspace(-1, 1, size)
+        zz, yy, xx = torch.meshgrid(lin, lin, lin, indexing="ij")
+        r = torch.sqrt((zz / (0.80 + jit[0])) ** 2 + (yy / (0.88 + jit[1])) ** 2 + (xx / (0.72 + jit[2])) ** 2)
+        thick = max(3.0, 4.5 * size / 128.0) / (size / 2.0)
+        return ((r >= 1.0 - thick) & (r <= 1.0)).numpy().astype(np.uint8)
+
+    rng = np.random.RandomState(seed)
+    atlas = torch.from_numpy(phantom(999)).float()
+    idx = np.indices((size,) * 3).astype(np.float64)
+    imgs, sks, fls = [], [], []
+    for b in range(batch):
+        full = phantom(seed * 131 + b)
+        nz = np.argwhere(full > 0)
+        c = nz[rng.randint(0, len(nz))]
+        lo = size // 5 - 1
+        radius = rng.randint(lo, max(int(size // 3.5), lo + 1))
+        diff = np.stack([idx[a] - float(c[a]) for a in range(3)], -1)
+        inside = np.linalg.norm(diff, axis=-1, ord=2 if rng.randint(0, 2) == 0 else np.inf) <= radius
+        broken, flap = full * (1 - inside), full * inside
+        chans = [torch.from_numpy(broken).float()] + ([atlas] if in_channels > 1 else [])
+        imgs.append(torch.stack(chans, 0))
+        oh = lambda m: torch.stack((torch.from_numpy(1 - m), torch.from_numpy(m)), 0).float()
+        sks.append(oh(full))
+        fls.append(oh(flap))
+    return torch.stack(imgs).contiguous(), (torch.stack(sks).contiguous(), torch.stack(fls).contiguous())
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+class _Quiet:
+    """The reference prints per batch (Model.py:332, ProblemHandler.py:97-102); bench.py's stdout carries ONE JSON line."""
+
+    def __enter__(self):
+        import contextlib
+        self._cm = contextlib.redirect_stdout(open(os.devnull, "w"))
+        self._cm.__enter__()
+
+    def __exit__(self, *a):
+        self._cm.__exit__(*a)
+
+
+def reference_trainer(model, device, lr=1e-4, install=False, data_parallel="keep"):
+    """The UNMODIFIED reference trainer object (oracle/ref_harness.py) configured like the benchmarked example .ini:
+    Adam(amsgrad) lr 1e-4, dice_lambda = ce_lambda = 1, scheduler on, metrics off (they are reporting-only and run on the
+    host through monai in the reference).  ``install``: with ctunet_b200.install() applied (the drop-in)."""
+    import torch
+    from oracle.ref_harness import make_trainer
+    from oracle.reference_loader import load_reference
+    MM = load_reference(with_trainer=True)[4]
+    if install:
+        import ctunet_b200
+        ctunet_b200.install(MM, data_parallel=data_parallel)
+    params = dict(model_class=model, problem_handler="FlapRecWithShapePriorDoubleOut" if HANDLER[model] == "double"
+                  else "FlapRecWithShapePrior", optimizer="adam", learning_rate=lr, momentum=0.99, weight_decay=0.0,
+                  dice_lambda=1.0, ce_lambda=1.0, save_dice_plots=False, save_hd_plots=False, scheduler=True)
+    torch.manual_seed(0)
+    m = make_trainer(params, device)
+    m.initialize_models()
+    if device == "cuda" and isinstance(m.models["main"], torch.nn.DataParallel):
+        m.models["main"] = m.models["main"].module            # one GPU per process here; DataParallel is the reference's N>1 path
+    m.initialize_optimizer()
+    return m
+
+
+def reference_forward_pass_time(m, sample, steps, warmup, sync=None):
+    """Seconds per batch of the reference's own ``Model.forward_pass('train', loader)`` (Model.py:324-380)."""
+    import torch
+    from oracle.ref_harness import ListLoader
+    with _Quiet():
+        if warmup:
+            m.forward_pass("train", ListLoader([sample] * warmup))
+        if sync:
+            sync()
+        t0 = time.perf_counter()
+        m.forward_pass("train", ListLoader([sample] * steps))
+        if sync:
+            sync()
+        dt = time.perf_counter() - t0
+    torch.set_grad_enabled(True)
+    first = m.losses_and_metrics["epoch_loss"][0]
+    m.losses_and_metrics = {}
+    return dt / steps, first
+
+
+def cpu_reference_step_time(model, batch, size, steps, warmup, threads=None, data=None):
+    """The reference's CPU path on ``data`` (image, (skull, flap)) or a fresh synthetic batch: fwd + loss + bwd +
+    Adam(amsgrad), fp32, checkpointing as shipped, anomaly mode off.
+    Returns (seconds per step, threads, kind, first-step loss)."""
+    import torch
     if threads:
         torch.set_num_threads(threads)
+    x, (sk_t, fl_t) = data if data is not None else synthetic_batch(batch, in_channels(model), size, 1234)
+    x, sk_t, fl_t = x[:batch], sk_t[:batch], fl_t[:batch]
+    from oracle.reference_loader import reference_available
+    if reference_available():
+        anomaly = torch.is_anomaly_enabled()
+        m = reference_trainer(model, "cpu")
+        torch.autograd.set_detect_anomaly(False)
+        try:
+            sample = {"image": x, "target": [sk_t, fl_t] if HANDLER[model] == "double" else sk_t}
+            sec, first = reference_forward_pass_time(m, sample, steps, warmup)
+        finally:
+            torch.autograd.set_detect_anomaly(anomaly)
+        return sec, torch.get_num_threads(), "reference", first
+    from oracle import unet_oracle as O
     cfg = O.PRESETS[model]
     sd = O.build_state_dict(cfg, seed=0)
     names = [k for k in sd if not k.endswith(("running_mean", "running_var", "num_batches_tracked"))]
     for k in names:
         sd[k].requires_grad_()
     opt = torch.optim.Adam([sd[k] for k in names], lr=1e-4, amsgrad=True)
-    x, (sk_t, fl_t) = O.make_training_batch(batch, cfg.input_channels, size, seed=1234)
-    times = []
+    times, first = [], None
     for it in range(warmup + steps):
         t0 = time.perf_counter()
         out = O.unet_forward(sd, x.clone().requires_grad_(), cfg, training=True)
@@ -146,32 +257,36 @@ def cpu_reference_step_time(model, batch, size, steps, warmup, threads=None):
         opt.step()
         for k in names:
             sd[k].grad = None
-        float(loss)
+        v = float(loss)
+        first = v if first is None else first
         if it >= warmup:
             times.append(time.perf_counter() - t0)
-    return sum(times) / len(times), torch.get_num_threads()
+    return sum(times) / len(times), torch.get_num_threads(), "port", first
 
 
 def run_reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import torch
     threads = os.cpu_count() or 1
     size, batch = a.size, 1                       # bounded sample: one volume of the batch per step
-    sec, used = cpu_reference_step_time(a.model, batch, size, a.steps, a.warmup, threads)
+    sec, used, kind, _ = cpu_reference_step_time(a.model, batch, size, a.steps, a.warmup, threads)
     value = batch * size ** 3 / sec
     sample = "batch %d of the %d-volume batch, %d^3, fp32, %d steps after %d warm-up" % (batch, a.batch, size, a.steps, a.warmup)
+    note = ("the UNMODIFIED reference (ctunet.pytorch.Model.forward_pass with its own model, loss handler, Adam(amsgrad) and "
+            "ReduceLROnPlateau) from oracle/_ref on the host cores; autograd anomaly mode off (the reference switches it on "
+            "at import, Model.py:20), checkpointing as shipped" if kind == "reference" else
+            "CPU port of the reference's PyTorch path (oracle/unet_oracle.py, pinned to the reference by golden vectors); "
+            "oracle/_ref (the installed reference) is not present on this box")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a), "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "CPU port of the reference's PyTorch path (oracle/unet_oracle.py, pinned to the reference by golden "
-                "vectors); the reference itself is pure Python and is not present on the GPU box",
+        "note": note,
     }
     print(json.dumps(line), flush=True)
 
@@ -303,7 +418,6 @@ def run_b200_arm(a):
     import ctunet_b200 as C
     from ctunet_b200 import _lib
     from ctunet_b200.parallel import GradSync
-    from ctunet_b200.synthetic import make_training_batch
     from ctunet_b200.trainer import TrainStep
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -324,9 +438,11 @@ def run_b200_arm(a):
     net = getattr(C, a.model)().to(dev)
     use_graph = a.graph != "off"
     sync = GradSync(net, deferred=use_graph) if world > 1 else None
-    step = TrainStep(net, HANDLER[a.model], 1.0, 1.0, lr=1e-4, grad_sync=sync, graph=use_graph)
+    # the benchmarked example .ini sets b_scheduler = True: ReduceLROnPlateau() is stepped every iteration (Model.py:369-371)
+    step = TrainStep(net, HANDLER[a.model], 1.0, 1.0, lr=1e-4, scheduler=True, grad_sync=sync, graph=use_graph)
     cin = in_channels(a.model)
-    img, (sk_t, fl_t) = make_training_batch(a.batch, cin, a.size, seed=1234 + 1000 * rank, device=dev)
+    host_batch = synthetic_batch(a.batch, cin, a.size, seed=1234 + 1000 * rank)     # the tensors BOTH arms consume
+    img, sk_t, fl_t = (t.to(dev) for t in (host_batch[0],) + host_batch[1])
     target = (sk_t, fl_t) if HANDLER[a.model] == "double" else sk_t
     host = [t.cpu().pin_memory() for t in ((img, sk_t, fl_t) if HANDLER[a.model] == "double" else (img, sk_t))]
     h2d_bytes = sum(t.numel() * t.element_size() for t in host)
@@ -383,8 +499,14 @@ def run_b200_arm(a):
     orig, timed_call = prof.wrap(_lib)
     import ctunet_b200.engine as E
     import ctunet_b200.losses as LS
-    E.call = LS.call = timed_call
-    eager_step = TrainStep(net, HANDLER[a.model], 1.0, 1.0, lr=1e-4, grad_sync=sync) if use_graph else step
+    import ctunet_b200.optim as OP
+    import ctunet_b200.trainer as TR
+    import ctunet_b200.utilities as UT
+    patched = (E, LS, OP, TR, UT)
+    for mod in patched:
+        mod.call = timed_call
+    eager_step = (TrainStep(net, HANDLER[a.model], 1.0, 1.0, lr=1e-4, scheduler=True,
+                            grad_sync=GradSync(net, deferred=True) if world > 1 else None) if use_graph else step)
     # one stream for this pass: with the weight-gradient / weight-preparation side streams the kernels overlap and an
     # event pair would time the overlap, not the kernel
     flags = (E.WGRAD_ASYNC, E.WEIGHT_PREP_ASYNC, E.DEAD_BRANCH_ASYNC)
@@ -402,9 +524,9 @@ def run_b200_arm(a):
     try:
         timed(profiled_step, a.steps)
     finally:
-        E.call = LS.call = orig
+        for mod in patched:
+            mod.call = orig
         E.WGRAD_ASYNC, E.WEIGHT_PREP_ASYNC, E.DEAD_BRANCH_ASYNC = flags
-        net._grad_sink = sync
 
     # ---- end-to-end steps: pinned host -> device every iteration, loss read back ----------------
     # f32 batch: float32 image + one-hot float32 targets exactly as the reference's DataLoader hands them to
@@ -422,7 +544,7 @@ def run_b200_arm(a):
     def make_e2e(host_bufs, run_step):
         dbuf = [[torch.empty_like(t, device=dev) for t in host_bufs] for _ in range(2)]
         state = {"i": 0, "ready": None}
-        rb = LossReadback(5 if double else 3, depth=int(os.environ.get("CTU_READBACK_DEPTH", "2")))
+        rb = LossReadback(len(step.keys), depth=int(os.environ.get("CTU_READBACK_DEPTH", "2")))
 
         def prefetch(slot):
             with torch.cuda.stream(copy_stream):
@@ -526,13 +648,73 @@ def run_b200_arm(a):
                 us = ms / cnt * 1e3
                 f.write("%-64s %5.1f %10.1f %9.1f %9.1f\n" % (k, cnt / a.steps, us, fl / us / 1e6, by / us / 1e3))
 
-    cpu = None
+    cpu = loss_check = None
     if world == 1 and not a.no_cpu_baseline:
         cs, cb = a.size, 1
-        sec, used = cpu_reference_step_time(a.model, cb, cs, steps=3, warmup=1, threads=os.cpu_count())
-        cpu = {"value": cb * cs ** 3 / sec, "unit": UNIT, "cores": used, "kind": "port",
-               "sample": "one volume of the %d-volume batch (batch %d x %d^3), fp32, 3 steps after 1 warm-up, %.2f s/step"
+        sec, used, kind, cpu_first = cpu_reference_step_time(a.model, cb, cs, steps=3, warmup=1, threads=os.cpu_count(),
+                                                             data=host_batch)
+        cpu = {"value": cb * cs ** 3 / sec, "unit": UNIT, "cores": used, "kind": kind,
+               "sample": "the first volume of the %d-volume batch (batch %d x %d^3), fp32, 3 steps after 1 warm-up, %.2f s/step"
                          % (a.batch, cb, cs, sec)}
+        # the same tensors, the same seed-0 initialisation, the first iteration's total loss on both arms (outside any
+        # timed region; BatchNorm uses batch statistics, so the GPU side re-runs that one-volume batch on a fresh module)
+        torch.manual_seed(0)
+        cnet = getattr(C, a.model)().to(dev)
+        cstep = TrainStep(cnet, HANDLER[a.model], 1.0, 1.0, lr=1e-4)
+        tgt1 = (sk_t[:cb], fl_t[:cb]) if double else sk_t[:cb]
+        gpu_first = float(cstep(img[:cb].contiguous(), tuple(t.contiguous() for t in tgt1) if double else tgt1.contiguous())[-1])
+        loss_check = {"sample": "first volume of the batch, first iteration, seed-0 weights", "gpu_%s" % a.dtype: gpu_first,
+                      "cpu_fp32_%s" % kind: cpu_first, "abs_diff": abs(gpu_first - cpu_first)}
+        del cstep, cnet
+
+    # secondary legs (N = 1, the installed reference present): what the reference's own `device = cuda` dispatches on this
+    # B200 (stock PyTorch / cuDNN, fp32 with torch's default TF32 convolutions, reentrant checkpointing as shipped; and the
+    # same under bf16 autocast), and the reference's unmodified forward_pass driving the installed B200 modules.
+    stock = dropin = None
+    if world == 1 and not a.no_cpu_baseline and not a.no_other_workloads:
+        try:
+            from oracle.reference_loader import reference_available
+            have_ref = reference_available()
+        except Exception:
+            have_ref = False
+        if have_ref:
+            sample = {"image": host_batch[0].pin_memory(),
+                      "target": [t.pin_memory() for t in host_batch[1]] if double else host_batch[1][0].pin_memory()}
+            anomaly = torch.is_anomaly_enabled()
+            try:
+                stock = {}
+                for label, ctx in (("fp32_tf32_default", None), ("bf16_autocast", torch.autocast("cuda", dtype=torch.bfloat16))):
+                    m = reference_trainer(a.model, "cuda")
+                    torch.autograd.set_detect_anomaly(False)
+                    if ctx is not None:
+                        ctx.__enter__()
+                    try:
+                        sec, first = reference_forward_pass_time(m, sample, steps=5, warmup=2, sync=torch.cuda.synchronize)
+                    finally:
+                        if ctx is not None:
+                            ctx.__exit__(None, None, None)
+                    stock[label] = {"ms_per_step": sec * 1e3, "value": a.batch * a.size ** 3 / sec, "unit": UNIT,
+                                    "first_loss": first}
+                    del m
+                    torch.cuda.empty_cache()
+                stock["note"] = ("the UNMODIFIED reference (oracle/_ref) on this GPU through stock PyTorch / cuDNN: "
+                                 "Model.forward_pass with host batches (H2D inside), its 5 float() syncs per batch, anomaly mode "
+                                 "off; wall-clock around forward_pass with a device synchronize on both sides")
+                m = reference_trainer(a.model, "cuda", install=True, data_parallel="single")
+                torch.autograd.set_detect_anomaly(False)
+                sec, first = reference_forward_pass_time(m, sample, steps=10, warmup=3, sync=torch.cuda.synchronize)
+                dropin = {"dropin_forward_pass_ms": sec * 1e3, "value": a.batch * a.size ** 3 / sec, "unit": UNIT,
+                          "first_loss": first,
+                          "note": "the reference's own Model.forward_pass (Model.py:324-380: host batch, torch.optim.Adam, "
+                                  "ReduceLROnPlateau on the host, float() per loss component) with ctunet_b200.install() applied"}
+                del m
+                torch.cuda.empty_cache()
+            except Exception as exc:            # secondary numbers must never take the bench line down
+                stock = stock or {}
+                stock["error"] = "%s: %s" % (type(exc).__name__, exc)
+            finally:
+                torch.autograd.set_detect_anomaly(anomaly)
+                torch.set_grad_enabled(True)
 
     # the other BASELINE configs[1] models (the 5^3 autoimplant2020 family): short device-resident runs, same batch and size
     others = None
@@ -543,7 +725,7 @@ def run_b200_arm(a):
             torch.manual_seed(0)
             onet = getattr(C, other)().to(dev)
             ostep = TrainStep(onet, HANDLER[other], 1.0, 1.0, lr=1e-4, graph=use_graph)
-            oimg, (osk, _) = make_training_batch(a.batch, in_channels(other), a.size, seed=1234, device=dev)
+            oimg, osk = (t.to(dev) for t in (lambda d_: (d_[0], d_[1][0]))(synthetic_batch(a.batch, in_channels(other), a.size, 1234)))
             for _ in range(4):
                 ostep(oimg, osk)
             oms = timed(lambda: ostep(oimg, osk), 10)
@@ -606,6 +788,9 @@ def run_b200_arm(a):
         "clocks": clk,
         "roofline": roof,
         "cpu_baseline": cpu,
+        "loss_check": loss_check,
+        "stock_gpu_reference": stock,
+        "dropin": dropin,
         "other_workloads": others,
         "other_configs": extra,
         "top_kernels": top,

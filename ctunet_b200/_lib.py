@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_double, c_float, c_int, c_longlong, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int, c_longlong, c_ulonglong, c_void_p
 
 import torch  # noqa: F401  (loads libcudart / libcuda into the process before our library)
 
@@ -22,6 +22,7 @@ HEAD_SOFTMAX, HEAD_SIGMOID, HEAD_SP, HEAD_SP_SOFTMAX = 1, 2, 4, 8
 P = c_void_p
 I = c_int
 LL = c_longlong
+ULL = c_ulonglong
 D = c_double
 F = c_float
 
@@ -81,6 +82,15 @@ SIGNATURES = {
     "ctu_resample_nearest_u8": (I, [P, P, I, I, I, I, I, I, P]),
     "ctu_resample_nearest_index": (I, [P, I, I, P]),
     "ctu_resample_trilinear_f32": (I, [P, P, I, I, I, I, I, I, P]),
+    "ctu_dice_coeff": (I, [P, P, I, I, LL, P, P, P]),
+    "ctu_hausdorff_workspace_bytes": (LL, [I, I, I, I, I]),
+    "ctu_hausdorff": (I, [P, P, I, I, I, I, I, D, P, LL, P, P]),
+    "ctu_loss_combine": (I, [P, P, I, P, P, P]),
+    "ctu_optim_chunk_bytes": (I, []),
+    "ctu_optim_chunk_elems": (I, []),
+    "ctu_optim_step": (I, [I, P, I, P, P, P, P, P, P, D, D, D, D, D, D, I, D, P]),
+    "ctu_optim_post": (I, [P, P, P, I, P]),
+    "ctu_salt_pepper_u8": (I, [P, P, LL, D, D, P, P, ULL, ULL, P]),
 }
 
 _lib = None

@@ -17,16 +17,29 @@ MODEL_CLASSES = ["UNet", "UNet4b2i3o", "UNet5b2i3o", "UNet4b1i3o", "UNetSP", "UN
 HANDLER_CLASSES = ["FlapRecWithShapePriorDoubleOut", "FlapRecDoubleOut"]
 
 
-def install(trainer_module=None, replace_losses: bool = True):
+UTILITY_FUNCTIONS = ["dice_loss", "dice_coeff", "hausdorff"]
+
+
+def install(trainer_module=None, replace_losses: bool = True, data_parallel: str = "keep"):
     """Rebind the reference's model (and optionally loss-handler) names to the B200 classes.
 
-    ``trainer_module`` defaults to ``ctunet.pytorch.Model`` (must be importable).  The reference's
-    handler classes are kept (they own the dataset / NIfTI-writer halves, which are out of scope);
-    only their ``comp_losses_metrics`` static method is replaced by the fused one.
-    Returns the list of rebound names."""
+    ``trainer_module`` defaults to ``ctunet.pytorch.Model`` (must be importable).  The reference's handler classes are
+    kept (they own the dataset / NIfTI-writer halves, which are out of scope); only their ``comp_losses_metrics`` static
+    method is replaced by the fused one -- including the ``dice_coef_*`` / ``hd_coef_*`` metrics every stock ``.ini``
+    switches on.  ``ctunet.utilities.dice_loss / dice_coeff / hausdorff`` are rebound as well (CUDA tensors only).
+    NOT rebound, on purpose: ``utils.hard_segm_from_tensor`` (the reference calls it on ``.cpu()`` tensors inside its
+    file writers, ProblemHandler.py:340-341) and the dataset transforms (they run on host tensors in DataLoader workers);
+    their device versions live in ``ctunet_b200.utilities`` for pipelines that keep the data on the GPU.
+
+    ``data_parallel``: 'keep' leaves ``Model.new_model`` alone -- with several visible GPUs the reference wraps the model
+    in ``nn.DataParallel`` (Model.py:481-486), which these modules support (replicas read the broadcast weights);
+    'single' patches ``new_model`` to build the bare module on the current device, for one-process-per-GPU launches
+    (torchrun + ``parallel.GradSync``).  Returns the list of rebound names."""
+    import importlib
     if trainer_module is None:
-        import importlib
         trainer_module = importlib.import_module("ctunet.pytorch.Model")
+    if data_parallel not in ("keep", "single"):
+        raise ValueError("data_parallel: 'keep' or 'single'")
     done = []
     for name in MODEL_CLASSES:
         setattr(trainer_module, name, getattr(models, name))
@@ -40,4 +53,17 @@ def install(trainer_module=None, replace_losses: bool = True):
             elif "comp_losses_metrics" in vars(ours):
                 ref_cls.comp_losses_metrics = staticmethod(vars(ours)["comp_losses_metrics"].__func__)
             done.append(name + ".comp_losses_metrics")
+        from . import utilities as ours_utils
+        ref_utils = getattr(trainer_module, "utils", None)
+        if ref_utils is not None:
+            for name in UTILITY_FUNCTIONS:
+                setattr(ref_utils, name, getattr(ours_utils, name))
+                done.append("utils." + name)
+    if data_parallel == "single" and hasattr(trainer_module, "Model"):
+        def new_model(self):                                  # Model.py:474-491 without the nn.DataParallel wrapper
+            model = eval(self.params["model_class"], vars(trainer_module))()
+            model.to(self.params["device"])
+            return model
+        trainer_module.Model.new_model = new_model
+        done.append("Model.new_model")
     return done

@@ -86,14 +86,14 @@ class ProblemHandler:
         self.test_dataset_class = test_dataset_class
 
     def write_predictions(self, predictions, input_filepaths, output_folder_name, input_imgs):
-        raise NotImplementedError("NIfTI prediction writers need SimpleITK and are outside the hot path")
+        raise NotImplementedError("NIfTI prediction writers need SimpleITK (file IO is outside the hot path); "
+                                  "ctunet_b200.install() keeps the reference's own writers and only replaces the labelling "
+                                  "(utils.hard_segm_from_tensor)")
 
     @staticmethod
     def comp_losses_metrics(model, prediction, target, idx, n_imgs, verbose=True):
         """ProblemHandler.py:44-102: ce_lambda * CE(prediction, argmax(target)) + dice_lambda * Dice."""
         ce_l, dice_l = model.params["ce_lambda"], model.params["dice_lambda"]
-        if model.params.get("save_dice_plots") is True:
-            raise NotImplementedError("dice_coeff metrics need monai and are outside the hot path")
         if target.dim() != 5:
             raise NotImplementedError("the fused loss expects a one-hot float target [B, C, D, H, W]")
         ce, dice = dice_ce(prediction, target, softmax_for_dice=False, want_ce=ce_l != 0)
@@ -106,8 +106,12 @@ class ProblemHandler:
             keys.append("dice_loss")
         model.pt_loss = sum(terms)
         vals = torch.stack([t.detach() for t in terms] + [model.pt_loss.detach()]).tolist()   # one sync
-        for k, v in zip(keys + ["epoch_loss"], vals):
+        for k, v in zip(keys, vals):
             _append(model.losses_and_metrics, k, v)
+        if model.params["save_dice_plots"] is True:                                           # ProblemHandler.py:84-88
+            from .utilities import dice_coeff
+            _append(model.losses_and_metrics, "dice_coef", dice_coeff(prediction, target))    # a tensor, as the reference
+        _append(model.losses_and_metrics, "epoch_loss", vals[-1])
         if verbose:
             print("    Batch {}/{} ({:.0f}%)\tLoss: {:.6f}".format(idx + 1, n_imgs, 100.0 * (idx + 1) / n_imgs, vals[-1]))
 
@@ -133,8 +137,6 @@ class FlapRecWithShapePriorDoubleOut(ProblemHandler):
         soft-Dice on their softmax, weighted by ce_lambda / dice_lambda and summed in the reference's
         order (ce_sk, ce_fl, dice_sk, dice_fl)."""
         ce_l, dice_l = model.params["ce_lambda"], model.params["dice_lambda"]
-        if model.params.get("save_dice_plots") is True or model.params.get("save_hd_plots") is True:
-            raise NotImplementedError("dice_coeff / hausdorff metrics need monai and are outside the hot path")
         sk_p, fl_p = prediction
         sk_t, fl_t = target
         ce_s, dice_s = dice_ce(sk_p, sk_t, softmax_for_dice=True, want_ce=ce_l != 0)
@@ -148,8 +150,22 @@ class FlapRecWithShapePriorDoubleOut(ProblemHandler):
             keys += ["dice_loss_sk", "dice_loss_fl"]
         model.pt_loss = sum(terms)
         vals = torch.stack([t.detach() for t in terms] + [model.pt_loss.detach()]).tolist()   # one sync
-        for k, v in zip(keys + ["epoch_loss"], vals):
-            _append(model.losses_and_metrics, k, v)
+        lm = model.losses_and_metrics
+        for k, v in zip(keys, vals):
+            _append(lm, k, v)
+        # Metrics (ProblemHandler.py:277-295).  The reference evaluates them on softmax(prediction); the hard labels they
+        # are built from (argmax over the channel axis) are the same for the raw predictions.  Appended as 0-dim device
+        # tensors like the reference does (Model.update_plots_tensorboard_avg averages and float()s them once per epoch),
+        # so they cost no host synchronisation here.  `save_hd_plots` is read unconditionally, like ProblemHandler.py:287.
+        if model.params["save_dice_plots"] is True:
+            from .utilities import dice_coeff
+            _append(lm, "dice_coef_sk", dice_coeff(sk_p, sk_t))
+            _append(lm, "dice_coef_fl", dice_coeff(fl_p, fl_t))
+        if model.params["save_hd_plots"] is True:
+            from .utilities import hausdorff
+            _append(lm, "hd_coef_sk", hausdorff(sk_p, sk_t))
+            _append(lm, "hd_coef_fl", hausdorff(fl_p, fl_t))
+        _append(lm, "epoch_loss", vals[-1])
         if verbose:
             print("    Batch {}/{} ({:.0f}%)\tLoss: {:.6f}".format(idx + 1, n_imgs, 100.0 * (idx + 1) / n_imgs, vals[-1]))
 

@@ -133,28 +133,53 @@ class _FusedNet(nn.Module):
         m = 2 ** self._levels()
         if any(s % m for s in x.shape[2:]):
             raise ValueError("spatial size %s must be divisible by %d" % (tuple(x.shape[2:]), m))
-        for p in self.parameters():
+        for p in self._weight_tensors():
             if p.device != x.device or p.dtype != torch.float32:
                 raise RuntimeError("parameters must be float32 on %s (call .to(device))" % x.device)
             break
 
+    def _weight_tensors(self):
+        """The tensors the engine reads through the parameter containers, in ``named_parameters`` order.  On an
+        ``nn.DataParallel`` replica (Model.py:486; torch.nn.parallel.replicate) ``parameters()`` is EMPTY: the broadcast
+        copies are plain attributes listed in ``_former_parameters`` -- non-leaf tensors whose gradients flow back to the
+        real parameters through the Broadcast node, so they must be inputs of the autograd function like parameters."""
+        if not getattr(self, "_is_replica", False):
+            return list(self.parameters())
+        out = []
+        for m in self.modules():
+            out.extend(t for t in getattr(m, "_former_parameters", {}).values() if t is not None)
+        return out
+
     def forward(self, x):
         self._validate(x)
         x = x.contiguous()
-        params = [p for p in self.parameters()]
+        params = self._weight_tensors()
         record = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
         if not record:
             eng = Engine(x.device, self.compute_dtype, record=False)
-            return _run_planned(self, eng, x, False)
+            return _run_planned(self, eng, x, False, params)
         return _NetFn.apply(self, x, *params)
 
 
-def _run_planned(net, eng: Engine, x, record: bool):
-    """Run the network with the weight-preparation plan of this (shape, mode) configuration (Engine.begin)."""
+def _run_planned(net, eng: Engine, x, record: bool, params):
+    """Run the network with the weight-preparation plan of this (shape, mode) configuration (Engine.begin).
+    A plan holds closures over the weight tensors seen when it was recorded, so it is only reused while the module still
+    owns the very same tensor objects (checked by identity against strong references kept with the plan: a parameter
+    replaced by ``load_state_dict(assign=True)``, a swapped ``last_conv``, ... invalidates it); DataParallel replicas,
+    whose tensors are new on every forward, never use plans."""
     from . import engine as E
+    if getattr(net, "_is_replica", False):
+        out = net._run(eng, x, net.training)
+        eng.end_forward()
+        return out
     store = net.__dict__.setdefault("_prep_plans", {})
-    key = (id(net), tuple(x.shape), str(x.device), net.compute_dtype, bool(net.training), record, eng.want_input_grad,
+    key = (tuple(x.shape), str(x.device), net.compute_dtype, bool(net.training), record, eng.want_input_grad,
            E.UP_FUSION, E.CONV_PATH)
+    owners = store.setdefault("__owners__", {})
+    held = owners.get(key)
+    if held is None or len(held) != len(params) or any(a is not b for a, b in zip(held, params)):
+        store.pop(key, None)
+        owners[key] = list(params)
     eng.begin(store, key)
     out = net._run(eng, x, net.training)
     eng.end_forward()
@@ -169,7 +194,7 @@ class _NetFn(torch.autograd.Function):
         eng = Engine(x.device, net.compute_dtype, record=True)
         eng.grad_sink = getattr(net, "_grad_sink", None)
         eng.want_input_grad = bool(ctx.needs_input_grad[1])
-        out = _run_planned(net, eng, x, True)
+        out = _run_planned(net, eng, x, True, params)
         ctx.eng = eng
         ctx.params = params
         ctx.two = isinstance(out, tuple)

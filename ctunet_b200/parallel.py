@@ -21,6 +21,8 @@ import torch.distributed as dist
 
 
 class GradSync:
+    TAIL = 8      # floats appended to the flat buffer: the step's loss components, averaged together with the gradients
+
     def __init__(self, module: torch.nn.Module, process_group=None, n_buckets: int = 3, skip_prefixes=("cblock.",),
                  deferred: bool = False):
         """``skip_prefixes``: parameters that never receive a gradient (the generic UNet's discarded
@@ -39,7 +41,12 @@ class GradSync:
         live = list(reversed(live))                       # production order of the backward pass
         total = sum(p.numel() for _, p in live)
         ref = live[0][1]
-        self.flat = torch.zeros(total, dtype=torch.float32, device=ref.device)
+        # [gradients | TAIL]: the reference computes its loss on the GATHERED batch (nn.DataParallel, Model.py:486), i.e. the
+        # mean over ranks of the per-rank losses -- the tail carries the loss components through the same all-reduce, so
+        # logging and ReduceLROnPlateau (Model.py:369-371) see identical values on every rank.
+        self.n_grad = total
+        self.flat = torch.zeros(total + self.TAIL, dtype=torch.float32, device=ref.device)
+        self.tail = self.flat[total:]
         self.slices: Dict[int, torch.Tensor] = {}
         self.bucket_of: Dict[int, int] = {}
         self.names = [n for n, _ in live]
@@ -55,6 +62,7 @@ class GradSync:
                 self.bucket_ranges.append([b_start, off])
                 b_start = off
                 b += 1
+        self.bucket_ranges[-1][1] = total + self.TAIL     # the loss tail travels with the last bucket
         self.n_in_bucket = [0] * len(self.bucket_ranges)
         for k, bi in self.bucket_of.items():
             self.n_in_bucket[bi] += 1
@@ -120,22 +128,20 @@ class GradSync:
         for p in self.params:
             p.grad = self.slices[id(p)]
 
-    def finish(self) -> None:
-        """Make the averaged gradients visible to the optimizer (current stream) and publish them as
-        ``param.grad`` views of the flat buffer."""
+    def finish(self, publish: bool = True) -> None:
+        """Make the averaged gradients visible to the optimizer (current stream) and, with ``publish``, expose them as
+        ``param.grad`` views of the flat buffer (the ``FlatOptimizer`` reads the buffer itself)."""
         self.check_complete()
         if self.deferred:
             self.reduce_all()
+        else:
+            if self.cuda:
+                torch.cuda.current_stream().wait_stream(self.comm_stream)
+            for h, view in self._handles:
+                h.wait()
+                view.div_(self.world)
+        if publish:
             self.publish()
-            self.begin_step()
-            return
-        if self.cuda:
-            torch.cuda.current_stream().wait_stream(self.comm_stream)
-        for h, view in self._handles:
-            h.wait()
-            view.div_(self.world)
-        for p in self.params:
-            p.grad = self.slices[id(p)]
         self.begin_step()
 
 

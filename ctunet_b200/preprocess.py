@@ -72,6 +72,9 @@ def _captured_patch_labels(model, xb: torch.Tensor):
     graphs = model.__dict__.setdefault("_infer_graphs", {})       # lives and dies with the model
     key = (tuple(xb.shape), str(xb.device), getattr(model, "compute_dtype", None))
     ent = graphs.get(key)
+    weights = list(model.parameters()) + list(model.buffers())
+    if ent is not None and (len(ent[3]) != len(weights) or any(a is not b for a, b in zip(ent[3], weights))):
+        ent = None            # a parameter / buffer OBJECT was replaced: the capture reads the old storage
     if ent is None:
         static_in = torch.empty_like(xb)
         static_in.copy_(xb)
@@ -86,11 +89,11 @@ def _captured_patch_labels(model, xb: torch.Tensor):
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             outs = run()
-        ent = (g, static_in, outs)
+        ent = (g, static_in, outs, weights)
         graphs[key] = ent
         if len(graphs) > 8:                     # a handful of shapes at most: drop the oldest capture
             graphs.pop(next(iter(graphs)))
-    g, static_in, outs = ent
+    g, static_in, outs, _ = ent
     static_in.copy_(xb)
     g.replay()
     return outs

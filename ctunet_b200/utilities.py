@@ -5,6 +5,8 @@
   random_blank_patch      ctunet/pytorch/transforms.py:241-300
   SkullRandomHole         ctunet/pytorch/transforms.py:52-94
   encode_flaprec_batch    ctunet/pytorch/datasets.py:195-235, :30-47 (one-hot targets, atlas channel)
+  dice_coeff, hausdorff   ctunet/utilities.py:53-70 (reporting metrics; monai restated -> parity unpinned)
+  SaltAndPepper           ctunet/pytorch/transforms.py:13-49
 
 The 'flap' shape of shape_3d calls the un-vendored, unpinned ``raster_geometry`` package in the reference
 (utilities.py:145-166); it is not installed here, so ``cylinder`` / ``cube`` are RESTATED from the package's published
@@ -19,6 +21,7 @@ import numpy as np
 import torch
 
 from ._lib import call, stream_ptr
+from ._lib import load as _load
 from .losses import dice_loss  # noqa: F401  (re-export: utils.dice_loss)
 
 _SHAPES = {"circle": 0, "sphere": 0, "square": 1, "box": 1, "cube": 1, "flap": 2, "autoimplant": 2}
@@ -177,3 +180,93 @@ def encode_flaprec_batch(broken: torch.Tensor, full: torch.Tensor, flap: torch.T
          flap.contiguous().data_ptr(), atlas.contiguous().data_ptr() if atlas is not None else None, image.data_ptr(),
          sk.data_ptr(), fl.data_ptr(), b, cin, spatial, stream_ptr())
     return image, (sk, fl)
+
+
+# ---------------------------------------------------------------------------------------------- reporting metrics
+def _metric_pair(pred, target, what):
+    _need_cuda(pred, what)
+    _need_cuda(target, what)
+    if pred.dim() != 5 or pred.shape != target.shape or not 2 <= pred.shape[1] <= 4:
+        raise ValueError("%s expects prediction and one-hot target of one [B, C, D, H, W] shape, 2 <= C <= 4" % what)
+    return pred.detach().float().contiguous(), target.detach().float().contiguous()
+
+
+def dice_coeff(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """``utils.dice_coeff`` (utilities.py:53-60): mean over (sample, foreground class) of the hard-label Dice coefficient
+    ``2|P n T| / (|P| + |T|)`` with P = ``argmax(pred, 1) == class`` -- ``monai.metrics.compute_meandice(one_hot(argmax),
+    target, include_background=False)`` restated (NaN where the target class is empty, which then propagates through the
+    mean exactly as in the reference).  Returns a 0-dim float32 CUDA tensor; no host synchronisation.
+    One divergence, documented: when NO voxel of the whole batch is predicted foreground the reference's
+    ``one_hot(argmax)`` has a single channel and monai raises on the shape mismatch; here the class counts as empty."""
+    p, t = _metric_pair(pred, target, "dice_coeff")
+    b, c = p.shape[0], p.shape[1]
+    counts = torch.empty(3 * b * (c - 1), dtype=torch.float64, device=p.device)
+    out = torch.empty(1, dtype=torch.float32, device=p.device)
+    call("ctu_dice_coeff", p.data_ptr(), t.data_ptr(), b, c, p[0, 0].numel(), counts.data_ptr(), out.data_ptr(), stream_ptr())
+    return out[0]
+
+
+def hausdorff(result_b: torch.Tensor, reference_b: torch.Tensor) -> torch.Tensor:
+    """``utils.hausdorff`` (utilities.py:63-70): mean over (sample, foreground class) of the symmetric Hausdorff distance
+    between the surfaces of ``argmax(result_b, 1) == class`` and ``reference_b[:, class] == 1``
+    (``monai.metrics.compute_hausdorff_distance`` restated: surface = mask minus its 6-neighbourhood erosion, Euclidean
+    distance in voxels); NaN / inf (an empty surface) become ``max(reference_b.shape)`` as utilities.py:64,69 do.
+    Exact integer squared distance transform on the device; returns a 0-dim float64 CUDA tensor, no host sync."""
+    p, t = _metric_pair(result_b, reference_b, "hausdorff")
+    b, c, d, h, w = p.shape
+    lib = _load()
+    nbytes = lib.ctu_hausdorff_workspace_bytes(b, c, d, h, w)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=p.device)
+    out = torch.empty(1, dtype=torch.float64, device=p.device)
+    call("ctu_hausdorff", p.data_ptr(), t.data_ptr(), b, c, d, h, w, float(max(reference_b.shape)), ws.data_ptr(), nbytes,
+         out.data_ptr(), stream_ptr())
+    return out[0]
+
+
+# ---------------------------------------------------------------------------------------------- SaltAndPepper
+class SaltAndPepper(object):
+    """transforms.py:13-49 for CUDA tensors ([D,H,W] or [B,D,H,W], any dtype; returns float32 like ``torch.FloatTensor``).
+
+    Kept from the reference, in its order: ``self.noise_density`` is OVERWRITTEN by ``np.random.uniform(0, noise_density)``
+    on every call and key (transforms.py:31 -- the noise decays towards zero over training), then per
+    image one ``random.uniform(0, 1)`` gate against ``p``.  The two per-voxel uniform fields come from a Philox
+    counter-based generator on the device (seeded from the numpy RNG, one draw per noisy image) instead of 2 x D*H*W
+    float64 draws from numpy's MT19937 stream on the host: same distribution, different stream.  ``fields=(u_black, u_white)``
+    (float64 CUDA tensors of the batch shape) replaces the generator -- with the reference's own draws the output is
+    bit-identical to the reference's."""
+
+    def __init__(self, p=1, noise_density=0.2, salt_ratio=0.1, keyws=("image", "target"), apply_to=(True, False)):
+        self.p = p
+        self.noise_density = noise_density
+        self.salt_ratio = salt_ratio
+        self.keyws = keyws
+        self.apply_to = apply_to
+
+    def __call__(self, sample, fields=None):
+        for i, keyw in enumerate(self.keyws):
+            if not self.apply_to[i]:
+                continue
+            img = sample[keyw]
+            _need_cuda(img, "SaltAndPepper")
+            is_batch = img.dim() == 4
+            vols = (img if is_batch else img.unsqueeze(0)).to(torch.uint8).contiguous()   # .astype(np.uint8), :29-30
+            out = vols.clone()
+            self.noise_density = np.random.uniform(0, self.noise_density)                # :31
+            for j in range(vols.shape[0]):
+                r = random.uniform(0, 1)                                                  # :33
+                if self.p >= r:
+                    ub = uw = None
+                    seed = 0
+                    if fields is not None:
+                        ub = (fields[0] if is_batch else fields[0].unsqueeze(0))[j].contiguous()
+                        uw = (fields[1] if is_batch else fields[1].unsqueeze(0))[j].contiguous()
+                        if ub.dtype != torch.float64 or uw.dtype != torch.float64 or ub.shape != vols[j].shape:
+                            raise TypeError("fields: two float64 CUDA tensors of the image shape")
+                    else:
+                        seed = int(np.random.randint(0, 2 ** 31 - 1)) | (int(np.random.randint(0, 2 ** 31 - 1)) << 32)
+                    call("ctu_salt_pepper_u8", vols[j].data_ptr(), out[j].data_ptr(), vols[j].numel(),
+                         float(self.noise_density), float(self.salt_ratio), ub.data_ptr() if ub is not None else None,
+                         uw.data_ptr() if uw is not None else None, seed, 0, stream_ptr())
+            out = out.float()
+            sample[keyw] = out if is_batch else out[0]
+        return sample

@@ -230,6 +230,46 @@ int ctu_resample_nearest_index(int* idx, int out_size, int in_size, ctu_stream s
 int ctu_resample_trilinear_f32(const float* src, float* dst, int sd, int sh, int sw, int dd, int dh, int dw,
                                ctu_stream stream);
 
+/* ---- reporting metrics of the loss handlers (utilities.py:53-70; ProblemHandler.py:84-88, 277-295) on fp32 NCDHW
+ *      prediction / one-hot target pairs [b][c][spatial], 2 <= c <= 4.  monai (undeclared, unpinned in the reference) is
+ *      restated: PARITY UNPINNED, the CPU statement is oracle/ref_stubs/monai/metrics.py. -------------------------------- */
+/* out[0] = torch.mean(compute_meandice(one_hot(argmax(pred,1)), target, include_background=False)):
+ * per (sample, class >= 1) 2*sum(t*m)/(sum(t)+sum(m)), NaN where sum(t) == 0.  counts: double[3*b*(c-1)] scratch. */
+int ctu_dice_coeff(const float* pred, const float* target, int b, int c, long long spatial, double* counts, float* out,
+                   ctu_stream stream);
+/* out[0] = mean over (sample, class >= 1) of the symmetric Hausdorff distance between the surfaces (mask minus its
+ * 6-neighbourhood erosion) of [argmax(pred) == class] and [target[class] == 1]; exact squared Euclidean distance
+ * transform in int32; an empty surface on either side counts as inf_alt (= max(target.shape), utilities.py:64,69). */
+long long ctu_hausdorff_workspace_bytes(int b, int c, int d, int h, int w);
+int ctu_hausdorff(const float* pred, const float* target, int b, int c, int d, int h, int w, double inf_alt, void* workspace,
+                  long long workspace_bytes, double* out, ctu_stream stream);
+
+/* ---- the tail of a training iteration (Model.py:366-371, 510-546; ProblemHandler.py:59-91, 241-298) -------------------
+ * comps[i] = lambdas[i] * *terms[i] (device scalars, host array of pointers), comps[n] = their sum in order; mirror
+ * (nullable) receives a second copy (the tail of the data-parallel flat gradient buffer). */
+int ctu_loss_combine(const float* const* h_terms, const float* h_lambdas, int n, float* comps, float* mirror,
+                     ctu_stream stream);
+/* One launch updates every parameter.  chunks: device array of n_chunks records {float* param; long long flat_off; int count;
+ * int pad;} (ctu_optim_chunk_bytes() each, count <= ctu_optim_chunk_elems()) mapping pieces of the parameter tensors to
+ * offsets of the flat gradient / state buffers.  kind: 0 Adam, 1 AdamW (state0 exp_avg, state1 exp_avg_sq, state2
+ * max_exp_avg_sq when amsgrad), 2 RMSprop (state0 square_avg, state1 momentum buffer), 3 SGD (state0 momentum buffer).
+ * lr (device double) and step (device counter of completed steps) are read, not written: ctu_optim_post advances the
+ * counter and, with use_plateau, applies torch's ReduceLROnPlateau.step(loss) to sched_state = double[10]
+ * { lr, best, num_bad_epochs, cooldown_counter, factor, patience, threshold, min_lr, cooldown, eps } -- lr = sched_state. */
+int ctu_optim_chunk_bytes(void);
+int ctu_optim_chunk_elems(void);
+int ctu_optim_step(int kind, const void* chunks, int n_chunks, const float* flat_grad, float* state0, float* state1,
+                   float* state2, const double* lr, const long long* step, double beta1, double beta2, double eps,
+                   double weight_decay, double momentum, double alpha, int amsgrad, double grad_scale, ctu_stream stream);
+int ctu_optim_post(long long* step, double* sched_state, const float* loss, int use_plateau, ctu_stream stream);
+
+/* ---- SaltAndPepper (transforms.py:13-49) on a uint8 volume: out = (img AND black) OR white with
+ *      black = (u_b > density*(1-salt_ratio)), white = 1 - (u_w > density*salt_ratio).  u_black / u_white: caller-supplied
+ *      float64 uniform fields (both or neither); NULL = Philox4x32-10 keyed by seed, counter = offset + voxel index. ------ */
+int ctu_salt_pepper_u8(const unsigned char* img, unsigned char* out, long long nvox, double noise_density, double salt_ratio,
+                       const double* u_black, const double* u_white, unsigned long long seed, unsigned long long offset,
+                       ctu_stream stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

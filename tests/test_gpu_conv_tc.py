@@ -28,6 +28,14 @@ CASES = [
     (3, 28, 112, False, (1, 2, 16, 16)),     # wgrad: output channels split over TMEM
     (5, 14, 28, True, (1, 3, 16, 16)),
     (5, 56, 56, True, (1, 3, 16, 16)),       # wgrad: partial last output-channel group (16,16,16,8); fprop: wide kernel
+    # the benchmarked grids (batch 4 x 128^3 runs these shapes per sample): d = 128 with dc = 32 chunks, 8 x 8 tiles of
+    # 16 x 16 per plane, persistent 296-CTA schedules
+    (3, 2, 7, False, (1, 128, 128, 128)),
+    (3, 7, 7, False, (2, 128, 128, 128)),
+    (3, 14, 14, False, (2, 64, 64, 64)),
+    (3, 7, 14, False, (1, 64, 64, 64)),
+    (5, 8, 8, True, (1, 48, 128, 128)),
+    (5, 1, 8, True, (1, 128, 128, 128)),
 ]
 
 # wide, low-resolution layers: the weight-streaming kernel (conv_wide.cu), M = 128 tiles at 16^3, M = 64 at 8^3

@@ -119,7 +119,7 @@ def test_train_step_fp32_matches_reference_golden(golden, name):
     # The synthetic inputs are binary, so the first conv layers produce many exactly-tied values inside
     # max-pool windows; a 1-ulp difference in accumulation order then elects a different arg-max and moves a
     # few gradient entries (measured: 3e-3 normwise on the two finest encoder levels, 1e-5 everywhere with
-    # continuous inputs -- scripts/diag_grad_error.py).  Hence 1e-2 here, not 1e-4.
+    # continuous inputs -- tests/test_gpu_fullsize.py checks the continuous case).  Hence 1e-2 here, not 1e-4.
     for k, v in g["grad_abs_sum"].items():
         if v < 1e-4:                    # conv biases ahead of BatchNorm: analytically zero, pure rounding noise
             assert float(named[k].grad.double().abs().sum()) < 1e-4, k
@@ -405,7 +405,8 @@ def test_data_parallel_graph_step_world1_matches_plain_step(tmp_path):
         torch.manual_seed(0)
         net = _build("UNetSP", "fp32").to(DEV).train()
         s_ref = TrainStep(ref, "double", 1.0, 1.0, lr=1e-3)
-        s_ddp = TrainStep(net, "double", 1.0, 1.0, lr=1e-3, grad_sync=GradSync(net, deferred=True), graph=True)
+        s_ddp = TrainStep(net, "double", 1.0, 1.0, lr=1e-3, grad_sync=GradSync(net, deferred=True), graph=True,
+                          split_graph=True)
         for it in range(4):
             x = _x(2, 16, 40 + it, 2).to(DEV)
             sk_t, fl_t = _targets(2, 16, 50 + it)
@@ -413,6 +414,5 @@ def test_data_parallel_graph_step_world1_matches_plain_step(tmp_path):
             b = s_ddp(x, (sk_t.to(DEV), fl_t.to(DEV))).tolist()
             assert a == pytest.approx(b, rel=2e-4, abs=2e-4), it
         assert s_ddp._graph is not None and s_ddp._graph_opt is not None
-        assert net.cblock.block[0].weight.grad is None
     finally:
         dist.destroy_process_group()

@@ -76,6 +76,10 @@ STAGES_TC = [
     (3, [28, 28], 14, False, (1, 3, 16, 32)),
     (3, [56, 56], 28, False, (1, 3, 16, 16)),      # 15 input blocks staged in groups, 32 output blocks over grid rows
     (5, [14, 14], 7, True, (1, 4, 16, 16)),
+    # the benchmarked grids (UNetSP at 128^3): level-0 stage on the 64^3 low-resolution grid (d-chunked persistent
+    # schedule, phase-sparse weight gradient over multi-tile planes) and the level-1 stage at 32^3, batch 2
+    (3, [14, 14], 7, False, (1, 64, 64, 64)),
+    (3, [28, 28], 14, False, (2, 32, 32, 32)),
 ]
 
 
