@@ -708,6 +708,7 @@ def run_b200_arm(a):
                           "note": "the reference's own Model.forward_pass (Model.py:324-380: host batch, torch.optim.Adam, "
                                   "ReduceLROnPlateau on the host, float() per loss component) with ctunet_b200.install() applied"}
                 del m
+                C.uninstall()
                 torch.cuda.empty_cache()
             except Exception as exc:            # secondary numbers must never take the bench line down
                 stock = stock or {}

@@ -13,6 +13,6 @@ from .losses import (dice_loss, dice_ce, ProblemHandler, FlapRec, FlapRecWithSha
 from .utilities import (hard_segm_from_tensor, shape_3d, blank_patch, random_blank_patch, encode_flaprec_batch,  # noqa: F401
                         SkullRandomHole, kth_nonzero, count_nonzero)
 from . import preprocess  # noqa: F401
-from .dropin import install, MODEL_CLASSES, HANDLER_CLASSES  # noqa: F401
+from .dropin import install, uninstall, MODEL_CLASSES, HANDLER_CLASSES  # noqa: F401
 
 __version__ = "0.1.0"

@@ -18,6 +18,27 @@ HANDLER_CLASSES = ["FlapRecWithShapePriorDoubleOut", "FlapRecDoubleOut"]
 
 
 UTILITY_FUNCTIONS = ["dice_loss", "dice_coeff", "hausdorff"]
+_MISSING = object()
+_SAVED = []          # (owner, attribute name, previous value in the owner's __dict__ or _MISSING), in rebinding order
+
+
+def _rebind(owner, name, value):
+    _SAVED.append((owner, name, vars(owner).get(name, _MISSING)))
+    setattr(owner, name, value)
+
+
+def uninstall() -> int:
+    """Undo every ``install()`` since the last ``uninstall()``: the reference's own classes, handlers and utility functions
+    are back.  Returns the number of restored names."""
+    n = len(_SAVED)
+    while _SAVED:
+        owner, name, old = _SAVED.pop()
+        if old is _MISSING:
+            if name in vars(owner):
+                delattr(owner, name)
+        else:
+            setattr(owner, name, old)
+    return n
 
 
 def install(trainer_module=None, replace_losses: bool = True, data_parallel: str = "keep"):
@@ -42,28 +63,28 @@ def install(trainer_module=None, replace_losses: bool = True, data_parallel: str
         raise ValueError("data_parallel: 'keep' or 'single'")
     done = []
     for name in MODEL_CLASSES:
-        setattr(trainer_module, name, getattr(models, name))
+        _rebind(trainer_module, name, getattr(models, name))
         done.append(name)
     if replace_losses:
         for name in HANDLER_CLASSES + ["ProblemHandler", "FlapRec", "FlapRecWithShapePrior"]:
             ref_cls = getattr(trainer_module, name, None)
             ours = getattr(losses, name)
             if ref_cls is None:
-                setattr(trainer_module, name, ours)
+                _rebind(trainer_module, name, ours)
             elif "comp_losses_metrics" in vars(ours):
-                ref_cls.comp_losses_metrics = staticmethod(vars(ours)["comp_losses_metrics"].__func__)
+                _rebind(ref_cls, "comp_losses_metrics", staticmethod(vars(ours)["comp_losses_metrics"].__func__))
             done.append(name + ".comp_losses_metrics")
         from . import utilities as ours_utils
         ref_utils = getattr(trainer_module, "utils", None)
         if ref_utils is not None:
             for name in UTILITY_FUNCTIONS:
-                setattr(ref_utils, name, getattr(ours_utils, name))
+                _rebind(ref_utils, name, getattr(ours_utils, name))
                 done.append("utils." + name)
     if data_parallel == "single" and hasattr(trainer_module, "Model"):
         def new_model(self):                                  # Model.py:474-491 without the nn.DataParallel wrapper
             model = eval(self.params["model_class"], vars(trainer_module))()
             model.to(self.params["device"])
             return model
-        trainer_module.Model.new_model = new_model
+        _rebind(trainer_module.Model, "new_model", new_model)
         done.append("Model.new_model")
     return done

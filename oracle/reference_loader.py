@@ -16,7 +16,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REFERENCE_ROOT = os.environ.get("CTUNET_REFERENCE_ROOT", "/root/reference")
-INSTALLED_ROOT = os.path.join(HERE, "_ref")
+INSTALLED_ROOT = os.environ.get("CTUNET_REFERENCE_INSTALL", os.path.join(HERE, "_ref"))
 STUBS = os.path.join(HERE, "ref_stubs")
 
 

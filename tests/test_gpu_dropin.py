@@ -13,29 +13,16 @@ DEV = "cuda"
 
 def _restore_after(fn):
     """install() rebinds names inside the live reference modules: undo it so other tests see the stock reference."""
-    from oracle.reference_loader import load_reference
-    MD, PH, UT, TR, MM = load_reference(with_trainer=True)
     import ctunet_b200
-    names = list(ctunet_b200.MODEL_CLASSES)
-    saved = {n: getattr(MM, n) for n in names}
-    handlers = ["ProblemHandler", "FlapRec", "FlapRecWithShapePrior", "FlapRecWithShapePriorDoubleOut", "FlapRecDoubleOut"]
-    saved_h = {c: getattr(PH, c).__dict__.get("comp_losses_metrics") for c in handlers}
-    saved_u = {n: getattr(UT, n) for n in ("dice_loss", "dice_coeff", "hausdorff")}
+    from oracle.reference_loader import load_reference
+    MM = load_reference(with_trainer=True)[4]
     anomaly = torch.is_anomaly_enabled()
     try:
         return fn(MM)
     finally:
+        ctunet_b200.uninstall()
         torch.autograd.set_detect_anomaly(anomaly)
         torch.set_grad_enabled(True)
-        for n, v in saved.items():
-            setattr(MM, n, v)
-        for c, v in saved_h.items():
-            if v is not None:
-                setattr(getattr(PH, c), "comp_losses_metrics", v)
-            elif "comp_losses_metrics" in getattr(PH, c).__dict__:
-                delattr(getattr(PH, c), "comp_losses_metrics")
-        for n, v in saved_u.items():
-            setattr(UT, n, v)
 
 
 @pytest.mark.skipif(not reference_available(), reason="reference not present (oracle/_ref is built by oracle/build_ref.py)")

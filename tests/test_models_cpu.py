@@ -102,6 +102,7 @@ def test_install_rebinds_reference_names():
     trainer.FlapRecWithShapePriorDoubleOut = RefDouble
     trainer.UNetSP = object
     done = C.install(trainer)
+    C.dropin._SAVED.clear()                # (a throw-away module: nothing to restore)
     assert eval("UNetSP", vars(trainer)) is C.UNetSP
     assert eval("recAE_v2_fixed", vars(trainer)) is C.recAE_v2_fixed
     assert "UNetSP" in done and "FlapRecWithShapePriorDoubleOut.comp_losses_metrics" in done
@@ -118,33 +119,44 @@ def test_install_into_real_reference_when_present():
     import ctunet_b200 as C
     load_reference()
     trainer = importlib.import_module("ctunet.pytorch.Model")
-    saved = {k: getattr(trainer, k) for k in C.MODEL_CLASSES}
+    ref_cls = trainer.UNetSP
     ph = trainer.FlapRecWithShapePriorDoubleOut.comp_losses_metrics
-    base = trainer.ProblemHandler.comp_losses_metrics
     try:
         C.install()
         assert type(eval("UNetSP", vars(trainer))()).__module__ == "ctunet_b200.models"
+        assert trainer.FlapRecWithShapePriorDoubleOut.comp_losses_metrics is not ph
     finally:
-        for k, v in saved.items():
-            setattr(trainer, k, v)
-        trainer.FlapRecWithShapePriorDoubleOut.comp_losses_metrics = staticmethod(ph)
-        trainer.ProblemHandler.comp_losses_metrics = staticmethod(base)
+        assert C.uninstall() > 0
         torch.autograd.set_detect_anomaly(False)
+    assert trainer.UNetSP is ref_cls and trainer.FlapRecWithShapePriorDoubleOut.comp_losses_metrics is ph
+    assert trainer.utils.dice_coeff.__module__ == "ctunet.utilities"
 
 
 def test_bench_reference_arm_prints_contract_line():
-    """`bench.py --impl reference` (the CPU port of the reference's path, the one place besides tests / smoke that may run
-    oracle/) needs no GPU and prints one JSON line with the keys the driver reads."""
+    """`bench.py --impl reference` (the reference's CPU path: the installed reference from oracle/_ref or /root/reference
+    when present, else the oracle port -- the one place besides tests / smoke that may run oracle/) needs no GPU and prints
+    one JSON line with the keys the driver reads; both variants are exercised."""
     import json
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--size", "32", "--steps", "1",
-                          "--warmup", "0"], capture_output=True, text=True, timeout=300, cwd=root)
-    assert out.returncode == 0, out.stderr[-2000:]
-    line = json.loads(out.stdout.strip().splitlines()[-1])
-    assert line["impl"] == "reference" and line["unit"] == "voxels/s" and line["value"] > 0
-    assert line["higher_is_better"] is True and line["gpu_launches"] == 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
-    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    from oracle.reference_loader import reference_available
+    kinds = []
+    for hide in (False, True):
+        env = dict(os.environ)
+        if hide:                 # point the loader at nothing: the port must take over
+            env["CTUNET_REFERENCE_ROOT"] = "/nonexistent"
+            env["CTUNET_REFERENCE_INSTALL"] = "/nonexistent"
+        out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--size", "32", "--steps",
+                              "1", "--warmup", "0"], capture_output=True, text=True, timeout=300, cwd=root, env=env)
+        assert out.returncode == 0, out.stderr[-2000:]
+        lines = out.stdout.strip().splitlines()
+        assert len(lines) == 1, lines                     # the reference's own prints must not reach stdout
+        line = json.loads(lines[-1])
+        assert line["impl"] == "reference" and line["unit"] == "voxels/s" and line["value"] > 0
+        assert line["higher_is_better"] is True and line["gpu_launches"] == 0
+        assert line["cpu_baseline"]["cores"] >= 1
+        assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+        kinds.append(line["cpu_baseline"]["kind"])
+    assert kinds[1] == "port" and kinds[0] == ("reference" if reference_available() else "port")

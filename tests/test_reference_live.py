@@ -94,25 +94,18 @@ def test_install_rebinds_the_names_the_reference_evals():
     import ctunet_b200
     from oracle.reference_loader import load_reference
     MD, PH, UT, TR, MM = load_reference(with_trainer=True)
-    saved = {n: getattr(MM, n) for n in ctunet_b200.MODEL_CLASSES}
-    saved_h = {c: PH.__dict__[c].__dict__.get("comp_losses_metrics") for c in
-               ("ProblemHandler", "FlapRecWithShapePriorDoubleOut")}
-    saved_u = {n: getattr(UT, n) for n in ("dice_loss", "dice_coeff", "hausdorff")}
+    ref_hard = UT.hard_segm_from_tensor
     try:
         done = ctunet_b200.install(MM)
         assert MM.UNetSP is ctunet_b200.UNetSP and eval("UNetSP", vars(MM)) is ctunet_b200.UNetSP
         assert "utils.dice_coeff" in done and MM.utils.dice_coeff is ctunet_b200.utilities.dice_coeff
         h = eval("FlapRecWithShapePriorDoubleOut", vars(MM))()
         assert h.comp_losses_metrics.__module__ == "ctunet_b200.losses"
-        assert MM.utils.hard_segm_from_tensor is UT.hard_segm_from_tensor        # deliberately NOT rebound
+        assert MM.utils.hard_segm_from_tensor is ref_hard                        # deliberately NOT rebound
     finally:
-        for n, v in saved.items():
-            setattr(MM, n, v)
-        for c, v in saved_h.items():
-            if v is not None:
-                setattr(getattr(PH, c), "comp_losses_metrics", v)
-        for n, v in saved_u.items():
-            setattr(UT, n, v)
+        ctunet_b200.uninstall()
+    assert MM.UNetSP is MD.UNetSP and UT.dice_coeff.__module__ == "ctunet.utilities"
+    assert eval("FlapRecWithShapePriorDoubleOut", vars(MM))().comp_losses_metrics.__module__ == "ctunet.pytorch.ProblemHandler"
 
 
 def test_stock_example_inis_parse_and_name_installed_classes():
