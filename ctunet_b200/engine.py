@@ -41,6 +41,8 @@ WEIGHT_PREP_ASYNC = True
 WGRAD_ASYNC = True
 # The discarded center block of the generic UNet runs on a third stream (Engine.off_critical_path).
 DEAD_BRANCH_ASYNC = True
+# The SP head's backward pass recovers the sigmoid values from the forward outputs instead of recomputing the logits.
+HEAD_FROM_OUTPUTS = True
 _SIDE = {}
 
 
@@ -614,8 +616,9 @@ class Engine:
 
                 # product mode: the SP head's backward pass reads the forward outputs instead of recomputing the
                 # sigmoids (fp32 check mode keeps the recomputation: s2 = (s1+s2) - s1 loses a few ulps)
-                o0 = out0.data_ptr() if self.dtype == CTU_BF16 else None
-                o1 = out1.data_ptr() if (out1 is not None and self.dtype == CTU_BF16) else None
+                from_out = HEAD_FROM_OUTPUTS and self.dtype == CTU_BF16
+                o0 = out0.data_ptr() if from_out else None
+                o1 = out1.data_ptr() if (out1 is not None and from_out) else None
 
                 def params():      # parameter gradients: a leaf, beside the weight gradients (second stream)
                     call("ctu_head_bwd", self.dtype, pa, ca, ns, weight.data_ptr(), bias.data_ptr(), cout, flags, p0, p1,

@@ -40,6 +40,7 @@ def test_reference_forward_pass_with_dropin_installed(example):
         assert params["save_dice_plots"] is True
         params.setdefault("save_hd_plots", False)             # quirk 7: the key is read unconditionally
         params["learning_rate"] = 1e-3
+        params["resume_model"] = ""                           # (the stock files point at the author's private checkpoints)
         name = params["model_class"]
         cfg = O.PRESETS[name]
         double = cfg.head != "plain"
@@ -72,7 +73,8 @@ def test_reference_forward_pass_with_dropin_installed(example):
     net = net.module if isinstance(net, torch.nn.DataParallel) else net
     first_bn = "d_blocks.0.block.1" if cfg.family == "generic" else "dblock1.1"
     assert int(net.state_dict()[first_bn + ".num_batches_tracked"]) == 6    # 3 steps x 2 (eval adds none)
-    assert type(m.params["scheduler"]).__name__ == "ReduceLROnPlateau"
+    if "scheduler" in m.params:                                             # Model.py:544-546: created iff the key exists
+        assert type(m.params["scheduler"]).__name__ == "ReduceLROnPlateau"
     # the reference's own class loads what the drop-in trained (bare state_dict, Model.py:282)
     from oracle.reference_loader import load_reference
     ref_cls = getattr(load_reference()[0], m.params["model_class"])
@@ -106,7 +108,9 @@ def test_data_parallel_replica_trains():
     assert any(v is not None for v in via_replica.values())
     for n, g in plain.items():
         if g is None:
-            assert via_replica[n] is None, n
+            # Broadcast's backward hands an unused input zeros rather than None (so does the reference under DataParallel:
+            # the dead center block then sees an all-zero gradient and Adam leaves it where it is)
+            assert via_replica[n] is None or not bool(via_replica[n].any()), n
         else:
             assert via_replica[n] is not None, n
             assert torch.allclose(via_replica[n], g, rtol=1e-4, atol=1e-6 + 1e-4 * float(g.abs().max())), n

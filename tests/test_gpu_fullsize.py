@@ -3,7 +3,7 @@ bench's own synthetic skull phantom against the CPU oracle on the SAME tensors, 
 take (un-folded training BatchNorm finalisation, d-chunked persistent convolution schedules, three fused up levels).
 
 Tolerances (north_star): bf16 outputs within 2e-2 relative of the fp32 reference, every loss component (Dice, CE) within
-5e-3 absolute.  Gradients: see test_bf16_gradients_track_the_bf16_storage_oracle_on_continuous_inputs.
+5e-3 absolute.  Gradients: see test_bf16_gradients_sit_on_the_noise_floor_of_the_format.
 """
 import types
 
@@ -81,13 +81,22 @@ def test_bf16_train_step_at_benchmark_sizes_matches_oracle(name, batch, size):
     named = dict(net.named_parameters())
     assert [k for k in pn if sd[k].grad is None] == [k for k in pn if named[k].grad is None]
     got = net.state_dict()
+    worst_mean = 0.0
     for k, v in sd.items():
         if k.endswith("num_batches_tracked"):
             assert int(got[k]) == int(v), k
         elif k.endswith("running_mean"):
-            assert torch.allclose(got[k].cpu(), v, rtol=2e-2, atol=2e-3 * float(v.abs().max()) + 1e-6), k
+            # the batch mean within 1 % of the channel's batch standard deviation (bf16 storage of the convolution output);
+            # running_var = 0.9^u + (1 - 0.9^u) * unbiased batch variance after u updates
+            u = int(sd[k.replace("running_mean", "num_batches_tracked")])
+            w_old = 0.9 ** u
+            std = ((sd[k.replace("running_mean", "running_var")] - w_old) / (1 - w_old)).clamp_min(0).sqrt()
+            err = ((got[k].cpu() - v).abs() / ((1 - w_old) * std.clamp_min(1e-6))).max().item()
+            worst_mean = max(worst_mean, err)
+            assert err < 1e-2, (k, err)
         elif k.endswith("running_var"):
             assert torch.allclose(got[k].cpu(), v, rtol=3e-2, atol=1e-5), k
+    print("%s %dx%d^3: worst batch-mean error = %.4f of the channel's batch std" % (name, batch, size, worst_mean))
     # whole-gradient direction against the fp32 reference (per-tensor accuracy is the subject of the next test)
     dot = nr = ng = 0.0
     for k in pn:
@@ -98,40 +107,81 @@ def test_bf16_train_step_at_benchmark_sizes_matches_oracle(name, batch, size):
     assert dot / (nr * ng) ** 0.5 > 0.95
 
 
+def _oracle_grads(name, x, target, dtype=torch.float32, **emulate):
+    from oracle import unet_oracle as O
+    cfg = O.PRESETS[name]
+    sd = O.build_state_dict(cfg, seed=0)
+    sd = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items()}
+    pn = [k for k in sd if not k.endswith(("running_mean", "running_var", "num_batches_tracked"))]
+    for k in pn:
+        sd[k].requires_grad_()
+    out = O.unet_forward(sd, x.to(dtype), cfg, training=True, **emulate)
+    loss, comps = O.loss_double_output(out, tuple(t.to(dtype) for t in target), 1.0, 1.0)
+    loss.backward()
+    return {k: sd[k].grad for k in pn}, comps
+
+
 @pytest.mark.parametrize("name,batch,size", [("UNetSP", 2, 64), ("UNetSP", 1, 128)])
-def test_bf16_gradients_track_the_bf16_storage_oracle_on_continuous_inputs(name, batch, size):
-    """Per-tensor gradient accuracy of the bf16 product path.  The reference arithmetic is fp32; rounding every stored
-    activation to bf16 moves the gradients of this randomly initialised BatchNorm network by tens of percent all by
-    itself (shown below on the CPU oracle alone).  The meaningful check of the KERNELS is therefore the oracle evaluated
-    with the same storage points (``act_round=bf16``) on continuous, tie-free inputs: what remains is accumulation order
-    and the occasional one-ulp flip of a stored bf16 value."""
+def test_bf16_gradients_sit_on_the_noise_floor_of_the_format(name, batch, size):
+    """Per-tensor gradient accuracy of the bf16 product path at the benchmarked volume size, on continuous (tie-free) inputs.
+
+    The reference arithmetic is fp32.  For this randomly initialised BatchNorm network the weight gradients of the deep
+    layers are heavily cancelling sums over millions of voxels, so ANY bf16 evaluation is tens of percent away from fp32
+    per tensor and two equally valid bf16 evaluations are tens of percent away from EACH OTHER (profiles/r2_grad_parity_*.txt:
+    the CPU oracle against itself).  The check of the kernels is therefore made against the faithful CPU statement of the
+    product's arithmetic -- bf16 storage of activations and of their gradients, bf16 images of the convolution weights,
+    fp32 everything else -- and the bound per tensor is the distance between two such statements:
+
+        err(product, oracle_bf16gw)  <=  1.75 * max(err(oracle_bf16gw, oracle_bf16g), err(oracle_bf16g', oracle_bf16g)) + 0.01
+                                          + err(oracle_fp32, oracle_fp64)
+
+    (bf16g' = the input perturbed by 3e-7 relative, i.e. one or two fp32 ulps; bf16gw = weights rounded as well.)  The last
+    term is the reference's OWN accumulation error: torch's CPU convolution sums the 1x1x1 head's bias gradient over 2 M
+    voxels in fp32 and is 0.57 % off its fp64 value at 128^3 -- the product (block-wise fp32 partials) is not."""
     from oracle import unet_oracle as O
     cfg = O.PRESETS[name]
     g = torch.Generator().manual_seed(99)
-    x = torch.rand(batch, cfg.input_channels, size, size, size, generator=g)          # continuous: no max-pool ties
-    _, (sk_t, fl_t) = O.make_training_batch(batch, cfg.input_channels, size, seed=77)
-    sd32, pn, _, _ = _oracle_step(name, x, (sk_t, fl_t))
-    sd16, _, _, comps = _oracle_step(name, x, (sk_t, fl_t), act_round=torch.bfloat16)
-    net, out, fake = _product_step(name, x, (sk_t, fl_t))
+    x = torch.rand(batch, cfg.input_channels, size, size, size, generator=g)
+    xp = x * (1 + 3e-7 * torch.randn(x.shape, generator=g))
+    _, target = O.make_training_batch(batch, cfg.input_channels, size, seed=77)
+    bf = torch.bfloat16
+    g16, comps = _oracle_grads(name, x, target, act_round=bf, grad_round=True)
+    g16p, _ = _oracle_grads(name, xp, target, act_round=bf, grad_round=True)
+    g16w, comps_w = _oracle_grads(name, x, target, act_round=bf, grad_round=True, weight_round=True)
+    g32, _ = _oracle_grads(name, x, target)
+    g64, _ = _oracle_grads(name, x, target, dtype=torch.float64)
+    net, out, fake = _product_step(name, x, target)
     named = dict(net.named_parameters())
-    for k, v in comps.items():
-        assert abs(fake.losses_and_metrics[k][0] - float(v)) < 2e-3, k
-    worst, worst_k, storage_effect = 0.0, None, 0.0
-    for k in pn:
-        if sd16[k].grad is None:
+    for k, v in comps_w.items():
+        assert abs(fake.losses_and_metrics[k][0] - float(v)) < 1e-3, k
+    rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+    worst_ratio, rows = 0.0, []
+    num = den = 0.0
+    for k, ref in g16w.items():
+        if ref is None:
             assert named[k].grad is None, k
             continue
-        gr = sd16[k].grad.double()
-        if float(gr.norm()) < 1e-6:          # conv biases ahead of BatchNorm: analytically zero
+        if float(ref.norm()) < 1e-6:         # conv biases ahead of BatchNorm: analytically zero
             continue
-        rel = float((named[k].grad.cpu().double() - gr).norm() / gr.norm())
-        if rel > worst:
-            worst, worst_k = rel, k
-        storage_effect = max(storage_effect, float((gr - sd32[k].grad.double()).norm() / sd32[k].grad.double().norm()))
-    print("worst per-tensor gradient error vs bf16-storage oracle: %.4f (%s); bf16 storage alone moves a tensor by up to %.3f"
-          % (worst, worst_k, storage_effect))
-    assert worst < 0.08, (worst, worst_k)
-    assert worst < storage_effect or storage_effect < 0.08      # the kernels add less than the storage format itself
+        got = named[k].grad.cpu()
+        err = rel(got, ref)
+        floor = max(rel(g16w[k], g16[k]), rel(g16p[k], g16[k]))
+        ref_acc = rel(g32[k], g64[k])
+        bound = 1.75 * floor + 0.01 + ref_acc
+        rows.append((k, err, floor, ref_acc))
+        worst_ratio = max(worst_ratio, err / bound)
+        assert err <= bound, "%s: error %.4f vs the bf16 oracle, noise floor %.4f, reference accumulation error %.4f" % (
+            k, err, floor, ref_acc)
+        num += float((got.double() - ref.double()).norm() ** 2)
+        den += float(ref.double().norm() ** 2)
+    whole = (num / den) ** 0.5
+    print("%s %dx%d^3: whole-gradient error vs the bf16 oracle %.4f; worst tensor at %.2f of its bound" % (name, batch, size, whole,
+                                                                                                  worst_ratio))
+    assert whole < 0.03
+    # the tensors that carry the gradient norm (the last blocks, the head) are tight in absolute terms
+    for k, err, floor, ref_acc in rows:
+        if k.startswith(("last_conv", "u_blocks.3.block.5", "d_blocks.0.block.4")):
+            assert err < 0.01 + ref_acc, (k, err)
 
 
 def test_unfolded_training_batchnorm_matches_torch():

@@ -102,6 +102,8 @@ def _run_stage(mode, case, force):
     xr = [x.clone().requires_grad_() for x in xs]
     t = ct(torch.cat(xr, 1))
     yr = cv(t)
+    if mode == "bf16":
+        yr.register_hook(_bf)      # the product stores dy (the BatchNorm backward's output) in bf16: so does the reference
     ar = F.relu(F.batch_norm(yr, None, None, bn.weight, bn.bias, True, 0.1, 1e-5))
     ar.backward(dA)
     ref_grads = {"ct.w": ct.weight.grad.clone(), "ct.b": ct.bias.grad.clone(), "cv.w": cv.weight.grad.clone(),
@@ -163,4 +165,5 @@ def test_fused_up_stage_bf16_tensor_path(case):
         rel = ((gg[name] - rg[name]).norm() / rg[name].norm()).item()
         # the transposed convolution's bias gradient is a sum of BatchNorm-centred (zero-mean) gradients over every
         # voxel: a small signal under bf16 storage of dy, checked at fp32 accuracy in the check-mode test above
+        print("%s: |ref| %.3e  normwise err %.3e" % (name, rg[name].norm().item(), rel))
         assert rel <= (1.5e-1 if name == "ct.b" else 5e-2), "%s normwise err %.3e" % (name, rel)
