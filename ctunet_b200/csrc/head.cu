@@ -5,7 +5,7 @@
 //   UNetSPSmall    : ... -> softmax(skull), softmax(flap)              models.py:364-365
 //   legacy         : softmax(lc)                                       models.py:535-538
 // Backward recomputes lc from the sources (they are needed for dW anyway) and chains back.
-#include "common.cuh"
+#include "loss_math.cuh"
 
 namespace ctu {
 
@@ -31,6 +31,12 @@ struct HeadParams {
     float* db;
     int n;
     long long spatial;
+    // fused head + loss (ctu_head_loss_fwd / ctu_head_loss_bwd): one-hot float targets and the per-sample loss sums
+    const float* tgt0;
+    const float* tgt1;
+    double* lsums;        // [pairs][n][4]: sum q*t, sum q*q, sum t*t, CE sum
+    int softmax_for_dice, want_ce;
+    float g_ce, g_dice;
 };
 
 // wsm[o][cbt*8]: weight of output o for (blocked, padded) input lane; pad lanes 0.
@@ -56,7 +62,11 @@ template <int CO> struct HeadVals {
     float o0[2], o1[2];   // SP outputs (after optional pair softmax)
 };
 
-template <int CO>
+// FAST (the fused head + loss kernels only): approximate exponential / reciprocal (abs. error ~1e-7 on the outputs)
+template <bool FAST> __device__ __forceinline__ float head_exp(float x) { return FAST ? __expf(x) : expf(x); }
+template <bool FAST> __device__ __forceinline__ float head_div(float a, float b) { return FAST ? __fdividef(a, b) : a / b; }
+
+template <int CO, bool FAST = false>
 __device__ __forceinline__ void head_forward_chain(HeadVals<CO>& h, int flags) {
     if (flags & CTU_HEAD_SOFTMAX) {
         float mx = h.lc[0];
@@ -65,17 +75,18 @@ __device__ __forceinline__ void head_forward_chain(HeadVals<CO>& h, int flags) {
         float sum = 0.f;
 #pragma unroll
         for (int o = 0; o < CO; ++o) {
-            h.sm[o] = expf(h.lc[o] - mx);
+            h.sm[o] = head_exp<FAST>(h.lc[o] - mx);
             sum += h.sm[o];
         }
 #pragma unroll
-        for (int o = 0; o < CO; ++o) h.sm[o] /= sum;
+        for (int o = 0; o < CO; ++o) h.sm[o] = head_div<FAST>(h.sm[o], sum);
     } else {
 #pragma unroll
         for (int o = 0; o < CO; ++o) h.sm[o] = h.lc[o];
     }
 #pragma unroll
-    for (int o = 0; o < CO; ++o) h.sg[o] = (flags & CTU_HEAD_SIGMOID) ? 1.f / (1.f + expf(-h.sm[o])) : h.sm[o];
+    for (int o = 0; o < CO; ++o)
+        h.sg[o] = (flags & CTU_HEAD_SIGMOID) ? head_div<FAST>(1.f, 1.f + head_exp<FAST>(-h.sm[o])) : h.sm[o];
     if (CO == 3 && (flags & (CTU_HEAD_SP | CTU_HEAD_SP_SOFTMAX))) {
         h.o0[0] = h.sg[0];
         h.o0[1] = h.sg[1] + h.sg[CO - 1];
@@ -83,14 +94,14 @@ __device__ __forceinline__ void head_forward_chain(HeadVals<CO>& h, int flags) {
         h.o1[1] = h.sg[1];
         if (flags & CTU_HEAD_SP_SOFTMAX) {
             float m0 = fmaxf(h.o0[0], h.o0[1]);
-            float e0 = expf(h.o0[0] - m0), e1 = expf(h.o0[1] - m0);
-            h.o0[0] = e0 / (e0 + e1);
-            h.o0[1] = e1 / (e0 + e1);
+            float e0 = head_exp<FAST>(h.o0[0] - m0), e1 = head_exp<FAST>(h.o0[1] - m0);
+            h.o0[0] = head_div<FAST>(e0, e0 + e1);
+            h.o0[1] = head_div<FAST>(e1, e0 + e1);
             float m1 = fmaxf(h.o1[0], h.o1[1]);
-            e0 = expf(h.o1[0] - m1);
-            e1 = expf(h.o1[1] - m1);
-            h.o1[0] = e0 / (e0 + e1);
-            h.o1[1] = e1 / (e0 + e1);
+            e0 = head_exp<FAST>(h.o1[0] - m1);
+            e1 = head_exp<FAST>(h.o1[1] - m1);
+            h.o1[0] = head_div<FAST>(e0, e0 + e1);
+            h.o1[1] = head_div<FAST>(e1, e0 + e1);
         }
     }
 }
@@ -432,6 +443,389 @@ static int head_bwd_launch(const HeadParams& p, int part, cudaStream_t stream) {
     return head_bwd_launch_part<T, CO, 0>(p, stream);
 }
 
+
+// ------------------------------------------------------------------------------------------------ fused head + loss
+// The training step never needs the network outputs themselves -- only the loss sums and, in the backward pass, the
+// gradient with respect to the head's inputs.  The fused kernels recompute the head (14 multiply-adds per output) from
+// the blocked sources and feed the loss arithmetic of loss_math.cuh in registers: the two fp32 [B,2,D,H,W] outputs and
+// their gradients (64 B per voxel, written once and read twice each) never touch HBM.
+//   forward : reads 16 B per source block + the one-hot targets, accumulates the per-sample sums (grid.y = sample)
+//   backward: the same reads, writes the source gradients (PART 1) / reduces the parameter gradients (PART 2)
+// PAIRS = 2: the SP heads (outputs skull = o0, flap = o1, two classes each; ProblemHandler.py:228-298);
+// PAIRS = 1: the plain head with CO classes against one target (ProblemHandler.py:59-91).
+template <typename T, int CO, int CBT, int PAIRS>
+__global__ void __launch_bounds__(kHeadThreads, 2) head_loss_fwd_kernel(HeadParams p) {
+    extern __shared__ float hsm[];
+    float* wsm = hsm;
+    float* bsm = hsm + CO * CBT * 8;
+    load_head_weights<CO>(p, wsm, bsm);
+    __syncthreads();
+    constexpr int C = PAIRS == 2 ? 2 : CO;
+    const int n = blockIdx.y;
+    float acc[PAIRS][4];
+#pragma unroll
+    for (int q = 0; q < PAIRS; ++q)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[q][i] = 0.f;
+    const float* t0 = p.tgt0 + (long long)n * C * p.spatial;
+    const float* t1 = PAIRS == 2 ? p.tgt1 + (long long)n * C * p.spatial : nullptr;
+    auto voxel = [&](const V8 (&xs)[CBT], const float (&ta)[C], const float (&tb)[C]) {
+        HeadVals<CO> h;
+        head_logits_of<CO, CBT>(wsm, bsm, h, xs);
+        head_forward_chain<CO, true>(h, p.flags);
+        if (PAIRS == 2) {
+            loss_voxel_fwd2(h.o0[0], h.o0[1], ta[0], ta[C - 1], p.softmax_for_dice, p.want_ce, acc[0]);
+            loss_voxel_fwd2(h.o1[0], h.o1[1], tb[0], tb[C - 1], p.softmax_for_dice, p.want_ce, acc[PAIRS - 1]);
+        } else if (C == 2) {
+            loss_voxel_fwd2(h.sg[0], h.sg[CO - 1], ta[0], ta[C - 1], p.softmax_for_dice, p.want_ce, acc[0]);
+        } else {
+            float x[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) x[c] = h.sg[c < CO ? c : 0];
+            loss_voxel_fwd<C>(x, ta, p.softmax_for_dice, p.want_ce, acc[0]);
+        }
+    };
+    if ((p.spatial & 1) == 0) {
+        // two x-adjacent voxels per thread and iteration: 2 x CBT 16-byte source loads + 8-byte target loads in flight
+        const long long groups = p.spatial >> 1;
+        for (long long gi = (long long)blockIdx.x * kHeadThreads + threadIdx.x; gi < groups; gi += (long long)gridDim.x * kHeadThreads) {
+            const long long s = gi << 1;
+            V8 xs[2][CBT];
+#pragma unroll
+            for (int v = 0; v < 2; ++v) head_load<T, CBT>(p, n, s + v, xs[v]);
+            float ta[C][2], tb[C][2];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const float2 a = __ldg(reinterpret_cast<const float2*>(t0 + c * p.spatial + s));
+                ta[c][0] = a.x; ta[c][1] = a.y;
+                if (PAIRS == 2) {
+                    const float2 b = __ldg(reinterpret_cast<const float2*>(t1 + c * p.spatial + s));
+                    tb[c][0] = b.x; tb[c][1] = b.y;
+                } else {
+                    tb[c][0] = tb[c][1] = 0.f;
+                }
+            }
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+                float ua[C], ub[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) ua[c] = ta[c][v], ub[c] = tb[c][v];
+                voxel(xs[v], ua, ub);
+            }
+        }
+    } else {
+        for (long long s = (long long)blockIdx.x * kHeadThreads + threadIdx.x; s < p.spatial; s += (long long)gridDim.x * kHeadThreads) {
+            V8 xs[CBT];
+            head_load<T, CBT>(p, n, s, xs);
+            float ua[C], ub[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                ua[c] = __ldg(t0 + c * p.spatial + s);
+                ub[c] = PAIRS == 2 ? __ldg(t1 + c * p.spatial + s) : 0.f;
+            }
+            voxel(xs, ua, ub);
+        }
+    }
+    __shared__ float red[kHeadThreads / 32][PAIRS * 4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < PAIRS; ++q)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float v = warp_sum(acc[q][i]);
+            if (lane == 0) red[warp][q * 4 + i] = v;
+        }
+    __syncthreads();
+    if (threadIdx.x < PAIRS * 4) {
+        double v = 0.0;
+        for (int wq = 0; wq < kHeadThreads / 32; ++wq) v += (double)red[wq][threadIdx.x];
+        const int q = threadIdx.x >> 2, i = threadIdx.x & 3;
+        atomicAdd(p.lsums + ((long long)q * p.n + n) * 4 + i, v);
+    }
+}
+
+// comps = [ce_lambda * CE per pair] + [dice_lambda * Dice per pair] + [total], the order of ProblemHandler.py:241-298
+__global__ void head_loss_finalize_kernel(const double* __restrict__ sums, int pairs, int nb, long long spatial, float ce_lambda,
+                                          float dice_lambda, float* __restrict__ comps, float* __restrict__ mirror) {
+    const double eps = 0.0000001;
+    float ce[2], dice[2];
+    for (int q = 0; q < pairs; ++q) {
+        double dsum = 0.0, c = 0.0;
+        for (int i = 0; i < nb; ++i) {
+            const double* s4 = sums + ((long long)q * nb + i) * 4;
+            dsum += (s4[0] + eps) / (s4[1] + s4[2] + eps);
+            c += s4[3];
+        }
+        ce[q] = (float)(c / ((double)nb * (double)spatial));
+        dice[q] = (float)(1.0 - 2.0 * dsum / (double)nb);
+    }
+    int k = 0;
+    float total = 0.f;
+    if (ce_lambda != 0.f)
+        for (int q = 0; q < pairs; ++q, ++k) {
+            comps[k] = ce_lambda * ce[q];
+            total = k == 0 ? comps[k] : total + comps[k];
+        }
+    if (dice_lambda != 0.f)
+        for (int q = 0; q < pairs; ++q, ++k) {
+            comps[k] = dice_lambda * dice[q];
+            total = k == 0 ? comps[k] : total + comps[k];
+        }
+    comps[k] = total;
+    if (mirror)
+        for (int i = 0; i <= k; ++i) mirror[i] = comps[i];
+}
+
+// Source gradients; the logit gradients dlc [n][CO][spatial] (fp32 planes) are stored for head_param_grad_kernel, so the
+// parameter-gradient launch (a leaf of the backward pass, second stream) is pure multiply-add streaming.
+template <typename T, int CO, int CBT, int PAIRS>
+__global__ void __launch_bounds__(kHeadThreads, 2) head_loss_bwd_kernel(HeadParams p) {
+    extern __shared__ float hsm[];
+    float* wsm = hsm;
+    float* bsm = hsm + CO * CBT * 8;
+    load_head_weights<CO>(p, wsm, bsm);
+    __syncthreads();
+    constexpr int C = PAIRS == 2 ? 2 : CO;
+    const int n = blockIdx.y;
+    float kt[PAIRS], kq[PAIRS];
+#pragma unroll
+    for (int q = 0; q < PAIRS; ++q) dice_coefficients(p.lsums + ((long long)q * p.n + n) * 4, p.n, p.g_dice, kt[q], kq[q]);
+    const float kce = p.want_ce ? p.g_ce / ((float)p.n * (float)p.spatial) : 0.f;
+    const float* t0 = p.tgt0 + (long long)n * C * p.spatial;
+    const float* t1 = PAIRS == 2 ? p.tgt1 + (long long)n * C * p.spatial : nullptr;
+    float* dlc_out = p.out0 + (long long)n * CO * p.spatial;       // (out0 doubles as the dlc buffer in this kernel)
+    auto voxel = [&](const V8 (&xs)[CBT], const float (&ta)[C], const float (&tb)[C], long long s, float (&dlc)[CO]) {
+        HeadVals<CO> h;
+        head_logits_of<CO, CBT>(wsm, bsm, h, xs);
+        head_forward_chain<CO, true>(h, p.flags);
+        float dsg[CO];
+        if (PAIRS == 2) {
+            float g00, g01, g10, g11;
+            loss_voxel_bwd2(h.o0[0], h.o0[1], ta[0], ta[C - 1], p.softmax_for_dice, p.want_ce, kt[0], kq[0], kce, g00, g01);
+            loss_voxel_bwd2(h.o1[0], h.o1[1], tb[0], tb[C - 1], p.softmax_for_dice, p.want_ce, kt[PAIRS - 1], kq[PAIRS - 1], kce,
+                            g10, g11);
+            if (p.flags & CTU_HEAD_SP_SOFTMAX) {
+                float d0 = g00 * h.o0[0] + g01 * h.o0[1];
+                g00 = h.o0[0] * (g00 - d0);
+                g01 = h.o0[1] * (g01 - d0);
+                float d1 = g10 * h.o1[0] + g11 * h.o1[1];
+                g10 = h.o1[0] * (g10 - d1);
+                g11 = h.o1[1] * (g11 - d1);
+            }
+            dsg[0] = g00;
+            dsg[CO > 1 ? 1 : 0] = g01 - g10 + g11;
+            dsg[CO - 1] = g01;
+        } else if (C == 2) {
+            loss_voxel_bwd2(h.sg[0], h.sg[CO - 1], ta[0], ta[C - 1], p.softmax_for_dice, p.want_ce, kt[0], kq[0], kce, dsg[0],
+                            dsg[CO - 1]);
+        } else {
+            float x[C], gx[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) x[c] = h.sg[c < CO ? c : 0];
+            loss_voxel_bwd<C>(x, ta, p.softmax_for_dice, p.want_ce, kt[0], kq[0], kce, gx);
+#pragma unroll
+            for (int o = 0; o < CO; ++o) dsg[o] = gx[o < C ? o : 0];
+        }
+        float dsm[CO];
+#pragma unroll
+        for (int o = 0; o < CO; ++o) dsm[o] = (p.flags & CTU_HEAD_SIGMOID) ? dsg[o] * h.sg[o] * (1.f - h.sg[o]) : dsg[o];
+        if (p.flags & CTU_HEAD_SOFTMAX) {
+            float dot = 0.f;
+#pragma unroll
+            for (int o = 0; o < CO; ++o) dot += dsm[o] * h.sm[o];
+#pragma unroll
+            for (int o = 0; o < CO; ++o) dlc[o] = h.sm[o] * (dsm[o] - dot);
+        } else {
+#pragma unroll
+            for (int o = 0; o < CO; ++o) dlc[o] = dsm[o];
+        }
+#pragma unroll
+        for (int c = 0; c < CBT; ++c) {
+            const int q = head_block_source(p, c);
+            const int b = c - p.m.cboff[q];
+            T* dp = reinterpret_cast<T*>(p.dsrc[q]);
+            V8 g;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float a = 0.f;
+#pragma unroll
+                for (int o = 0; o < CO; ++o) a = fmaf(dlc[o], wsm[o * CBT * 8 + c * 8 + j], a);
+                g.v[j] = a;
+            }
+            if (dp != nullptr) Vec8<T>::store(dp + (((long long)n * p.src_cb[q] + b) * p.spatial + s) * 8, g);
+        }
+    };
+    if ((p.spatial & 1) == 0) {
+        const long long groups = p.spatial >> 1;
+        for (long long gi = (long long)blockIdx.x * kHeadThreads + threadIdx.x; gi < groups; gi += (long long)gridDim.x * kHeadThreads) {
+            const long long s = gi << 1;
+            V8 xs[2][CBT];
+#pragma unroll
+            for (int v = 0; v < 2; ++v) head_load<T, CBT>(p, n, s + v, xs[v]);
+            float ta[C][2], tb[C][2];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const float2 a = __ldg(reinterpret_cast<const float2*>(t0 + c * p.spatial + s));
+                ta[c][0] = a.x; ta[c][1] = a.y;
+                if (PAIRS == 2) {
+                    const float2 b = __ldg(reinterpret_cast<const float2*>(t1 + c * p.spatial + s));
+                    tb[c][0] = b.x; tb[c][1] = b.y;
+                } else {
+                    tb[c][0] = tb[c][1] = 0.f;
+                }
+            }
+            float dl[2][CO];
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+                float ua[C], ub[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) ua[c] = ta[c][v], ub[c] = tb[c][v];
+                voxel(xs[v], ua, ub, s + v, dl[v]);
+            }
+#pragma unroll
+            for (int o = 0; o < CO; ++o)
+                *reinterpret_cast<float2*>(dlc_out + o * p.spatial + s) = make_float2(dl[0][o], dl[1][o]);
+        }
+    } else {
+        for (long long s = (long long)blockIdx.x * kHeadThreads + threadIdx.x; s < p.spatial; s += (long long)gridDim.x * kHeadThreads) {
+            V8 xs[CBT];
+            head_load<T, CBT>(p, n, s, xs);
+            float ua[C], ub[C], dl[CO];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                ua[c] = __ldg(t0 + c * p.spatial + s);
+                ub[c] = PAIRS == 2 ? __ldg(t1 + c * p.spatial + s) : 0.f;
+            }
+            voxel(xs, ua, ub, s, dl);
+#pragma unroll
+            for (int o = 0; o < CO; ++o) dlc_out[o * p.spatial + s] = dl[o];
+        }
+    }
+}
+
+// dW[o][c] = sum_voxels dlc[o] * x[c], db[o] = sum_voxels dlc[o] from the stored logit gradients
+template <typename T, int CO, int CBT>
+__global__ void __launch_bounds__(kHeadThreads) head_param_grad_kernel(HeadParams p) {
+    extern __shared__ float hsm[];
+    float* red = hsm;                               // [8 warps][CO*CBT*8 + CO]
+    float gw[CO][CBT * 8], gb[CO];
+#pragma unroll
+    for (int o = 0; o < CO; ++o) {
+        gb[o] = 0.f;
+#pragma unroll
+        for (int l = 0; l < CBT * 8; ++l) gw[o][l] = 0.f;
+    }
+    const long long total = (long long)p.n * p.spatial;
+    for (long long i = (long long)blockIdx.x * kHeadThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kHeadThreads) {
+        const int n = (int)(i / p.spatial);
+        const long long s = i - (long long)n * p.spatial;
+        V8 xs[CBT];
+        head_load<T, CBT>(p, n, s, xs);
+        float dlc[CO];
+#pragma unroll
+        for (int o = 0; o < CO; ++o) dlc[o] = __ldg(p.dout0 + ((long long)n * CO + o) * p.spatial + s);
+#pragma unroll
+        for (int o = 0; o < CO; ++o) {
+            gb[o] += dlc[o];
+#pragma unroll
+            for (int c = 0; c < CBT; ++c)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) gw[o][c * 8 + j] = fmaf(dlc[o], xs[c].v[j], gw[o][c * 8 + j]);
+        }
+    }
+    constexpr int NV = CO * CBT * 8 + CO;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 0; o < CO; ++o) {
+#pragma unroll
+        for (int l = 0; l < CBT * 8; ++l) {
+            float v = warp_sum(gw[o][l]);
+            if (lane == 0) red[warp * NV + o * CBT * 8 + l] = v;
+        }
+        float v = warp_sum(gb[o]);
+        if (lane == 0) red[warp * NV + CO * CBT * 8 + o] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NV; i += kHeadThreads) {
+        float v = 0.f;
+        for (int wq = 0; wq < kHeadThreads / 32; ++wq) v += red[wq * NV + i];
+        if (i < CO * CBT * 8) {
+            const int o = i / (CBT * 8), l = i % (CBT * 8);
+            const int cib = l >> 3, ci = l & 7;
+            int sq = 0;
+            for (int q = 1; q < CTU_MAX_SRC; ++q)
+                if (q < p.m.nsrc && cib >= p.m.cboff[q]) sq = q;
+            const int cl = (cib - p.m.cboff[sq]) * 8 + ci;
+            if (cl < p.m.ch[sq]) atomicAdd(p.dw + (long long)o * p.m.c_total + p.m.choff[sq] + cl, v);
+        } else {
+            atomicAdd(p.db + (i - CO * CBT * 8), v);
+        }
+    }
+}
+
+template <typename T, int CO, int PAIRS>
+static int head_loss_fwd_launch(const HeadParams& p, cudaStream_t stream) {
+    const size_t smem = (size_t)(CO * p.m.cb_total * 8 + 8) * sizeof(float);
+    const long long per = ((p.spatial & 1) == 0 ? p.spatial >> 1 : p.spatial);
+    long long gx = (per + kHeadThreads - 1) / kHeadThreads;
+    const long long cap = (148 * 16 + p.n - 1) / p.n;
+    if (gx > cap) gx = cap;
+    dim3 grid((unsigned)gx, p.n);
+    switch (p.m.cb_total) {
+        case 1: head_loss_fwd_kernel<T, CO, 1, PAIRS><<<grid, kHeadThreads, smem, stream>>>(p); break;
+        case 2: head_loss_fwd_kernel<T, CO, 2, PAIRS><<<grid, kHeadThreads, smem, stream>>>(p); break;
+        case 3: head_loss_fwd_kernel<T, CO, 3, PAIRS><<<grid, kHeadThreads, smem, stream>>>(p); break;
+        default: head_loss_fwd_kernel<T, CO, 4, PAIRS><<<grid, kHeadThreads, smem, stream>>>(p); break;
+    }
+    return check_launch("ctu_head_loss_fwd");
+}
+
+template <typename T, int CO, int PAIRS>
+static int head_loss_bwd_launch(const HeadParams& p, cudaStream_t stream) {
+    const int cbt = p.m.cb_total;
+    const size_t smem = (size_t)(CO * cbt * 8 + 8) * sizeof(float);
+    const long long per = ((p.spatial & 1) == 0 ? p.spatial >> 1 : p.spatial);
+    long long gx = (per + kHeadThreads - 1) / kHeadThreads;
+    const long long cap = (148 * 16 + p.n - 1) / p.n;
+    if (gx > cap) gx = cap;
+    dim3 grid((unsigned)gx, p.n);
+    switch (cbt) {
+        case 1: head_loss_bwd_kernel<T, CO, 1, PAIRS><<<grid, kHeadThreads, smem, stream>>>(p); break;
+        case 2: head_loss_bwd_kernel<T, CO, 2, PAIRS><<<grid, kHeadThreads, smem, stream>>>(p); break;
+        case 3: head_loss_bwd_kernel<T, CO, 3, PAIRS><<<grid, kHeadThreads, smem, stream>>>(p); break;
+        default: head_loss_bwd_kernel<T, CO, 4, PAIRS><<<grid, kHeadThreads, smem, stream>>>(p); break;
+    }
+    return check_launch("ctu_head_loss_bwd");
+}
+
+template <typename T, int CO>
+static int head_param_grad_launch(const HeadParams& p, cudaStream_t stream) {
+    const int cbt = p.m.cb_total;
+    const int nv = CO * cbt * 8 + CO;
+    const size_t smem = (size_t)((kHeadThreads / 32) * nv) * sizeof(float);
+    int grid = head_grid((long long)p.n * p.spatial);
+    if (grid > 148 * 2) grid = 148 * 2;          // every block ends with CO*(Cin+1) same-address atomics
+    switch (cbt) {
+        case 1: head_param_grad_kernel<T, CO, 1><<<grid, kHeadThreads, smem, stream>>>(p); break;
+        case 2: head_param_grad_kernel<T, CO, 2><<<grid, kHeadThreads, smem, stream>>>(p); break;
+        case 3: head_param_grad_kernel<T, CO, 3><<<grid, kHeadThreads, smem, stream>>>(p); break;
+        default: head_param_grad_kernel<T, CO, 4><<<grid, kHeadThreads, smem, stream>>>(p); break;
+    }
+    return check_launch("ctu_head_param_grad");
+}
+
+static int head_loss_setup(HeadParams& p, int flags, int cout, const float* tgt0, const float* tgt1, double* sums,
+                           int softmax_for_dice, float ce_lambda, float dice_lambda, int& pairs, const char* what) {
+    pairs = (flags & (CTU_HEAD_SP | CTU_HEAD_SP_SOFTMAX)) ? 2 : 1;
+    CTU_REQUIRE(tgt0 && (pairs == 1 || tgt1) && sums, "%s: missing target / sums", what);
+    CTU_REQUIRE(ce_lambda != 0.f || dice_lambda != 0.f, "%s: both loss weights are zero", what);
+    CTU_REQUIRE(pairs == 2 || cout >= 2 || ce_lambda == 0.f, "%s: CrossEntropy needs at least two classes", what);
+    p.tgt0 = tgt0; p.tgt1 = tgt1; p.lsums = sums;
+    p.softmax_for_dice = softmax_for_dice; p.want_ce = ce_lambda != 0.f;
+    p.g_ce = ce_lambda; p.g_dice = dice_lambda;
+    return CTU_OK;
+}
+
 }  // namespace ctu
 
 using namespace ctu;
@@ -494,6 +888,90 @@ int ctu_head_bwd(int dtype, const void* const* h_srcs, const int* h_src_channels
             case 2: return head_bwd_launch<T, 2>(p, part, (cudaStream_t)stream);
             case 3: return head_bwd_launch<T, 3>(p, part, (cudaStream_t)stream);
             default: return head_bwd_launch<T, 4>(p, part, (cudaStream_t)stream);
+        }
+    });
+    return CTU_OK;
+}
+
+int ctu_head_loss_fwd(int dtype, const void* const* h_srcs, const int* h_src_channels, int nsrc, const float* w,
+                      const float* bias, int cout, int flags, const float* target0, const float* target1,
+                      int softmax_for_dice, float ce_lambda, float dice_lambda, double* sums, float* comps, float* mirror,
+                      int n, long long spatial, ctu_stream stream) {
+    HeadParams p = {};
+    int rc = head_setup(p, h_srcs, h_src_channels, nsrc, w, bias, cout, flags, n, spatial, "ctu_head_loss_fwd");
+    if (rc != CTU_OK) return rc;
+    int pairs = 1;
+    rc = head_loss_setup(p, flags, cout, target0, target1, sums, softmax_for_dice, ce_lambda, dice_lambda, pairs, "ctu_head_loss_fwd");
+    if (rc != CTU_OK) return rc;
+    CTU_REQUIRE(comps != nullptr, "ctu_head_loss_fwd: comps is null");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 4 * pairs * n, st);
+    if (e != cudaSuccess) {
+        set_error("ctu_head_loss_fwd: memset: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    CTU_DISPATCH_DTYPE(dtype, {
+        if (pairs == 2) rc = head_loss_fwd_launch<T, 3, 2>(p, st);
+        else switch (cout) {
+            case 1: rc = head_loss_fwd_launch<T, 1, 1>(p, st); break;
+            case 2: rc = head_loss_fwd_launch<T, 2, 1>(p, st); break;
+            case 3: rc = head_loss_fwd_launch<T, 3, 1>(p, st); break;
+            default: rc = head_loss_fwd_launch<T, 4, 1>(p, st); break;
+        }
+    });
+    if (rc != CTU_OK) return rc;
+    head_loss_finalize_kernel<<<1, 1, 0, st>>>(sums, pairs, n, spatial, ce_lambda, dice_lambda, comps, mirror);
+    return check_launch("head_loss_finalize_kernel");
+}
+
+int ctu_head_loss_bwd(int dtype, const void* const* h_srcs, const int* h_src_channels, int nsrc, const float* w,
+                      const float* bias, int cout, int flags, const float* target0, const float* target1,
+                      int softmax_for_dice, float ce_lambda, float dice_lambda, const double* sums, void* const* h_dsrcs,
+                      float* dlogits, int n, long long spatial, ctu_stream stream) {
+    HeadParams p = {};
+    int rc = head_setup(p, h_srcs, h_src_channels, nsrc, w, bias, cout, flags, n, spatial, "ctu_head_loss_bwd");
+    if (rc != CTU_OK) return rc;
+    int pairs = 1;
+    rc = head_loss_setup(p, flags, cout, target0, target1, const_cast<double*>(sums), softmax_for_dice, ce_lambda, dice_lambda,
+                         pairs, "ctu_head_loss_bwd");
+    if (rc != CTU_OK) return rc;
+    CTU_REQUIRE(h_dsrcs != nullptr && dlogits != nullptr, "ctu_head_loss_bwd: missing output buffers");
+    for (int i = 0; i < nsrc; ++i) p.dsrc[i] = h_dsrcs[i];
+    p.out0 = dlogits;
+    cudaStream_t st = (cudaStream_t)stream;
+    CTU_DISPATCH_DTYPE(dtype, {
+        if (pairs == 2) return head_loss_bwd_launch<T, 3, 2>(p, st);
+        switch (cout) {
+            case 1: return head_loss_bwd_launch<T, 1, 1>(p, st);
+            case 2: return head_loss_bwd_launch<T, 2, 1>(p, st);
+            case 3: return head_loss_bwd_launch<T, 3, 1>(p, st);
+            default: return head_loss_bwd_launch<T, 4, 1>(p, st);
+        }
+    });
+    return CTU_OK;
+}
+
+int ctu_head_param_grad(int dtype, const void* const* h_srcs, const int* h_src_channels, int nsrc, const float* dlogits,
+                        int cout, float* dw, float* db, int n, long long spatial, ctu_stream stream) {
+    HeadParams p = {};
+    static const float dummy_w = 0.f;
+    int rc = head_setup(p, h_srcs, h_src_channels, nsrc, &dummy_w, nullptr, cout, 0, n, spatial, "ctu_head_param_grad");
+    if (rc != CTU_OK) return rc;
+    CTU_REQUIRE(dlogits && dw && db, "ctu_head_param_grad: null pointer");
+    p.dout0 = dlogits; p.dw = dw; p.db = db;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * cout * p.m.c_total, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(db, 0, sizeof(float) * cout, st);
+    if (e != cudaSuccess) {
+        set_error("ctu_head_param_grad: memset: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    CTU_DISPATCH_DTYPE(dtype, {
+        switch (cout) {
+            case 1: return head_param_grad_launch<T, 1>(p, st);
+            case 2: return head_param_grad_launch<T, 2>(p, st);
+            case 3: return head_param_grad_launch<T, 3>(p, st);
+            default: return head_param_grad_launch<T, 4>(p, st);
         }
     });
     return CTU_OK;

@@ -5,40 +5,11 @@
 // One pass computes, per sample, sum(p*t), sum(p*p), sum(t*t) and the CE sum (double accumulators in
 // global memory, warp-shuffle reductions); a second tiny kernel forms the two scalars so the step
 // stays free of host synchronisation.
-#include "common.cuh"
+#include "loss_math.cuh"
 
 namespace ctu {
 
 constexpr int kLossThreads = 256;
-
-template <int C>
-__device__ __forceinline__ void softmax_c(const float (&x)[C], float (&p)[C], float& lse) {
-    float mx = x[0];
-#pragma unroll
-    for (int c = 1; c < C; ++c) mx = fmaxf(mx, x[c]);
-    float sum = 0.f;
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-        p[c] = expf(x[c] - mx);
-        sum += p[c];
-    }
-#pragma unroll
-    for (int c = 0; c < C; ++c) p[c] /= sum;
-    lse = mx + logf(sum);
-}
-
-template <int C>
-__device__ __forceinline__ int first_argmax(const float (&t)[C]) {
-    int bi = 0;
-    float best = t[0];
-#pragma unroll
-    for (int c = 1; c < C; ++c)
-        if (t[c] > best || (t[c] != t[c] && best == best)) {
-            best = t[c];
-            bi = c;
-        }
-    return bi;
-}
 
 template <int C>
 __global__ void __launch_bounds__(kLossThreads) dice_ce_fwd_kernel(const float* __restrict__ pred,

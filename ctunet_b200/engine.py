@@ -102,6 +102,9 @@ class Engine:
         self._side = None
         self._wgrad_stream = None
         self._dead_stream = None
+        # set by trainer.TrainStep: (targets, softmax_for_dice, ce_lambda, dice_lambda, comps, mirror) -- the head then
+        # runs fused with the loss (csrc/head.cu: head_loss_*), produces no output tensors and wires its own backward
+        self.fused_loss = None
 
     # ------------------------------------------------------------------ weight preparation on a side stream
     def begin(self, store: dict, key) -> None:
@@ -597,6 +600,8 @@ class Engine:
         s0 = srcs[0]
         pa, ca, ns = self._src_args(srcs)
         sp = bool(flags & (_lib.HEAD_SP | _lib.HEAD_SP_SOFTMAX))
+        if self.fused_loss is not None:
+            return self._head_loss(list(srcs), weight, bias, flags, sp)
         if sp:
             out0 = self.f32(s0.n, 2, s0.d, s0.h, s0.w)
             out1 = self.f32(s0.n, 2, s0.d, s0.h, s0.w)
@@ -646,6 +651,56 @@ class Engine:
             self.head_bwd = bwd
         return (out0, out1) if sp else out0
 
+    def _head_loss(self, srcs, weight, bias, flags, sp):
+        """Head + Dice / CrossEntropy in one pass over the sources (training step only): see csrc/head.cu."""
+        targets, softmax_for_dice, ce_l, dice_l, comps, mirror = self.fused_loss
+        cout = weight.shape[0]
+        s0 = srcs[0]
+        targets = list(targets) if isinstance(targets, (tuple, list)) else [targets]
+        if len(targets) != (2 if sp else 1):
+            raise ValueError("the %s head takes %d target tensor(s), got %d" % ("SP" if sp else "plain", 2 if sp else 1, len(targets)))
+        want = (s0.n, 2 if sp else cout, s0.d, s0.h, s0.w)
+        for t in targets:
+            if tuple(t.shape) != want or t.dtype != torch.float32 or not t.is_contiguous() or t.device != s0.buf.device:
+                raise TypeError("targets: contiguous float32 one-hot tensors of shape %s on %s" % (want, s0.buf.device))
+        pa, ca, ns = self._src_args(srcs)
+        t0, t1 = targets[0].data_ptr(), (targets[1].data_ptr() if sp else None)
+        sums = self.f64(4 * len(targets) * s0.n)
+        call("ctu_head_loss_fwd", self.dtype, pa, ca, ns, weight.data_ptr(), bias.data_ptr(), cout, flags, t0, t1,
+             int(softmax_for_dice), float(ce_l), float(dice_l), sums.data_ptr(), comps.data_ptr(),
+             mirror.data_ptr() if mirror is not None else None, s0.n, s0.spatial, stream_ptr())
+        if self.record:
+            def bwd(g0=None, g1=None):
+                pa, ca, ns = self._src_args(srcs)
+                dsrcs = [self.new_act(s.c, s.n, s.d, s.h, s.w) for s in srcs]
+                dw, db = self._grad_buffer(weight), self._grad_buffer(bias)
+                dlc = self.f32(s0.n, cout, s0.d, s0.h, s0.w)
+                # source gradients (the critical path); the logit gradients are kept for the parameter gradients
+                call("ctu_head_loss_bwd", self.dtype, pa, ca, ns, weight.data_ptr(), bias.data_ptr(), cout, flags, t0, t1,
+                     int(softmax_for_dice), float(ce_l), float(dice_l), sums.data_ptr(), ptr_array([d.ptr for d in dsrcs]),
+                     dlc.data_ptr(), s0.n, s0.spatial, stream_ptr())
+                for s, d in zip(srcs, dsrcs):
+                    self._set_agrad(s, d)
+
+                def params():      # parameter gradients: a leaf, beside the weight gradients (second stream)
+                    call("ctu_head_param_grad", self.dtype, pa, ca, ns, dlc.data_ptr(), cout, dw.data_ptr(), db.data_ptr(),
+                         s0.n, s0.spatial, stream_ptr())
+                    self._pgrad_done(((weight, dw), (bias, db)))
+
+                if WGRAD_ASYNC:
+                    main = torch.cuda.current_stream()
+                    side = _side_stream(self.device, 1)
+                    side.wait_stream(main)
+                    with torch.cuda.stream(side):
+                        params()
+                    dlc.record_stream(side)
+                    self._wgrad_stream = side
+                else:
+                    params()
+
+            self.head_bwd = bwd
+        return None
+
     # ------------------------------------------------------------------ backward driver
     def run_tape(self):
         """Run the recorded backward closures (last stage first) and join the weight-gradient stream."""
@@ -656,7 +711,7 @@ class Engine:
             torch.cuda.current_stream().wait_stream(self._wgrad_stream)
             self._wgrad_stream = None
 
-    def backward(self, g0, g1):
+    def backward(self, g0=None, g1=None):
         # (drop the closure first: it references the engine AND the forward outputs, i.e. the autograd graph -- a cycle
         # that would keep this pass's AccumulateGrad nodes alive until the next garbage collection)
         fn, self.head_bwd = self.head_bwd, None

@@ -30,6 +30,9 @@ from .models import _run_planned
 from .optim import FlatOptimizer
 from .parallel import GradSync
 
+# The head and the Dice + CrossEntropy loss as ONE pass over the head's inputs (forward) and one more (backward); off = the
+# separate head / loss kernels the drop-in modules use behind the reference's model / handler split.
+FUSED_HEAD_LOSS = True
 GRAPH_WARMUP = 2      # eager iterations before the capture (allocator pools, cached constants, weight-preparation plan)
 
 
@@ -146,11 +149,17 @@ class TrainStep:
         eng = Engine(image.device, net.compute_dtype, record=True)
         eng.grad_sink = self.grads
         eng.want_input_grad = bool(self.input_requires_grad)
-        out = _run_planned(net, eng, image.contiguous(), True, params)
         mirror = self.grads.tail if self.world > 1 else None
-        saved, _ = self.spec.forward(out, target, self._comps, mirror)
-        dpreds = [_pair_bwd(s, self._g) for s in saved]
-        eng.backward(dpreds[0], dpreds[1] if len(dpreds) > 1 else None)
+        if FUSED_HEAD_LOSS:
+            # the head runs fused with the loss: the fp32 network outputs and their gradients are never materialised
+            eng.fused_loss = (target, self.handler == "double", self.spec.ce_lambda, self.spec.dice_lambda, self._comps, mirror)
+            _run_planned(net, eng, image.contiguous(), True, params)
+            eng.backward()
+        else:
+            out = _run_planned(net, eng, image.contiguous(), True, params)
+            saved, _ = self.spec.forward(out, target, self._comps, mirror)
+            dpreds = [_pair_bwd(s, self._g) for s in saved]
+            eng.backward(dpreds[0], dpreds[1] if len(dpreds) > 1 else None)
         self.grads.check_complete()
         # world > 1: the averaged components come back in the tail of the flat buffer
         return self.grads.tail[:self.spec.n_terms + 1] if self.world > 1 else self._comps

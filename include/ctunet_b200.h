@@ -185,6 +185,27 @@ int ctu_head_bwd(int dtype, const void* const* h_srcs, const int* h_src_channels
                  const float* out1, void* const* h_dsrcs,
                  float* dw, float* db, int n, long long spatial, ctu_stream stream);
 
+/* ---- fused head + loss for the training step (models.py:255-259, 319-330, 535-538 + ProblemHandler.py:59-91, 228-298):
+ *      the head is recomputed from the blocked sources and fed to the Dice + CrossEntropy arithmetic in registers, so the
+ *      fp32 network outputs and their gradients never touch HBM.  target0 / target1: one-hot float32 [n][C][spatial]
+ *      (SP heads: two targets with C = 2; plain head: target0 with C = cout, target1 = NULL).  softmax_for_dice as
+ *      ctu_dice_ce_fwd.  sums: double[4 * pairs * n] (zeroed by the forward call, read by the backward calls).
+ *      comps: float[terms + 1] = [ce_lambda * CE per pair] (if ce_lambda != 0) + [dice_lambda * Dice per pair]
+ *      (if dice_lambda != 0) + [total]; mirror (nullable): a second copy (tail of the data-parallel gradient buffer). */
+int ctu_head_loss_fwd(int dtype, const void* const* h_srcs, const int* h_src_channels, int nsrc, const float* w,
+                      const float* bias, int cout, int flags, const float* target0, const float* target1,
+                      int softmax_for_dice, float ce_lambda, float dice_lambda, double* sums, float* comps, float* mirror,
+                      int n, long long spatial, ctu_stream stream);
+/* d(total) / d(sources) into h_dsrcs; also stores the logit gradients dlogits [n][cout][spatial] (fp32) for
+ * ctu_head_param_grad, which reduces dW [cout][cin_total] and db [cout] (zeroed by the call) from them and the sources --
+ * a leaf of the backward pass that can run on another stream. */
+int ctu_head_loss_bwd(int dtype, const void* const* h_srcs, const int* h_src_channels, int nsrc, const float* w,
+                      const float* bias, int cout, int flags, const float* target0, const float* target1,
+                      int softmax_for_dice, float ce_lambda, float dice_lambda, const double* sums, void* const* h_dsrcs,
+                      float* dlogits, int n, long long spatial, ctu_stream stream);
+int ctu_head_param_grad(int dtype, const void* const* h_srcs, const int* h_src_channels, int nsrc, const float* dlogits,
+                        int cout, float* dw, float* db, int n, long long spatial, ctu_stream stream);
+
 /* ---- loss: soft Dice (utilities.py:39-50) + CrossEntropy (ProblemHandler.py:67-70, 247-257) on
  *      one prediction/target pair, fp32 NCDHW [b][c][spatial], c <= 4.
  * sums: double[4*b] (zeroed by the call): sum p*t, sum p*p, sum t*t, CE sum.

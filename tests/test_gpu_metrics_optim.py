@@ -266,3 +266,44 @@ def test_eval_step_matches_oracle(graph):
         assert lab.dtype == torch.float32 and lab.shape == (2, 32, 32, 32)
         agree = (lab.cpu() == O.hard_segm_from_tensor(r)).float().mean().item()
         assert agree > 0.9999
+
+
+# ------------------------------------------------------------------------------------------------ fused head + loss
+@pytest.mark.parametrize("name,handler,mode,lams", [("UNetSP", "double", "fp32", (1.0, 1.0)), ("UNetSP", "double", "bf16", (1.0, 0.5)),
+                                                    ("UNetSPSmall", "double", "fp32", (1.0, 1.0)), ("UNetDO", "double", "fp32", (1.0, 0.0)),
+                                                    ("recAE_v2_fixed", "single", "fp32", (1.0, 1.0)),
+                                                    ("UNet4_2IC", "single", "bf16", (0.0, 2.0))])
+def test_fused_head_loss_equals_separate_kernels(name, handler, mode, lams):
+    """trainer.FUSED_HEAD_LOSS: head + Dice/CE in one pass (csrc/head.cu head_loss_*) against the separate head, loss and
+    head-backward kernels on the same network: identical loss components, identical flat gradient buffer."""
+    import ctunet_b200 as C
+    import ctunet_b200.trainer as TR
+    from oracle import unet_oracle as O
+    cfg = O.PRESETS[name]
+    size = 32
+    x, (sk_t, fl_t) = O.make_training_batch(2, cfg.input_channels, size, seed=13)
+    target = (sk_t.to(DEV), fl_t.to(DEV)) if handler == "double" else sk_t.to(DEV)
+    res = []
+    for fused in (False, True):
+        C.set_compute_dtype(mode)
+        torch.manual_seed(0)
+        net = getattr(C, name)().to(DEV)
+        C.set_compute_dtype("bf16")
+        step = TR.TrainStep(net, handler, dice_lambda=lams[0], ce_lambda=lams[1], lr=1e-4)
+        old = TR.FUSED_HEAD_LOSS
+        TR.FUSED_HEAD_LOSS = fused
+        try:
+            comps = step._forward_backward(x.to(DEV), target).clone()
+        finally:
+            TR.FUSED_HEAD_LOSS = old
+        torch.cuda.synchronize()
+        res.append((comps.cpu(), step.grads.flat[:step.grads.n_grad].clone().cpu(), step.keys))
+    (c0, g0, k0), (c1, g1, k1) = res
+    assert k0 == k1 and len(c0) == len(k0)
+    assert torch.allclose(c0, c1, rtol=1e-6, atol=1e-7), (c0, c1)
+    scale = float(g0.abs().max())
+    assert scale > 0
+    # same arithmetic per voxel; only the summation order of the parameter-gradient partials differs
+    assert float((g0 - g1).abs().max()) <= (2e-5 if mode == "fp32" else 2e-3) * scale
+    rel = float((g0 - g1).norm() / g0.norm())
+    assert rel < (1e-5 if mode == "fp32" else 2e-3), rel
