@@ -93,6 +93,15 @@ SIGNATURES = {
     "ctu_optim_chunk_elems": (I, []),
     "ctu_optim_step": (I, [I, P, I, P, P, P, P, P, P, D, D, D, D, D, D, I, D, P]),
     "ctu_optim_post": (I, [P, P, P, I, P]),
+    "ctu_peer_flag_bytes": (I, []),
+    "ctu_peer_alloc": (I, [LL, P, P]),
+    "ctu_peer_open": (I, [P, P]),
+    "ctu_peer_close": (I, [P]),
+    "ctu_peer_free": (I, [P]),
+    "ctu_peer_signal": (I, [P, P, I, I, P]),
+    "ctu_peer_wait_done": (I, [P, P, I, I, P]),
+    "ctu_optim_step_peer": (I, [I, P, I, P, P, I, I, P, P, P, P, P, D, D, D, D, D, D, I, D, P, LL, I, P]),
+    "ctu_peer_error": (I, [P]),
     "ctu_salt_pepper_u8": (I, [P, P, LL, D, D, P, P, ULL, ULL, P]),
 }
 

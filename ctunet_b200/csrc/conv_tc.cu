@@ -18,6 +18,8 @@
 //     BatchNorm, so the statistics pass over y disappears).
 #include "tc_ptx.cuh"
 
+#include <stdlib.h>
+
 namespace ctu {
 
 constexpr int TC_TH = 16, TC_TW = 16;   // output tile (h, w) per plane = 2 MMA tiles of 16x8
@@ -866,6 +868,288 @@ __global__ void __launch_bounds__(WG_THREADS) conv3d_wgrad_tc_kernel(const __gri
     }
 }
 
+
+// ================================================================================================ wgrad, kd and kh in N
+// Second formulation of the 3x3x3 weight gradient for narrow layers (round 2).  The kernel above issues one MMA per
+// (dy plane, kd, x halo row) with N = kh x Cout = 24..48: for 8-channel layers the tensor pipe is saturated by MMA COUNT
+// (tiny N, ~25-29 cycles each at 8 issuing warps per SM) while DRAM idles at 18 %.  Here the work is owned by X planes
+// and rows: x row (z, y) of a 16 x 16 tile (no halo rows or planes) meets the 3 x 3 neighbourhood of dy rows
+// (z - 1 .. z + 1) x (y - 1 .. y + 1).  The dy box is fetched by ONE 5-D TMA per step through a tensor map whose
+// dimension order is (w, cob, d, h, n), so it lands in shared memory as [h (18 rows)][d (3 planes)][cob][w][8]: for a fixed
+// x row the nine (kh, kd) rows x all output blocks are n-groups at a uniform 256-byte stride, i.e. ONE MMA
+// (M = 64 = 8 kw lags x 8 input lanes, N = 9 x Cout, K = 16 voxels) replaces three, and the d / h borders (volume edge or
+// neighbouring tile) are TMA's out-of-bounds zero fill -- every product is computed exactly once, by the owner of the x
+// voxel.  16 MMAs per (plane, tile, input block) instead of 54.  Accumulators [64 x 9*Cout] per (input block, row parity)
+// stay in TMEM for the whole CTA and are flushed with fp32 atomics into the packed gradient.
+struct Wg2Params {
+    float* dwp;
+    int cb, cob_n;              // totals
+    int cbg, nobx;              // input blocks / output blocks per CTA group
+    int n_cbgroups, n_ngroups;
+    int split;                  // accumulators per input block: the 16 rows of a plane are dealt to `split` issuers
+    int n, d, h, w;
+    int tiles_h, tiles_w, dchunks, dc, total_items;
+    uint32_t xplane_bytes, xslot_bytes, dyslot_bytes, tmem_cols, ns;
+    int nsrc, src_cb[CTU_MAX_SRC], src_cboff[CTU_MAX_SRC];
+};
+
+__global__ void __launch_bounds__(WG_THREADS) conv3d_wgrad_tc2_kernel(const __grid_constant__ TcMaps xmaps,
+                                                                      const __grid_constant__ CUtensorMap dymap, Wg2Params p) {
+    constexpr int K = 3, PAD = 1;
+    constexpr int WW = TC_TW + K - 1;
+    constexpr uint32_t ROW = WW * 16;              // one x row of one channel block (w halo included)
+    constexpr uint32_t DYBLK = TC_TW * 16;         // one channel block of one dy row
+    constexpr int DYROWS = TC_TH + K - 1;
+    const uint32_t NS = p.ns;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const uint32_t s_base = smem_u32(smem);
+    const uint32_t s_x = s_base;
+    const uint32_t s_dy = s_x + NS * p.xslot_bytes;
+    const uint32_t s_bar = s_dy + NS * p.dyslot_bytes;
+    const uint32_t b_full = s_bar, b_empty = s_bar + 8 * TC_MAX_SLOTS, b_done = s_bar + 16 * TC_MAX_SLOTS;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (b_done + 8 - s_base));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = blockIdx.y;
+    const int cbg_i = grp % p.n_cbgroups, ng_i = grp / p.n_cbgroups;
+    const int cb0 = cbg_i * p.cbg;
+    const int ncb = (p.cb - cb0) < p.cbg ? (p.cb - cb0) : p.cbg;
+    const int ob0 = ng_i * p.nobx;
+    const int nob = (p.cob_n - ob0) < p.nobx ? (p.cob_n - ob0) : p.nobx;
+    const int nobx = p.nobx;
+    const uint32_t dyrow = (uint32_t)(K * nobx) * DYBLK;      // one dy row: 3 planes x all channel blocks
+    const int ncol = K * K * nobx * 8;                        // MMA N = TMEM columns per accumulator
+
+    if (threadIdx.x == 0) {
+        for (uint32_t i = 0; i < NS; ++i) {
+            mbar_init(b_full + 8 * i, 1);
+            mbar_init(b_empty + 8 * i, WG_ISSUERS);
+        }
+        mbar_init(b_done, WG_ISSUERS);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(p.tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int items_per_n = p.tiles_h * p.tiles_w * p.dchunks;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            Ring pr = {0, 0};
+            const uint32_t bytes = (uint32_t)ncb * TC_TH * ROW + (uint32_t)DYROWS * dyrow;
+            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+                const int n = item / items_per_n;
+                int r = item % items_per_n;
+                const int dci = r % p.dchunks; r /= p.dchunks;
+                const int twi = r % p.tiles_w, thi = r / p.tiles_w;
+                const int z0 = dci * p.dc, h0 = thi * TC_TH, w0 = twi * TC_TW;
+                const int nd = (p.d - z0) < p.dc ? (p.d - z0) : p.dc;
+                for (int j = 0; j < nd; ++j, pr.next(NS)) {
+                    mbar_wait(b_empty + 8 * pr.slot, pr.phase ^ 1);
+                    mbar_expect_tx(b_full + 8 * pr.slot, bytes);
+                    for (int b = 0; b < ncb; ++b) {
+                        int s = 0;
+#pragma unroll
+                        for (int q = 1; q < CTU_MAX_SRC; ++q)
+                            if (q < p.nsrc && cb0 + b >= p.src_cboff[q]) s = q;
+                        tma_load_4d(s_x + pr.slot * p.xslot_bytes + b * p.xplane_bytes, &xmaps.m[s], (w0 - PAD) * 8, h0, z0 + j,
+                                    n * p.src_cb[s] + (cb0 + b - p.src_cboff[s]), b_full + 8 * pr.slot);
+                    }
+                    // dy rows h0-1 .. h0+16, planes z-1 .. z+1, all output blocks of the group
+                    tma_load_5d(s_dy + pr.slot * p.dyslot_bytes, &dymap, w0 * 8, ob0, z0 + j - PAD, h0 - PAD, n,
+                                b_full + 8 * pr.slot);
+                }
+            }
+        }
+    } else {
+        // D=f32, A=B=bf16, both MN-major (bits 15, 16), N at [17,23), M=64 at [24,29)
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(ncol >> 3) << 17) |
+                               (4u << 24);
+        const uint32_t a_hi = 1u | (1u << 14);                    // SBO = 16 B: m-group g = lag g (kw)
+        const uint32_t b_hi = (DYBLK >> 4) | (1u << 14);          // SBO = 256 B: next (kh row, kd plane, channel block)
+        const uint32_t lbo = 8u << 16;                            // second 8-voxel core matrix: +128 B
+        const int q = warp - 1;
+        const int S = p.split;
+        const int nacc = ncb * S;                                 // accumulator e = b * S + s
+        const uint32_t leader = elect_one();
+        uint32_t first = 1;
+        Ring cons = {0, 0};
+        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+            const int r0 = item % items_per_n;
+            const int z0 = (r0 % p.dchunks) * p.dc;
+            const int nd = (p.d - z0) < p.dc ? (p.d - z0) : p.dc;
+            for (int j = 0; j < nd; ++j, cons.next(NS)) {
+                mbar_wait(b_full + 8 * cons.slot, cons.phase);
+                tc_fence_after();
+                const uint32_t dy16 = ((s_dy + cons.slot * p.dyslot_bytes) >> 4) | lbo;
+                for (int e = q; e < nacc; e += WG_ISSUERS) {
+                    const int b = e / S, s = e - b * S;
+                    const uint32_t x16 = ((s_x + cons.slot * p.xslot_bytes + b * p.xplane_bytes) >> 4) | lbo;
+                    const uint32_t tcol = tmem_base + (uint32_t)e * ncol;
+                    for (int r = s; r < TC_TH; r += S)   // x row r meets dy rows r-1 .. r+1 = box rows r .. r+2
+                        umma_bf16_lead(leader, tcol, x16 + r * (ROW >> 4), a_hi, dy16 + r * (dyrow >> 4), b_hi, idesc,
+                                       (r == s) ? (first ^ 1u) : 1u);
+                }
+                first = 0;
+                umma_commit_lead(leader, b_empty + 8 * cons.slot);
+            }
+        }
+        umma_commit_lead(leader, b_done);
+        __syncwarp();
+        // flush: M=64 accumulators sit in lanes 0-15 of every 32-lane quarter (row = quarter*16 + lane)
+        const int quarter = warp & 3;
+        mbar_wait(b_done, 0);
+        tc_fence_after();
+        const int row = quarter * 16 + (lane & 15);
+        const int lag = row >> 3, ci = row & 7;
+        const bool useful = lane < 16 && lag < K;
+        constexpr int taps = K * K * K;
+        for (int a = 0; a < nacc; ++a) {
+            const int b = a / S;
+            for (int g = 0; g < ncol / 8; ++g) {           // n-group g = (box row kh', box plane i, output block)
+                const int khp = g / (K * nobx), i = (g / nobx) % K, ob = g % nobx;
+                if (ob >= nob) continue;
+                // dy row = x row + kh' - 1 = x row - kh + 1  ->  kh = 2 - kh';  dy plane = x plane + i - 1  ->  kd = 2 - i
+                const int tap = ((K - 1 - i) * K + (K - 1 - khp)) * K + lag;
+                float v[8];
+                tmem_ld8(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)a * ncol + g * 8, v);
+                if (useful) {
+                    float* dst = p.dwp + ((((long long)(ob0 + ob) * p.cb + cb0 + b) * taps + tap) * 64 + ci * 8);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        if (v[c] != 0.f) atomicAdd(dst + c, v[c]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    }
+}
+
+struct Wg2Geom {
+    int cb, cob_n, cbg, nobx, n_cbgroups, n_ngroups, split;
+    uint32_t xplane_bytes, xslot_bytes, dyslot_bytes, tmem_cols, ns;
+    size_t smem;
+};
+
+// dense 3x3x3 only; N = 72 * nobx <= 216, all accumulators of a CTA in <= 512 TMEM columns
+static bool wg2_geometry(int k, int cb, int cout, int h, int w, Wg2Geom& g) {
+    if (k != 3 || h % TC_TH || w % TC_TW || cb < 1 || cout < 1) return false;
+    g.cb = cb;
+    g.cob_n = (cout + 7) / 8;
+    g.nobx = g.cob_n < 3 ? g.cob_n : (g.cob_n % 3 == 0 ? 3 : 2);
+    const int ncol = 72 * g.nobx;
+    // input blocks per CTA and row split: aim at 4 busy issuers in <= 256 columns (two CTAs per SM), never above 512
+    g.cbg = cb;
+    while (g.cbg > 1 && g.cbg * ncol > 512) g.cbg = (g.cbg + 1) / 2;
+    if (g.cbg * ncol > 512) return false;
+    {
+        const int ngr = (cb + g.cbg - 1) / g.cbg;
+        g.cbg = (cb + ngr - 1) / ngr;
+    }
+    // Measured on B200 (scripts/bench_wgrad.py, 7->7 at 4x128^3): one issuer per CTA and two CTAs per SM with a 6-deep
+    // ring (117 us) beats two issuers alternating rows into two accumulators (139 us) and one deep CTA per SM (145 us).
+    g.split = 1;
+    if (const char* e = getenv("CTU_WG2_SPLIT")) g.split = atoi(e);       // (tuning knobs, scripts/bench_wgrad.py)
+    const int ww = TC_TW + k - 1;
+    g.xplane_bytes = ((uint32_t)TC_TH * ww * 16 + 127u) & ~127u;
+    g.xslot_bytes = g.xplane_bytes * g.cbg;
+    g.dyslot_bytes = (uint32_t)(TC_TH + k - 1) * k * g.nobx * TC_TW * 16;
+    const size_t fixed = 8 * (2 * TC_MAX_SLOTS + 3) + 16 + 1024;
+    const uint32_t cols = (uint32_t)g.cbg * g.split * ncol;
+    g.tmem_cols = 32;
+    while (g.tmem_cols < cols) g.tmem_cols *= 2;
+    if (g.tmem_cols > 512) return false;
+    const size_t budget = g.tmem_cols > 256 ? 200 * 1024 : 112 * 1024;
+    g.ns = 2;
+    while (g.ns < 6 && fixed + (size_t)(g.ns + 1) * (g.xslot_bytes + g.dyslot_bytes) <= budget) ++g.ns;
+    if (const char* e = getenv("CTU_WG2_NS")) g.ns = (uint32_t)atoi(e);
+    g.smem = fixed + (size_t)g.ns * (g.xslot_bytes + g.dyslot_bytes);
+    if (g.smem > 220 * 1024) return false;
+    g.n_cbgroups = (cb + g.cbg - 1) / g.cbg;
+    g.n_ngroups = (g.cob_n + g.nobx - 1) / g.nobx;
+    return true;
+}
+
+static int conv3d_wgrad_tc2(const void* const* h_srcs, const int* h_src_channels, int nsrc, const void* dy, float* dwp,
+                            int cout, int n, int d, int h, int w, const Wg2Geom& g, cudaStream_t stream) {
+    TcMaps xmaps;
+    CUtensorMap dymap;
+    for (int i = 0; i < CTU_MAX_SRC; ++i) {       // x boxes: 16 rows x 18 voxels (w halo only)
+        const int j = i < nsrc ? i : 0;
+        int rc = make_map(&xmaps.m[i], h_srcs[j], n * ((h_src_channels[j] + 7) / 8), d, h, w, TC_TW + 2, TC_TH);
+        if (rc != CTU_OK) return rc;
+    }
+    {
+        // dy as (w*8, cob, d, h, n): the box [18 rows][3 planes][nobx][16 voxels] lands in shared memory as [h][d][cob][w][8]
+        auto encode = get_encode();
+        if (!encode) {
+            set_error("cuTensorMapEncodeTiled entry point not found");
+            return CTU_ERR_UNSUPPORTED;
+        }
+        const cuuint64_t plane_b = (cuuint64_t)d * h * w * 16;
+        const cuuint64_t gdim[5] = {(cuuint64_t)w * 8, (cuuint64_t)g.cob_n, (cuuint64_t)d, (cuuint64_t)h, (cuuint64_t)n};
+        const cuuint64_t gstr[4] = {plane_b, (cuuint64_t)h * w * 16, (cuuint64_t)w * 16, plane_b * g.cob_n};
+        const cuuint32_t box[5] = {(cuuint32_t)TC_TW * 8, (cuuint32_t)g.nobx, 3, (cuuint32_t)(TC_TH + 2), 1};
+        const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        CUresult cr = encode(&dymap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(dy), gdim, gstr, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) {
+            set_error("cuTensorMapEncodeTiled(dy, wgrad2) failed (%d)", (int)cr);
+            return CTU_ERR_INVALID;
+        }
+    }
+    Wg2Params p = {};
+    p.dwp = dwp;
+    p.cb = g.cb; p.cob_n = g.cob_n; p.cbg = g.cbg; p.nobx = g.nobx; p.n_cbgroups = g.n_cbgroups; p.n_ngroups = g.n_ngroups;
+    p.split = g.split;
+    p.n = n; p.d = d; p.h = h; p.w = w;
+    p.tiles_h = h / TC_TH; p.tiles_w = w / TC_TW;
+    p.xplane_bytes = g.xplane_bytes; p.xslot_bytes = g.xslot_bytes; p.dyslot_bytes = g.dyslot_bytes; p.tmem_cols = g.tmem_cols;
+    p.ns = g.ns;
+    p.nsrc = nsrc;
+    for (int i = 0, off = 0; i < CTU_MAX_SRC; ++i) {
+        p.src_cb[i] = i < nsrc ? (h_src_channels[i] + 7) / 8 : 0;
+        p.src_cboff[i] = off;
+        off += p.src_cb[i];
+    }
+    int ctas_per_sm = (int)((227 * 1024) / (g.smem + 1024));
+    if (ctas_per_sm > 512 / (int)g.tmem_cols) ctas_per_sm = 512 / (int)g.tmem_cols;
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    if (ctas_per_sm > 4) ctas_per_sm = 4;
+    if (const char* e = getenv("CTU_WG2_CTAS")) ctas_per_sm = atoi(e);
+    const int groups = g.n_cbgroups * g.n_ngroups;
+    int gx = (148 * ctas_per_sm + groups - 1) / groups;
+    // d-chunks cost nothing here (no halo planes): cut until the resident CTAs get >= 4 items each, chunks of >= 4 planes
+    const int tiles = n * p.tiles_h * p.tiles_w;
+    int dc = d;
+    while (dc > 32 && (long long)tiles * ((d + dc - 1) / dc) < 4LL * gx) dc = (dc + 1) / 2;
+    while (dc > 4 && (long long)tiles * ((d + dc - 1) / dc) < 2LL * gx) dc = (dc + 1) / 2;
+    if (const char* e = getenv("CTU_WG2_DC")) dc = atoi(e);
+    p.dc = dc;
+    p.dchunks = (d + dc - 1) / dc;
+    p.total_items = tiles * p.dchunks;
+    if (gx > p.total_items) gx = p.total_items;
+    if (gx < 1) gx = 1;
+    cudaError_t e = cudaFuncSetAttribute(conv3d_wgrad_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+    if (e != cudaSuccess) {
+        set_error("conv3d wgrad2 tensor path: smem %zu: %s", g.smem, cudaGetErrorString(e));
+        return (int)e;
+    }
+    conv3d_wgrad_tc2_kernel<<<dim3(gx, groups), WG_THREADS, g.smem, stream>>>(xmaps, dymap, p);
+    return check_launch("ctu_conv3d_wgrad(tcgen05, kd+kh in N)");
+}
+
 // sum of dy over voxels per channel (bias gradient of convolutions that carry a bias: the legacy 5^3 family)
 __global__ void tc_channel_sum_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ dbias, int cout, int cob_n,
                                       long long spatial) {
@@ -984,6 +1268,20 @@ int conv3d_wgrad_tc(const void* const* h_srcs, const int* h_src_channels, int ns
     if (cbt < 0 || !wg_geometry(k, cbt, cout, h, w, g, phase_cout)) {
         set_error("conv3d wgrad tensor path: shape k=%d blocks=%d cout=%d %dx%dx%d not covered", k, cbt, cout, d, h, w);
         return CTU_ERR_UNSUPPORTED;
+    }
+    {
+        // narrow dense 3x3x3 layers: the (kd, kh)-in-N formulation (a third of the MMAs); CTU_WGRAD_V1=1 keeps the first one
+        static const bool v1 = getenv("CTU_WGRAD_V1") != nullptr;
+        Wg2Geom g2;
+        // (measured: a gain for one input and one output block -- 7->7 180 -> 117 us, 2->7 178 -> 115 us at 4x128^3 -- and
+        // none once N = 72 * blocks exceeds ~100: 14->14 at 4x64^3 81 vs 82 us; CTU_WGRAD_V2_ALL=1 routes every covered shape)
+        static const bool all2 = getenv("CTU_WGRAD_V2_ALL") != nullptr;
+        if (!v1 && !g.sparse && k == 3 && (all2 ? (cbt <= 4 && cout <= 32) : (cbt == 1 && cout <= 8)) &&
+            wg2_geometry(k, cbt, cout, h, w, g2)) {
+            int rc2 = conv3d_wgrad_tc2(h_srcs, h_src_channels, nsrc, dy, dwp, cout, n, d, h, w, g2, stream);
+            if (rc2 == CTU_OK && dbias != nullptr) rc2 = channel_sum_bias(dy, dbias, cout, g2.cob_n, n, (long long)d * h * w, stream);
+            return rc2;
+        }
     }
     TcMaps xmaps;
     CUtensorMap dymap;

@@ -79,6 +79,23 @@ class FlatOptimizer:
         """Current learning rate (host read: synchronises)."""
         return float(self.sched[0])
 
+    def step_peer(self, sync, n_tail: int, grad_scale: float = 1.0):
+        """All-reduce + update in one launch over the peer-mapped gradient buffers of ``sync`` (parallel.PeerGradSync): the
+        gradient of every element is the rank-ordered mean over all ranks; the first ``n_tail`` floats of the loss tail are
+        averaged into ``sync.tail_avg``, whose last entry (the total loss) then feeds the plateau scheduler."""
+        if [p.data_ptr() for p in self.params] != self._param_ptrs:
+            raise RuntimeError("a parameter's storage moved after the optimizer was built (re-create the TrainStep)")
+        h = self.hyper
+        st = stream_ptr()
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        call("ctu_optim_step_peer", KINDS[self.kind], self.chunks.data_ptr(), self.n_chunks, sync.h_grads, sync.h_flags,
+             sync.world, sync.rank, ptr(self.state0), ptr(self.state1), ptr(self.state2), self.sched.data_ptr(),
+             self.step_count.data_ptr(), h["beta1"], h["beta2"], h["eps"], h["weight_decay"], h["momentum"], h["alpha"],
+             h["amsgrad"], float(grad_scale), sync.tail_avg.data_ptr(), sync.n_grad, int(n_tail), st)
+        use = int(self.plateau)
+        loss = sync.tail_avg[n_tail - 1:n_tail]
+        call("ctu_optim_post", self.step_count.data_ptr(), self.sched.data_ptr(), loss.data_ptr() if use else None, use, st)
+
     def step(self, loss: torch.Tensor = None, grad_scale: float = 1.0):
         """Enqueue the update; ``loss`` (device float scalar) feeds the plateau scheduler AFTER the update, the order of
         Model.py:367-371.  No host synchronisation."""

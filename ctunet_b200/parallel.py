@@ -45,7 +45,7 @@ class GradSync:
         # mean over ranks of the per-rank losses -- the tail carries the loss components through the same all-reduce, so
         # logging and ReduceLROnPlateau (Model.py:369-371) see identical values on every rank.
         self.n_grad = total
-        self.flat = torch.zeros(total + self.TAIL, dtype=torch.float32, device=ref.device)
+        self.flat = self._alloc_flat(total + self.TAIL, ref.device)
         self.tail = self.flat[total:]
         self.slices: Dict[int, torch.Tensor] = {}
         self.bucket_of: Dict[int, int] = {}
@@ -72,6 +72,9 @@ class GradSync:
         self._remaining: List[int] = []
         self._handles = []
         self.begin_step()
+
+    def _alloc_flat(self, n: int, device) -> torch.Tensor:
+        return torch.zeros(n, dtype=torch.float32, device=device)
 
     # -- engine-facing ---------------------------------------------------------------------------
     def buffer_for(self, param) -> Optional[torch.Tensor]:
@@ -143,6 +146,92 @@ class GradSync:
         if publish:
             self.publish()
         self.begin_step()
+
+
+class _RawCudaBuffer:
+    """A caller-owned device allocation seen through ``__cuda_array_interface__`` (zero-copy ``torch.as_tensor``)."""
+
+    def __init__(self, ptr: int, n_floats: int):
+        self.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+class PeerGradSync(GradSync):
+    """Gradient exchange over NVLink peer memory, fused with the optimizer (csrc/peer.cu): every rank's flat gradient
+    buffer sits in an IPC-shared allocation that all ranks of the node map; the optimizer kernel reads element f from ALL
+    ranks, averages in rank order and applies the update in one pass.  No NCCL call inside the step -- the whole iteration
+    (forward, loss, backward, exchange, optimizer, scheduler) is ONE CUDA graph, and nothing on the host sits between the
+    ranks.  ``torch.distributed`` is only used to hand the IPC handles around at construction."""
+
+    def __init__(self, module: torch.nn.Module, process_group=None, skip_prefixes=("cblock.",)):
+        from . import _lib
+        self._lib = _lib
+        self._base = None
+        super().__init__(module, process_group, n_buckets=1, skip_prefixes=skip_prefixes, deferred=True)
+        if not self.cuda:
+            raise RuntimeError("PeerGradSync needs CUDA devices")
+        self.rank = dist.get_rank(process_group) if self.world > 1 else 0
+        lib = _lib.load()
+        handles = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(handles, bytes(self._handle), group=process_group)
+        else:
+            handles = [bytes(self._handle)]
+        self._opened = []
+        bases = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                bases.append(self._base)
+                continue
+            import ctypes
+            out = ctypes.c_void_p()
+            buf = (ctypes.c_ubyte * 64).from_buffer_copy(h)
+            rc = lib.ctu_peer_open(buf, ctypes.byref(out))
+            if rc != 0:
+                raise RuntimeError("ctu_peer_open(rank %d) failed (%d): %s -- peer access over NVLink is required" % (r, rc, _lib.last_error()))
+            self._opened.append(out.value)
+            bases.append(out.value)
+        fb = lib.ctu_peer_flag_bytes()
+        self.h_flags = _lib.ptr_array(bases)
+        self.h_grads = _lib.ptr_array([b + fb for b in bases])
+        self.tail_avg = torch.zeros(self.TAIL, dtype=torch.float32, device=self.flat.device)
+        if self.world > 1:
+            dist.barrier(group=process_group)           # every rank has mapped every buffer before the first step
+
+    def _alloc_flat(self, n: int, device) -> torch.Tensor:
+        import ctypes
+        lib = self._lib.load()
+        fb = lib.ctu_peer_flag_bytes()
+        ptr = ctypes.c_void_p()
+        self._handle = (ctypes.c_ubyte * 64)()
+        with torch.cuda.device(device):
+            rc = lib.ctu_peer_alloc(fb + 4 * n, ctypes.byref(ptr), self._handle)
+        if rc != 0:
+            raise RuntimeError("ctu_peer_alloc failed (%d): %s" % (rc, self._lib.last_error()))
+        self._base = ptr.value
+        self._raw = _RawCudaBuffer(self._base + fb, n)
+        return torch.as_tensor(self._raw, device=device)
+
+    # the exchange is inside the optimizer kernel: nothing to do between backward and the update
+    def reduce_all(self) -> None:
+        pass
+
+    def wait_released(self) -> None:
+        """Enqueue: every peer has finished reading this rank's previous gradients (before the buffer is written again)."""
+        self._lib.call("ctu_peer_wait_done", self.h_grads, self.h_flags, self.world, self.rank, self._lib.stream_ptr())
+
+    def signal(self) -> None:
+        """Enqueue: this rank's gradients (and loss tail) of the current step are complete."""
+        self._lib.call("ctu_peer_signal", self.h_grads, self.h_flags, self.world, self.rank, self._lib.stream_ptr())
+
+    def error(self) -> int:
+        return int(self._lib.load().ctu_peer_error(self._base))
+
+    def close(self) -> None:
+        lib = self._lib.load()
+        torch.cuda.synchronize()
+        for p in self._opened:
+            lib.ctu_peer_close(p)
+        self._opened = []
 
 
 def shard_range(n_items: int, rank: int, world: int):

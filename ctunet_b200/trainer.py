@@ -28,7 +28,7 @@ from ._lib import call, ptr_array, stream_ptr
 from .engine import Engine
 from .models import _run_planned
 from .optim import FlatOptimizer
-from .parallel import GradSync
+from .parallel import GradSync, PeerGradSync
 
 # The head and the Dice + CrossEntropy loss as ONE pass over the head's inputs (forward) and one more (backward); off = the
 # separate head / loss kernels the drop-in modules use behind the reference's model / handler split.
@@ -120,6 +120,8 @@ class TrainStep:
         # gradients always land in ONE flat buffer: the optimizer is a single launch over it, data parallel or not
         self.grads = grad_sync if grad_sync is not None else GradSync(model, deferred=True)
         self.world = self.grads.world
+        # gradient exchange inside the optimizer kernel over NVLink peer memory: no collective call in the step
+        self.peer = isinstance(self.grads, PeerGradSync)
         dev = self.grads.flat.device
         if not self.grads.flat.is_cuda:
             raise RuntimeError("TrainStep runs on CUDA only (no CPU fallback): move the model to the GPU first")
@@ -132,7 +134,7 @@ class TrainStep:
         self._comps = torch.zeros(self.spec.n_terms + 1, dtype=torch.float32, device=dev)
         self.graph = bool(graph)
         # two captured graphs around one eager all-reduce (data parallel), or one graph for the whole iteration
-        self.split_graph = (self.world > 1) if split_graph is None else bool(split_graph)
+        self.split_graph = (self.world > 1 and not self.peer) if split_graph is None else bool(split_graph)
         self._graph = None
         self._graph_opt = None
         self._static = None
@@ -149,7 +151,9 @@ class TrainStep:
         eng = Engine(image.device, net.compute_dtype, record=True)
         eng.grad_sink = self.grads
         eng.want_input_grad = bool(self.input_requires_grad)
-        mirror = self.grads.tail if self.world > 1 else None
+        mirror = self.grads.tail if (self.world > 1 or self.peer) else None
+        if self.peer:
+            self.grads.wait_released()                        # the flat buffer (loss tail first) is about to be rewritten
         if FUSED_HEAD_LOSS:
             # the head runs fused with the loss: the fp32 network outputs and their gradients are never materialised
             eng.fused_loss = (target, self.handler == "double", self.spec.ce_lambda, self.spec.dice_lambda, self._comps, mirror)
@@ -161,11 +165,17 @@ class TrainStep:
             dpreds = [_pair_bwd(s, self._g) for s in saved]
             eng.backward(dpreds[0], dpreds[1] if len(dpreds) > 1 else None)
         self.grads.check_complete()
+        if self.peer:
+            self.grads.signal()
+            return self.grads.tail_avg[:self.spec.n_terms + 1]       # filled by the fused exchange + optimizer kernel
         # world > 1: the averaged components come back in the tail of the flat buffer
         return self.grads.tail[:self.spec.n_terms + 1] if self.world > 1 else self._comps
 
     def _update(self, comps):
-        self.optimizer.step(loss=comps[self.spec.n_terms:self.spec.n_terms + 1])
+        if self.peer:
+            self.optimizer.step_peer(self.grads, self.spec.n_terms + 1)
+        else:
+            self.optimizer.step(loss=comps[self.spec.n_terms:self.spec.n_terms + 1])
 
     def _eager(self, image, target):
         comps = self._forward_backward(image, target)

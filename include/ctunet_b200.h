@@ -284,6 +284,30 @@ int ctu_optim_step(int kind, const void* chunks, int n_chunks, const float* flat
                    double weight_decay, double momentum, double alpha, int amsgrad, double grad_scale, ctu_stream stream);
 int ctu_optim_post(long long* step, double* sched_state, const float* loss, int use_plateau, ctu_stream stream);
 
+/* ---- data-parallel gradient exchange fused with the optimizer over NVLink peer memory (replaces nn.DataParallel's
+ *      reduce / broadcast, Model.py:481-486; one process per GPU).  Every rank's flat gradient buffer lives in an
+ *      IPC-shared allocation: [flag page of ctu_peer_flag_bytes()] [flat fp32 gradients | loss tail].  h_grads[r] / h_flags[r]:
+ *      HOST arrays of the world's device pointers as mapped into THIS process (own rank included). ---------------------- */
+int ctu_peer_flag_bytes(void);
+/* setup-time only (the step itself never allocates): cudaMalloc + zero + cudaIpcGetMemHandle / OpenMemHandle */
+int ctu_peer_alloc(long long bytes, void** ptr, unsigned char* handle64);
+int ctu_peer_open(const unsigned char* handle64, void** ptr);
+int ctu_peer_close(void* ptr);
+int ctu_peer_free(void* ptr);
+/* after the last gradient kernel of a step: publish "my gradients of step seq+1 are complete" to every peer */
+int ctu_peer_signal(const void* const* h_grads, void* const* h_flags, int world, int rank, ctu_stream stream);
+/* before the first gradient write of a step: every peer has finished reading this rank's previous gradients */
+int ctu_peer_wait_done(const void* const* h_grads, void* const* h_flags, int world, int rank, ctu_stream stream);
+/* ctu_optim_step with the gradient of element f = mean over ranks (summed in rank order) of h_grads[r][f], read through
+ * the peer pointers once every rank has signalled; also averages the tail_n loss floats at tail_off into tail_out and
+ * releases the peers' buffers.  One launch = all-reduce + optimizer. */
+int ctu_optim_step_peer(int kind, const void* chunks, int n_chunks, const void* const* h_grads, void* const* h_flags, int world,
+                        int rank, float* state0, float* state1, float* state2, const double* lr, const long long* step,
+                        double beta1, double beta2, double eps, double weight_decay, double momentum, double alpha, int amsgrad,
+                        double grad_scale, float* tail_out, long long tail_off, int tail_n, ctu_stream stream);
+/* host read (synchronises): 0 ok, 1 a peer's gradients never arrived, 2 a peer never released this rank's buffer */
+int ctu_peer_error(const void* flags);
+
 /* ---- SaltAndPepper (transforms.py:13-49) on a uint8 volume: out = (img AND black) OR white with
  *      black = (u_b > density*(1-salt_ratio)), white = 1 - (u_w > density*salt_ratio).  u_black / u_white: caller-supplied
  *      float64 uniform fields (both or neither); NULL = Philox4x32-10 keyed by seed, counter = offset + voxel index. ------ */

@@ -307,3 +307,35 @@ def test_fused_head_loss_equals_separate_kernels(name, handler, mode, lams):
     assert float((g0 - g1).abs().max()) <= (2e-5 if mode == "fp32" else 2e-3) * scale
     rel = float((g0 - g1).norm() / g0.norm())
     assert rel < (1e-5 if mode == "fp32" else 2e-3), rel
+
+
+# ------------------------------------------------------------------------------------------------ peer-memory exchange
+@pytest.mark.parametrize("graph", [False, True])
+def test_peer_exchange_single_rank_equals_plain_step(graph):
+    """parallel.PeerGradSync (csrc/peer.cu: all-reduce + optimizer in one kernel over IPC-mapped gradient buffers) with a
+    world of one rank -- the flag protocol, the rank-ordered mean, the averaged loss tail and the fused update -- against
+    the plain single-GPU step.  (Two and eight ranks: scripts/check_peer_ddp.py under torchrun on the GPU box.)"""
+    import ctunet_b200 as C
+    from ctunet_b200.parallel import PeerGradSync
+    from ctunet_b200.synthetic import make_training_batch
+    from ctunet_b200.trainer import TrainStep
+    img, (sk_t, fl_t) = make_training_batch(2, 2, 32, seed=5, device=DEV)
+    nets, steps = [], []
+    for peer in (False, True):
+        C.set_compute_dtype("fp32")
+        torch.manual_seed(0)
+        net = C.UNetSP().to(DEV)
+        C.set_compute_dtype("bf16")
+        nets.append(net)
+        steps.append(TrainStep(net, "double", 1.0, 1.0, lr=1e-3, scheduler=True, grad_sync=PeerGradSync(net) if peer else None,
+                               graph=graph))
+    assert steps[1].peer and not steps[1].split_graph
+    for it in range(5):
+        a = steps[0](img, (sk_t, fl_t)).tolist()
+        b = steps[1](img, (sk_t, fl_t)).tolist()
+        assert a == pytest.approx(b, rel=2e-4, abs=2e-4), it
+    assert steps[1].grads.error() == 0
+    assert int(steps[1].optimizer.step_count) == 5
+    for (k, p), (_, q) in zip(nets[0].named_parameters(), nets[1].named_parameters()):
+        assert float((p - q).abs().max()) <= 2e-3 * 5 + 1e-6, k          # Adam: rounding-level gradient noise -> <= lr per step
+    steps[1].grads.close()
