@@ -45,6 +45,10 @@ def parse():
                     help="skip the short device-resident runs of the legacy 5^3 models reported under other_workloads")
     ap.add_argument("--kernels-out", default=None, help="write the full per-kernel timing table to this file")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
+                    help="data-parallel gradient exchange: peer = all-reduce fused with the optimizer over NVLink peer memory "
+                         "(parallel.PeerGradSync, the whole step is one CUDA graph; auto), nccl = one NCCL all-reduce between "
+                         "two captured graphs")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="capture the training step in CUDA graphs (auto = on; data parallel: two graphs around one eager "
                          "NCCL all-reduce of the flat gradient buffer)")
@@ -417,7 +421,7 @@ def run_b200_arm(a):
     import torch.distributed as dist
     import ctunet_b200 as C
     from ctunet_b200 import _lib
-    from ctunet_b200.parallel import GradSync
+    from ctunet_b200.parallel import GradSync, PeerGradSync
     from ctunet_b200.trainer import TrainStep
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -437,13 +441,17 @@ def run_b200_arm(a):
     torch.manual_seed(0)
     net = getattr(C, a.model)().to(dev)
     use_graph = a.graph != "off"
-    sync = GradSync(net, deferred=use_graph) if world > 1 else None
+    peer = world > 1 and a.exchange != "nccl"
+    sync = (PeerGradSync(net) if peer else GradSync(net, deferred=use_graph)) if world > 1 else None
     # the benchmarked example .ini sets b_scheduler = True: ReduceLROnPlateau() is stepped every iteration (Model.py:369-371)
     step = TrainStep(net, HANDLER[a.model], 1.0, 1.0, lr=1e-4, scheduler=True, grad_sync=sync, graph=use_graph)
     cin = in_channels(a.model)
     host_batch = synthetic_batch(a.batch, cin, a.size, seed=1234 + 1000 * rank)     # the tensors BOTH arms consume
     img, sk_t, fl_t = (t.to(dev) for t in (host_batch[0],) + host_batch[1])
-    target = (sk_t, fl_t) if HANDLER[a.model] == "double" else sk_t
+    # double-output handler: the targets are handed over as the uint8 label masks the one-hot tensors are built from
+    # (datasets.py:209-214) -- the fused head + loss kernels read them directly; `e2e_f32_batch` below keeps the float format
+    label_masks = [t.to(torch.uint8).contiguous() for t in (sk_t[:, 1], fl_t[:, 1])]
+    target = tuple(label_masks) if HANDLER[a.model] == "double" else sk_t
     host = [t.cpu().pin_memory() for t in ((img, sk_t, fl_t) if HANDLER[a.model] == "double" else (img, sk_t))]
     h2d_bytes = sum(t.numel() * t.element_size() for t in host)
     # L2 hygiene: a step streams several GB of activations (>> 126 MB L2) between consecutive uses of any buffer
@@ -567,8 +575,12 @@ def run_b200_arm(a):
 
         return one, rb
 
-    e2e_step, rb = make_e2e(host, lambda b: step(b[0], (b[1], b[2]) if len(b) == 3 else b[1]))
-    for _ in range(3):
+    step_f32 = step
+    if double:       # the reference DataLoader's format: a second driver over the same network, captured with float targets
+        sync_f32 = (PeerGradSync(net) if peer else GradSync(net, deferred=use_graph)) if world > 1 else None
+        step_f32 = TrainStep(net, HANDLER[a.model], 1.0, 1.0, lr=1e-4, scheduler=True, grad_sync=sync_f32, graph=use_graph)
+    e2e_step, rb = make_e2e(host, lambda b: step_f32(b[0], (b[1], b[2]) if len(b) == 3 else b[1]))
+    for _ in range(4):
         e2e_step()
     ms_e2e = timed(e2e_step, a.steps, after=rb.drain)
     d2h_bytes = rb.bytes_per_step
@@ -576,7 +588,7 @@ def run_b200_arm(a):
     e2e_u8 = None
     if double:
         # uint8 masks: broken skull = image channel 0, full skull = target 0 class 1, flap = target 1 class 1
-        host_u8 = [t.to(torch.uint8).cpu().pin_memory() for t in (img[:, 0], sk_t[:, 1], fl_t[:, 1])]
+        host_u8 = [t.to(torch.uint8).cpu().pin_memory() for t in (img[:, 0], label_masks[0], label_masks[1])]
         atlas_dev = img[0, 1].contiguous() if cin > 1 else None
 
         u8_step, rb8 = make_e2e(host_u8, lambda b: step.step_from_masks(b[0], b[1], b[2], atlas_dev))
@@ -586,9 +598,9 @@ def run_b200_arm(a):
         e2e_u8 = {"value": a.batch * a.size ** 3 * world / (ms_u8 * 1e-3), "unit": UNIT, "ms_per_step": ms_u8,
                   "h2d_bytes_per_step": sum(t.numel() for t in host_u8), "d2h_bytes_per_step": rb8.bytes_per_step,
                   "note": "TrainStep.step_from_masks: the batch's three uint8 masks (broken skull, full skull, flap) from "
-                          "pinned host memory, double-buffered H2D, encoded on the device (ctu_encode_flaprec_u8: float "
-                          "image + atlas channel + one-hot float targets, datasets.py:195-235) into the captured step's "
-                          "inputs; loss components read back every step, one step late"}
+                          "pinned host memory, double-buffered H2D; the float image + atlas channel are encoded on the device "
+                          "(ctu_encode_flaprec_u8, datasets.py:195-235) into the captured step's input and the label masks "
+                          "feed the fused head + loss kernels as they are; loss components read back every step, one step late"}
 
     # nvidia-smi was sampling (every 50 ms) from the start of the timed `value` loop to the end of the e2e loops
     clk = clocks.stop() if rank == 0 else None
@@ -780,7 +792,9 @@ def run_b200_arm(a):
         "dtype": a.dtype, "data": "synthetic",
         "config": {"workload": workload_name(a), "global_batch": a.batch * world, "parallelism": "dp%d" % world,
                    "l2": flush_note, "conv_path": "tcgen05" if _lib.load().ctu_has_tensor_path() else "cuda-core",
-                   "cuda_graph": use_graph},
+                   "cuda_graph": use_graph,
+                   "gradient_exchange": None if world == 1 else ("peer memory over NVLink, fused with the optimizer kernel" if peer
+                                                                 else "NCCL all-reduce between two captured graphs")},
         "e2e": e2e_main,
         "e2e_f32_batch": e2e_f32 if e2e_main is not e2e_f32 else None,
         "gpu_launches": launches,

@@ -69,8 +69,8 @@ SIGNATURES = {
     "ctu_bn_relu_bwd_apply": (I, [I, P, P, P, P, P, P, D, P, P, P, I, I, I, I, I, I, P]),
     "ctu_head_fwd": (I, [I, P, P, I, P, P, I, I, P, P, I, LL, P]),
     "ctu_head_bwd": (I, [I, P, P, I, P, P, I, I, P, P, P, P, P, P, P, I, LL, P]),
-    "ctu_head_loss_fwd": (I, [I, P, P, I, P, P, I, I, P, P, I, F, F, P, P, P, I, LL, P]),
-    "ctu_head_loss_bwd": (I, [I, P, P, I, P, P, I, I, P, P, I, F, F, P, P, P, I, LL, P]),
+    "ctu_head_loss_fwd": (I, [I, P, P, I, P, P, I, I, P, P, I, I, F, F, P, P, P, I, LL, P]),
+    "ctu_head_loss_bwd": (I, [I, P, P, I, P, P, I, I, P, P, I, I, F, F, P, P, P, I, LL, P]),
     "ctu_head_param_grad": (I, [I, P, P, I, P, I, P, P, I, LL, P]),
     "ctu_dice_ce_fwd": (I, [P, P, I, I, LL, I, I, P, P, P]),
     "ctu_dice_ce_bwd": (I, [P, P, I, I, LL, I, I, P, P, P, P]),

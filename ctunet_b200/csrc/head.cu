@@ -35,6 +35,7 @@ struct HeadParams {
     const float* tgt0;
     const float* tgt1;
     double* lsums;        // [pairs][n][4]: sum q*t, sum q*q, sum t*t, CE sum
+    int tgt_u8;           // targets are uint8 class-1 masks [n][spatial] (two classes) instead of one-hot float [n][C][spatial]
     int softmax_for_dice, want_ce;
     float g_ce, g_dice;
 };
@@ -453,7 +454,37 @@ static int head_bwd_launch(const HeadParams& p, int part, cudaStream_t stream) {
 //   backward: the same reads, writes the source gradients (PART 1) / reduces the parameter gradients (PART 2)
 // PAIRS = 2: the SP heads (outputs skull = o0, flap = o1, two classes each; ProblemHandler.py:228-298);
 // PAIRS = 1: the plain head with CO classes against one target (ProblemHandler.py:59-91).
-template <typename T, int CO, int CBT, int PAIRS>
+// Two x-adjacent voxels of the targets of one pair: one-hot float planes, or a uint8 class-1 mask (t = [1 - m, m]).
+template <int C, bool U8>
+__device__ __forceinline__ void head_load_targets2(const float* tf, long long spatial, int n, long long s, float (&t)[C][2]) {
+    if (U8) {
+        const unsigned char* m = reinterpret_cast<const unsigned char*>(tf) + (long long)n * spatial + s;
+        const uchar2 v = *reinterpret_cast<const uchar2*>(m);
+        const float a = v.x ? 1.f : 0.f, b = v.y ? 1.f : 0.f;
+        t[0][0] = 1.f - a; t[0][1] = 1.f - b;
+        t[C - 1][0] = a; t[C - 1][1] = b;
+    } else {
+        const float* base = tf + (long long)n * C * spatial + s;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const float2 v = __ldg(reinterpret_cast<const float2*>(base + c * spatial));
+            t[c][0] = v.x; t[c][1] = v.y;
+        }
+    }
+}
+template <int C, bool U8>
+__device__ __forceinline__ void head_load_targets1(const float* tf, long long spatial, int n, long long s, float (&t)[C]) {
+    if (U8) {
+        const float a = reinterpret_cast<const unsigned char*>(tf)[(long long)n * spatial + s] ? 1.f : 0.f;
+        t[0] = 1.f - a;
+        t[C - 1] = a;
+    } else {
+#pragma unroll
+        for (int c = 0; c < C; ++c) t[c] = __ldg(tf + ((long long)n * C + c) * spatial + s);
+    }
+}
+
+template <typename T, int CO, int CBT, int PAIRS, bool TU8>
 __global__ void __launch_bounds__(kHeadThreads, 2) head_loss_fwd_kernel(HeadParams p) {
     extern __shared__ float hsm[];
     float* wsm = hsm;
@@ -467,8 +498,6 @@ __global__ void __launch_bounds__(kHeadThreads, 2) head_loss_fwd_kernel(HeadPara
     for (int q = 0; q < PAIRS; ++q)
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc[q][i] = 0.f;
-    const float* t0 = p.tgt0 + (long long)n * C * p.spatial;
-    const float* t1 = PAIRS == 2 ? p.tgt1 + (long long)n * C * p.spatial : nullptr;
     auto voxel = [&](const V8 (&xs)[CBT], const float (&ta)[C], const float (&tb)[C]) {
         HeadVals<CO> h;
         head_logits_of<CO, CBT>(wsm, bsm, h, xs);
@@ -495,16 +524,9 @@ __global__ void __launch_bounds__(kHeadThreads, 2) head_loss_fwd_kernel(HeadPara
             for (int v = 0; v < 2; ++v) head_load<T, CBT>(p, n, s + v, xs[v]);
             float ta[C][2], tb[C][2];
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-                const float2 a = __ldg(reinterpret_cast<const float2*>(t0 + c * p.spatial + s));
-                ta[c][0] = a.x; ta[c][1] = a.y;
-                if (PAIRS == 2) {
-                    const float2 b = __ldg(reinterpret_cast<const float2*>(t1 + c * p.spatial + s));
-                    tb[c][0] = b.x; tb[c][1] = b.y;
-                } else {
-                    tb[c][0] = tb[c][1] = 0.f;
-                }
-            }
+            for (int c = 0; c < C; ++c) ta[c][0] = ta[c][1] = tb[c][0] = tb[c][1] = 0.f;
+            head_load_targets2<C, TU8>(p.tgt0, p.spatial, n, s, ta);
+            if (PAIRS == 2) head_load_targets2<C, TU8>(p.tgt1, p.spatial, n, s, tb);
 #pragma unroll
             for (int v = 0; v < 2; ++v) {
                 float ua[C], ub[C];
@@ -519,10 +541,9 @@ __global__ void __launch_bounds__(kHeadThreads, 2) head_loss_fwd_kernel(HeadPara
             head_load<T, CBT>(p, n, s, xs);
             float ua[C], ub[C];
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-                ua[c] = __ldg(t0 + c * p.spatial + s);
-                ub[c] = PAIRS == 2 ? __ldg(t1 + c * p.spatial + s) : 0.f;
-            }
+            for (int c = 0; c < C; ++c) ua[c] = ub[c] = 0.f;
+            head_load_targets1<C, TU8>(p.tgt0, p.spatial, n, s, ua);
+            if (PAIRS == 2) head_load_targets1<C, TU8>(p.tgt1, p.spatial, n, s, ub);
             voxel(xs, ua, ub);
         }
     }
@@ -578,7 +599,7 @@ __global__ void head_loss_finalize_kernel(const double* __restrict__ sums, int p
 
 // Source gradients; the logit gradients dlc [n][CO][spatial] (fp32 planes) are stored for head_param_grad_kernel, so the
 // parameter-gradient launch (a leaf of the backward pass, second stream) is pure multiply-add streaming.
-template <typename T, int CO, int CBT, int PAIRS>
+template <typename T, int CO, int CBT, int PAIRS, bool TU8>
 __global__ void __launch_bounds__(kHeadThreads, 2) head_loss_bwd_kernel(HeadParams p) {
     extern __shared__ float hsm[];
     float* wsm = hsm;
@@ -591,8 +612,6 @@ __global__ void __launch_bounds__(kHeadThreads, 2) head_loss_bwd_kernel(HeadPara
 #pragma unroll
     for (int q = 0; q < PAIRS; ++q) dice_coefficients(p.lsums + ((long long)q * p.n + n) * 4, p.n, p.g_dice, kt[q], kq[q]);
     const float kce = p.want_ce ? p.g_ce / ((float)p.n * (float)p.spatial) : 0.f;
-    const float* t0 = p.tgt0 + (long long)n * C * p.spatial;
-    const float* t1 = PAIRS == 2 ? p.tgt1 + (long long)n * C * p.spatial : nullptr;
     float* dlc_out = p.out0 + (long long)n * CO * p.spatial;       // (out0 doubles as the dlc buffer in this kernel)
     auto voxel = [&](const V8 (&xs)[CBT], const float (&ta)[C], const float (&tb)[C], long long s, float (&dlc)[CO]) {
         HeadVals<CO> h;
@@ -664,16 +683,9 @@ __global__ void __launch_bounds__(kHeadThreads, 2) head_loss_bwd_kernel(HeadPara
             for (int v = 0; v < 2; ++v) head_load<T, CBT>(p, n, s + v, xs[v]);
             float ta[C][2], tb[C][2];
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-                const float2 a = __ldg(reinterpret_cast<const float2*>(t0 + c * p.spatial + s));
-                ta[c][0] = a.x; ta[c][1] = a.y;
-                if (PAIRS == 2) {
-                    const float2 b = __ldg(reinterpret_cast<const float2*>(t1 + c * p.spatial + s));
-                    tb[c][0] = b.x; tb[c][1] = b.y;
-                } else {
-                    tb[c][0] = tb[c][1] = 0.f;
-                }
-            }
+            for (int c = 0; c < C; ++c) ta[c][0] = ta[c][1] = tb[c][0] = tb[c][1] = 0.f;
+            head_load_targets2<C, TU8>(p.tgt0, p.spatial, n, s, ta);
+            if (PAIRS == 2) head_load_targets2<C, TU8>(p.tgt1, p.spatial, n, s, tb);
             float dl[2][CO];
 #pragma unroll
             for (int v = 0; v < 2; ++v) {
@@ -692,10 +704,9 @@ __global__ void __launch_bounds__(kHeadThreads, 2) head_loss_bwd_kernel(HeadPara
             head_load<T, CBT>(p, n, s, xs);
             float ua[C], ub[C], dl[CO];
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-                ua[c] = __ldg(t0 + c * p.spatial + s);
-                ub[c] = PAIRS == 2 ? __ldg(t1 + c * p.spatial + s) : 0.f;
-            }
+            for (int c = 0; c < C; ++c) ua[c] = ub[c] = 0.f;
+            head_load_targets1<C, TU8>(p.tgt0, p.spatial, n, s, ua);
+            if (PAIRS == 2) head_load_targets1<C, TU8>(p.tgt1, p.spatial, n, s, ub);
             voxel(xs, ua, ub, s, dl);
 #pragma unroll
             for (int o = 0; o < CO; ++o) dlc_out[o * p.spatial + s] = dl[o];
@@ -772,10 +783,10 @@ static int head_loss_fwd_launch(const HeadParams& p, cudaStream_t stream) {
     if (gx > cap) gx = cap;
     dim3 grid((unsigned)gx, p.n);
     switch (p.m.cb_total) {
-        case 1: head_loss_fwd_kernel<T, CO, 1, PAIRS><<<grid, kHeadThreads, smem, stream>>>(p); break;
-        case 2: head_loss_fwd_kernel<T, CO, 2, PAIRS><<<grid, kHeadThreads, smem, stream>>>(p); break;
-        case 3: head_loss_fwd_kernel<T, CO, 3, PAIRS><<<grid, kHeadThreads, smem, stream>>>(p); break;
-        default: head_loss_fwd_kernel<T, CO, 4, PAIRS><<<grid, kHeadThreads, smem, stream>>>(p); break;
+        case 1: if (p.tgt_u8) head_loss_fwd_kernel<T, CO, 1, PAIRS, true><<<grid, kHeadThreads, smem, stream>>>(p); else head_loss_fwd_kernel<T, CO, 1, PAIRS, false><<<grid, kHeadThreads, smem, stream>>>(p); break;
+        case 2: if (p.tgt_u8) head_loss_fwd_kernel<T, CO, 2, PAIRS, true><<<grid, kHeadThreads, smem, stream>>>(p); else head_loss_fwd_kernel<T, CO, 2, PAIRS, false><<<grid, kHeadThreads, smem, stream>>>(p); break;
+        case 3: if (p.tgt_u8) head_loss_fwd_kernel<T, CO, 3, PAIRS, true><<<grid, kHeadThreads, smem, stream>>>(p); else head_loss_fwd_kernel<T, CO, 3, PAIRS, false><<<grid, kHeadThreads, smem, stream>>>(p); break;
+        default: if (p.tgt_u8) head_loss_fwd_kernel<T, CO, 4, PAIRS, true><<<grid, kHeadThreads, smem, stream>>>(p); else head_loss_fwd_kernel<T, CO, 4, PAIRS, false><<<grid, kHeadThreads, smem, stream>>>(p); break;
     }
     return check_launch("ctu_head_loss_fwd");
 }
@@ -790,10 +801,10 @@ static int head_loss_bwd_launch(const HeadParams& p, cudaStream_t stream) {
     if (gx > cap) gx = cap;
     dim3 grid((unsigned)gx, p.n);
     switch (cbt) {
-        case 1: head_loss_bwd_kernel<T, CO, 1, PAIRS><<<grid, kHeadThreads, smem, stream>>>(p); break;
-        case 2: head_loss_bwd_kernel<T, CO, 2, PAIRS><<<grid, kHeadThreads, smem, stream>>>(p); break;
-        case 3: head_loss_bwd_kernel<T, CO, 3, PAIRS><<<grid, kHeadThreads, smem, stream>>>(p); break;
-        default: head_loss_bwd_kernel<T, CO, 4, PAIRS><<<grid, kHeadThreads, smem, stream>>>(p); break;
+        case 1: if (p.tgt_u8) head_loss_bwd_kernel<T, CO, 1, PAIRS, true><<<grid, kHeadThreads, smem, stream>>>(p); else head_loss_bwd_kernel<T, CO, 1, PAIRS, false><<<grid, kHeadThreads, smem, stream>>>(p); break;
+        case 2: if (p.tgt_u8) head_loss_bwd_kernel<T, CO, 2, PAIRS, true><<<grid, kHeadThreads, smem, stream>>>(p); else head_loss_bwd_kernel<T, CO, 2, PAIRS, false><<<grid, kHeadThreads, smem, stream>>>(p); break;
+        case 3: if (p.tgt_u8) head_loss_bwd_kernel<T, CO, 3, PAIRS, true><<<grid, kHeadThreads, smem, stream>>>(p); else head_loss_bwd_kernel<T, CO, 3, PAIRS, false><<<grid, kHeadThreads, smem, stream>>>(p); break;
+        default: if (p.tgt_u8) head_loss_bwd_kernel<T, CO, 4, PAIRS, true><<<grid, kHeadThreads, smem, stream>>>(p); else head_loss_bwd_kernel<T, CO, 4, PAIRS, false><<<grid, kHeadThreads, smem, stream>>>(p); break;
     }
     return check_launch("ctu_head_loss_bwd");
 }
@@ -814,13 +825,15 @@ static int head_param_grad_launch(const HeadParams& p, cudaStream_t stream) {
     return check_launch("ctu_head_param_grad");
 }
 
-static int head_loss_setup(HeadParams& p, int flags, int cout, const float* tgt0, const float* tgt1, double* sums,
+static int head_loss_setup(HeadParams& p, int flags, int cout, const void* tgt0, const void* tgt1, int target_u8, double* sums,
                            int softmax_for_dice, float ce_lambda, float dice_lambda, int& pairs, const char* what) {
     pairs = (flags & (CTU_HEAD_SP | CTU_HEAD_SP_SOFTMAX)) ? 2 : 1;
+    CTU_REQUIRE(!target_u8 || pairs == 2 || cout == 2, "%s: uint8 mask targets need two classes", what);
+    p.tgt_u8 = target_u8 ? 1 : 0;
     CTU_REQUIRE(tgt0 && (pairs == 1 || tgt1) && sums, "%s: missing target / sums", what);
     CTU_REQUIRE(ce_lambda != 0.f || dice_lambda != 0.f, "%s: both loss weights are zero", what);
     CTU_REQUIRE(pairs == 2 || cout >= 2 || ce_lambda == 0.f, "%s: CrossEntropy needs at least two classes", what);
-    p.tgt0 = tgt0; p.tgt1 = tgt1; p.lsums = sums;
+    p.tgt0 = reinterpret_cast<const float*>(tgt0); p.tgt1 = reinterpret_cast<const float*>(tgt1); p.lsums = sums;
     p.softmax_for_dice = softmax_for_dice; p.want_ce = ce_lambda != 0.f;
     p.g_ce = ce_lambda; p.g_dice = dice_lambda;
     return CTU_OK;
@@ -894,14 +907,15 @@ int ctu_head_bwd(int dtype, const void* const* h_srcs, const int* h_src_channels
 }
 
 int ctu_head_loss_fwd(int dtype, const void* const* h_srcs, const int* h_src_channels, int nsrc, const float* w,
-                      const float* bias, int cout, int flags, const float* target0, const float* target1,
+                      const float* bias, int cout, int flags, const void* target0, const void* target1, int target_u8,
                       int softmax_for_dice, float ce_lambda, float dice_lambda, double* sums, float* comps, float* mirror,
                       int n, long long spatial, ctu_stream stream) {
     HeadParams p = {};
     int rc = head_setup(p, h_srcs, h_src_channels, nsrc, w, bias, cout, flags, n, spatial, "ctu_head_loss_fwd");
     if (rc != CTU_OK) return rc;
     int pairs = 1;
-    rc = head_loss_setup(p, flags, cout, target0, target1, sums, softmax_for_dice, ce_lambda, dice_lambda, pairs, "ctu_head_loss_fwd");
+    rc = head_loss_setup(p, flags, cout, target0, target1, target_u8, sums, softmax_for_dice, ce_lambda, dice_lambda, pairs,
+                         "ctu_head_loss_fwd");
     if (rc != CTU_OK) return rc;
     CTU_REQUIRE(comps != nullptr, "ctu_head_loss_fwd: comps is null");
     cudaStream_t st = (cudaStream_t)stream;
@@ -925,15 +939,15 @@ int ctu_head_loss_fwd(int dtype, const void* const* h_srcs, const int* h_src_cha
 }
 
 int ctu_head_loss_bwd(int dtype, const void* const* h_srcs, const int* h_src_channels, int nsrc, const float* w,
-                      const float* bias, int cout, int flags, const float* target0, const float* target1,
+                      const float* bias, int cout, int flags, const void* target0, const void* target1, int target_u8,
                       int softmax_for_dice, float ce_lambda, float dice_lambda, const double* sums, void* const* h_dsrcs,
                       float* dlogits, int n, long long spatial, ctu_stream stream) {
     HeadParams p = {};
     int rc = head_setup(p, h_srcs, h_src_channels, nsrc, w, bias, cout, flags, n, spatial, "ctu_head_loss_bwd");
     if (rc != CTU_OK) return rc;
     int pairs = 1;
-    rc = head_loss_setup(p, flags, cout, target0, target1, const_cast<double*>(sums), softmax_for_dice, ce_lambda, dice_lambda,
-                         pairs, "ctu_head_loss_bwd");
+    rc = head_loss_setup(p, flags, cout, target0, target1, target_u8, const_cast<double*>(sums), softmax_for_dice, ce_lambda,
+                         dice_lambda, pairs, "ctu_head_loss_bwd");
     if (rc != CTU_OK) return rc;
     CTU_REQUIRE(h_dsrcs != nullptr && dlogits != nullptr, "ctu_head_loss_bwd: missing output buffers");
     for (int i = 0; i < nsrc; ++i) p.dsrc[i] = h_dsrcs[i];

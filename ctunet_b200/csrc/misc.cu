@@ -176,9 +176,11 @@ __global__ void encode_flaprec_kernel(const unsigned char* __restrict__ broken, 
     const int b = blockIdx.y;
     const long long v0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 16;
     if (v0 >= spatial) return;
+    const bool tg = skull_t != nullptr;       // image only: the fused head + loss kernels read the uint8 masks themselves
+    const uint4 zero = make_uint4(0, 0, 0, 0);
     const uint4 ub = *reinterpret_cast<const uint4*>(broken + b * spatial + v0);
-    const uint4 uf = *reinterpret_cast<const uint4*>(full + b * spatial + v0);
-    const uint4 ul = *reinterpret_cast<const uint4*>(flap + b * spatial + v0);
+    const uint4 uf = tg ? *reinterpret_cast<const uint4*>(full + b * spatial + v0) : zero;
+    const uint4 ul = tg ? *reinterpret_cast<const uint4*>(flap + b * spatial + v0) : zero;
     const uint32_t wb[4] = {ub.x, ub.y, ub.z, ub.w}, wf[4] = {uf.x, uf.y, uf.z, uf.w}, wl[4] = {ul.x, ul.y, ul.z, ul.w};
     float* img0 = image + (long long)b * cin * spatial + v0;
     float* sk0 = skull_t + (long long)b * 2 * spatial + v0;
@@ -193,10 +195,12 @@ __global__ void encode_flaprec_kernel(const unsigned char* __restrict__ broken, 
             vl[j] = ((wl[i] >> (8 * j)) & 0xffu) ? 1.f : 0.f;
         }
         *reinterpret_cast<float4*>(img0 + 4 * i) = make_float4(vb[0], vb[1], vb[2], vb[3]);
-        *reinterpret_cast<float4*>(sk0 + 4 * i) = make_float4(1.f - vf[0], 1.f - vf[1], 1.f - vf[2], 1.f - vf[3]);
-        *reinterpret_cast<float4*>(sk0 + spatial + 4 * i) = make_float4(vf[0], vf[1], vf[2], vf[3]);
-        *reinterpret_cast<float4*>(fl0 + 4 * i) = make_float4(1.f - vl[0], 1.f - vl[1], 1.f - vl[2], 1.f - vl[3]);
-        *reinterpret_cast<float4*>(fl0 + spatial + 4 * i) = make_float4(vl[0], vl[1], vl[2], vl[3]);
+        if (tg) {
+            *reinterpret_cast<float4*>(sk0 + 4 * i) = make_float4(1.f - vf[0], 1.f - vf[1], 1.f - vf[2], 1.f - vf[3]);
+            *reinterpret_cast<float4*>(sk0 + spatial + 4 * i) = make_float4(vf[0], vf[1], vf[2], vf[3]);
+            *reinterpret_cast<float4*>(fl0 + 4 * i) = make_float4(1.f - vl[0], 1.f - vl[1], 1.f - vl[2], 1.f - vl[3]);
+            *reinterpret_cast<float4*>(fl0 + spatial + 4 * i) = make_float4(vl[0], vl[1], vl[2], vl[3]);
+        }
         if (cin > 1) *reinterpret_cast<float4*>(img0 + spatial + 4 * i) = *reinterpret_cast<const float4*>(atlas + v0 + 4 * i);
     }
 }
@@ -428,8 +432,9 @@ int ctu_flap_mask_u8(const unsigned char* img, unsigned char* masked, unsigned c
 int ctu_encode_flaprec_u8(const unsigned char* broken, const unsigned char* full, const unsigned char* flap,
                           const float* atlas, float* image, float* skull_target, float* flap_target, int batch,
                           int in_channels, long long spatial, ctu_stream stream) {
-    CTU_REQUIRE(broken && full && flap && image && skull_target && flap_target && batch > 0 && spatial > 0,
-                "ctu_encode_flaprec_u8: bad arguments");
+    CTU_REQUIRE(broken && image && batch > 0 && spatial > 0, "ctu_encode_flaprec_u8: bad arguments");
+    CTU_REQUIRE((skull_target != nullptr) == (flap_target != nullptr) && (skull_target == nullptr || (full && flap)),
+                "ctu_encode_flaprec_u8: both targets (with both label masks) or neither");
     CTU_REQUIRE(in_channels == 1 || (in_channels == 2 && atlas), "ctu_encode_flaprec_u8: 1 input channel, or 2 with an atlas");
     CTU_REQUIRE(spatial % 16 == 0, "ctu_encode_flaprec_u8: the volume size must be a multiple of 16 voxels");
     dim3 grid(cdiv(spatial / 16, 256), batch);

@@ -660,13 +660,20 @@ class Engine:
         if len(targets) != (2 if sp else 1):
             raise ValueError("the %s head takes %d target tensor(s), got %d" % ("SP" if sp else "plain", 2 if sp else 1, len(targets)))
         want = (s0.n, 2 if sp else cout, s0.d, s0.h, s0.w)
+        u8 = int(targets[0].dtype == torch.uint8)
+        if u8:                              # label masks [B, D, H, W] (two classes), 1 byte per voxel instead of 8
+            want = (s0.n, s0.d, s0.h, s0.w)
+            if not sp and cout != 2:
+                raise TypeError("uint8 mask targets need a two-class output")
         for t in targets:
-            if tuple(t.shape) != want or t.dtype != torch.float32 or not t.is_contiguous() or t.device != s0.buf.device:
-                raise TypeError("targets: contiguous float32 one-hot tensors of shape %s on %s" % (want, s0.buf.device))
+            if (tuple(t.shape) != want or t.dtype != (torch.uint8 if u8 else torch.float32) or not t.is_contiguous()
+                    or t.device != s0.buf.device):
+                raise TypeError("targets: contiguous float32 one-hot tensors [B, C, D, H, W] or uint8 label masks [B, D, H, W] "
+                                "on %s (expected shape %s)" % (s0.buf.device, want))
         pa, ca, ns = self._src_args(srcs)
         t0, t1 = targets[0].data_ptr(), (targets[1].data_ptr() if sp else None)
         sums = self.f64(4 * len(targets) * s0.n)
-        call("ctu_head_loss_fwd", self.dtype, pa, ca, ns, weight.data_ptr(), bias.data_ptr(), cout, flags, t0, t1,
+        call("ctu_head_loss_fwd", self.dtype, pa, ca, ns, weight.data_ptr(), bias.data_ptr(), cout, flags, t0, t1, u8,
              int(softmax_for_dice), float(ce_l), float(dice_l), sums.data_ptr(), comps.data_ptr(),
              mirror.data_ptr() if mirror is not None else None, s0.n, s0.spatial, stream_ptr())
         if self.record:
@@ -676,7 +683,7 @@ class Engine:
                 dw, db = self._grad_buffer(weight), self._grad_buffer(bias)
                 dlc = self.f32(s0.n, cout, s0.d, s0.h, s0.w)
                 # source gradients (the critical path); the logit gradients are kept for the parameter gradients
-                call("ctu_head_loss_bwd", self.dtype, pa, ca, ns, weight.data_ptr(), bias.data_ptr(), cout, flags, t0, t1,
+                call("ctu_head_loss_bwd", self.dtype, pa, ca, ns, weight.data_ptr(), bias.data_ptr(), cout, flags, t0, t1, u8,
                      int(softmax_for_dice), float(ce_l), float(dice_l), sums.data_ptr(), ptr_array([d.ptr for d in dsrcs]),
                      dlc.data_ptr(), s0.n, s0.spatial, stream_ptr())
                 for s, d in zip(srcs, dsrcs):

@@ -240,16 +240,30 @@ class TrainStep:
         return self._static_out
 
     def step_from_masks(self, broken: torch.Tensor, full: torch.Tensor, flap: torch.Tensor, atlas=None):
-        """One iteration from the uint8 masks of a batch ([B,D,H,W] each, on the device): the float image (+ atlas
-        channel) and the two one-hot targets of datasets.py:195-235 are produced by ``ctu_encode_flaprec_u8`` --
-        straight into the captured graph's static inputs once the step is captured -- so a training loop ships
-        3 bytes per voxel over PCIe instead of 24."""
+        """One iteration from the uint8 masks of a batch ([B,D,H,W] each, on the device): the float image (+ atlas channel)
+        of datasets.py:195-235 is produced by ``ctu_encode_flaprec_u8`` straight into the captured graph's static input,
+        and the label masks ARE the targets -- the fused head + loss kernels read them as uint8 (``one_hot`` of a {0,1}
+        label is [1 - m, m]), so a training loop ships 3 bytes per voxel over PCIe instead of 24 and the one-hot float
+        targets (16 bytes per voxel, read twice per step) never exist.  Without the fused head + loss, or when the step was
+        captured with float targets, the one-hot targets are encoded as well."""
         from .utilities import encode_flaprec_batch
         if self.handler != "double":
             raise ValueError("step_from_masks feeds the double-output handler (full skull + flap targets)")
+        masks = FUSED_HEAD_LOSS and (self._graph is None or self._static[1].dtype == torch.uint8)
         if self._graph is not None:
-            encode_flaprec_batch(broken, full, flap, atlas, out=(self._static[0], (self._static[1], self._static[2])))
+            if masks:
+                encode_flaprec_batch(broken, full, flap, atlas, out=(self._static[0], None))
+                for dst, src in ((self._static[1], full), (self._static[2], flap)):
+                    if dst.data_ptr() != src.data_ptr():
+                        dst.copy_(src, non_blocking=True)
+            else:
+                encode_flaprec_batch(broken, full, flap, atlas, out=(self._static[0], (self._static[1], self._static[2])))
             return self._replay()
+        if masks:
+            image = torch.empty((broken.shape[0], 1 if atlas is None else 2) + tuple(broken.shape[1:]), dtype=torch.float32,
+                                device=broken.device)
+            encode_flaprec_batch(broken, full, flap, atlas, out=(image, None))
+            return self(image, (full.contiguous(), flap.contiguous()))
         image, target = encode_flaprec_batch(broken, full, flap, atlas)
         return self(image, target)
 

@@ -156,7 +156,9 @@ def encode_flaprec_batch(broken: torch.Tensor, full: torch.Tensor, flap: torch.T
     image [B,Cin,D,H,W] float32 (channel 0 = the broken skull, channel 1 = ``atlas`` [D,H,W] float32 as
     ``load_atlas_and_append_at_axis`` appends it, datasets.py:30-47) and the two targets
     ``one_hot(label, 2).movedim(-1, 1).float()`` [B,2,D,H,W] (datasets.py:209-214).  The host then ships 3 bytes per
-    voxel instead of 24.  ``out = (image, (skull_target, flap_target))`` writes into existing tensors."""
+    voxel instead of 24.  ``out = (image, (skull_target, flap_target))`` writes into existing tensors;
+    ``out = (image, None)`` produces the image only (the fused head + loss kernels of the training step read the uint8
+    label masks themselves)."""
     for t in (broken, full, flap):
         _need_cuda(t, "encode_flaprec_batch")
         if t.dtype != torch.uint8 or t.dim() != 4 or t.shape != broken.shape:
@@ -171,6 +173,10 @@ def encode_flaprec_batch(broken: torch.Tensor, full: torch.Tensor, flap: torch.T
         image = torch.empty((b, cin) + vol, dtype=torch.float32, device=broken.device)
         sk = torch.empty((b, 2) + vol, dtype=torch.float32, device=broken.device)
         fl = torch.empty_like(sk)
+    elif out[1] is None:
+        image, sk, fl = out[0], None, None
+        if image.dtype != torch.float32 or tuple(image.shape) != (b, cin) + vol or not image.is_contiguous() or not image.is_cuda:
+            raise TypeError("encode_flaprec_batch: out image must be contiguous float32 CUDA [B, C, D, H, W]")
     else:
         image, (sk, fl) = out
         for t, c in ((image, cin), (sk, 2), (fl, 2)):
@@ -178,8 +184,8 @@ def encode_flaprec_batch(broken: torch.Tensor, full: torch.Tensor, flap: torch.T
                 raise TypeError("encode_flaprec_batch: out tensors must be contiguous float32 CUDA [B, C, D, H, W]")
     call("ctu_encode_flaprec_u8", broken.contiguous().data_ptr(), full.contiguous().data_ptr(),
          flap.contiguous().data_ptr(), atlas.contiguous().data_ptr() if atlas is not None else None, image.data_ptr(),
-         sk.data_ptr(), fl.data_ptr(), b, cin, spatial, stream_ptr())
-    return image, (sk, fl)
+         sk.data_ptr() if sk is not None else None, fl.data_ptr() if fl is not None else None, b, cin, spatial, stream_ptr())
+    return image, ((sk, fl) if sk is not None else None)
 
 
 # ---------------------------------------------------------------------------------------------- reporting metrics

@@ -188,19 +188,21 @@ int ctu_head_bwd(int dtype, const void* const* h_srcs, const int* h_src_channels
 /* ---- fused head + loss for the training step (models.py:255-259, 319-330, 535-538 + ProblemHandler.py:59-91, 228-298):
  *      the head is recomputed from the blocked sources and fed to the Dice + CrossEntropy arithmetic in registers, so the
  *      fp32 network outputs and their gradients never touch HBM.  target0 / target1: one-hot float32 [n][C][spatial]
- *      (SP heads: two targets with C = 2; plain head: target0 with C = cout, target1 = NULL).  softmax_for_dice as
+ *      (SP heads: two targets with C = 2; plain head: target0 with C = cout, target1 = NULL); with target_u8 the targets
+ *      are uint8 class-1 masks [n][spatial] instead (two classes: the label volumes of datasets.py:209-214 before the
+ *      one-hot encoding -- 1 byte per voxel and target instead of 8).  softmax_for_dice as
  *      ctu_dice_ce_fwd.  sums: double[4 * pairs * n] (zeroed by the forward call, read by the backward calls).
  *      comps: float[terms + 1] = [ce_lambda * CE per pair] (if ce_lambda != 0) + [dice_lambda * Dice per pair]
  *      (if dice_lambda != 0) + [total]; mirror (nullable): a second copy (tail of the data-parallel gradient buffer). */
 int ctu_head_loss_fwd(int dtype, const void* const* h_srcs, const int* h_src_channels, int nsrc, const float* w,
-                      const float* bias, int cout, int flags, const float* target0, const float* target1,
+                      const float* bias, int cout, int flags, const void* target0, const void* target1, int target_u8,
                       int softmax_for_dice, float ce_lambda, float dice_lambda, double* sums, float* comps, float* mirror,
                       int n, long long spatial, ctu_stream stream);
 /* d(total) / d(sources) into h_dsrcs; also stores the logit gradients dlogits [n][cout][spatial] (fp32) for
  * ctu_head_param_grad, which reduces dW [cout][cin_total] and db [cout] (zeroed by the call) from them and the sources --
  * a leaf of the backward pass that can run on another stream. */
 int ctu_head_loss_bwd(int dtype, const void* const* h_srcs, const int* h_src_channels, int nsrc, const float* w,
-                      const float* bias, int cout, int flags, const float* target0, const float* target1,
+                      const float* bias, int cout, int flags, const void* target0, const void* target1, int target_u8,
                       int softmax_for_dice, float ce_lambda, float dice_lambda, const double* sums, void* const* h_dsrcs,
                       float* dlogits, int n, long long spatial, ctu_stream stream);
 int ctu_head_param_grad(int dtype, const void* const* h_srcs, const int* h_src_channels, int nsrc, const float* dlogits,
@@ -233,6 +235,7 @@ int ctu_kth_nonzero_u8(const unsigned char* img, int d, int h, int w, long long 
 int ctu_flap_mask_u8(const unsigned char* img, unsigned char* masked, unsigned char* extracted, int d, int h, int w,
                      const int* center, double size, int shape, double c_diam, ctu_stream stream);
 
+/* (skull_target = flap_target = NULL: the image only -- the fused head + loss kernels read the uint8 label masks directly) */
 /* ---- batch encoding on the device (datasets.py:195-235, :30-47): uint8 masks [batch][spatial] ->
  *      image [batch][in_channels][spatial] float32 (channel 0 = broken skull, channel 1 = atlas [spatial], nullable for
  *      1-channel models) and the two one-hot float32 targets [batch][2][spatial] (datasets.py:209-214). ---------- */

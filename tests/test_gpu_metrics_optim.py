@@ -339,3 +339,27 @@ def test_peer_exchange_single_rank_equals_plain_step(graph):
     for (k, p), (_, q) in zip(nets[0].named_parameters(), nets[1].named_parameters()):
         assert float((p - q).abs().max()) <= 2e-3 * 5 + 1e-6, k          # Adam: rounding-level gradient noise -> <= lr per step
     steps[1].grads.close()
+
+
+@pytest.mark.parametrize("name,handler", [("UNetSP", "double"), ("recAE_v2_fixed", "single")])
+def test_uint8_mask_targets_equal_one_hot_float_targets(name, handler):
+    """The fused head + loss kernels accept the label masks themselves (uint8 [B,D,H,W], datasets.py:209-214 before the
+    one-hot encoding): bit-identical loss components and gradients to the float one-hot targets."""
+    import ctunet_b200 as C
+    import ctunet_b200.trainer as TR
+    from oracle import unet_oracle as O
+    cfg = O.PRESETS[name]
+    x, (sk_t, fl_t) = O.make_training_batch(2, cfg.input_channels, 32, seed=17)
+    onehot = (sk_t.to(DEV), fl_t.to(DEV)) if handler == "double" else sk_t.to(DEV)
+    masks = tuple(t[:, 1].to(torch.uint8).contiguous().to(DEV) for t in (sk_t, fl_t))
+    masks = masks if handler == "double" else masks[0]
+    res = []
+    for tgt in (onehot, masks):
+        torch.manual_seed(0)
+        net = getattr(C, name)().to(DEV)
+        step = TR.TrainStep(net, handler, 1.0, 1.0, lr=1e-4)
+        comps = step._forward_backward(x.to(DEV), tgt).clone()
+        torch.cuda.synchronize()
+        res.append((comps.cpu(), step.grads.flat[:step.grads.n_grad].clone().cpu()))
+    assert torch.equal(res[0][0], res[1][0])
+    assert float((res[0][1] - res[1][1]).abs().max()) <= 1e-6 * float(res[0][1].abs().max())   # atomics order only
