@@ -602,6 +602,24 @@ def run_b200_arm(a):
                           "(ctu_encode_flaprec_u8, datasets.py:195-235) into the captured step's input and the label masks "
                           "feed the fused head + loss kernels as they are; loss components read back every step, one step late"}
 
+    e2e_bits = None
+    if double:
+        # bit-packed masks: 3 bits per voxel over PCIe (at 8 GPUs the 25 MB/step/rank of uint8 masks alone slow the step by
+        # 0.3 ms through host-side contention -- scripts/diag_e2e.py -- so the wire format matters more than the copy time)
+        from ctunet_b200.utilities import pack_mask_bits
+        host_bits = [pack_mask_bits(t.cpu()).pin_memory() for t in (img[:, 0], label_masks[0], label_masks[1])]
+        vol_shape = tuple(img.shape[2:])
+        bit_step, rbb = make_e2e(host_bits, lambda b: step.step_from_bits(b[0], b[1], b[2], vol_shape, atlas_dev))
+        for _ in range(3):
+            bit_step()
+        ms_bits = timed(bit_step, a.steps, after=rbb.drain)
+        e2e_bits = {"value": a.batch * a.size ** 3 * world / (ms_bits * 1e-3), "unit": UNIT, "ms_per_step": ms_bits,
+                    "h2d_bytes_per_step": sum(t.numel() for t in host_bits), "d2h_bytes_per_step": rbb.bytes_per_step,
+                    "note": "TrainStep.step_from_bits: the batch's three binary masks (broken skull, full skull, flap) BIT-PACKED in "
+                            "pinned host memory, double-buffered H2D, expanded on the device (ctu_encode_flaprec_bits: float image "
+                            "+ atlas channel + uint8 label masks, datasets.py:195-235) straight into the captured step's inputs; "
+                            "loss components read back every step, one step late"}
+
     # nvidia-smi was sampling (every 50 ms) from the start of the timed `value` loop to the end of the e2e loops
     clk = clocks.stop() if rank == 0 else None
     vox_per_step = a.batch * a.size ** 3 * world
@@ -751,7 +769,7 @@ def run_b200_arm(a):
                "d2h_bytes_per_step": d2h_bytes,
                "note": "TrainStep.__call__: float32 image + one-hot float32 targets from pinned host memory (the reference "
                        "DataLoader's format), double-buffered H2D, loss components read back every step one step late"}
-    e2e_main = e2e_u8 if e2e_u8 is not None else e2e_f32
+    e2e_main = e2e_bits if e2e_bits is not None else (e2e_u8 if e2e_u8 is not None else e2e_f32)
     # BASELINE configs 4 and 5 (secondary numbers, same GPU): sliding-window inference over a synthetic 512x512x256 volume
     # (32 patches of 128^3, 8 per batch, eval-mode model + argmax) and the preprocessing chain on the int16 HU volume
     extra = None
@@ -797,6 +815,7 @@ def run_b200_arm(a):
                                                                  else "NCCL all-reduce between two captured graphs")},
         "e2e": e2e_main,
         "e2e_f32_batch": e2e_f32 if e2e_main is not e2e_f32 else None,
+        "e2e_u8_masks": e2e_u8 if e2e_main is not e2e_u8 else None,
         "gpu_launches": launches,
         "gpu_launches_note": "C-ABI entry points in the timed region (each enqueues >= 1 kernel of this library)"
                              + ("; the step is replayed from a CUDA graph captured once" if use_graph else ""),

@@ -11,7 +11,8 @@ from .models import (UNet, UNet4b1i3o, UNet4b2i3o, UNet5b2i3o, UNetDO, UNetSP, U
 from .losses import (dice_loss, dice_ce, ProblemHandler, FlapRec, FlapRecWithShapePrior,  # noqa: F401
                      FlapRecWithShapePriorDoubleOut, FlapRecDoubleOut)
 from .utilities import (hard_segm_from_tensor, shape_3d, blank_patch, random_blank_patch, encode_flaprec_batch,  # noqa: F401
-                        SkullRandomHole, kth_nonzero, count_nonzero)
+                        SkullRandomHole, SaltAndPepper, kth_nonzero, count_nonzero, dice_coeff, hausdorff,
+                        pack_mask_bits, encode_flaprec_bits)
 from . import preprocess  # noqa: F401
 from .dropin import install, uninstall, MODEL_CLASSES, HANDLER_CLASSES  # noqa: F401
 

@@ -39,6 +39,8 @@ SIGNATURES = {
     "ctu_conv_pack_weight_dgrad": (I, [P, P, I, I, I, P, I, P]),
     "ctu_conv_unpack_wgrad": (I, [P, P, I, I, I, P, P]),
     "ctu_conv3d_fprop": (I, [I, P, P, I, P, P, P, P, I, I, I, I, I, I, I, I, P]),
+    "ctu_conv_tc_bnred_supported": (I, [I, I, P, I, I, I, I]),
+    "ctu_conv3d_dgrad_bnred": (I, [P, P, I, P, P, I, I, I, I, I, I, P, P, P, I, P]),
     "ctu_conv_tc_supported": (I, [I, I, P, I, I, I, I]),
     "ctu_conv_tc_wgrad_supported": (I, [I, I, P, I, I, I, I]),
     "ctu_conv_tc_wimg_bytes": (LL, [I, I, P, I]),
@@ -79,6 +81,7 @@ SIGNATURES = {
     "ctu_kth_nonzero_u8": (I, [P, I, I, I, LL, P, P, P]),
     "ctu_flap_mask_u8": (I, [P, P, P, I, I, I, P, D, I, D, P]),
     "ctu_encode_flaprec_u8": (I, [P, P, P, P, P, P, P, I, I, LL, P]),
+    "ctu_encode_flaprec_bits": (I, [P, P, P, P, P, P, P, I, I, LL, P]),
     "ctu_hu_window": (I, [P, P, LL, F, F, P]),
     "ctu_hu_threshold": (I, [P, P, LL, I, P]),
     "ctu_resample_nearest_f32": (I, [P, P, I, I, I, I, I, I, P]),

@@ -327,7 +327,8 @@ static int launch_wgrad(const WgradParams& p, int k, cudaStream_t stream) {
 
 // implemented in conv_tc.cu
 int conv3d_fprop_tc(const void* const* h_srcs, const int* h_src_channels, int nsrc, const float* wp, const float* bias,
-                    void* y, double* stats, int stat_cout, int cout, int k, int n, int d, int h, int w, cudaStream_t stream);
+                    void* y, double* stats, int stat_cout, int cout, int k, int n, int d, int h, int w, cudaStream_t stream,
+                    const void* bn_y = nullptr, const float* bn_ss = nullptr, int bn_pm = 0);
 int conv3d_wgrad_tc(const void* const* h_srcs, const int* h_src_channels, int nsrc, const void* dy, float* dwp,
                     float* dbias, int phase_cout, int cout, int k, int n, int d, int h, int w, cudaStream_t stream);
 // implemented in conv_wide.cu
@@ -382,6 +383,20 @@ int ctu_conv3d_fprop(int dtype, const void* const* h_srcs, const int* h_src_chan
     if (rc == CTU_OK && bn_sums != nullptr)
         rc = ctu_bn_stats(dtype, y, stat_cout, ((cout + 7) / 8) / cob_nat, n, (long long)d * h * w, bn_sums, stream);
     return rc;
+}
+
+int ctu_conv3d_dgrad_bnred(const void* const* h_srcs, const int* h_src_channels, int nsrc, const void* wimg, void* dx,
+                           int cout, int k, int n, int d, int h, int w, const void* bn_y, const float* bn_ss,
+                           double* bn_sums2, int bn_y_phase_major, ctu_stream stream) {
+    SrcMap m;
+    int rc = make_srcmap(m, nsrc, h_src_channels);
+    if (rc != CTU_OK) return rc;
+    CTU_REQUIRE(h_srcs && wimg && dx && bn_y && bn_ss && bn_sums2 && cout > 0 && n > 0 && d > 0 && h > 0 && w > 0,
+                "ctu_conv3d_dgrad_bnred: bad arguments");
+    CTU_REQUIRE(!bn_y_phase_major || (d % 2 == 0 && h % 2 == 0 && w % 2 == 0), "ctu_conv3d_dgrad_bnred: phase-major y needs even dims");
+    for (int i = 0; i < nsrc; ++i) CTU_REQUIRE(h_srcs[i] != nullptr, "ctu_conv3d_dgrad_bnred: null source %d", i);
+    return conv3d_fprop_tc(h_srcs, h_src_channels, nsrc, (const float*)wimg, nullptr, dx, bn_sums2, cout, cout, k, n, d, h, w,
+                           (cudaStream_t)stream, bn_y, bn_ss, bn_y_phase_major);
 }
 
 int ctu_conv3d_wgrad(int dtype, const void* const* h_srcs, const int* h_src_channels, int nsrc, const void* dy,

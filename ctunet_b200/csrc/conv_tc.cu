@@ -95,6 +95,11 @@ struct TcParams {
     uint32_t wimg_bytes, plane_bytes, slot_bytes;   // plane_bytes: one channel block of one plane, padded to 128
     uint32_t tmem_cols;
     uint32_t ns;                                    // plane ring depth (more slots = more TMA loads in flight)
+    // BNRED kernels (data gradient feeding a BatchNorm+ReLU backward): y of that BatchNorm (natural or phase-major
+    // layout), its ss = scale | shift | mean | invstd; `stats` then receives sum(dz) | sum(dz * xhat)
+    const __nv_bfloat16* bn_y;
+    const float* bn_ss;
+    int bn_pm;
 };
 
 // fp32 packed weights [cob][cib][tap][ci][co] -> the bf16 B-tile images, one per output-block group of `cobg`
@@ -124,7 +129,11 @@ __global__ void tc_pack_wimg_kernel(const float* __restrict__ wp, __nv_bfloat16*
 // three (five) kd taps ride in the MMA N dimension: the activation tile is read from shared memory once per
 // plane instead of once per kd (SS-mode UMMA is bound by the A-operand read, ~64 B/clk, not by the math, when N
 // is this small).  The epilogue thread of a voxel column adds P[kd] of K consecutive planes in registers.
-template <int K, int COB>
+// BNRED: the output IS dA of a BatchNorm+ReLU stage whose only consumer this convolution is (models.py:26-32): instead of
+// the sums of the outputs the epilogue accumulates the two reductions of the BatchNorm backward pass,
+// sum(dz) and sum(dz * xhat) with dz = dA * [scale * y + shift > 0], reading y (16 B per voxel and block) while the
+// gradient tile is still in registers -- the separate reduce pass over y and dA (ctu_bn_relu_bwd_reduce) disappears.
+template <int K, int COB, bool BNRED = false>
 __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel(const __grid_constant__ TcMaps maps,
                                                                                  TcParams p) {
     constexpr int PAD = K / 2;
@@ -146,6 +155,7 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (b_w + 8 - s_base));
     float* st_red = reinterpret_cast<float*>(smem + (b_w + 32 - s_base));   // [4*TC_WB epilogue warps][NSLOT*16]
     float* st_bias = st_red + 4 * TC_WB * 32;                               // [CP] bias of this CTA's output blocks
+    float* st_bn = st_bias + 32;                                            // BNRED: [4][CP] scale | shift | mean | invstd
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -170,6 +180,11 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
     if (threadIdx.x >= 64 && threadIdx.x < 64 + CP) {   // bias -> shared memory (read per plane by every epilogue thread)
         const int ch = blockIdx.y * CP + (int)threadIdx.x - 64;
         st_bias[threadIdx.x - 64] = (p.bias != nullptr && ch < p.cout) ? p.bias[ch] : 0.f;
+        if (BNRED) {
+            const int cpad = p.cobo * 8;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) st_bn[q * CP + threadIdx.x - 64] = ch < cpad ? p.bn_ss[q * cpad + ch] : 0.f;
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -373,7 +388,26 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
 #else
                             if (o.v[0] == 1234.567f) Vec8<__nv_bfloat16>::store(ycol, o);
 #endif
-                            if (want_stats) {
+                            if (BNRED) {
+                                long long yoff;
+                                if (p.bn_pm) {      // y phase-major: [n][8 phases x cob][d/2][h/2][w/2][8]
+                                    const int q = ((gz & 1) << 2) | ((gy & 1) << 1) | (gx & 1);
+                                    const long long ps = ((long long)(gz >> 1) * (p.h >> 1) + (gy >> 1)) * (p.w >> 1) + (gx >> 1);
+                                    yoff = ((((long long)n * 8 + q) * p.cob_n + ob0 + ob) * (plane >> 3) + ps) * 8;
+                                } else {
+                                    yoff = (((long long)n * p.cob_n + ob0 + ob) * plane + ((long long)gz * p.h + gy) * p.w + gx) * 8;
+                                }
+                                const V8 yv = Vec8<__nv_bfloat16>::load(p.bn_y + yoff);
+#pragma unroll
+                                for (int c = 0; c < 8; ++c) {
+                                    const int cc = ob * 8 + c;
+                                    const float av = fmaf(yv.v[c], st_bn[cc], st_bn[CP + cc]);
+                                    const float dz = av > 0.f ? o.v[c] : 0.f;
+                                    const float xhat = (yv.v[c] - st_bn[2 * CP + cc]) * st_bn[3 * CP + cc];
+                                    s1[(ob % NSLOT) * 8 + c] += dz;
+                                    s2[(ob % NSLOT) * 8 + c] = fmaf(dz, xhat, s2[(ob % NSLOT) * 8 + c]);
+                                }
+                            } else if (want_stats) {
 #pragma unroll
                                 for (int c = 0; c < 8; ++c) {
                                     s1[(ob % NSLOT) * 8 + c] += o.v[c];
@@ -475,7 +509,7 @@ static bool tc_geometry(int k, int cb, int cout, int h, int w, TcGeom& g) {
         g.nt = (k * cobg * 8 + 15) / 16 * 16;
         g.wimg_bytes = (uint32_t)g.nm * g.nt * 32;
         const size_t fixed = ((g.wimg_bytes + 1023u) & ~1023u) + ((g.nm * 8 + 15) & ~15) +
-                             8 * (2 * TC_MAX_SLOTS + 4 * TC_WB + 2) + 32 + 4 * TC_WB * 32 * 4 + 128 + 1024;
+                             8 * (2 * TC_MAX_SLOTS + 4 * TC_WB + 2) + 32 + 4 * TC_WB * 32 * 4 + 128 + 512 + 1024;
         // the wide-output variants are limited to one CTA per SM by registers: give their ring the whole SM
         g.ns = pick_slots(g.ncg > 1 ? 4 : 3, fixed, g.slot_bytes, cobg >= 2 ? 200 * 1024 : 100 * 1024);
         g.smem = fixed + (size_t)g.ns * g.slot_bytes;
@@ -537,7 +571,8 @@ static int make_src_maps(TcMaps& maps, const void* const* h_srcs, const int* h_s
 // stat_cout: number of NATURAL channels the statistics are taken over: cout for an ordinary convolution, cout / 8
 // phases for the phase-major output of the fused up-sampling stage (natural block = output block % ceil(stat_cout/8))
 int conv3d_fprop_tc(const void* const* h_srcs, const int* h_src_channels, int nsrc, const float* wp, const float* bias,
-                    void* y, double* stats, int stat_cout, int cout, int k, int n, int d, int h, int w, cudaStream_t stream) {
+                    void* y, double* stats, int stat_cout, int cout, int k, int n, int d, int h, int w, cudaStream_t stream,
+                    const void* bn_y, const float* bn_ss, int bn_pm) {
     TcGeom g;
     const int cb = total_blocks(nsrc, h_src_channels);
     if (cb < 0 || !tc_geometry(k, cb, cout, h, w, g)) {
@@ -556,6 +591,14 @@ int conv3d_fprop_tc(const void* const* h_srcs, const int* h_src_channels, int ns
     p.cstat = stat_cout;
     const bool fuse_stats = stats != nullptr && (g.cobg <= 2 || p.cobo <= 2);
     p.stats = fuse_stats ? stats : nullptr;
+    const bool bnred = bn_y != nullptr;
+    if (bnred && !(k == 3 && g.cobg <= 2 && bn_ss != nullptr && stats != nullptr && stat_cout == cout)) {
+        set_error("conv3d tensor path: BatchNorm-backward reduction fused only for 3x3x3 with <= 16 output channels");
+        return CTU_ERR_UNSUPPORTED;
+    }
+    p.bn_y = reinterpret_cast<const __nv_bfloat16*>(bn_y);
+    p.bn_ss = bn_ss;
+    p.bn_pm = bn_pm;
     p.cb = g.cb; p.cbg = g.cbg; p.ncg = g.ncg; p.cob_n = g.cob_n; p.nt = g.nt; p.cout = cout;
     p.nsrc = nsrc;
     for (int i = 0, off = 0; i < CTU_MAX_SRC; ++i) {
@@ -625,7 +668,9 @@ int conv3d_fprop_tc(const void* const* h_srcs, const int* h_src_channels, int ns
         kern<<<dim3(gx, g.ngroups), threads, g.smem, stream>>>(maps, p);
         return check_launch("ctu_conv3d_fprop(tcgen05)");
     };
-    if (k == 3 && g.cobg == 1) rc = go(conv3d_tc_kernel<3, 1>);
+    if (bnred && g.cobg == 1) rc = go(conv3d_tc_kernel<3, 1, true>);
+    else if (bnred) rc = go(conv3d_tc_kernel<3, 2, true>);
+    else if (k == 3 && g.cobg == 1) rc = go(conv3d_tc_kernel<3, 1>);
     else if (k == 3 && g.cobg == 2) rc = go(conv3d_tc_kernel<3, 2>);
     else if (k == 3 && g.cobg == 4) rc = go(conv3d_tc_kernel<3, 4>);
     else if (k == 5 && g.cobg == 1) rc = go(conv3d_tc_kernel<5, 1>);
@@ -1364,6 +1409,13 @@ int ctu_conv_tc_supported(int k, int nsrc, const int* h_src_channels, int cout, 
     TcGeom g;
     const int cb = total_blocks(nsrc, h_src_channels);
     return (cb > 0 && tc_geometry(k, cb, cout, h, w, g)) ? 1 : 0;
+}
+
+int ctu_conv_tc_bnred_supported(int k, int nsrc, const int* h_src_channels, int cout, int d, int h, int w) {
+    (void)d;
+    TcGeom g;
+    const int cb = total_blocks(nsrc, h_src_channels);
+    return (k == 3 && cb > 0 && tc_geometry(k, cb, cout, h, w, g) && g.cobg <= 2) ? 1 : 0;
 }
 
 int ctu_conv_tc_wgrad_supported(int k, int nsrc, const int* h_src_channels, int cout, int d, int h, int w) {

@@ -205,6 +205,42 @@ __global__ void encode_flaprec_kernel(const unsigned char* __restrict__ broken, 
     }
 }
 
+// The same encoding from BIT-PACKED masks (1 bit per voxel, voxel v = bit v & 7 of byte v >> 3, i.e. numpy's
+// packbits(bitorder="little")): binary volumes cross PCIe at 3 bits per voxel instead of 24 bytes (float batch) or 3 bytes
+// (uint8 masks).  Writes the float image (+ atlas channel) and, for the fused head + loss kernels, the two uint8 label masks.
+// 16 voxels per thread: one 16-bit load per mask, four 16-byte image stores, one 16-byte store per label mask.
+__global__ void encode_flaprec_bits_kernel(const unsigned char* __restrict__ broken, const unsigned char* __restrict__ full,
+                                           const unsigned char* __restrict__ flap, const float* __restrict__ atlas,
+                                           float* __restrict__ image, unsigned char* __restrict__ full_m,
+                                           unsigned char* __restrict__ flap_m, int cin, long long spatial) {
+    const int b = blockIdx.y;
+    const long long v0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (v0 >= spatial) return;
+    const long long byte0 = ((long long)b * spatial + v0) >> 3;
+    const unsigned int wb = *reinterpret_cast<const unsigned short*>(broken + byte0);
+    float* img0 = image + (long long)b * cin * spatial + v0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        *reinterpret_cast<float4*>(img0 + 4 * i) = make_float4((float)((wb >> (4 * i)) & 1u), (float)((wb >> (4 * i + 1)) & 1u),
+                                                               (float)((wb >> (4 * i + 2)) & 1u), (float)((wb >> (4 * i + 3)) & 1u));
+        if (cin > 1) *reinterpret_cast<float4*>(img0 + spatial + 4 * i) = *reinterpret_cast<const float4*>(atlas + v0 + 4 * i);
+    }
+    if (full_m != nullptr) {
+        const unsigned int wf = *reinterpret_cast<const unsigned short*>(full + byte0);
+        const unsigned int wl = *reinterpret_cast<const unsigned short*>(flap + byte0);
+        uint32_t of[4], ol[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            of[i] = ((wf >> (4 * i)) & 1u) | (((wf >> (4 * i + 1)) & 1u) << 8) | (((wf >> (4 * i + 2)) & 1u) << 16) |
+                    (((wf >> (4 * i + 3)) & 1u) << 24);
+            ol[i] = ((wl >> (4 * i)) & 1u) | (((wl >> (4 * i + 1)) & 1u) << 8) | (((wl >> (4 * i + 2)) & 1u) << 16) |
+                    (((wl >> (4 * i + 3)) & 1u) << 24);
+        }
+        *reinterpret_cast<uint4*>(full_m + (long long)b * spatial + v0) = make_uint4(of[0], of[1], of[2], of[3]);
+        *reinterpret_cast<uint4*>(flap_m + (long long)b * spatial + v0) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+    }
+}
+
 __global__ void hu_window_kernel(const short* __restrict__ hu, float* __restrict__ out, long long nvox, float lo,
                                  float hi) {
     const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -441,6 +477,20 @@ int ctu_encode_flaprec_u8(const unsigned char* broken, const unsigned char* full
     encode_flaprec_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(broken, full, flap, atlas, image, skull_target, flap_target,
                                                                   in_channels, spatial);
     return check_launch("ctu_encode_flaprec_u8");
+}
+
+int ctu_encode_flaprec_bits(const unsigned char* broken_bits, const unsigned char* full_bits, const unsigned char* flap_bits,
+                            const float* atlas, float* image, unsigned char* full_mask, unsigned char* flap_mask, int batch,
+                            int in_channels, long long spatial, ctu_stream stream) {
+    CTU_REQUIRE(broken_bits && image && batch > 0 && spatial > 0, "ctu_encode_flaprec_bits: bad arguments");
+    CTU_REQUIRE((full_mask != nullptr) == (flap_mask != nullptr) && (full_mask == nullptr || (full_bits && flap_bits)),
+                "ctu_encode_flaprec_bits: both label masks (with both bit volumes) or neither");
+    CTU_REQUIRE(in_channels == 1 || (in_channels == 2 && atlas), "ctu_encode_flaprec_bits: 1 input channel, or 2 with an atlas");
+    CTU_REQUIRE(spatial % 16 == 0, "ctu_encode_flaprec_bits: the volume size must be a multiple of 16 voxels");
+    dim3 grid(cdiv(spatial / 16, 256), batch);
+    encode_flaprec_bits_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(broken_bits, full_bits, flap_bits, atlas, image, full_mask,
+                                                                       flap_mask, in_channels, spatial);
+    return check_launch("ctu_encode_flaprec_bits");
 }
 
 int ctu_hu_window(const short* hu, float* out, long long nvox, float lo, float hi, ctu_stream stream) {

@@ -41,6 +41,12 @@ WEIGHT_PREP_ASYNC = True
 WGRAD_ASYNC = True
 # The discarded center block of the generic UNet runs on a third stream (Engine.off_critical_path).
 DEAD_BRANCH_ASYNC = True
+# The reduce pass of the BatchNorm+ReLU backward (sum dz, sum dz*xhat) folded into the epilogue of the data-gradient
+# convolution that produces dA, when that convolution is the stage's only consumer and runs on the tcgen05 kernel.
+# Correct (tests/test_gpu_upfuse.py) but OFF: measured on B200 it LOSES -- the epilogue is the bottleneck of the narrow
+# convolutions, and the extra 16-byte load + 4 flops per element cost more there (six launches, +0.28 ms per step) than the
+# separate bandwidth-bound reduce passes they replace (-0.2 ms): UNetSP step 4.40 -> 4.68 ms.
+BN_BWD_FUSE = False
 # The SP head's backward pass recovers the sigmoid values from the forward outputs instead of recomputing the logits.
 HEAD_FROM_OUTPUTS = True
 _SIDE = {}
@@ -58,12 +64,13 @@ class Act:
 
     ``c_nat`` is set on the PHASE-MAJOR output of the fused up-sampling stage: the tensor then holds 8 phases x
     8*ceil(c_nat/8) channels on the low-resolution grid (block q*cb_nat + b), i.e. a [c_nat] x (2d, 2h, 2w) volume."""
-    __slots__ = ("buf", "c", "n", "d", "h", "w", "sums", "c_nat")
+    __slots__ = ("buf", "c", "n", "d", "h", "w", "sums", "c_nat", "bn")
 
     def __init__(self, buf, c, n, d, h, w):
         self.buf, self.c, self.n, self.d, self.h, self.w = buf, c, n, d, h, w
         self.sums = None        # per-channel sum / sum of squares written by the producing conv's epilogue
         self.c_nat = 0
+        self.bn = None          # set on the output of a recorded BatchNorm+ReLU stage: see Engine.bn_relu (backward fusion)
 
     @property
     def cb(self):
@@ -201,6 +208,13 @@ class Engine:
         if self.grad_sink is not None:
             self.grad_sink.delivered(param)
 
+    def _consume(self, srcs):
+        """Count the consumers of BatchNorm+ReLU outputs (the backward fusion needs exactly one)."""
+        if self.record:
+            for s in srcs:
+                if s.bn is not None:
+                    s.bn["consumers"] += 1
+
     @staticmethod
     def _src_args(srcs: Sequence[Act]):
         return ptr_array([s.ptr for s in srcs]), int_array([s.c for s in srcs]), len(srcs)
@@ -337,7 +351,17 @@ class Engine:
                 if not need[i]:
                     continue
                 dx = self.new_act(s.c, s.n, s.d, s.h, s.w)
-                self._conv_launch([dy], wkd[i], tc_d[i], None, dx, s.c, k, None)
+                info = s.bn
+                if (BN_BWD_FUSE and info is not None and info["consumers"] == 1 and not info["pool"] and tc_d[i] == 1
+                        and self.dtype == CTU_BF16
+                        and lib.ctu_conv_tc_bnred_supported(k, 1, int_array([cout]), s.c, s.d, s.h, s.w)):
+                    # dx is dA of a BatchNorm+ReLU stage consumed only here: its backward reductions ride in this epilogue
+                    sums2 = self.f64(2 * ((s.c + 7) // 8 * 8))
+                    call("ctu_conv3d_dgrad_bnred", ptr_array([dy.ptr]), int_array([cout]), 1, wkd[i].data_ptr(), dx.ptr, s.c, k,
+                         s.n, s.d, s.h, s.w, info["y"].ptr, info["ss"].data_ptr(), sums2.data_ptr(), info["pm"], stream_ptr())
+                    info["sums2"] = sums2
+                else:
+                    self._conv_launch([dy], wkd[i], tc_d[i], None, dx, s.c, k, None)
                 self._set_agrad(s, dx)
 
         if leaf_input and WGRAD_ASYNC and any(need):
@@ -368,6 +392,7 @@ class Engine:
         ``leaf_input``: ``srcs[0]`` is the network input (its gradient is a leaf of the backward pass)."""
         cout = weight.shape[0]
         srcs = list(srcs)
+        self._consume(srcs)
         need = [bool(n) and self.record for n in need_src_grad]
         wk, tc, wkd, tc_d, _, _ = self._conv_weights("conv", srcs, need, weight, k, cout)
         y = self._conv_fwd(srcs, wk, tc, bias, k, cout, 0, bn_stats)
@@ -430,6 +455,7 @@ class Engine:
             return wn, b3n
 
         all_srcs = list(srcs) + [self._ones(srcs[0])]
+        self._consume(srcs)
         need = [bool(n) and self.record for n in need_src_grad] + [False]
         wk, tc, wkd, tc_d, wn, extra = self._conv_weights("up_conv", all_srcs, need, None, 3, co8, compose)
         b3n = extra[0]
@@ -472,6 +498,7 @@ class Engine:
     def convt(self, srcs: Sequence[Act], weight, bias, need_src_grad: Sequence[bool]) -> Act:
         cout = weight.shape[1]
         s0 = srcs[0]
+        self._consume(srcs)
         pa, ca, ns = self._src_args(srcs)
         lib = _lib.load()
         wp = self.f32(lib.ctu_convt_wpack_floats(cout, ns, ca))
@@ -552,6 +579,7 @@ class Engine:
         if self.record:
             if not training:
                 raise RuntimeError("backward through eval-mode BatchNorm is not supported by the fused path")
+            a.bn = {"y": y, "ss": ss, "pm": pm, "pool": bool(pool), "consumers": 0, "sums2": None}
 
             def bwd():
                 dA = self.agrads.pop(id(a), None)
@@ -577,11 +605,14 @@ class Engine:
                         self._wgrad_stream = side
                     else:
                         update()
-                sums2 = self.f64(2 * cpad)
                 pA = dA.ptr if dA is not None else None
                 pP = dP.ptr if dP is not None else None
-                call("ctu_bn_relu_bwd_reduce", self.dtype, y.ptr, ss.data_ptr(), pA, pP, sums2.data_ptr(),
-                     c, yn, yd, yh, yw, pm, st)
+                sums2 = a.bn["sums2"]
+                a.bn = None                                           # (drop the reference cycle through the closure)
+                if sums2 is None or dP is not None:                  # not produced by the consumer's epilogue: reduce here
+                    sums2 = self.f64(2 * cpad)
+                    call("ctu_bn_relu_bwd_reduce", self.dtype, y.ptr, ss.data_ptr(), pA, pP, sums2.data_ptr(),
+                         c, yn, yd, yh, yw, pm, st)
                 dy = self.new_act(y.c, y.n, y.d, y.h, y.w)          # same layout as y (phase-major stays phase-major)
                 dg, db = self._grad_buffer(bn.weight), self._grad_buffer(bn.bias)
                 call("ctu_bn_relu_bwd_apply", self.dtype, y.ptr, ss.data_ptr(), bn.weight.data_ptr(), pA, pP,
@@ -600,6 +631,7 @@ class Engine:
         s0 = srcs[0]
         pa, ca, ns = self._src_args(srcs)
         sp = bool(flags & (_lib.HEAD_SP | _lib.HEAD_SP_SOFTMAX))
+        self._consume(srcs)
         if self.fused_loss is not None:
             return self._head_loss(list(srcs), weight, bias, flags, sp)
         if sp:

@@ -267,6 +267,22 @@ class TrainStep:
         image, target = encode_flaprec_batch(broken, full, flap, atlas)
         return self(image, target)
 
+    def step_from_bits(self, broken_bits: torch.Tensor, full_bits: torch.Tensor, flap_bits: torch.Tensor, vol_shape, atlas=None):
+        """``step_from_masks`` for BIT-PACKED masks ([B, D*H*W/8] uint8 each on the device, ``utilities.pack_mask_bits``):
+        3 bits per voxel over PCIe.  ``ctu_encode_flaprec_bits`` expands them straight into the captured step's static
+        inputs -- the float image (+ atlas) and the two uint8 label masks the fused head + loss kernels read."""
+        from .utilities import encode_flaprec_bits
+        if self.handler != "double" or not FUSED_HEAD_LOSS:
+            raise ValueError("step_from_bits feeds the double-output handler through the fused head + loss kernels")
+        if self._graph is not None:
+            if self._static[1].dtype != torch.uint8:
+                raise RuntimeError("the step was captured with float targets: capture it through step_from_bits / step_from_masks")
+            encode_flaprec_bits(broken_bits, full_bits, flap_bits, vol_shape, atlas,
+                                out=(self._static[0], (self._static[1], self._static[2])))
+            return self._replay()
+        image, masks = encode_flaprec_bits(broken_bits, full_bits, flap_bits, vol_shape, atlas)
+        return self(image, masks)
+
     @property
     def lr(self) -> float:
         return self.optimizer.lr

@@ -188,6 +188,48 @@ def encode_flaprec_batch(broken: torch.Tensor, full: torch.Tensor, flap: torch.T
     return image, ((sk, fl) if sk is not None else None)
 
 
+def pack_mask_bits(mask: torch.Tensor) -> torch.Tensor:
+    """uint8 {0,1} mask [..., S] -> bit-packed uint8 [..., S / 8], voxel v = bit ``v & 7`` of byte ``v >> 3`` (numpy
+    ``packbits(bitorder="little")``): the wire format of ``encode_flaprec_bits`` / ``TrainStep.step_from_bits``.  Works on
+    host or device tensors (a data pipeline would emit this format directly)."""
+    flat = (mask.reshape(mask.shape[0], -1) != 0).to(torch.uint8)
+    if flat.shape[1] % 8:
+        raise ValueError("the volume size must be a multiple of 8 voxels")
+    w = torch.tensor([1, 2, 4, 8, 16, 32, 64, 128], dtype=torch.uint8, device=mask.device)
+    return (flat.view(flat.shape[0], -1, 8) * w).sum(-1, dtype=torch.int32).to(torch.uint8).contiguous()
+
+
+def encode_flaprec_bits(broken_bits, full_bits, flap_bits, vol_shape, atlas=None, out=None):
+    """``encode_flaprec_batch`` from bit-packed masks ([B, D*H*W/8] uint8 each, ``pack_mask_bits``): returns / fills
+    ``(image float32 [B,Cin,D,H,W], (full_mask, flap_mask) uint8 [B,D,H,W])`` -- the label masks are what the fused head +
+    loss kernels of ``trainer.TrainStep`` take as targets."""
+    for t in (broken_bits, full_bits, flap_bits):
+        _need_cuda(t, "encode_flaprec_bits")
+        if t.dtype != torch.uint8 or t.dim() != 2 or t.shape != broken_bits.shape or not t.is_contiguous():
+            raise TypeError("encode_flaprec_bits expects three contiguous uint8 [B, D*H*W/8] bit volumes of one shape")
+    b = broken_bits.shape[0]
+    vol = tuple(vol_shape)
+    spatial = vol[0] * vol[1] * vol[2]
+    if broken_bits.shape[1] * 8 != spatial:
+        raise ValueError("bit volumes of %d bytes do not match the volume shape %s" % (broken_bits.shape[1], vol))
+    cin = 1 if atlas is None else 2
+    if atlas is not None and (atlas.dtype != torch.float32 or tuple(atlas.shape) != vol or not atlas.is_cuda):
+        raise TypeError("atlas: float32 CUDA volume of the mask shape")
+    if out is None:
+        image = torch.empty((b, cin) + vol, dtype=torch.float32, device=broken_bits.device)
+        fm = torch.empty((b,) + vol, dtype=torch.uint8, device=broken_bits.device)
+        lm = torch.empty_like(fm)
+    else:
+        image, (fm, lm) = out
+        for t, shp, dt in ((image, (b, cin) + vol, torch.float32), (fm, (b,) + vol, torch.uint8), (lm, (b,) + vol, torch.uint8)):
+            if t.dtype != dt or tuple(t.shape) != shp or not t.is_contiguous() or not t.is_cuda:
+                raise TypeError("encode_flaprec_bits: out = (float32 image [B,C,D,H,W], (uint8 [B,D,H,W], uint8 [B,D,H,W]))")
+    call("ctu_encode_flaprec_bits", broken_bits.data_ptr(), full_bits.data_ptr(), flap_bits.data_ptr(),
+         atlas.contiguous().data_ptr() if atlas is not None else None, image.data_ptr(), fm.data_ptr(), lm.data_ptr(), b, cin,
+         spatial, stream_ptr())
+    return image, (fm, lm)
+
+
 # ---------------------------------------------------------------------------------------------- reporting metrics
 def _metric_pair(pred, target, what):
     _need_cuda(pred, what)

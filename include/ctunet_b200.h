@@ -83,6 +83,15 @@ int ctu_conv_unpack_wgrad(const float* dwp, float* dw, int cout, int k, int nsrc
 int ctu_conv3d_fprop(int dtype, const void* const* h_srcs, const int* h_src_channels, int nsrc, const void* wp,
                      const float* bias, void* y, double* bn_sums, int stat_cout, int cout, int k, int n, int d, int h,
                      int w, int use_tensor_path, ctu_stream stream);
+/* The data gradient (tensor path 1: bf16, wimg from ctu_conv_tc_pack_weight of the dgrad-packed weights) whose output dx is
+ * dA of a BatchNorm+ReLU stage that only this convolution consumes (models.py:26-32): the epilogue also reduces the two sums
+ * of the BatchNorm backward pass, bn_sums2 = double[2*cpad] = sum(dz) | sum(dz * xhat), dz = dx * [scale*y + shift > 0],
+ * from bn_y (the BatchNorm's input, natural layout or phase-major) and bn_ss (as written by ctu_bn_finalize) -- it replaces
+ * ctu_bn_relu_bwd_reduce for that stage.  Shapes accepted by ctu_conv_tc_bnred_supported (3x3x3, <= 16 output channels). */
+int ctu_conv_tc_bnred_supported(int k, int nsrc, const int* h_src_channels, int cout, int d, int h, int w);
+int ctu_conv3d_dgrad_bnred(const void* const* h_srcs, const int* h_src_channels, int nsrc, const void* wimg, void* dx,
+                           int cout, int k, int n, int d, int h, int w, const void* bn_y, const float* bn_ss,
+                           double* bn_sums2, int bn_y_phase_major, ctu_stream stream);
 /* tcgen05 path: coverage predicate, size of the weight image, and the re-pack fp32 packed -> image */
 int ctu_conv_tc_supported(int k, int nsrc, const int* h_src_channels, int cout, int d, int h, int w);
 int ctu_conv_tc_wgrad_supported(int k, int nsrc, const int* h_src_channels, int cout, int d, int h, int w);
@@ -242,6 +251,13 @@ int ctu_flap_mask_u8(const unsigned char* img, unsigned char* masked, unsigned c
 int ctu_encode_flaprec_u8(const unsigned char* broken, const unsigned char* full, const unsigned char* flap,
                           const float* atlas, float* image, float* skull_target, float* flap_target, int batch,
                           int in_channels, long long spatial, ctu_stream stream);
+
+/* the same from BIT-PACKED masks [batch][spatial / 8] (voxel v = bit v & 7 of byte v >> 3: numpy packbits, bitorder
+ * "little"): image as above, and (nullable, both or neither) the uint8 label masks [batch][spatial] that
+ * ctu_head_loss_fwd / _bwd take with target_u8 = 1.  Binary volumes cross PCIe at 3 bits per voxel. */
+int ctu_encode_flaprec_bits(const unsigned char* broken_bits, const unsigned char* full_bits, const unsigned char* flap_bits,
+                            const float* atlas, float* image, unsigned char* full_mask, unsigned char* flap_mask, int batch,
+                            int in_channels, long long spatial, ctu_stream stream);
 
 /* ---- CT preprocessing (no reference implementation: oracle/unet_oracle.py defines it) -------- */
 int ctu_hu_window(const short* hu, float* out, long long nvox, float lo, float hi, ctu_stream stream);

@@ -371,22 +371,28 @@ def test_step_from_masks_equals_step_from_float_batch(graph):
     img, (sk_t, fl_t) = make_training_batch(2, 2, 32, seed=77, device=DEV)
     masks = [t.to(torch.uint8).contiguous() for t in (img[:, 0], sk_t[:, 1], fl_t[:, 1])]
     atlas = img[0, 1].contiguous()
+    from ctunet_b200.utilities import pack_mask_bits
+    bits = [pack_mask_bits(m) for m in masks]
     hist = []
-    for use_masks in (False, True):
+    for use_masks in (False, True, "bits"):
         torch.manual_seed(0)
         net = _build("UNetSP", "bf16").to(DEV).train()
         step = TrainStep(net, "double", 1.0, 1.0, lr=1e-5, graph=graph)
         rb, vals = LossReadback(5), []
         for _ in range(4):
-            comps = step.step_from_masks(*masks, atlas) if use_masks else step(img, (sk_t, fl_t))
+            if use_masks == "bits":          # bit-packed masks: 3 bits per voxel on the wire
+                comps = step.step_from_bits(*bits, tuple(img.shape[2:]), atlas)
+            else:
+                comps = step.step_from_masks(*masks, atlas) if use_masks else step(img, (sk_t, fl_t))
             prev = rb.push(comps)
             if prev is not None:
                 vals.append(prev)
         vals.append(rb.drain())
         assert len(vals) == 4 and all(len(v) == 5 for v in vals)
         hist.append(vals)
-    for a, b in zip(hist[0], hist[1]):
-        assert a == pytest.approx(b, rel=2e-3, abs=2e-3)      # same inputs; only atomic accumulation order differs
+    for other in hist[1:]:
+        for a, b in zip(hist[0], other):
+            assert a == pytest.approx(b, rel=2e-3, abs=2e-3)      # same inputs; only atomic accumulation order differs
     assert hist[0][0][-1] == pytest.approx(sum(hist[0][0][:-1]), rel=1e-5)
 
 

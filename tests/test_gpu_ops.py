@@ -434,3 +434,28 @@ def test_errors_are_loud():
     with pytest.raises(RuntimeError):
         _lib.call("ctu_pack_ncdhw", None, None, 0, 1, 1, 1, None)     # null pointers -> error code + message
     assert "bad arguments" in _lib.last_error()
+
+
+def test_encode_flaprec_bits_is_bit_exact():
+    """Bit-packed masks (numpy packbits, bitorder='little') -> float image + atlas channel + uint8 label masks: identical to
+    the uint8-mask encoding (datasets.py:195-235) and to the oracle's one-hot targets."""
+    import numpy as np
+    from ctunet_b200.utilities import encode_flaprec_batch, encode_flaprec_bits, pack_mask_bits
+    from oracle import unet_oracle as O
+    g = torch.Generator().manual_seed(4)
+    shp = (2, 8, 12, 16)
+    broken, full, flap = ((torch.rand(shp, generator=g) > t).to(torch.uint8) for t in (0.5, 0.4, 0.8))
+    atlas = torch.rand(shp[1:], generator=g)
+    bits = [pack_mask_bits(m) for m in (broken, full, flap)]
+    for m, b in zip((broken, full, flap), bits):
+        assert np.array_equal(b.numpy(), np.packbits(m.numpy().reshape(2, -1), axis=1, bitorder="little"))
+        assert torch.equal(pack_mask_bits(m.to(DEV)).cpu(), b)
+    img, (fm, lm) = encode_flaprec_bits(*[b.to(DEV) for b in bits], shp[1:], atlas.to(DEV))
+    ref_img, (ref_sk, ref_fl) = O.encode_flaprec_batch(broken, full, flap, atlas)
+    assert torch.equal(img.cpu(), ref_img)
+    assert torch.equal(fm.cpu(), full) and torch.equal(lm.cpu(), flap)
+    assert torch.equal(torch.stack((1 - fm, fm), 1).float().cpu(), ref_sk)
+    img2, _ = encode_flaprec_batch(broken.to(DEV), full.to(DEV), flap.to(DEV), atlas.to(DEV))
+    assert torch.equal(img, img2)
+    img1, _ = encode_flaprec_bits(*[b.to(DEV) for b in bits], shp[1:])          # one input channel
+    assert img1.shape == (2, 1) + shp[1:] and torch.equal(img1[:, 0].cpu(), broken.float())

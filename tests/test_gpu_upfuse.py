@@ -167,3 +167,51 @@ def test_fused_up_stage_bf16_tensor_path(case):
         # voxel: a small signal under bf16 storage of dy, checked at fp32 accuracy in the check-mode test above
         print("%s: |ref| %.3e  normwise err %.3e" % (name, rg[name].norm().item(), rel))
         assert rel <= (1.5e-1 if name == "ct.b" else 5e-2), "%s normwise err %.3e" % (name, rel)
+
+
+@pytest.mark.parametrize("phase_major", [False, True])
+@pytest.mark.parametrize("c_mid", [7, 14])
+def test_bn_backward_reduction_fused_into_dgrad_epilogue(phase_major, c_mid):
+    """engine.BN_BWD_FUSE: sum(dz) / sum(dz * xhat) of the BatchNorm+ReLU backward come out of the epilogue of the
+    data-gradient convolution that produces dA (conv3d_tc_kernel<.., BNRED>) instead of a separate pass over y and dA --
+    same gradients as the unfused path, for a natural y (conv -> BN -> conv) and a phase-major y (fused up stage -> BN -> conv)."""
+    import torch.nn as nn
+    import ctunet_b200.engine as E
+    g = torch.Generator().manual_seed(31 + c_mid)
+    n, d, h, w = 2, 6, 16, 32
+    x = _bf(torch.randn(n, 12, d, h, w, generator=g))
+    ct = nn.ConvTranspose3d(12, 12, 2, 2).to(DEV)
+    cv1 = nn.Conv3d(12, c_mid, 3, 1, 1, bias=False).to(DEV)
+    bn = nn.BatchNorm3d(c_mid).to(DEV)
+    cv2 = nn.Conv3d(c_mid, 9, 3, 1, 1, bias=False).to(DEV)
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.uniform_(-0.3, 0.3)
+    dy2 = None
+    res = []
+    for fuse in (False, True):
+        E.BN_BWD_FUSE = fuse
+        try:
+            eng = E.Engine(torch.device(DEV), "bf16", record=True)
+            xa = eng.pack(x.to(DEV))
+            if phase_major:
+                y1 = eng.up_conv([xa], ct, cv1, 3, [True], True)
+                assert y1.c_nat == c_mid
+            else:
+                y1 = eng.conv([xa], cv1.weight, None, 3, [True], bn_stats=True)
+            a = eng.bn_relu(y1, bn, True)
+            y2 = eng.conv([a], cv2.weight, None, 3, [True])
+            if dy2 is None:
+                dy2 = _bf(torch.randn(n, 9, y2.d, y2.h, y2.w, generator=g)).to(DEV)
+            eng.agrads[id(y2)] = eng.pack(dy2)
+            eng.run_tape()
+            torch.cuda.synchronize()
+            out = {"dx": eng.unpack(eng.agrads[id(xa)]).cpu(), "bn.w": eng.pgrads[id(bn.weight)].cpu(),
+                   "bn.b": eng.pgrads[id(bn.bias)].cpu(), "cv1": eng.pgrads[id(cv1.weight)].cpu(),
+                   "cv2": eng.pgrads[id(cv2.weight)].cpu()}
+            res.append(out)
+        finally:
+            E.BN_BWD_FUSE = False
+    for k in res[0]:
+        a0, a1 = res[0][k], res[1][k]
+        assert float((a0 - a1).abs().max()) <= 2e-3 * float(a0.abs().max()) + 1e-6, k      # fp32 partials in another order
