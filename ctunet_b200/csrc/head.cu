@@ -839,6 +839,65 @@ static int head_loss_setup(HeadParams& p, int flags, int cout, const void* tgt0,
     return CTU_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------ head -> hard labels
+// Inference epilogue: hard_segm_from_tensor (utilities.py:103-124: argmax over the channel axis as float32, first maximum
+// wins) of every head output, computed in the head kernel itself (same arithmetic as head_fwd_kernel + argmax_kernel) and
+// written either as [n][spatial] planes (origins == NULL) or scattered into full [D][H][W] label volumes at the patch
+// origins of a sliding-window pass -- the fp32 [B,2,p,p,p] outputs, the separate argmax pass and the stitch copies vanish.
+template <typename T, int CO, int CBT>
+__global__ void __launch_bounds__(kHeadThreads) head_labels_kernel(HeadParams p, const int* __restrict__ origins, int patch, int vd,
+                                                                   int vh, int vw) {
+    extern __shared__ float hsm[];
+    float* wsm = hsm;
+    float* bsm = hsm + CO * CBT * 8;
+    load_head_weights<CO>(p, wsm, bsm);
+    __syncthreads();
+    const long long total = (long long)p.n * p.spatial;
+    const bool sp = (p.flags & (CTU_HEAD_SP | CTU_HEAD_SP_SOFTMAX)) != 0;
+    for (long long i = (long long)blockIdx.x * kHeadThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kHeadThreads) {
+        const int n = (int)(i / p.spatial);
+        const long long s = i % p.spatial;
+        HeadVals<CO> h;
+        V8 xs[CBT];
+        head_logits<T, CO, CBT>(p, wsm, bsm, n, s, h, xs);
+        head_forward_chain<CO>(h, p.flags);
+        float l0, l1 = 0.f;
+        if (sp) {
+            l0 = (h.o0[1] > h.o0[0] || (h.o0[1] != h.o0[1] && h.o0[0] == h.o0[0])) ? 1.f : 0.f;
+            l1 = (h.o1[1] > h.o1[0] || (h.o1[1] != h.o1[1] && h.o1[0] == h.o1[0])) ? 1.f : 0.f;
+        } else {
+            int bi = 0;
+            float best = h.sg[0];
+#pragma unroll
+            for (int c = 1; c < CO; ++c)
+                if (h.sg[c] > best || (h.sg[c] != h.sg[c] && best == best)) best = h.sg[c], bi = c;
+            l0 = (float)bi;
+        }
+        long long dst = i;
+        if (origins != nullptr) {
+            const int x = (int)(s % patch), y = (int)((s / patch) % patch), z = (int)(s / ((long long)patch * patch));
+            dst = ((long long)(origins[3 * n] + z) * vh + origins[3 * n + 1] + y) * vw + origins[3 * n + 2] + x;
+        }
+        p.out0[dst] = l0;
+        if (sp) p.out1[dst] = l1;
+    }
+}
+
+template <typename T, int CO>
+static int head_labels_launch(const HeadParams& p, const int* origins, int patch, int vd, int vh, int vw, cudaStream_t stream) {
+    const size_t smem = (size_t)(CO * p.m.cb_total * 8 + 8) * sizeof(float);
+    const long long total = (long long)p.n * p.spatial;
+    const int grid = (int)((total + kHeadThreads - 1) / kHeadThreads > 148 * 32 ? 148 * 32 : (total + kHeadThreads - 1) / kHeadThreads);
+    switch (p.m.cb_total) {
+        case 1: head_labels_kernel<T, CO, 1><<<grid, kHeadThreads, smem, stream>>>(p, origins, patch, vd, vh, vw); break;
+        case 2: head_labels_kernel<T, CO, 2><<<grid, kHeadThreads, smem, stream>>>(p, origins, patch, vd, vh, vw); break;
+        case 3: head_labels_kernel<T, CO, 3><<<grid, kHeadThreads, smem, stream>>>(p, origins, patch, vd, vh, vw); break;
+        default: head_labels_kernel<T, CO, 4><<<grid, kHeadThreads, smem, stream>>>(p, origins, patch, vd, vh, vw); break;
+    }
+    return check_launch("ctu_head_labels");
+}
+
 }  // namespace ctu
 
 using namespace ctu;
@@ -986,6 +1045,28 @@ int ctu_head_param_grad(int dtype, const void* const* h_srcs, const int* h_src_c
             case 2: return head_param_grad_launch<T, 2>(p, st);
             case 3: return head_param_grad_launch<T, 3>(p, st);
             default: return head_param_grad_launch<T, 4>(p, st);
+        }
+    });
+    return CTU_OK;
+}
+
+int ctu_head_labels(int dtype, const void* const* h_srcs, const int* h_src_channels, int nsrc, const float* w, const float* bias,
+                    int cout, int flags, const int* origins, int patch, int vd, int vh, int vw, float* labels0, float* labels1,
+                    int n, long long spatial, ctu_stream stream) {
+    HeadParams p = {};
+    int rc = head_setup(p, h_srcs, h_src_channels, nsrc, w, bias, cout, flags, n, spatial, "ctu_head_labels");
+    if (rc != CTU_OK) return rc;
+    const bool sp = (flags & (CTU_HEAD_SP | CTU_HEAD_SP_SOFTMAX)) != 0;
+    CTU_REQUIRE(labels0 && (!sp || labels1), "ctu_head_labels: missing output");
+    CTU_REQUIRE(origins == nullptr || (patch > 0 && (long long)patch * patch * patch == spatial && vd >= patch && vh >= patch && vw >= patch),
+                "ctu_head_labels: scatter mode needs spatial = patch^3 inside the volume");
+    p.out0 = labels0; p.out1 = labels1;
+    CTU_DISPATCH_DTYPE(dtype, {
+        switch (cout) {
+            case 1: return head_labels_launch<T, 1>(p, origins, patch, vd, vh, vw, (cudaStream_t)stream);
+            case 2: return head_labels_launch<T, 2>(p, origins, patch, vd, vh, vw, (cudaStream_t)stream);
+            case 3: return head_labels_launch<T, 3>(p, origins, patch, vd, vh, vw, (cudaStream_t)stream);
+            default: return head_labels_launch<T, 4>(p, origins, patch, vd, vh, vw, (cudaStream_t)stream);
         }
     });
     return CTU_OK;

@@ -74,6 +74,45 @@ __global__ void pack4_kernel(const float* __restrict__ src, T* __restrict__ dst,
     Vec8<T>::store(out + 24, r);
 }
 
+// Patch gather for sliding-window inference: B patches of p^3 voxels out of a float32 [C][D][H][W] volume at the origins
+// listed in device memory -> blocked [B][Cb][p][p][p][8].  Four x-consecutive voxels per thread (16-byte loads per channel).
+template <typename T>
+__global__ void pack_patches_kernel(const float* __restrict__ vol, const int* __restrict__ origins, T* __restrict__ dst, int c,
+                                    int cb, int D, int H, int W, int p, long long total4) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total4) return;
+    const int p4 = p >> 2;
+    const int x4 = (int)(i % p4);
+    long long r = i / p4;
+    const int y = (int)(r % p); r /= p;
+    const int z = (int)(r % p); r /= p;
+    const int b = (int)(r % cb);
+    const int n = (int)(r / cb);
+    const int oz = origins[3 * n], oy = origins[3 * n + 1], ox = origins[3 * n + 2];
+    const long long plane = (long long)D * H * W;
+    const long long src0 = ((long long)(oz + z) * H + (oy + y)) * W + ox + 4 * x4;
+    float4 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int ch = b * 8 + j;
+        v[j] = ch < c ? __ldg(reinterpret_cast<const float4*>(vol + ch * plane + src0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    T* out = dst + (((((long long)n * cb + b) * p + z) * p + y) * p + 4 * x4) * 8;
+    V8 q;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) q.v[j] = v[j].x;
+    Vec8<T>::store(out, q);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) q.v[j] = v[j].y;
+    Vec8<T>::store(out + 8, q);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) q.v[j] = v[j].z;
+    Vec8<T>::store(out + 16, q);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) q.v[j] = v[j].w;
+    Vec8<T>::store(out + 24, q);
+}
+
 template <typename T>
 __global__ void unpack_kernel(const T* __restrict__ src, float* __restrict__ dst, int c, int cb, long long spatial,
                               long long total) {
@@ -171,6 +210,17 @@ int ctu_pack_ncdhw(const float* src, void* dst, int dtype, int n, int c, long lo
         CTU_DISPATCH_DTYPE(dtype, (pack_kernel<T><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(src, (T*)dst, c, cb, spatial, total)));
     }
     return check_launch("ctu_pack_ncdhw");
+}
+
+int ctu_pack_patches(const float* vol, const int* origins, void* dst, int dtype, int n, int c, int vd, int vh, int vw, int patch,
+                     ctu_stream stream) {
+    CTU_REQUIRE(vol && origins && dst && n > 0 && c > 0 && vd > 0 && vh > 0 && vw > 0, "ctu_pack_patches: bad arguments");
+    CTU_REQUIRE(patch > 0 && patch % 4 == 0 && vw % 4 == 0, "ctu_pack_patches: patch size and volume width must be multiples of 4");
+    const int cb = (c + 7) / 8;
+    const long long total4 = (long long)n * cb * patch * patch * (patch / 4);
+    CTU_DISPATCH_DTYPE(dtype, (pack_patches_kernel<T><<<cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(
+                                  vol, origins, (T*)dst, c, cb, vd, vh, vw, patch, total4)));
+    return check_launch("ctu_pack_patches");
 }
 
 int ctu_unpack_ncdhw(const void* src, float* dst, int dtype, int n, int c, long long spatial, ctu_stream stream) {

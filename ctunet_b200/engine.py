@@ -112,6 +112,10 @@ class Engine:
         # set by trainer.TrainStep: (targets, softmax_for_dice, ce_lambda, dice_lambda, comps, mirror) -- the head then
         # runs fused with the loss (csrc/head.cu: head_loss_*), produces no output tensors and wires its own backward
         self.fused_loss = None
+        # inference epilogue (models._FusedNet.predict_labels): (vol, origins, patch) replaces the input pack by a patch
+        # gather, (labels, origins, patch, dims) makes the head write hard labels (scattered at the origins when given)
+        self.patch_src = None
+        self.label_dst = None
 
     # ------------------------------------------------------------------ weight preparation on a side stream
     def begin(self, store: dict, key) -> None:
@@ -260,6 +264,13 @@ class Engine:
 
     # ------------------------------------------------------------------ layout
     def pack(self, x: torch.Tensor) -> Act:
+        if self.patch_src is not None:
+            vol, origins, patch = self.patch_src
+            c, vd, vh, vw = vol.shape
+            a = self.new_act(c, origins.shape[0], patch, patch, patch)
+            call("ctu_pack_patches", vol.data_ptr(), origins.data_ptr(), a.ptr, self.dtype, origins.shape[0], c, vd, vh, vw, patch,
+                 stream_ptr())
+            return a
         n, c, d, h, w = x.shape
         a = self.new_act(c, n, d, h, w)
         call("ctu_pack_ncdhw", x.data_ptr(), a.ptr, self.dtype, n, c, d * h * w, stream_ptr())
@@ -632,6 +643,15 @@ class Engine:
         pa, ca, ns = self._src_args(srcs)
         sp = bool(flags & (_lib.HEAD_SP | _lib.HEAD_SP_SOFTMAX))
         self._consume(srcs)
+        if self.label_dst is not None:
+            labels, origins, patch, dims = self.label_dst
+            if len(labels) != (2 if sp else 1):
+                raise ValueError("the %s head produces %d label volume(s)" % ("SP" if sp else "plain", 2 if sp else 1))
+            vd, vh, vw = dims if origins is not None else (0, 0, 0)
+            call("ctu_head_labels", self.dtype, pa, ca, ns, weight.data_ptr(), bias.data_ptr(), cout, flags,
+                 origins.data_ptr() if origins is not None else None, int(patch), vd, vh, vw, labels[0].data_ptr(),
+                 labels[1].data_ptr() if sp else None, s0.n, s0.spatial, stream_ptr())
+            return None
         if self.fused_loss is not None:
             return self._head_loss(list(srcs), weight, bias, flags, sp)
         if sp:

@@ -161,7 +161,44 @@ class _FusedNet(nn.Module):
         return _NetFn.apply(self, x, *params)
 
 
-def _run_planned(net, eng: Engine, x, record: bool, params):
+    @torch.no_grad()
+    def predict_labels(self, x=None, *, vol=None, origins=None, patch=None, out=None):
+        """The 'test' branch of the reference (Model.py:376-380 + ProblemHandler.py:338-343): eval-mode forward and
+        ``hard_segm_from_tensor`` of every output, as float32 label volumes -- the head kernel writes the labels itself.
+        Either ``x`` [B,C,D,H,W] (labels [B,D,H,W] per output), or sliding-window mode: ``vol`` float32 [C,D,H,W] on the device,
+        ``origins`` device int32 [B,3] (z, y, x) and ``patch``: the B patches are gathered from ``vol`` by one kernel and
+        their labels scattered into the full-size volumes ``out`` (a list of float32 [D,H,W] tensors, one per output)."""
+        was = self.training
+        self.eval()
+        try:
+            params = self._weight_tensors()
+            if vol is None:
+                self._validate(x)
+                x = x.contiguous()
+                eng = Engine(x.device, self.compute_dtype, record=False)
+                n_out = 2 if getattr(self, "_head_mode", "plain") != "plain" else 1
+                labels = [torch.empty((x.shape[0],) + tuple(x.shape[2:]), dtype=torch.float32, device=x.device) for _ in range(n_out)]
+                eng.label_dst = (labels, None, 0, None)
+                _run_planned(self, eng, x, False, params)
+                return tuple(labels)
+            if not (vol.is_cuda and vol.dtype == torch.float32 and vol.dim() == 4 and vol.is_contiguous()):
+                raise TypeError("vol: contiguous float32 CUDA tensor [C, D, H, W]")
+            if not (origins.is_cuda and origins.dtype == torch.int32 and origins.dim() == 2 and origins.shape[1] == 3):
+                raise TypeError("origins: CUDA int32 tensor [B, 3]")
+            m = 2 ** self._levels()
+            if patch % m or patch % 4 or vol.shape[3] % 4:
+                raise ValueError("patch size %d must be divisible by %d (and the volume width by 4)" % (patch, max(m, 4)))
+            eng = Engine(vol.device, self.compute_dtype, record=False)
+            eng.patch_src = (vol, origins.contiguous(), int(patch))
+            eng.label_dst = (list(out), origins.contiguous(), int(patch), tuple(vol.shape[1:]))
+            shape = torch.empty((origins.shape[0], vol.shape[0], patch, patch, patch), device="meta")
+            _run_planned(self, eng, shape, False, params, device=vol.device)
+            return tuple(out)
+        finally:
+            self.train(was)
+
+
+def _run_planned(net, eng: Engine, x, record: bool, params, device=None):
     """Run the network with the weight-preparation plan of this (shape, mode) configuration (Engine.begin).
     A plan holds closures over the weight tensors seen when it was recorded, so it is only reused while the module still
     owns the very same tensor objects (checked by identity against strong references kept with the plan: a parameter
@@ -173,8 +210,8 @@ def _run_planned(net, eng: Engine, x, record: bool, params):
         eng.end_forward()
         return out
     store = net.__dict__.setdefault("_prep_plans", {})
-    key = (tuple(x.shape), str(x.device), net.compute_dtype, bool(net.training), record, eng.want_input_grad,
-           E.UP_FUSION, E.CONV_PATH)
+    key = (tuple(x.shape), str(device if device is not None else x.device), net.compute_dtype, bool(net.training), record,
+           eng.want_input_grad, E.UP_FUSION, E.CONV_PATH, eng.patch_src is not None, eng.label_dst is not None)
     owners = store.setdefault("__owners__", {})
     held = owners.get(key)
     if held is None or len(held) != len(params) or any(a is not b for a, b in zip(held, params)):

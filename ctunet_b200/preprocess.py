@@ -99,11 +99,44 @@ def _captured_patch_labels(model, xb: torch.Tensor):
     return outs
 
 
+def _captured_fused_pass(model, vol, patch, batch, n_out):
+    """(static volume, static label volumes, static origins [batch, 3], graph) of one fused patch-batch pass
+    (gather -> network -> labels scattered at the origins), captured once per (model weights, volume shape, patch, batch)."""
+    graphs = model.__dict__.setdefault("_infer_graphs", {})
+    key = ("fused", tuple(vol.shape), str(vol.device), int(patch), int(batch), getattr(model, "compute_dtype", None))
+    weights = list(model.parameters()) + list(model.buffers())
+    ent = graphs.get(key)
+    if ent is not None and (len(ent[4]) != len(weights) or any(a is not b for a, b in zip(ent[4], weights))):
+        ent = None
+    if ent is None:
+        st_vol = vol.clone()
+        st_outs = [torch.zeros(tuple(vol.shape[1:]), dtype=torch.float32, device=vol.device) for _ in range(n_out)]
+        st_org = torch.zeros((batch, 3), dtype=torch.int32, device=vol.device)
+        model.predict_labels(vol=st_vol, origins=st_org, patch=patch, out=st_outs)      # warm-up: plans, allocator pools
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            model.predict_labels(vol=st_vol, origins=st_org, patch=patch, out=st_outs)
+        ent = (st_vol, st_outs, st_org, g, weights)
+        graphs[key] = ent
+        if len(graphs) > 8:
+            graphs.pop(next(iter(graphs)))
+    return ent[:4]
+
+
 @torch.no_grad()
-def sliding_window_argmax(model, vol: torch.Tensor, patch: int = 128, batch: int = 4, graph: bool = True):
+def sliding_window_argmax(model, vol: torch.Tensor, patch: int = 128, batch: int = 4, graph: bool = True, fused: bool = True,
+                          rank: int = 0, world: int = 1, group=None):
     """Eval-mode model over the non-overlapping ``patch``^3 grid of ``vol`` [Cin, D, H, W]; returns the
     stitched float32 label volume(s) (one per model output), as ``hard_segm_from_tensor`` would label
-    each patch (utilities.py:103-124).  ``graph``: replay every full patch batch from a captured CUDA graph."""
+    each patch (utilities.py:103-124).
+
+    ``fused`` (the B200 modules): per patch batch ONE gather kernel builds the blocked input from ``vol`` at the patch
+    origins and the head kernel writes the hard labels straight into the full-size output volumes
+    (``model.predict_labels``) -- no slicing / stacking, no fp32 [B,2,p,p,p] outputs, no separate argmax, no stitch copies.
+    Otherwise: slices stacked on the host side of the API and (``graph``) every full patch batch replayed from a captured
+    CUDA graph.  ``world`` > 1: the patches are sharded over the ranks (``parallel.shard_range``, no data-path collective in
+    the forward passes) and the disjoint label patches are merged by one all-reduce of the label volumes."""
     if vol.dim() != 4:
         raise ValueError("expected [Cin, D, H, W]")
     c, d, h, w = vol.shape
@@ -112,20 +145,57 @@ def sliding_window_argmax(model, vol: torch.Tensor, patch: int = 128, batch: int
     was_training = model.training
     model.eval()
     origins = [(z, y, x) for z in range(0, d, patch) for y in range(0, h, patch) for x in range(0, w, patch)]
+    if world > 1:
+        from .parallel import shard_range
+        lo, hi = shard_range(len(origins), rank, world)
+        origins = origins[lo:hi]
     outs = None
-    for i in range(0, len(origins), batch):
-        chunk = origins[i:i + batch]
-        xb = torch.stack([vol[:, z:z + patch, y:y + patch, x:x + patch] for z, y, x in chunk]).contiguous()
-        if graph and vol.is_cuda:
-            labs = _captured_patch_labels(model, xb)
+    if fused and vol.is_cuda and hasattr(model, "predict_labels") and vol.dtype == torch.float32:
+        vol = vol.contiguous()
+        n_out = 2 if getattr(model, "_head_mode", "plain") != "plain" else 1
+        org = torch.tensor(origins, dtype=torch.int32, device=vol.device).view(-1, 3)
+        nfull = (len(origins) // batch) * batch if graph else 0
+        if nfull:
+            # one captured graph per (volume shape, patch, batch): ~110 launches per patch batch are host-bound below batch 8
+            st_vol, st_outs, st_org, g = _captured_fused_pass(model, vol, patch, batch, n_out)
+            if st_vol.data_ptr() != vol.data_ptr():
+                st_vol.copy_(vol)
+            if world > 1:
+                for o in st_outs:
+                    o.zero_()
+            for i in range(0, nfull, batch):
+                st_org.copy_(org[i:i + batch])
+                g.replay()
+            for i in range(nfull, len(origins), batch):          # a ragged last batch runs eagerly on the same buffers
+                model.predict_labels(vol=st_vol, origins=org[i:i + batch], patch=patch, out=st_outs)
+            outs = [o.clone() for o in st_outs]                   # the static buffers belong to the capture
         else:
-            o = model(xb)
-            o = o if isinstance(o, tuple) else (o,)
-            labs = [hard_segm_from_tensor(ok) for ok in o]
-        if outs is None:
-            outs = [torch.empty((d, h, w), dtype=torch.float32, device=vol.device) for _ in labs]
-        for k, lab in enumerate(labs):
-            for j, (z, y, x) in enumerate(chunk):
-                outs[k][z:z + patch, y:y + patch, x:x + patch] = lab[j]
+            alloc = torch.zeros if world > 1 else torch.empty
+            outs = [alloc((d, h, w), dtype=torch.float32, device=vol.device) for _ in range(n_out)]
+            for i in range(0, len(origins), batch):
+                model.predict_labels(vol=vol, origins=org[i:i + batch], patch=patch, out=outs)
+    else:
+        for i in range(0, len(origins), batch):
+            chunk = origins[i:i + batch]
+            xb = torch.stack([vol[:, z:z + patch, y:y + patch, x:x + patch] for z, y, x in chunk]).contiguous()
+            if graph and vol.is_cuda:
+                labs = _captured_patch_labels(model, xb)
+            else:
+                o = model(xb)
+                o = o if isinstance(o, tuple) else (o,)
+                labs = [hard_segm_from_tensor(ok) for ok in o]
+            if outs is None:
+                alloc = torch.zeros if world > 1 else torch.empty
+                outs = [alloc((d, h, w), dtype=torch.float32, device=vol.device) for _ in labs]
+            for k, lab in enumerate(labs):
+                for j, (z, y, x) in enumerate(chunk):
+                    outs[k][z:z + patch, y:y + patch, x:x + patch] = lab[j]
+    if world > 1:
+        import torch.distributed as dist
+        if outs is None:                      # a rank without patches still takes part in the merge
+            n_out = 2 if getattr(model, "_head_mode", "plain") != "plain" else 1
+            outs = [torch.zeros((d, h, w), dtype=torch.float32, device=vol.device) for _ in range(n_out)]
+        for o in outs:
+            dist.all_reduce(o, op=dist.ReduceOp.SUM, group=group)     # disjoint supports: the sum IS the stitch
     model.train(was_training)
     return outs

@@ -336,10 +336,8 @@ class EvalStep:
         return torch.cat(vals)
 
     def _labels_impl(self, image):
-        from .utilities import hard_segm_from_tensor
-        out = self._forward(image)
-        outs = out if isinstance(out, tuple) else (out,)
-        return tuple(hard_segm_from_tensor(o) for o in outs)
+        # the head kernel writes the hard labels itself (no fp32 outputs, no separate argmax pass)
+        return self.model.predict_labels(image)
 
     def _run(self, which, fn, tensors):
         if not self.graph:

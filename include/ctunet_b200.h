@@ -57,6 +57,10 @@ int ctu_has_tensor_path(void);
 /* ---- layout: fp32 NCDHW (the reference's tensors, Model.py:343) <-> blocked ---------------- */
 int ctu_pack_ncdhw(const float* src, void* dst, int dtype, int n, int c, long long spatial, ctu_stream stream);
 int ctu_unpack_ncdhw(const void* src, float* dst, int dtype, int n, int c, long long spatial, ctu_stream stream);
+/* sliding-window inference (BASELINE config 4): n patches of patch^3 voxels gathered from a float32 [c][vd][vh][vw] volume at
+ * the DEVICE int[n][3] origins (z, y, x) into the blocked layout -- no host-side slicing / stacking */
+int ctu_pack_patches(const float* vol, const int* origins, void* dst, int dtype, int n, int c, int vd, int vh, int vw, int patch,
+                     ctu_stream stream);
 
 /* ---- Conv3d k^3, stride 1, "same" zero padding (nn.Conv3d at models.py:26,29,38,41,71,76,
  *      403,407,430,434,483,487), k in {1,3,5}.  Weights are re-packed from the native
@@ -186,6 +190,13 @@ int ctu_bn_relu_bwd_apply(int dtype, const void* y, const float* ss, const float
 int ctu_head_fwd(int dtype, const void* const* h_srcs, const int* h_src_channels, int nsrc, const float* w,
                  const float* bias, int cout, int flags, float* out0, float* out1, int n, long long spatial,
                  ctu_stream stream);
+/* head + hard_segm_from_tensor (utilities.py:103-124) in one kernel: float32 labels = argmax over the channels of every head
+ * output (first maximum wins, as ctu_argmax_channels).  origins == NULL: labels0 / labels1 are [n][spatial] planes;
+ * origins = DEVICE int[n][3]: every sample is a patch^3 patch scattered into the [vd][vh][vw] label volumes at its origin
+ * (the stitch of a sliding-window pass).  labels1 only for the SP heads. */
+int ctu_head_labels(int dtype, const void* const* h_srcs, const int* h_src_channels, int nsrc, const float* w, const float* bias,
+                    int cout, int flags, const int* origins, int patch, int vd, int vh, int vw, float* labels0, float* labels1,
+                    int n, long long spatial, ctu_stream stream);
 /* dsrcs[i] nullable; dw [cout][cin_total] and db [cout] are zeroed by the call.  dw = db = NULL: source gradients only;
  * every dsrcs[i] NULL: parameter gradients only (two launches that can run on different streams) */
 /* out0 / out1 (nullable): the outputs ctu_head_fwd produced; with them the plain-sigmoid SP head skips the logits */

@@ -459,3 +459,38 @@ def test_encode_flaprec_bits_is_bit_exact():
     assert torch.equal(img, img2)
     img1, _ = encode_flaprec_bits(*[b.to(DEV) for b in bits], shp[1:])          # one input channel
     assert img1.shape == (2, 1) + shp[1:] and torch.equal(img1[:, 0].cpu(), broken.float())
+
+
+@pytest.mark.parametrize("name,mode", [("UNetSP", "fp32"), ("UNetSP", "bf16"), ("recAE_v2_fixed", "bf16")])
+def test_fused_sliding_window_equals_unfused(name, mode):
+    """Patch gather kernel + head-writes-labels (model.predict_labels, BASELINE config 4) against the unfused pipeline of the
+    same modules (slice / stack -> forward -> ctu_argmax_channels -> stitch): BIT-identical label volumes, and the direct
+    [B,D,H,W] label path equals hard_segm_from_tensor of the forward outputs."""
+    import ctunet_b200 as C
+    from ctunet_b200 import preprocess as P
+    from oracle import unet_oracle as O
+    cfg = O.PRESETS[name]
+    C.set_compute_dtype(mode)
+    torch.manual_seed(0)
+    net = getattr(C, name)().to(DEV).eval()
+    C.set_compute_dtype("bf16")
+    g = torch.Generator().manual_seed(12)
+    vol = (torch.rand(cfg.input_channels, 32, 64, 96, generator=g) > 0.7).float().to(DEV)
+    a = P.sliding_window_argmax(net, vol, patch=32, batch=4, fused=True)                  # captured patch batches + ragged tail
+    a2 = P.sliding_window_argmax(net, vol, patch=32, batch=4, fused=True, graph=False)
+    b = P.sliding_window_argmax(net, vol, patch=32, batch=4, fused=False, graph=False)
+    assert len(a) == len(b) == (2 if cfg.head != "plain" else 1)
+    for u, u2, v in zip(a, a2, b):
+        assert u.shape == (32, 64, 96) and u.dtype == torch.float32
+        assert torch.equal(u, v) and torch.equal(u2, v)
+    vol2 = vol.flip(3).contiguous()                                                       # a second volume through the same capture
+    for u, v in zip(P.sliding_window_argmax(net, vol2, patch=32, batch=4), P.sliding_window_argmax(net, vol2, patch=32, batch=4,
+                                                                                             fused=False, graph=False)):
+        assert torch.equal(u, v)
+    x = torch.stack([vol[:, :, :32, :32], vol[:, :, 32:, 64:]]).contiguous()
+    labs = net.predict_labels(x)
+    with torch.no_grad():
+        out = net(x)
+    out = out if isinstance(out, tuple) else (out,)
+    for lab, o in zip(labs, out):
+        assert torch.equal(lab, C.hard_segm_from_tensor(o))
