@@ -24,6 +24,7 @@ namespace ctu {
 
 constexpr int TC_TH = 16, TC_TW = 16;   // output tile (h, w) per plane = 2 MMA tiles of 16x8
 constexpr int TC_WB = TC_TW / 8;
+constexpr int TC_MAX_STAGES = 4;         // TMEM accumulator stages per 16x8 tile (fprop/dgrad)
 // fprop/dgrad: warp 0 TMA producer, warps 1..2 MMA issuers (one per 16x8 tile), warps 3..10 epilogue (4 per tile)
 // wgrad: warp 0 TMA producer, warps 1..4 MMA issuers (accumulators dealt round-robin) and final flush
 constexpr int WG_ISSUERS = 4;
@@ -95,6 +96,8 @@ struct TcParams {
     uint32_t wimg_bytes, plane_bytes, slot_bytes;   // plane_bytes: one channel block of one plane, padded to 128
     uint32_t tmem_cols;
     uint32_t ns;                                    // plane ring depth (more slots = more TMA loads in flight)
+    uint32_t stmask, stshift;                       // TMEM accumulator stages per tile = stmask + 1 = 1 << stshift (2 or 4)
+    int balance;                                    // 1: every CTA walks an equal share of the (column, z) plane sequence
     // BNRED kernels (data gradient feeding a BatchNorm+ReLU backward): y of that BatchNorm (natural or phase-major
     // layout), its ss = scale | shift | mean | invstd; `stats` then receives sum(dz) | sum(dz * xhat)
     const __nv_bfloat16* bn_y;
@@ -124,6 +127,51 @@ __global__ void tc_pack_wimg_kernel(const float* __restrict__ wp, __nv_bfloat16*
     wimg[i] = __float2bfloat16_rn(v);
 }
 
+// The work of one launch is the sequence of output planes (n, h-tile, w-tile, z), z fastest.  balance = 1: CTA b of G
+// owns the contiguous share [total*b/G, total*(b+1)/G) of it -- every CTA computes the same number of planes (+-1), cut
+// into segments at the column ends (a segment re-reads K - 1 halo planes, like a d-chunk); balance = 0: fixed d-chunks of
+// dc planes dealt round-robin (the round count quantises: 1024 items on 296 CTAs are 4 rounds for 3.46 rounds of work).
+struct TcWalk {
+    long long p, pend;
+    int item;
+    template <class P>
+    __device__ __forceinline__ void init(const P& q) {
+        const long long total = (long long)q.n * q.tiles_h * q.tiles_w * q.d;
+        p = total * blockIdx.x / gridDim.x;
+        pend = total * (blockIdx.x + 1) / gridDim.x;
+        item = blockIdx.x;
+    }
+    template <class P>
+    __device__ __forceinline__ bool next(const P& q, int& n, int& thi, int& twi, int& z0, int& nd) {
+        const int tiles = q.tiles_h * q.tiles_w;
+        if (q.balance) {
+            if (p >= pend) return false;
+            const long long col = p / q.d;
+            z0 = (int)(p - col * q.d);
+            const long long rem = pend - p;
+            nd = (long long)(q.d - z0) < rem ? (q.d - z0) : (int)rem;
+            p += nd;
+            n = (int)(col / tiles);
+            const int r = (int)(col % tiles);
+            thi = r / q.tiles_w;
+            twi = r % q.tiles_w;
+            return true;
+        }
+        if (item >= q.total_items) return false;
+        const int items_per_n = tiles * q.dchunks;
+        n = item / items_per_n;
+        int r = item % items_per_n;
+        const int dci = r % q.dchunks;
+        r /= q.dchunks;
+        twi = r % q.tiles_w;
+        thi = r / q.tiles_w;
+        z0 = dci * q.dc;
+        nd = (q.d - z0) < q.dc ? (q.d - z0) : q.dc;
+        item += gridDim.x;
+        return true;
+    }
+};
+
 // One CTA walks (n, 16x16 h-w tile, d-chunk) items plane by plane.  For every INPUT plane and every 16x8 tile a
 // single accumulation group of tc_mmas_per_kd() MMAs computes P[voxel][kd][co] = sum_{kh,kw,ci} x * W, i.e. the
 // three (five) kd taps ride in the MMA N dimension: the activation tile is read from shared memory once per
@@ -149,9 +197,9 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
     const uint32_t s_tab = s_planes + NS * p.slot_bytes;                    // per-MMA descriptor low words (A, B)
     const int nm = tc_mmas_per_kd(K, p.cb, p.cbg);
     const uint32_t s_bar = s_tab + ((nm * 8u + 15u) & ~15u);
-    // barriers: plane_full[NS], plane_empty[NS], acc_full[2 stages][TC_WB tiles], acc_empty[2][TC_WB], w_full
+    // barriers: plane_full[NS], plane_empty[NS], acc_full[<= 4 stages][TC_WB tiles], acc_empty[<= 4][TC_WB], w_full
     const uint32_t b_full = s_bar, b_empty = s_bar + 8 * TC_MAX_SLOTS, b_afull = s_bar + 16 * TC_MAX_SLOTS,
-                   b_aempty = b_afull + 8 * 2 * TC_WB, b_w = b_aempty + 8 * 2 * TC_WB;
+                   b_aempty = b_afull + 8 * TC_MAX_STAGES * TC_WB, b_w = b_aempty + 8 * TC_MAX_STAGES * TC_WB;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (b_w + 8 - s_base));
     float* st_red = reinterpret_cast<float*>(smem + (b_w + 32 - s_base));   // [4*TC_WB epilogue warps][NSLOT*16]
     float* st_bias = st_red + 4 * TC_WB * 32;                               // [CP] bias of this CTA's output blocks
@@ -164,7 +212,7 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
             mbar_init(b_full + 8 * i, 1);
             mbar_init(b_empty + 8 * i, TC_WB);      // every issuer warp releases the slot
         }
-        for (int i = 0; i < 2 * TC_WB; ++i) {
+        for (int i = 0; i < TC_MAX_STAGES * TC_WB; ++i) {
             mbar_init(b_afull + 8 * i, 1);
             mbar_init(b_aempty + 8 * i, 4);
         }
@@ -191,8 +239,6 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int items_per_n = p.tiles_h * p.tiles_w * p.dchunks;
-
     if (warp == 0) {
         // ===================================================================== TMA producer
         if (lane == 0) {
@@ -202,13 +248,11 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
                 bulk_load_1d(s_w + off, reinterpret_cast<const unsigned char*>(p.wimg) + (size_t)blockIdx.y * p.wimg_bytes + off, sz, b_w);
             }
             Ring pr = {0, 0};
-            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-                const int n = item / items_per_n;
-                int r = item % items_per_n;
-                const int dci = r % p.dchunks; r /= p.dchunks;
-                const int twi = r % p.tiles_w, thi = r / p.tiles_w;
-                const int z0 = dci * p.dc, h0 = thi * TC_TH, w0 = twi * TC_TW;
-                const int nd = (p.d - z0) < p.dc ? (p.d - z0) : p.dc;
+            TcWalk walk;
+            walk.init(p);
+            int n, thi, twi, z0, nd;
+            while (walk.next(p, n, thi, twi, z0, nd)) {
+                const int h0 = thi * TC_TH, w0 = twi * TC_TW;
                 for (int pl = 0; pl < nd + K - 1; ++pl) {
                     for (int g = 0; g < p.ncg; ++g, pr.next(NS)) {
                         const int b0 = g * p.cbg;
@@ -252,18 +296,18 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
             mbar_wait(b_w, 0);
             uint32_t step = 0;
             Ring cons = {0, 0};
-            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-                const int r0 = item % items_per_n;
-                const int z0 = (r0 % p.dchunks) * p.dc;
-                const int nd = (p.d - z0) < p.dc ? (p.d - z0) : p.dc;
+            TcWalk walk;
+            walk.init(p);
+            int n_, thi_, twi_, z0_, nd;
+            while (walk.next(p, n_, thi_, twi_, z0_, nd)) {
                 for (int pl = 0; pl < nd + K - 1; ++pl, ++step) {
-                    const uint32_t stage = step & 1;
+                    const uint32_t stage = step & p.stmask;
                     const uint32_t d_tmem = tmem_base + (stage * TC_WB + t) * p.nt;
                     uint32_t b_lo = (s_w >> 4) | (8u << 16);          // B: LBO = 128 B (second 8-wide K chunk)
                     uint32_t acc = 0;
                     for (int g = 0; g < p.ncg; ++g, cons.next(NS)) {
                         mbar_wait(b_full + 8 * cons.slot, cons.phase);
-                        if (g == 0) mbar_wait(b_aempty + 8 * (stage * TC_WB + t), ((step >> 1) & 1) ^ 1);
+                        if (g == 0) mbar_wait(b_aempty + 8 * (stage * TC_WB + t), ((step >> p.stshift) & 1) ^ 1);
                         tc_fence_after();
                         const uint32_t a16 = (s_planes + cons.slot * p.slot_bytes + t * 128u) >> 4;
                         const int gb = (p.cb - g * p.cbg) < p.cbg ? (p.cb - g * p.cbg) : p.cbg;
@@ -321,13 +365,11 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
 #pragma unroll
         for (int i = 0; i < NSLOT * 8; ++i) s1[i] = s2[i] = 0.f;
         uint32_t step = 0;
-        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-            const int n = item / items_per_n;
-            int r = item % items_per_n;
-            const int dci = r % p.dchunks; r /= p.dchunks;
-            const int twi = r % p.tiles_w, thi = r / p.tiles_w;
-            const int z0 = dci * p.dc, h0 = thi * TC_TH, w0 = twi * TC_TW;
-            const int nd = (p.d - z0) < p.dc ? (p.d - z0) : p.dc;
+        TcWalk walk;
+        walk.init(p);
+        int n, thi, twi, z0, nd;
+        while (walk.next(p, n, thi, twi, z0, nd)) {
+            const int h0 = thi * TC_TH, w0 = twi * TC_TW;
             const int gy = h0 + hh, gx = w0 + te * 8 + wl;
             const bool inb = gy < p.h && gx < p.w;
             __nv_bfloat16* ycol = p.y + (((long long)n * p.cob_n + ob0) * plane + ((long long)gy) * p.w + gx) * 8;
@@ -335,12 +377,20 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
             for (int i = 0; i < K; ++i)
 #pragma unroll
                 for (int c = 0; c < CP; ++c) part[i][c] = 0.f;
-            for (int pl = 0; pl < nd + K - 1; ++pl, ++step) {
-                const uint32_t stage = step & 1;
-                mbar_wait(b_afull + 8 * (stage * TC_WB + te), (step >> 1) & 1);
+            // The partial sums of output plane j live in part[j % K]: the plane loop is unrolled K-fold so that every slot
+            // index is a compile-time constant (no register rotation per plane).
+            const int npl = nd + K - 1;
+            for (int pl0 = 0; pl0 < npl; pl0 += K) {
+#pragma unroll
+            for (int u = 0; u < K; ++u) {
+                const int pl = pl0 + u;
+                if (pl >= npl) break;
+                const uint32_t stage = step & p.stmask;
+                mbar_wait(b_afull + 8 * (stage * TC_WB + te), (step >> p.stshift) & 1);
+                ++step;
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (stage * TC_WB + te) * p.nt;
-                // P[kd] of input plane pl feeds output plane pl - kd, kept in part[K-1-kd]
+                // P[kd] of input plane pl feeds output plane pl - kd, kept in part[(pl - kd) % K] = part[(u - kd + K) % K]
                 // all loads of up to two output blocks in flight, one wait
                 constexpr int OBB = COB < 2 ? COB : 2;
 #ifdef CTU_DBG_NOEPI
@@ -363,14 +413,15 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
                             tmem_ld8_pin(raw[kd][ob]);
 #pragma unroll
                             for (int c = 0; c < 8; ++c)
-                                part[K - 1 - kd][(ob0b + ob) * 8 + c] += __uint_as_float(raw[kd][ob][c]);
+                                part[(u - kd + K) % K][(ob0b + ob) * 8 + c] += __uint_as_float(raw[kd][ob][c]);
                         }
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(b_aempty + 8 * (stage * TC_WB + te));
-                // output plane j = pl - (K-1) is complete
+                // output plane j = pl - (K-1) is complete; its slot (u + 1) % K then starts over for plane pl + 1
                 const int j = pl - (K - 1);
+                float (&done)[CP] = part[(u + 1) % K];
                 if (j >= 0) {
                     const int gz = z0 + j;
 #pragma unroll
@@ -378,7 +429,7 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
                         V8 o;
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
-                            float v = part[0][ob * 8 + c];
+                            float v = done[ob * 8 + c];
                             if (has_bias) v += st_bias[ob * 8 + c];
                             o.v[c] = round_to<__nv_bfloat16>(v);
                         }
@@ -418,11 +469,8 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
                     }
                 }
 #pragma unroll
-                for (int i = 0; i + 1 < K; ++i)
-#pragma unroll
-                    for (int c = 0; c < CP; ++c) part[i][c] = part[i + 1][c];
-#pragma unroll
-                for (int c = 0; c < CP; ++c) part[K - 1][c] = 0.f;
+                for (int c = 0; c < CP; ++c) done[c] = 0.f;
+            }
             }
         }
         if (want_stats) {
@@ -462,6 +510,19 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
 }
 
 // ------------------------------------------------------------------------------------------------ host
+// TcWalk mode of a launch.  Equal plane shares remove the round quantisation of fixed d-chunks, but the CTAs then sit at
+// staggered depths (neighbouring tiles no longer read their common halo at the same time) and a share that straddles a
+// column end pays the K - 1 halo planes twice.  Measured on B200 (scripts/bench_kernels.py, us, chunks -> shares):
+//   fprop 7->7 at 4x128^3 94.9 -> 84.7, 2->7 95.2 -> 85.6, 64->14 at 4x64^3 88.3 -> 84.5, 14->14 at 4x64^3 47.5 -> 47.6;
+//   but 4-block outputs 146 -> 169 ([14,14,1]->64 at 4x64^3), 53 -> 58 (128->28 at 4x32^3), 30 -> 33 (28->28 at 4x32^3);
+//   wgrad (first formulation) 244 -> 240, 135 -> 127, 84.4 -> 79.5, 49.3 -> 47.0; (kd,kh)-in-N formulation 116 -> 124.
+// Hence: shares for fprop / dgrad with <= 2 output blocks per CTA and >= 16 planes per CTA, and for the first wgrad
+// formulation; fixed chunks elsewhere.  CTU_TC_BALANCE=0 / 1 forces one mode everywhere (A/B runs).
+static int tc_balance(bool by_rule) {
+    static const int forced = getenv("CTU_TC_BALANCE") ? atoi(getenv("CTU_TC_BALANCE")) : -1;
+    return forced >= 0 ? (forced ? 1 : 0) : (by_rule ? 1 : 0);
+}
+
 PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
     if (!fn) {
@@ -477,6 +538,7 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 struct TcGeom {
     int cb, cbg, ncg, cob_n, cobg, ngroups, nt, nm;
     uint32_t wimg_bytes, plane_bytes, slot_bytes, tmem_cols, ns;   // wimg_bytes: ONE group's image
+    uint32_t stages;                                               // TMEM accumulator stages per 16x8 tile
     size_t smem;
 };
 
@@ -509,7 +571,7 @@ static bool tc_geometry(int k, int cb, int cout, int h, int w, TcGeom& g) {
         g.nt = (k * cobg * 8 + 15) / 16 * 16;
         g.wimg_bytes = (uint32_t)g.nm * g.nt * 32;
         const size_t fixed = ((g.wimg_bytes + 1023u) & ~1023u) + ((g.nm * 8 + 15) & ~15) +
-                             8 * (2 * TC_MAX_SLOTS + 4 * TC_WB + 2) + 32 + 4 * TC_WB * 32 * 4 + 128 + 512 + 1024;
+                             8 * (2 * TC_MAX_SLOTS + 2 * TC_MAX_STAGES * TC_WB + 2) + 32 + 4 * TC_WB * 32 * 4 + 128 + 512 + 1024;
         // the wide-output variants are limited to one CTA per SM by registers: give their ring the whole SM
         g.ns = pick_slots(g.ncg > 1 ? 4 : 3, fixed, g.slot_bytes, cobg >= 2 ? 200 * 1024 : 100 * 1024);
         g.smem = fixed + (size_t)g.ns * g.slot_bytes;
@@ -521,7 +583,12 @@ static bool tc_geometry(int k, int cb, int cout, int h, int w, TcGeom& g) {
         if (cobg == 1) return false;
     }
     g.ngroups = (g.cob_n + g.cobg - 1) / g.cobg;
-    uint32_t cols = 2 * TC_WB * g.nt;
+    // accumulator stages per tile: two.  (Four -- CTU_TC_STAGES=4, possible while 4 x 2 x N <= 512 TMEM columns -- were measured
+    // neutral on the narrow layers: 7->7 at 4x128^3 84.7 vs 84.5 us; the issuers do not wait on the epilogue.)
+    g.stages = 2u;
+    static const int stages_env = getenv("CTU_TC_STAGES") ? atoi(getenv("CTU_TC_STAGES")) : 0;
+    if (stages_env == 4 && (uint32_t)(4 * TC_WB * g.nt) <= 512u) g.stages = 4u;
+    uint32_t cols = g.stages * TC_WB * g.nt;
     g.tmem_cols = 32;
     while (g.tmem_cols < cols) g.tmem_cols *= 2;
     return g.tmem_cols <= 512;
@@ -611,6 +678,8 @@ int conv3d_fprop_tc(const void* const* h_srcs, const int* h_src_channels, int ns
     const int tiles = n * p.tiles_h * p.tiles_w;
     p.wimg_bytes = g.wimg_bytes; p.plane_bytes = g.plane_bytes; p.slot_bytes = g.slot_bytes; p.tmem_cols = g.tmem_cols;
     p.ns = g.ns;
+    p.stmask = g.stages - 1;
+    p.stshift = g.stages == 4 ? 2 : 1;
     if (fuse_stats) {
         cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(double) * 2 * p.cobo * 8, stream);
         if (e != cudaSuccess) {
@@ -663,7 +732,9 @@ int conv3d_fprop_tc(const void* const* h_srcs, const int* h_src_channels, int ns
         p.dchunks = (d + dc - 1) / dc;
         p.total_items = tiles * p.dchunks;
         int gx = (148 * occ) / g.ngroups;
-        if (gx > p.total_items) gx = p.total_items;
+        p.balance = tc_balance(g.cobg <= 2 && (long long)tiles * d >= 16LL * (gx > 0 ? gx : 1));
+        const long long units = p.balance ? (long long)tiles * d : (long long)p.total_items;
+        if (gx > units) gx = (int)units;
         if (gx < 1) gx = 1;
         kern<<<dim3(gx, g.ngroups), threads, g.smem, stream>>>(maps, p);
         return check_launch("ctu_conv3d_fprop(tcgen05)");
@@ -700,6 +771,7 @@ struct WgParams {
     int n_cbgroups, n_ngroups;
     int n, d, h, w;
     int tiles_h, tiles_w, dchunks, dc, total_items;
+    int balance;                // TcWalk: equal shares of the plane sequence instead of round-robin d-chunks
     uint32_t plane_bytes, xslot_bytes, dyslot_bytes, tmem_cols;
     uint32_t ns, nds;           // x-plane / dy-plane ring depths
     int nsrc, src_cb[CTU_MAX_SRC], src_cboff[CTU_MAX_SRC];   // concatenated sources of x
@@ -773,18 +845,14 @@ __global__ void __launch_bounds__(WG_THREADS) conv3d_wgrad_tc_kernel(const __gri
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int items_per_n = p.tiles_h * p.tiles_w * p.dchunks;
-
     if (warp == 0) {
         if (lane == 0) {
             Ring pr = {0, 0}, dr = {0, 0};
-            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-                const int n = item / items_per_n;
-                int r = item % items_per_n;
-                const int dci = r % p.dchunks; r /= p.dchunks;
-                const int twi = r % p.tiles_w, thi = r / p.tiles_w;
-                const int z0 = dci * p.dc, h0 = thi * TC_TH, w0 = twi * TC_TW;
-                const int nd = (p.d - z0) < p.dc ? (p.d - z0) : p.dc;
+            TcWalk walk;
+            walk.init(p);
+            int n, thi, twi, z0, nd;
+            while (walk.next(p, n, thi, twi, z0, nd)) {
+                const int h0 = thi * TC_TH, w0 = twi * TC_TW;
                 for (int pl = 0; pl < nd + K - 1; ++pl, pr.next(NS)) {
                     mbar_wait(b_xempty + 8 * pr.slot, pr.phase ^ 1);
                     mbar_expect_tx(b_xfull + 8 * pr.slot, (uint32_t)ncb * HH * WW * 16);
@@ -830,10 +898,10 @@ __global__ void __launch_bounds__(WG_THREADS) conv3d_wgrad_tc_kernel(const __gri
         const uint32_t leader = elect_one();
         uint32_t base = 0, waited = 0, first = 1;
         Ring cons = {0, 0}, head = {0, 0}, dyr = {0, 0};
-        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-            const int r0 = item % items_per_n;
-            const int z0 = (r0 % p.dchunks) * p.dc;
-            const int nd = (p.d - z0) < p.dc ? (p.d - z0) : p.dc;
+        TcWalk walk;
+        walk.init(p);
+        int n_, thi_, twi_, z0_, nd;
+        while (walk.next(p, n_, thi_, twi_, z0_, nd)) {
             for (int j = 0; j < nd; ++j) {
                 while (waited < base + j + K) {
                     mbar_wait(b_xfull + 8 * cons.slot, cons.phase);
@@ -934,6 +1002,7 @@ struct Wg2Params {
     int split;                  // accumulators per input block: the 16 rows of a plane are dealt to `split` issuers
     int n, d, h, w;
     int tiles_h, tiles_w, dchunks, dc, total_items;
+    int balance;                // TcWalk
     uint32_t xplane_bytes, xslot_bytes, dyslot_bytes, tmem_cols, ns;
     int nsrc, src_cb[CTU_MAX_SRC], src_cboff[CTU_MAX_SRC];
 };
@@ -982,19 +1051,15 @@ __global__ void __launch_bounds__(WG_THREADS) conv3d_wgrad_tc2_kernel(const __gr
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int items_per_n = p.tiles_h * p.tiles_w * p.dchunks;
-
     if (warp == 0) {
         if (lane == 0) {
             Ring pr = {0, 0};
             const uint32_t bytes = (uint32_t)ncb * TC_TH * ROW + (uint32_t)DYROWS * dyrow;
-            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-                const int n = item / items_per_n;
-                int r = item % items_per_n;
-                const int dci = r % p.dchunks; r /= p.dchunks;
-                const int twi = r % p.tiles_w, thi = r / p.tiles_w;
-                const int z0 = dci * p.dc, h0 = thi * TC_TH, w0 = twi * TC_TW;
-                const int nd = (p.d - z0) < p.dc ? (p.d - z0) : p.dc;
+            TcWalk walk;
+            walk.init(p);
+            int n, thi, twi, z0, nd;
+            while (walk.next(p, n, thi, twi, z0, nd)) {
+                const int h0 = thi * TC_TH, w0 = twi * TC_TW;
                 for (int j = 0; j < nd; ++j, pr.next(NS)) {
                     mbar_wait(b_empty + 8 * pr.slot, pr.phase ^ 1);
                     mbar_expect_tx(b_full + 8 * pr.slot, bytes);
@@ -1025,10 +1090,10 @@ __global__ void __launch_bounds__(WG_THREADS) conv3d_wgrad_tc2_kernel(const __gr
         const uint32_t leader = elect_one();
         uint32_t first = 1;
         Ring cons = {0, 0};
-        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-            const int r0 = item % items_per_n;
-            const int z0 = (r0 % p.dchunks) * p.dc;
-            const int nd = (p.d - z0) < p.dc ? (p.d - z0) : p.dc;
+        TcWalk walk;
+        walk.init(p);
+        int n_, thi_, twi_, z0_, nd;
+        while (walk.next(p, n_, thi_, twi_, z0_, nd)) {
             for (int j = 0; j < nd; ++j, cons.next(NS)) {
                 mbar_wait(b_full + 8 * cons.slot, cons.phase);
                 tc_fence_after();
@@ -1184,7 +1249,8 @@ static int conv3d_wgrad_tc2(const void* const* h_srcs, const int* h_src_channels
     p.dc = dc;
     p.dchunks = (d + dc - 1) / dc;
     p.total_items = tiles * p.dchunks;
-    if (gx > p.total_items) gx = p.total_items;
+    p.balance = tc_balance(false);
+    if (gx > p.total_items) gx = p.total_items;     // (every CTA ends with an atomic flush of its accumulators: no more CTAs than chunks)
     if (gx < 1) gx = 1;
     cudaError_t e = cudaFuncSetAttribute(conv3d_wgrad_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
     if (e != cudaSuccess) {
@@ -1373,7 +1439,8 @@ int conv3d_wgrad_tc(const void* const* h_srcs, const int* h_src_channels, int ns
     if (ctas_per_sm > 512 / (int)g.tmem_cols) ctas_per_sm = 512 / (int)g.tmem_cols;
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     int gx = (148 * ctas_per_sm + groups - 1) / groups;
-    if (gx > p.total_items) gx = p.total_items;
+    p.balance = tc_balance(true);
+    if (gx > p.total_items) gx = p.total_items;     // (every CTA ends with an atomic flush of its accumulators: no more CTAs than chunks)
     if (gx < 1) gx = 1;
     dim3 grid(gx, groups);
     auto go = [&](auto kern) -> int {

@@ -16,6 +16,8 @@ from __future__ import annotations
 
 from typing import Callable, Dict, List, Optional, Sequence
 
+import os
+
 import torch
 
 from . import _lib
@@ -52,10 +54,31 @@ HEAD_FROM_OUTPUTS = True
 _SIDE = {}
 
 
+# Stream priorities (captured into the graph's kernel nodes): the layer chain and the weight preparation it waits for run
+# at HIGH priority, the leaves -- weight gradients, the dead center block, the network-input gradient -- at the default one.
+# A leaf and the next link of the chain become runnable at the same moment (both wait for the same dy); without priorities
+# the block scheduler took whichever was enqueued first, and a persistent weight-gradient kernel then held every SM (and its
+# TMEM) for 100-250 us while the chain -- the critical path -- waited (CUPTI timeline, scripts/trace_step.py).
+STREAM_PRIORITIES = os.environ.get("CTU_PRIO", "1") == "1"
+# The weight gradient of a layer waits for that layer's data gradients (it then runs beside the BatchNorm kernels of the layer
+# below) instead of racing them for the SMs.  (A/B: CTU_WGRAD_AFTER=0/1)
+WGRAD_AFTER_DGRAD = os.environ.get("CTU_WGRAD_AFTER", "0") == "1"
+_SIDE_HIGH = (0,)          # which: 0 weight preparation, 1 weight gradients, 2 dead branch, 3 network-input gradient
+
+
 def _side_stream(device, which=0):
     key = (str(device), which)
     if key not in _SIDE:
-        _SIDE[key] = torch.cuda.Stream(device=device)
+        prio = -1 if (STREAM_PRIORITIES and which in _SIDE_HIGH) else 0
+        _SIDE[key] = torch.cuda.Stream(device=device, priority=prio)
+    return _SIDE[key]
+
+
+def chain_stream(device):
+    """The high-priority stream a step is captured on (trainer.TrainStep / EvalStep graph mode)."""
+    key = (str(device), "chain")
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=device, priority=-1 if STREAM_PRIORITIES else 0)
     return _SIDE[key]
 
 
@@ -108,6 +131,7 @@ class Engine:
         self._pi = 0
         self._side = None
         self._wgrad_stream = None
+        self._input_grad_stream = None
         self._dead_stream = None
         # set by trainer.TrainStep: (targets, softmax_for_dice, ce_lambda, dice_lambda, comps, mirror) -- the head then
         # runs fused with the loss (csrc/head.cu: head_loss_*), produces no output tensors and wires its own backward
@@ -347,16 +371,23 @@ class Engine:
                 if after_wgrad is not None:
                     after_wgrad()
 
+        def launch_wgrad():
+            if dw_out is None:
+                return
             if WGRAD_ASYNC:
                 main = torch.cuda.current_stream()
                 side = _side_stream(self.device, 1)
-                side.wait_stream(main)                      # dy (and everything before it) is ready
+                side.wait_stream(main)                      # dy (and everything enqueued before this point) is ready
                 with torch.cuda.stream(side):
                     wgrad()
                 dy.buf.record_stream(side)
                 self._wgrad_stream = side
             else:
                 wgrad()
+
+        if not WGRAD_AFTER_DGRAD:
+            launch_wgrad()
+
         def dgrads():
             for i, s in enumerate(srcs):
                 if not need[i]:
@@ -380,16 +411,18 @@ class Engine:
             # input that requires grad, Model.py:351-352; nothing consumes it): a leaf like the weight gradients, so it is
             # computed and converted to NCDHW on the second stream, off the critical path; run_tape() joins that stream.
             main = torch.cuda.current_stream()
-            side = _side_stream(self.device, 1)
+            side = _side_stream(self.device, 3)        # its own stream: beside the first layer's weight gradient, not behind it
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 dgrads()
                 self.input_grad = self.unpack(self.agrads.pop(id(srcs[0])))
             self.input_grad.record_stream(main)
             dy.buf.record_stream(side)
-            self._wgrad_stream = side
+            self._input_grad_stream = side
         else:
             dgrads()
+        if WGRAD_AFTER_DGRAD:
+            launch_wgrad()
 
     def _pgrad_done(self, pairs):
         """Register parameter gradients produced on the current stream (see _add_pgrad)."""
@@ -769,6 +802,9 @@ class Engine:
         if self._wgrad_stream is not None:                   # weight gradients -> visible to the optimizer's stream
             torch.cuda.current_stream().wait_stream(self._wgrad_stream)
             self._wgrad_stream = None
+        if self._input_grad_stream is not None:
+            torch.cuda.current_stream().wait_stream(self._input_grad_stream)
+            self._input_grad_stream = None
 
     def backward(self, g0=None, g1=None):
         # (drop the closure first: it references the engine AND the forward outputs, i.e. the autograd graph -- a cycle

@@ -24,6 +24,7 @@ from typing import Optional
 import torch
 
 from . import _lib
+from . import engine as E
 from ._lib import call, ptr_array, stream_ptr
 from .engine import Engine
 from .models import _run_planned
@@ -204,7 +205,7 @@ class TrainStep:
             g = torch.cuda.CUDAGraph()
             l0 = _lib.launches
             if not self.split_graph:
-                with torch.cuda.graph(g):                     # records the launches; nothing executes here
+                with torch.cuda.graph(g, stream=E.chain_stream(st_img.device)):   # records the launches; nothing executes here
                     self._static_out = self._forward_backward(st_img, st_tgt)
                     self.grads.begin_step()
                     self._update(self._static_out)
@@ -213,7 +214,7 @@ class TrainStep:
                 # buffer), ONE eager NCCL all-reduce of that buffer, graph 2 = optimizer + scheduler
                 if not self.grads.deferred:
                     raise RuntimeError("graph mode needs GradSync(deferred=True)")
-                with torch.cuda.graph(g):
+                with torch.cuda.graph(g, stream=E.chain_stream(st_img.device)):
                     self._static_out = self._forward_backward(st_img, st_tgt)
                 self.grads.begin_step()
                 g2 = torch.cuda.CUDAGraph()
