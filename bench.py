@@ -336,7 +336,7 @@ def describe(name, args, esize):
             cin = sum(ca[i] for i in range(ns))
             o = 9 if name == "ctu_conv3d_fprop" else 8
             cout, k, n, d, h, w = args[o], args[o + 1], args[o + 2], args[o + 3], args[o + 4], args[o + 5]
-            name = name + ("[tcgen05]" if args[o + 6] else "[cuda-core]")
+            name = name + ("[tcgen05]" if (args[o + 6] & 0xff) else "[cuda-core]")
             vox = n * d * h * w
             stat_cout = args[8] if name.startswith("ctu_conv3d_fprop") else 0
             if stat_cout or (ns > 1 and ca[ns - 1] == 1 and cout % 64 == 0):
@@ -363,7 +363,7 @@ def describe(name, args, esize):
             return ("%s %d->%d @%dx%dx%dx%d" % (name, cout, cs, n, d, h, w), 2.0 * vox * cs * cout * 8,
                     esize * vox * (cs + 8 * cout))
         if name == "ctu_bn_stats":
-            c, ph, n, sp = args[2], args[3], args[4], args[5]
+            c, ph, n, sp = args[2], args[3] & 0xff, args[4], args[5]
             return "%s c%d @%dx%d" % (name, c, n, sp * ph), 0.0, esize * c * n * sp * ph
         if name in ("ctu_bn_relu_fwd", "ctu_bn_relu_fwd_train"):
             o = 5 if name == "ctu_bn_relu_fwd" else 15

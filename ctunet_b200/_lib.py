@@ -17,6 +17,7 @@ LIB_PATH = os.environ.get("CTUNET_B200_LIB") or os.path.join(_HERE, "libctunet_b
 
 CTU_F32, CTU_BF16 = 0, 1
 CTU_MAX_SRC = 4
+CTU_ACCUM_PREZEROED = 0x100   # include/ctunet_b200.h: the caller zeroed the double accumulators
 HEAD_SOFTMAX, HEAD_SIGMOID, HEAD_SP, HEAD_SP_SOFTMAX = 1, 2, 4, 8
 
 P = c_void_p

@@ -473,9 +473,11 @@ using namespace ctu;
 extern "C" {
 
 int ctu_bn_stats(int dtype, const void* y, int c, int phases, int n, long long spatial, double* sums, ctu_stream stream) {
+    const bool prezeroed = (phases & CTU_ACCUM_PREZEROED) != 0;
+    phases &= ~CTU_ACCUM_PREZEROED;
     CTU_REQUIRE(y && sums && c > 0 && phases > 0 && n > 0 && spatial > 0, "ctu_bn_stats: bad arguments");
     const int cb = (c + 7) / 8;
-    cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * cb * 8, (cudaStream_t)stream);
+    cudaError_t e = prezeroed ? cudaSuccess : cudaMemsetAsync(sums, 0, sizeof(double) * 2 * cb * 8, (cudaStream_t)stream);
     if (e != cudaSuccess) {
         set_error("ctu_bn_stats: memset: %s", cudaGetErrorString(e));
         return (int)e;
@@ -588,10 +590,12 @@ static int bn_bwd(int dtype, BwdArgs& p, int n, bool apply, int y_phase_major, c
 
 int ctu_bn_relu_bwd_reduce(int dtype, const void* y, const float* ss, const void* dA, const void* dP, double* sums2,
                            int c, int n, int d, int h, int w, int y_phase_major, ctu_stream stream) {
+    const bool prezeroed = (y_phase_major & CTU_ACCUM_PREZEROED) != 0;
+    y_phase_major &= ~CTU_ACCUM_PREZEROED;
     CTU_REQUIRE(y && ss && sums2 && (dA || dP) && c > 0 && n > 0 && d > 0 && h > 0 && w > 0, "ctu_bn_relu_bwd_reduce: bad arguments");
     BwdArgs p = {};
     p.y = y; p.ss = ss; p.dA = dA; p.dP = dP; p.sums2 = sums2; p.c = c; p.cb = (c + 7) / 8; p.d = d; p.h = h; p.w = w;
-    cudaError_t e = cudaMemsetAsync(sums2, 0, sizeof(double) * 2 * p.cb * 8, (cudaStream_t)stream);
+    cudaError_t e = prezeroed ? cudaSuccess : cudaMemsetAsync(sums2, 0, sizeof(double) * 2 * p.cb * 8, (cudaStream_t)stream);
     if (e != cudaSuccess) {
         set_error("ctu_bn_relu_bwd_reduce: memset: %s", cudaGetErrorString(e));
         return (int)e;

@@ -328,7 +328,7 @@ static int launch_wgrad(const WgradParams& p, int k, cudaStream_t stream) {
 // implemented in conv_tc.cu
 int conv3d_fprop_tc(const void* const* h_srcs, const int* h_src_channels, int nsrc, const float* wp, const float* bias,
                     void* y, double* stats, int stat_cout, int cout, int k, int n, int d, int h, int w, cudaStream_t stream,
-                    const void* bn_y = nullptr, const float* bn_ss = nullptr, int bn_pm = 0);
+                    const void* bn_y = nullptr, const float* bn_ss = nullptr, int bn_pm = 0, int prezeroed = 0);
 int conv3d_wgrad_tc(const void* const* h_srcs, const int* h_src_channels, int nsrc, const void* dy, float* dwp,
                     float* dbias, int phase_cout, int cout, int k, int n, int d, int h, int w, cudaStream_t stream);
 // implemented in conv_wide.cu
@@ -349,6 +349,8 @@ int ctu_conv3d_fprop(int dtype, const void* const* h_srcs, const int* h_src_chan
     SrcMap m;
     int rc = make_srcmap(m, nsrc, h_src_channels);
     if (rc != CTU_OK) return rc;
+    const int prezeroed = use_tensor_path & CTU_ACCUM_PREZEROED;
+    use_tensor_path &= ~CTU_ACCUM_PREZEROED;
     CTU_REQUIRE(h_srcs && wp && y && cout > 0 && n > 0 && d > 0 && h > 0 && w > 0, "ctu_conv3d_fprop: bad arguments");
     if (stat_cout <= 0) stat_cout = cout;
     const int cob_nat = (stat_cout + 7) / 8;
@@ -364,11 +366,11 @@ int ctu_conv3d_fprop(int dtype, const void* const* h_srcs, const int* h_src_chan
             CTU_REQUIRE(nsrc == 1, "ctu_conv3d_fprop: the wide tensor path takes one source");
             rc = conv3d_fprop_wide(h_srcs[0], h_src_channels[0], wp, bias, y, cout, k, n, d, h, w, (cudaStream_t)stream);
             if (rc == CTU_OK && bn_sums != nullptr)
-                rc = ctu_bn_stats(dtype, y, stat_cout, ((cout + 7) / 8) / cob_nat, n, (long long)d * h * w, bn_sums, stream);
+                rc = ctu_bn_stats(dtype, y, stat_cout, (((cout + 7) / 8) / cob_nat) | prezeroed, n, (long long)d * h * w, bn_sums, stream);
             return rc;
         }
         return conv3d_fprop_tc(h_srcs, h_src_channels, nsrc, (const float*)wp, bias, y, bn_sums, stat_cout, cout, k, n, d,
-                               h, w, (cudaStream_t)stream);
+                               h, w, (cudaStream_t)stream, nullptr, nullptr, 0, prezeroed);
     }
     ConvParams p;
     for (int i = 0; i < CTU_MAX_SRC; ++i) {
@@ -381,7 +383,7 @@ int ctu_conv3d_fprop(int dtype, const void* const* h_srcs, const int* h_src_chan
     p.tiles_w = cdiv(w, p.tw); p.tiles_h = cdiv(h, p.th); p.tiles_d = cdiv(d, p.dg * RD);
     CTU_DISPATCH_DTYPE(dtype, rc = launch_fprop<T>(p, k, (cudaStream_t)stream));
     if (rc == CTU_OK && bn_sums != nullptr)
-        rc = ctu_bn_stats(dtype, y, stat_cout, ((cout + 7) / 8) / cob_nat, n, (long long)d * h * w, bn_sums, stream);
+        rc = ctu_bn_stats(dtype, y, stat_cout, (((cout + 7) / 8) / cob_nat) | prezeroed, n, (long long)d * h * w, bn_sums, stream);
     return rc;
 }
 

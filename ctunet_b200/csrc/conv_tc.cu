@@ -639,7 +639,7 @@ static int make_src_maps(TcMaps& maps, const void* const* h_srcs, const int* h_s
 // phases for the phase-major output of the fused up-sampling stage (natural block = output block % ceil(stat_cout/8))
 int conv3d_fprop_tc(const void* const* h_srcs, const int* h_src_channels, int nsrc, const float* wp, const float* bias,
                     void* y, double* stats, int stat_cout, int cout, int k, int n, int d, int h, int w, cudaStream_t stream,
-                    const void* bn_y, const float* bn_ss, int bn_pm) {
+                    const void* bn_y, const float* bn_ss, int bn_pm, int prezeroed) {
     TcGeom g;
     const int cb = total_blocks(nsrc, h_src_channels);
     if (cb < 0 || !tc_geometry(k, cb, cout, h, w, g)) {
@@ -680,7 +680,7 @@ int conv3d_fprop_tc(const void* const* h_srcs, const int* h_src_channels, int ns
     p.ns = g.ns;
     p.stmask = g.stages - 1;
     p.stshift = g.stages == 4 ? 2 : 1;
-    if (fuse_stats) {
+    if (fuse_stats && !prezeroed) {
         cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(double) * 2 * p.cobo * 8, stream);
         if (e != cudaSuccess) {
             set_error("conv3d tensor path: memset: %s", cudaGetErrorString(e));
@@ -747,7 +747,7 @@ int conv3d_fprop_tc(const void* const* h_srcs, const int* h_src_channels, int ns
     else if (k == 5 && g.cobg == 1) rc = go(conv3d_tc_kernel<5, 1>);
     else rc = go(conv3d_tc_kernel<5, 2>);
     if (rc == CTU_OK && stats != nullptr && !fuse_stats)   // wide layers (low resolution): separate statistics pass
-        rc = ctu_bn_stats(CTU_BF16, y, stat_cout, g.cob_n / p.cobo, n, (long long)d * h * w, stats, stream);
+        rc = ctu_bn_stats(CTU_BF16, y, stat_cout, (g.cob_n / p.cobo) | (prezeroed ? CTU_ACCUM_PREZEROED : 0), n, (long long)d * h * w, stats, stream);
     return rc;
 }
 

@@ -21,7 +21,7 @@ import os
 import torch
 
 from . import _lib
-from ._lib import CTU_BF16, CTU_F32, call, int_array, ptr_array, stream_ptr
+from ._lib import CTU_ACCUM_PREZEROED, CTU_BF16, CTU_F32, call, int_array, ptr_array, stream_ptr
 
 BN_MOMENTUM = 0.1
 BN_EPS = 1e-5
@@ -59,6 +59,7 @@ _SIDE = {}
 # A leaf and the next link of the chain become runnable at the same moment (both wait for the same dy); without priorities
 # the block scheduler took whichever was enqueued first, and a persistent weight-gradient kernel then held every SM (and its
 # TMEM) for 100-250 us while the chain -- the critical path -- waited (CUPTI timeline, scripts/trace_step.py).
+ACC_ARENA_DOUBLES = 32768   # 256 KB: every BatchNorm accumulator of a pass (forward sums + backward sums2)
 STREAM_PRIORITIES = os.environ.get("CTU_PRIO", "1") == "1"
 # The weight gradient of a layer waits for that layer's data gradients (it then runs beside the BatchNorm kernels of the layer
 # below) instead of racing them for the SMs.  (A/B: CTU_WGRAD_AFTER=0/1)
@@ -132,6 +133,8 @@ class Engine:
         self._side = None
         self._wgrad_stream = None
         self._input_grad_stream = None
+        self._arena = None
+        self._arena_used = 0
         self._dead_stream = None
         # set by trainer.TrainStep: (targets, softmax_for_dice, ce_lambda, dice_lambda, comps, mirror) -- the head then
         # runs fused with the loss (csrc/head.cu: head_loss_*), produces no output tensors and wires its own backward
@@ -220,6 +223,24 @@ class Engine:
     def f64(self, *shape):
         return torch.empty(shape, dtype=torch.float64, device=self.device)
 
+    def acc64(self, n: int) -> torch.Tensor:
+        """A ZEROED float64 accumulator of ``n`` entries (BatchNorm sums): a slice of one arena zeroed once per pass, so
+        the ~30 per-layer memset nodes leave the layer chain (``_pz`` tells the library not to enqueue its own)."""
+        if self._arena is None:
+            self._arena = torch.zeros(ACC_ARENA_DOUBLES, dtype=torch.float64, device=self.device)
+            self._arena_used = 0
+        n16 = (n + 15) // 16 * 16
+        if self._arena_used + n16 > ACC_ARENA_DOUBLES:
+            return self.f64(n)                       # (arena exhausted: an ordinary buffer, zeroed by the entry point)
+        t = self._arena[self._arena_used:self._arena_used + n]
+        self._arena_used += n16
+        t._ctu_prezeroed = True
+        return t
+
+    @staticmethod
+    def _pz(t) -> int:
+        return CTU_ACCUM_PREZEROED if (t is not None and getattr(t, "_ctu_prezeroed", False)) else 0
+
     def _grad_buffer(self, param) -> torch.Tensor:
         """Where a parameter-gradient kernel writes: a slice of the data-parallel flat buffer, or a new tensor."""
         if self.grad_sink is not None:
@@ -283,8 +304,8 @@ class Engine:
         s0 = srcs[0]
         pa, ca, ns = self._src_args(srcs)
         call("ctu_conv3d_fprop", self.dtype, pa, ca, ns, wk.data_ptr(), bias.data_ptr() if bias is not None else None,
-             y.ptr, sums.data_ptr() if sums is not None else None, stat_cout, cout, k, s0.n, s0.d, s0.h, s0.w, int(tc),
-             stream_ptr())
+             y.ptr, sums.data_ptr() if sums is not None else None, stat_cout, cout, k, s0.n, s0.d, s0.h, s0.w,
+             int(tc) | self._pz(sums), stream_ptr())
 
     # ------------------------------------------------------------------ layout
     def pack(self, x: torch.Tensor) -> Act:
@@ -336,7 +357,7 @@ class Engine:
         s0 = srcs[0]
         y = self.new_act(cout, s0.n, s0.d, s0.h, s0.w)
         if bn_stats:
-            y.sums = self.f64(2 * (((stat_cout or cout) + 7) // 8 * 8))
+            y.sums = self.acc64(2 * (((stat_cout or cout) + 7) // 8 * 8))
         self._conv_launch(srcs, wk, tc, bias, y, cout, k, y.sums, stat_cout)
         return y
 
@@ -595,8 +616,8 @@ class Engine:
         if training:
             sums = y.sums
             if sums is None:
-                sums = self.f64(2 * cpad)
-                call("ctu_bn_stats", self.dtype, y.ptr, c, 8 if pm else 1, y.n, y.spatial, sums.data_ptr(), st)
+                sums = self.acc64(2 * cpad)
+                call("ctu_bn_stats", self.dtype, y.ptr, c, (8 if pm else 1) | self._pz(sums), y.n, y.spatial, sums.data_ptr(), st)
             track = bn.track_running_stats and bn.running_mean is not None
             mom = BN_MOMENTUM if bn.momentum is None else float(bn.momentum)
         else:
@@ -654,9 +675,9 @@ class Engine:
                 sums2 = a.bn["sums2"]
                 a.bn = None                                           # (drop the reference cycle through the closure)
                 if sums2 is None or dP is not None:                  # not produced by the consumer's epilogue: reduce here
-                    sums2 = self.f64(2 * cpad)
+                    sums2 = self.acc64(2 * cpad)
                     call("ctu_bn_relu_bwd_reduce", self.dtype, y.ptr, ss.data_ptr(), pA, pP, sums2.data_ptr(),
-                         c, yn, yd, yh, yw, pm, st)
+                         c, yn, yd, yh, yw, pm | self._pz(sums2), st)
                 dy = self.new_act(y.c, y.n, y.d, y.h, y.w)          # same layout as y (phase-major stays phase-major)
                 dg, db = self._grad_buffer(bn.weight), self._grad_buffer(bn.bias)
                 call("ctu_bn_relu_bwd_apply", self.dtype, y.ptr, ss.data_ptr(), bn.weight.data_ptr(), pA, pP,

@@ -39,6 +39,10 @@ extern "C" {
 #define CTU_ERR_INVALID (-1)
 #define CTU_ERR_UNSUPPORTED (-2)
 #define CTU_MAX_SRC 4
+/* OR into `use_tensor_path` of ctu_conv3d_fprop, `phases` of ctu_bn_stats or `y_phase_major` of ctu_bn_relu_bwd_reduce:
+ * the caller has already zeroed the double accumulators (bn_sums / sums / sums2), so the entry point enqueues no memset of
+ * its own.  A step driver zeroes ONE arena for all of a pass's accumulators instead of ~30 memset nodes on the layer chain. */
+#define CTU_ACCUM_PREZEROED 0x100
 
 typedef enum { CTU_F32 = 0, CTU_BF16 = 1 } ctu_dtype;
 typedef void* ctu_stream; /* cudaStream_t */
