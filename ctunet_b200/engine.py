@@ -23,7 +23,6 @@ import torch
 from . import _lib
 from ._lib import CTU_ACCUM_PREZEROED, CTU_BF16, CTU_F32, call, int_array, ptr_array, stream_ptr
 
-BN_MOMENTUM = 0.1
 BN_EPS = 1e-5
 BN_FOLD_MAX_VOXELS = 4 * 64 ** 3      # see Engine.bn_relu
 
@@ -605,6 +604,18 @@ class Engine:
     def bn_relu(self, y: Act, bn, training: bool, extra_updates: int = 0, pool: bool = False):
         """Returns ``a`` or ``(a, pooled)``.  ``extra_updates``: additional running-stat updates applied
         when the backward pass runs (the reentrant-checkpoint recomputation of the reference)."""
+        # nn.BatchNorm3d configurations no preset of the reference uses (models.py:27,31 build BatchNorm3d(c) with the
+        # defaults) are refused rather than silently computed differently from torch:
+        if bn.momentum is None:
+            raise NotImplementedError("BatchNorm3d(momentum=None) (cumulative moving average) is not implemented")
+        if bool(bn.training) != bool(training):
+            raise NotImplementedError("a BatchNorm3d whose .training flag differs from the network's (frozen BatchNorm "
+                                      "inside a training net, or the reverse) is not implemented")
+        if not training and (not bn.track_running_stats or bn.running_mean is None or bn.running_var is None):
+            raise NotImplementedError("eval-mode BatchNorm3d without running statistics (track_running_stats=False) "
+                                      "is not implemented")
+        if not bn.affine:
+            raise NotImplementedError("BatchNorm3d(affine=False) is not implemented")
         pm = 1 if y.c_nat else 0                     # phase-major input: natural dims are twice the stored ones
         c = y.c_nat if pm else y.c
         cpad = (c + 7) // 8 * 8
@@ -619,7 +630,7 @@ class Engine:
                 sums = self.acc64(2 * cpad)
                 call("ctu_bn_stats", self.dtype, y.ptr, c, (8 if pm else 1) | self._pz(sums), y.n, y.spatial, sums.data_ptr(), st)
             track = bn.track_running_stats and bn.running_mean is not None
-            mom = BN_MOMENTUM if bn.momentum is None else float(bn.momentum)
+            mom = float(bn.momentum)
         else:
             call("ctu_bn_finalize", None, count, bn.weight.data_ptr(), bn.bias.data_ptr(), bn.running_mean.data_ptr(),
                  bn.running_var.data_ptr(), None, 0.0, float(bn.eps), c, 0, 0, ss.data_ptr(), st)
@@ -654,7 +665,7 @@ class Engine:
                 st = stream_ptr()
                 if extra_updates > 0 and bn.track_running_stats and bn.running_mean is not None:
                     # buffers only (nothing in this step reads them): beside the weight gradients, off the critical path
-                    mom = BN_MOMENTUM if bn.momentum is None else float(bn.momentum)
+                    mom = float(bn.momentum)
 
                     def update():
                         call("ctu_bn_running_update", sums.data_ptr(), count, bn.running_mean.data_ptr(),

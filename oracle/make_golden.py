@@ -41,7 +41,7 @@ def main():
     torch.set_num_threads(8)
     os.makedirs(OUT, exist_ok=True)
     MD, PH, UT, TR = load_reference()
-    gold = {"torch_version": torch.__version__, "classes": {}}
+    gold = {"torch_version": str(torch.__version__), "classes": {}}   # plain data only: the tests load it with weights_only=True
 
     # ---- (1) construction + eval forward known answers ----
     for name in CLASSES:

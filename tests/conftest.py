@@ -15,4 +15,4 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden():
     import torch
-    return torch.load(os.path.join(ROOT, "tests", "golden", "reference_golden.pt"), weights_only=False)
+    return torch.load(os.path.join(ROOT, "tests", "golden", "reference_golden.pt"), weights_only=True)

@@ -326,6 +326,25 @@ def test_cpu_input_raises():
         net(torch.zeros(1, 2, 24, 16, 16, device=DEV))
 
 
+def test_unsupported_batchnorm_configurations_raise():
+    """nn.BatchNorm3d variants no preset builds (frozen BatchNorm inside a training net, momentum=None, no running
+    statistics in eval mode) are refused instead of being computed differently from torch."""
+    x = torch.zeros(1, 2, 16, 16, 16, device=DEV)
+    net = _build("UNetSP", "bf16").to(DEV).train()
+    next(m for m in net.modules() if isinstance(m, torch.nn.BatchNorm3d)).eval()
+    with pytest.raises(NotImplementedError):
+        net(x)
+    net = _build("UNetSP", "bf16").to(DEV).train()
+    next(m for m in net.modules() if isinstance(m, torch.nn.BatchNorm3d)).momentum = None
+    with pytest.raises(NotImplementedError):
+        net(x)
+    net = _build("UNetSP", "bf16").to(DEV).eval()
+    bn = next(m for m in net.modules() if isinstance(m, torch.nn.BatchNorm3d))
+    bn.track_running_stats = False
+    with pytest.raises(NotImplementedError), torch.no_grad():
+        net(x)
+
+
 @pytest.mark.parametrize("mode,size", [("fp32", 16), ("bf16", 32)])
 def test_cuda_graph_step_matches_eager_step(mode, size):
     """TrainStep(graph=True): two eager iterations, one capture, then replays -- same losses, parameters and
