@@ -22,6 +22,15 @@
 
 namespace ctu {
 
+// -DCTU_TCPROF: CTA 0 of every fprop/dgrad launch prints where its roles spent their cycles (debug builds only)
+#ifdef CTU_TCPROF
+#define TCPROF_T0() const long long _t0 = clock64()
+#define TCPROF_ADD(acc) acc += clock64() - _t0
+#else
+#define TCPROF_T0()
+#define TCPROF_ADD(acc)
+#endif
+
 constexpr int TC_TH = 16, TC_TW = 16;   // output tile (h, w) per plane = 2 MMA tiles of 16x8
 constexpr int TC_WB = TC_TW / 8;
 constexpr int TC_MAX_STAGES = 4;         // TMEM accumulator stages per 16x8 tile (fprop/dgrad)
@@ -206,6 +215,10 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
     float* st_bn = st_bias + 32;                                            // BNRED: [4][CP] scale | shift | mean | invstd
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef CTU_TCPROF
+    long long prof_a = 0, prof_b = 0, prof_c = 0, prof_d = 0;
+    const long long prof_start = clock64();
+#endif
 
     if (threadIdx.x == 0) {
         for (uint32_t i = 0; i < NS; ++i) {
@@ -257,7 +270,7 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
                     for (int g = 0; g < p.ncg; ++g, pr.next(NS)) {
                         const int b0 = g * p.cbg;
                         const int gb = (p.cb - b0) < p.cbg ? (p.cb - b0) : p.cbg;
-                        mbar_wait(b_empty + 8 * pr.slot, pr.phase ^ 1);
+                        { TCPROF_T0(); mbar_wait(b_empty + 8 * pr.slot, pr.phase ^ 1); TCPROF_ADD(prof_a); }
 #ifdef CTU_DBG_NOTMA
                         mbar_arrive(b_full + 8 * pr.slot);
                         for (int b = 0; b < 0; ++b) {
@@ -306,9 +319,10 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
                     uint32_t b_lo = (s_w >> 4) | (8u << 16);          // B: LBO = 128 B (second 8-wide K chunk)
                     uint32_t acc = 0;
                     for (int g = 0; g < p.ncg; ++g, cons.next(NS)) {
-                        mbar_wait(b_full + 8 * cons.slot, cons.phase);
-                        if (g == 0) mbar_wait(b_aempty + 8 * (stage * TC_WB + t), ((step >> p.stshift) & 1) ^ 1);
+                        { TCPROF_T0(); mbar_wait(b_full + 8 * cons.slot, cons.phase); TCPROF_ADD(prof_a); }
+                        if (g == 0) { TCPROF_T0(); mbar_wait(b_aempty + 8 * (stage * TC_WB + t), ((step >> p.stshift) & 1) ^ 1); TCPROF_ADD(prof_b); }
                         tc_fence_after();
+                        TCPROF_T0();
                         const uint32_t a16 = (s_planes + cons.slot * p.slot_bytes + t * 128u) >> 4;
                         const int gb = (p.cb - g * p.cbg) < p.cbg ? (p.cb - g * p.cbg) : p.cbg;
                         const int pairs = gb >> 1;
@@ -343,9 +357,10 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
                                 b_lo += bstep;
                             }
                         }
-                        umma_commit_lead(leader, b_empty + 8 * cons.slot);
+                        TCPROF_ADD(prof_c);
+                        { TCPROF_T0(); umma_commit_lead(leader, b_empty + 8 * cons.slot); TCPROF_ADD(prof_d); }
                     }
-                    umma_commit_lead(leader, b_afull + 8 * (stage * TC_WB + t));
+                    { TCPROF_T0(); umma_commit_lead(leader, b_afull + 8 * (stage * TC_WB + t)); TCPROF_ADD(prof_d); }
                 }
             }
         }
@@ -386,8 +401,9 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
                 const int pl = pl0 + u;
                 if (pl >= npl) break;
                 const uint32_t stage = step & p.stmask;
-                mbar_wait(b_afull + 8 * (stage * TC_WB + te), (step >> p.stshift) & 1);
+                { TCPROF_T0(); mbar_wait(b_afull + 8 * (stage * TC_WB + te), (step >> p.stshift) & 1); TCPROF_ADD(prof_a); }
                 ++step;
+                TCPROF_T0();
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (stage * TC_WB + te) * p.nt;
                 // P[kd] of input plane pl feeds output plane pl - kd, kept in part[(pl - kd) % K] = part[(u - kd + K) % K]
@@ -419,6 +435,7 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(b_aempty + 8 * (stage * TC_WB + te));
+                TCPROF_ADD(prof_b);
                 // output plane j = pl - (K-1) is complete; its slot (u + 1) % K then starts over for plane pl + 1
                 const int j = pl - (K - 1);
                 float (&done)[CP] = part[(u + 1) % K];
@@ -488,6 +505,14 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
         }
     }
     // ------------------------------------------------------------------------- teardown
+#ifdef CTU_TCPROF
+    if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && (warp <= 1 || warp == 3)) {
+        const long long tot = clock64() - prof_start;
+        if (warp == 0) printf("TCPROF producer: total %lld wait_empty %lld\n", tot, prof_a);
+        else if (warp == 1) printf("TCPROF issuer  : total %lld wait_full %lld wait_aempty %lld mma %lld commit %lld\n", tot, prof_a, prof_b, prof_c, prof_d);
+        else printf("TCPROF epilogue: total %lld wait_afull %lld ld+add+release %lld\n", tot, prof_a, prof_b);
+    }
+#endif
     tc_fence_before();
     __syncthreads();
     if (p.stats != nullptr && threadIdx.x < NSLOT * 16) {
@@ -516,7 +541,8 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
 //   fprop 7->7 at 4x128^3 94.9 -> 84.7, 2->7 95.2 -> 85.6, 64->14 at 4x64^3 88.3 -> 84.5, 14->14 at 4x64^3 47.5 -> 47.6;
 //   but 4-block outputs 146 -> 169 ([14,14,1]->64 at 4x64^3), 53 -> 58 (128->28 at 4x32^3), 30 -> 33 (28->28 at 4x32^3);
 //   wgrad (first formulation) 244 -> 240, 135 -> 127, 84.4 -> 79.5, 49.3 -> 47.0; (kd,kh)-in-N formulation 116 -> 124.
-// Hence: shares for fprop / dgrad with <= 2 output blocks per CTA and >= 16 planes per CTA, and for the first wgrad
+// (5^3 layers -- four halo planes per segment -- were neutral: recAE_v2_fixed 8.96 -> 9.03, UNet4_2IC 8.74 -> 8.70 ms/step.)
+// Hence: shares for 3^3 fprop / dgrad with <= 2 output blocks per CTA and >= 16 planes per CTA, and for the first wgrad
 // formulation; fixed chunks elsewhere.  CTU_TC_BALANCE=0 / 1 forces one mode everywhere (A/B runs).
 static int tc_balance(bool by_rule) {
     static const int forced = getenv("CTU_TC_BALANCE") ? atoi(getenv("CTU_TC_BALANCE")) : -1;
@@ -732,7 +758,7 @@ int conv3d_fprop_tc(const void* const* h_srcs, const int* h_src_channels, int ns
         p.dchunks = (d + dc - 1) / dc;
         p.total_items = tiles * p.dchunks;
         int gx = (148 * occ) / g.ngroups;
-        p.balance = tc_balance(g.cobg <= 2 && (long long)tiles * d >= 16LL * (gx > 0 ? gx : 1));
+        p.balance = tc_balance(k == 3 && g.cobg <= 2 && (long long)tiles * d >= 16LL * (gx > 0 ? gx : 1));
         const long long units = p.balance ? (long long)tiles * d : (long long)p.total_items;
         if (gx > units) gx = (int)units;
         if (gx < 1) gx = 1;

@@ -40,7 +40,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 
 // W issuing warps; warp w cycles through A accumulators; L MMAs per warp.  mn_major: both operands MN-major (wgrad).
-__global__ void bench(int M, int N, int W, int A, int L, int mn_major, long long* out) {
+__global__ void bench(int M, int N, int W, int A, int L, int mn_major, long long* out, int sbo16 = 16, int astep16 = 2,
+                      int lbo16 = 8, int tcols = 512) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ uint64_t bars[8];
     __shared__ uint32_t tmem_slot;
@@ -53,7 +54,7 @@ __global__ void bench(int M, int N, int W, int A, int L, int mn_major, long long
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_slot)) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(tcols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -66,12 +67,12 @@ __global__ void bench(int M, int N, int W, int A, int L, int mn_major, long long
         if (mn_major) idesc |= (1u << 15) | (1u << 16);
         const uint32_t base = smem_u32(smem) >> 4;
         // K-major: SBO = 256 B between 8-row groups, LBO = 128 B; MN-major: SBO = 16 B (lag groups), LBO = 128 B
-        const uint32_t ahi = (mn_major ? 1u : 16u) | (1u << 14), bhi = 16u | (1u << 14);
-        const uint32_t alo = (base + warp * 64) | (8u << 16), blo = (base + 2048) | (8u << 16);
+        const uint32_t ahi = (mn_major ? 1u : (uint32_t)sbo16) | (1u << 14), bhi = 16u | (1u << 14);
+        const uint32_t alo = (base + warp * 64) | ((uint32_t)lbo16 << 16), blo = (base + 2048) | (8u << 16);
         long long t0 = clock64();
         for (int i = 0; i < L; ++i) {
             const uint32_t d = tmem + (uint32_t)((warp * A + (i % A)) * N);
-            mma(leader, d, alo + (i & 7) * 2, ahi, blo + (i & 3) * 2, bhi, idesc, i >= A ? 1u : 0u);
+            mma(leader, d, alo + (i & 7) * astep16, ahi, blo + (i & 3) * 2, bhi, idesc, i >= A ? 1u : 0u);
         }
         commit(leader, smem_u32(&bars[warp]));
         mbar_wait(smem_u32(&bars[warp]), 0);
@@ -80,7 +81,7 @@ __global__ void bench(int M, int N, int W, int A, int L, int mn_major, long long
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tcols) : "memory");
 }
 
 // Commit cost: every iteration issues `nm` MMAs (M=128, N=32) and `nc` tcgen05.commit onto mbarriers with a huge
@@ -127,6 +128,47 @@ __global__ void bench_commit(int W, int nm, int nc, int L, long long* out) {
 }
 
 int main() {
+    {
+        // two CTAs per SM (grid = 2 x 148, 256 TMEM columns each) against one CTA with the same number of issuing warps
+        {
+            long long* d_q;
+            cudaMalloc(&d_q, 8 * sizeof(long long));
+            cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+            printf("CTAs per SM x issuing warps per CTA (M=128, N=32): cycles per MMA per warp (CTA 0)\n");
+            for (int ctas = 1; ctas <= 2; ++ctas)
+                for (int W = 1; W <= 4; W *= 2) {
+                    bench<<<148 * ctas, 128, 64 * 1024>>>(128, 32, W, 2, 4096, 0, d_q, 16, 2, 8, 256);
+                    if (cudaDeviceSynchronize() != cudaSuccess) { printf("cta sweep failed\n"); return 1; }
+                    long long h[8];
+                    cudaMemcpy(h, d_q, sizeof(h), cudaMemcpyDeviceToHost);
+                    long long mx = 0;
+                    for (int w = 0; w < W; ++w) mx = h[w] > mx ? h[w] : mx;
+                    printf("ctas/SM=%d W=%d : %6.1f per warp, %6.1f aggregate per SM\n", ctas, W, (double)mx / 4096.0, (double)mx / (4096.0 * W * ctas));
+                }
+            cudaFree(d_q);
+        }
+        // A-operand layout sweep (K-major, M=128, N=32): SBO = pitch between 8-voxel row groups, start address step, LBO
+        long long* d_o;
+        cudaMalloc(&d_o, 8 * sizeof(long long));
+        cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        printf("A-operand layout sweep: M=128 N=32 K-major; SBO bytes, start-address step bytes, LBO bytes -> aggregate cycles per MMA\n");
+        const int sbos[] = {16, 18};
+        const int steps[] = {1};
+        const int lbos[] = {8, 328};
+        for (int W = 2; W <= 4; W *= 2)
+            for (int sb : sbos)
+                for (int st : steps)
+                    for (int lb : lbos) {
+                        bench<<<1, 128, 64 * 1024>>>(128, 32, W, 2, 4096, 0, d_o, sb, st, lb);
+                        if (cudaDeviceSynchronize() != cudaSuccess) { printf("layout sweep failed\n"); return 1; }
+                        long long h[8];
+                        cudaMemcpy(h, d_o, sizeof(h), cudaMemcpyDeviceToHost);
+                        long long mx = 0;
+                        for (int w = 0; w < W; ++w) mx = h[w] > mx ? h[w] : mx;
+                        printf("W=%d SBO=%4d step=%4d LBO=%5d : %6.1f\n", W, sb * 16, st * 16, lb * 16, (double)mx / (4096.0 * W));
+                    }
+        cudaFree(d_o);
+    }
     {
         long long* d_o;
         cudaMalloc(&d_o, 8 * sizeof(long long));
