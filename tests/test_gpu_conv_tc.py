@@ -28,7 +28,7 @@ CASES = [
     (3, 28, 112, False, (1, 2, 16, 16)),     # wgrad: output channels split over TMEM
     (5, 14, 28, True, (1, 3, 16, 16)),
     (5, 56, 56, True, (1, 3, 16, 16)),       # wgrad: partial last output-channel group (16,16,16,8); fprop: wide kernel
-    # the benchmarked grids (batch 4 x 128^3 runs these shapes per sample): d = 128 with dc = 32 chunks, 8 x 8 tiles of
+    # the benchmarked grids (batch 4 x 128^3 runs these shapes per sample): d = 128 (balanced plane shares, TcWalk; fixed d-chunks below 16 planes per CTA), 8 x 8 tiles of
     # 16 x 16 per plane, persistent 296-CTA schedules
     (3, 2, 7, False, (1, 128, 128, 128)),
     (3, 7, 7, False, (2, 128, 128, 128)),
