@@ -62,6 +62,7 @@ SIGNATURES = {
     "ctu_convt_wpack_dgrad_floats": (LL, [I, I]),
     "ctu_convt_pack_weight_dgrad": (I, [P, P, I, I, P, I, P]),
     "ctu_convt_unpack_wgrad": (I, [P, P, I, I, P, P]),
+    "ctu_gather_batch": (I, [I, P, P, P, P, P, P]),
     "ctu_convt2_fprop": (I, [I, P, P, I, P, P, P, I, I, I, I, I, P]),
     "ctu_convt2_dgrad": (I, [I, P, P, P, I, I, I, I, I, I, P]),
     "ctu_convt2_wgrad": (I, [I, P, P, I, P, P, P, I, I, I, I, I, P]),
@@ -150,6 +151,10 @@ def stream_ptr() -> int:
 
 def int_array(values):
     return (c_int * len(values))(*values)
+
+
+def ll_array(values):
+    return (c_longlong * len(values))(*values)
 
 
 def ptr_array(values):

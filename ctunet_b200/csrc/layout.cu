@@ -191,6 +191,39 @@ __global__ void conv_weight_dgrad_kernel(const float* __restrict__ native, float
     packed[i] = v;
 }
 
+
+// ---------------------------------------------------------------------------- batched index gather
+// Every weight re-packing of a pass (native fp32 -> packed fp32, -> bf16 UMMA image, data-gradient variants, the
+// weight-streaming image) is a fixed permutation + cast of a parameter tensor.  The permutations are computed once per
+// layer signature (engine.py runs the packing kernels above on index-valued inputs) and every later pass replays ALL of
+// them as jobs of one launch: dst[i] = idx[i] >= 0 ? src[idx[i]] : 0.
+constexpr int GATHER_MAX_JOBS = 96;       // 96 x 40 B of kernel parameters
+struct GatherJob {
+    const float* src;
+    void* dst;
+    const int* idx;
+    long long count;
+    int bf16;
+};
+struct GatherJobs {
+    GatherJob j[GATHER_MAX_JOBS];
+};
+
+__global__ void __launch_bounds__(256) gather_batch_kernel(const __grid_constant__ GatherJobs jobs) {
+    const GatherJob& job = jobs.j[blockIdx.y];
+    const long long n8 = job.count >> 3;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n8; q += (long long)gridDim.x * blockDim.x) {
+        const int4 i0 = __ldg(reinterpret_cast<const int4*>(job.idx) + 2 * q);
+        const int4 i1 = __ldg(reinterpret_cast<const int4*>(job.idx) + 2 * q + 1);
+        const int id[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+        V8 v;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v.v[e] = id[e] >= 0 ? __ldg(job.src + id[e]) : 0.f;
+        if (job.bf16) Vec8<__nv_bfloat16>::store(reinterpret_cast<__nv_bfloat16*>(job.dst) + 8 * q, v);
+        else Vec8<float>::store(reinterpret_cast<float*>(job.dst) + 8 * q, v);
+    }
+}
+
 }  // namespace ctu
 
 using namespace ctu;
@@ -296,6 +329,29 @@ int ctu_convt_pack_weight_dgrad(const float* w, float* wpd, int cout, int nsrc, 
 int ctu_convt_unpack_wgrad(const float* dwp, float* dw, int cout, int nsrc, const int* h_src_channels,
                            ctu_stream stream) {
     return pack_generic(dw, (float*)dwp, cout, 8, nsrc, h_src_channels, 1, 1, stream, "ctu_convt_unpack_wgrad");
+}
+
+int ctu_gather_batch(int njobs, const float* const* h_srcs, void* const* h_dsts, const int* const* h_idxs,
+                     const long long* h_counts, const int* h_dst_bf16, ctu_stream stream) {
+    CTU_REQUIRE(njobs > 0 && h_srcs && h_dsts && h_idxs && h_counts && h_dst_bf16, "ctu_gather_batch: bad arguments");
+    for (int j0 = 0; j0 < njobs; j0 += GATHER_MAX_JOBS) {
+        const int nj = (njobs - j0) < GATHER_MAX_JOBS ? (njobs - j0) : GATHER_MAX_JOBS;
+        GatherJobs jobs = {};
+        long long most = 0;
+        for (int j = 0; j < nj; ++j) {
+            GatherJob& g = jobs.j[j];
+            g.src = h_srcs[j0 + j]; g.dst = h_dsts[j0 + j]; g.idx = h_idxs[j0 + j]; g.count = h_counts[j0 + j];
+            g.bf16 = h_dst_bf16[j0 + j];
+            CTU_REQUIRE(g.src && g.dst && g.idx && g.count > 0 && g.count % 8 == 0, "ctu_gather_batch: bad job %d", j0 + j);
+            most = g.count > most ? g.count : most;
+        }
+        long long gx = cdiv(most / 8, 256);
+        if (gx > 148 * 8) gx = 148 * 8;
+        gather_batch_kernel<<<dim3((unsigned)gx, nj), 256, 0, (cudaStream_t)stream>>>(jobs);
+        int rc = check_launch("ctu_gather_batch");
+        if (rc != CTU_OK) return rc;
+    }
+    return CTU_OK;
 }
 
 }  // extern "C"

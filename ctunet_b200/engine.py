@@ -21,7 +21,7 @@ import os
 import torch
 
 from . import _lib
-from ._lib import CTU_ACCUM_PREZEROED, CTU_BF16, CTU_F32, call, int_array, ptr_array, stream_ptr
+from ._lib import CTU_ACCUM_PREZEROED, CTU_BF16, CTU_F32, call, int_array, ll_array, ptr_array, stream_ptr
 
 BN_EPS = 1e-5
 BN_FOLD_MAX_VOXELS = 4 * 64 ** 3      # see Engine.bn_relu
@@ -59,6 +59,9 @@ _SIDE = {}
 # the block scheduler took whichever was enqueued first, and a persistent weight-gradient kernel then held every SM (and its
 # TMEM) for 100-250 us while the chain -- the critical path -- waited (CUPTI timeline, scripts/trace_step.py).
 ACC_ARENA_DOUBLES = 32768   # 256 KB: every BatchNorm accumulator of a pass (forward sums + backward sums2)
+# Weight images as batched index gathers (one launch per group of stages) instead of 2-4 packing launches per stage.
+WEIGHT_GATHER = os.environ.get("CTU_WEIGHT_GATHER", "1") == "1"
+_WEIGHT_MAPS: Dict[tuple, tuple] = {}     # layer signature -> (idx int32, count, bf16?)
 STREAM_PRIORITIES = os.environ.get("CTU_PRIO", "1") == "1"
 # The weight gradient of a layer waits for that layer's data gradients (it then runs beside the BatchNorm kernels of the layer
 # below) instead of racing them for the SMs.  (A/B: CTU_WGRAD_AFTER=0/1)
@@ -134,6 +137,7 @@ class Engine:
         self._input_grad_stream = None
         self._arena = None
         self._arena_used = 0
+        self._gjobs = []                           # pending weight-image gathers (see _kernel_weights)
         self._dead_stream = None
         # set by trainer.TrainStep: (targets, softmax_for_dice, ce_lambda, dice_lambda, comps, mirror) -- the head then
         # runs fused with the loss (csrc/head.cu: head_loss_*), produces no output tensors and wires its own backward
@@ -163,14 +167,34 @@ class Engine:
         self._side = side
         side.wait_stream(main)
         with torch.cuda.stream(side):
-            for tag, fn in plan:
-                out = fn(self)
+            # Weight images are index gathers collected by _kernel_weights and launched in batches (ctu_gather_batch): one
+            # launch for every stage up to the next weight COMPOSITION (a real computation: the stages before it must not
+            # wait for it), one more right behind it.  All results of a batch share its event.
+            pending = []
+
+            def flush():
+                if not pending and not self._gjobs:
+                    return
+                self._flush_gathers()
                 ev = torch.cuda.Event()
                 ev.record(side)
+                for slot in pending:
+                    slot[2] = ev
+                pending.clear()
+
+            for tag, fn, heavy in plan:
+                if heavy:
+                    flush()
+                out = fn(self)
                 for t in out:
                     if isinstance(t, torch.Tensor):
                         t.record_stream(main)
-                self._results.append((tag, out, ev))
+                slot = [tag, out, None]
+                self._results.append(slot)
+                pending.append(slot)
+                if heavy:
+                    flush()
+            flush()
 
     def end_forward(self) -> None:
         """Publish a freshly recorded plan / join the side streams (required before a graph capture ends)."""
@@ -197,13 +221,15 @@ class Engine:
         self._dead_stream = side
         return torch.cuda.stream(side)
 
-    def _prepared(self, tag: str, fn):
-        """``fn(engine) -> tuple of tensors`` computed from parameters and static shapes only."""
-        if self._plan is None:
-            return fn(self)
-        if self._recording:
-            self._plan.append((tag, fn))
-            return fn(self)
+    def _prepared(self, tag: str, fn, heavy: bool = False):
+        """``fn(engine) -> tuple of tensors`` computed from parameters and static shapes only.  ``heavy``: the
+        preparation launches real work (a weight composition), see begin_forward()."""
+        if self._plan is None or self._recording:
+            if self._recording:
+                self._plan.append((tag, fn, heavy))
+            out = fn(self)
+            self._flush_gathers()               # inline use: the consumer is about to be enqueued on this stream
+            return out
         if self._pi >= len(self._results) or self._results[self._pi][0] != tag:
             raise RuntimeError("internal: weight preparation plan out of step at %r" % tag)
         _, out, ev = self._results[self._pi]
@@ -275,7 +301,69 @@ class Engine:
     def _kernel_weights(self, native, cout, k, chans, tc, dgrad_of=None, dims=None):
         """Kernel-ready weights of conv(cat(srcs with ``chans`` channels)) -> cout: the packed fp32 tensor (CUDA-core
         kernel) or the bf16 UMMA image (tcgen05 kernel).  ``dgrad_of = (i, cs)``: instead the weights of the data
-        gradient dy (cout channels) -> d(src i) (cs channels)."""
+        gradient dy (cout channels) -> d(src i) (cs channels).
+
+        Every variant is a fixed permutation + cast of ``native``: the permutation is computed once per signature
+        (``_weight_index_map`` runs the packing kernels on index-valued inputs) and the result is produced by one job of a
+        batched gather -- PENDING until ``_flush_gathers()`` (the callers in _prepared / begin_forward flush)."""
+        if not WEIGHT_GATHER:
+            return self._kernel_weights_chain(native, cout, k, chans, tc, dgrad_of, dims)
+        key = (tuple(native.shape), cout, k, tuple(chans), int(tc), dgrad_of, tuple(dims) if (tc == 2 and dims) else None,
+               str(self.device))
+        ent = _WEIGHT_MAPS.get(key)
+        if ent is None:
+            if torch.cuda.is_current_stream_capturing():
+                # (a capture without a preceding eager pass: the map construction must not become part of the graph)
+                return self._kernel_weights_chain(native, cout, k, chans, tc, dgrad_of, dims)
+            ent = self._weight_index_map(native, cout, k, chans, tc, dgrad_of, dims)
+            torch.cuda.current_stream().synchronize()      # once per signature: complete before any stream reads it
+            _WEIGHT_MAPS[key] = ent
+        idx, count, is_bf16 = ent
+        src = native if native.is_contiguous() else native.contiguous()
+        dst = (torch.empty(count * 2, dtype=torch.uint8, device=self.device) if is_bf16
+               else torch.empty(count, dtype=torch.float32, device=self.device))
+        self._gjobs.append((src, dst, idx, count, is_bf16))
+        return dst
+
+    def _weight_index_map(self, native, cout, k, chans, tc, dgrad_of, dims):
+        """(idx int32 [count], count, bf16?) with out[i] = native.flatten()[idx[i]] (idx < 0: a zero pad entry) for the chain
+        of packing launches of ``_kernel_weights_chain``.  The chain's last stage rounds to bf16 (8 significant bits), so the
+        1-based source index travels through it as three base-256 digits."""
+        n = native.numel()
+        if n >= (1 << 24):
+            raise RuntimeError("weight tensor too large for the index-map construction (%d elements)" % n)
+        ar = torch.arange(1, n + 1, dtype=torch.int64, device=self.device)
+        total = None
+        is_bf16 = bool(tc)
+        for digit in range(3 if is_bf16 else 1):
+            if is_bf16:
+                src = ((ar >> (8 * digit)) & 255).to(torch.float32).view(native.shape)
+            else:
+                src = ar.to(torch.float32).view(native.shape)          # fp32 holds every index below 2^24 exactly
+            out = self._kernel_weights_chain(src, cout, k, chans, tc, dgrad_of, dims)
+            vals = (out.view(torch.bfloat16) if is_bf16 else out).to(torch.float32).round().to(torch.int64)
+            total = vals << (8 * digit) if total is None else total + (vals << (8 * digit))
+        idx = (total - 1).to(torch.int32).contiguous()
+        count = idx.numel()
+        if count % 8:
+            raise RuntimeError("internal: weight image of %d entries is not a multiple of 8" % count)
+        return idx, count, is_bf16
+
+    def _flush_gathers(self):
+        """Launch the pending weight gathers as one batch on the current stream."""
+        jobs, self._gjobs = self._gjobs, []
+        if not jobs:
+            return
+        cur = torch.cuda.current_stream()
+        for src, dst, idx, _, _ in jobs:
+            for t in (src, dst, idx):
+                t.record_stream(cur)
+        call("ctu_gather_batch", len(jobs), ptr_array([j[0].data_ptr() for j in jobs]), ptr_array([j[1].data_ptr() for j in jobs]),
+             ptr_array([j[2].data_ptr() for j in jobs]), ll_array([j[3] for j in jobs]), int_array([int(j[4]) for j in jobs]),
+             stream_ptr())
+
+    def _kernel_weights_chain(self, native, cout, k, chans, tc, dgrad_of=None, dims=None):
+        """The packing launches themselves (native -> packed fp32 -> bf16 image): the definition the index maps are taken from."""
         lib = _lib.load()
         ca, ns, st = int_array(chans), len(chans), stream_ptr()
         if dgrad_of is None:
@@ -347,7 +435,7 @@ class Engine:
                 out.append(eng._kernel_weights(wn, cout, k, chans, tc_d[i], (i, chans[i]), dims=dims) if nd else None)
             return tuple(out) + (wn,) + extra
 
-        res = self._prepared(tag, prep)
+        res = self._prepared(tag, prep, heavy=compose is not None)
         ns = len(srcs)
         return res[0], tc_f, list(res[1:1 + ns]), tc_d, res[1 + ns], res[2 + ns:]
 

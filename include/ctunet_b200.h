@@ -135,6 +135,12 @@ int ctu_convt_pack_weight_dgrad(const float* w, float* wpd, int cout, int nsrc, 
                                 ctu_stream stream);
 int ctu_convt_unpack_wgrad(const float* dwp, float* dw, int cout, int nsrc, const int* h_src_channels,
                            ctu_stream stream);
+/* All weight re-packings of a pass in one launch: job j writes dst[i] = idx[i] >= 0 ? src[idx[i]] : 0 for i < counts[j]
+ * (dst float32, or bf16 where dst_bf16[j]); counts are multiples of 8; the arrays are HOST arrays of device pointers.  The
+ * index maps are the permutations the ctu_conv_*pack_weight* entry points above apply (computed once per layer shape by
+ * running them on index-valued inputs), so the result is bit-identical to the chain of packing launches it replaces. */
+int ctu_gather_batch(int njobs, const float* const* h_srcs, void* const* h_dsts, const int* const* h_idxs,
+                     const long long* h_counts, const int* h_dst_bf16, ctu_stream stream);
 int ctu_convt2_fprop(int dtype, const void* const* h_srcs, const int* h_src_channels, int nsrc, const float* wp,
                      const float* bias, void* y, int cout, int n, int d, int h, int w, ctu_stream stream);
 int ctu_convt2_dgrad(int dtype, const void* dy, const float* wpd, void* dx, int cout, int src_channels, int n, int d,

@@ -494,3 +494,37 @@ def test_fused_sliding_window_equals_unfused(name, mode):
     out = out if isinstance(out, tuple) else (out,)
     for lab, o in zip(labs, out):
         assert torch.equal(lab, C.hard_segm_from_tensor(o))
+
+
+def test_weight_gather_equals_packing_chain():
+    """Weight images produced by the batched index gather (engine._kernel_weights -> ctu_gather_batch) are bit-identical to the
+    chain of packing launches whose permutation they replay -- forward and data-gradient variants of the CUDA-core layout
+    (tc 0), the resident-weights tcgen05 image (tc 1) and the weight-streaming image (tc 2), single and concatenated sources."""
+    from ctunet_b200.engine import Engine, tc_variant
+    eng = Engine(torch.device(DEV), "bf16", record=False)
+    cases = [
+        (7, 3, [2], (2, 32, 32, 32)),
+        (14, 3, [7, 7], (1, 32, 32, 32)),
+        (64, 3, [14, 14, 1], (1, 16, 16, 16)),        # composed up-stage weights: 8 phases x 8 output channels
+        (56, 3, [56], (4, 16, 16, 16)),               # weight-streaming kernel
+        (8, 5, [1], (1, 32, 32, 32)),
+        (64, 5, [64], (2, 8, 8, 8)),
+        (5, 3, [3], (1, 12, 20, 20)),                 # not covered by the tensor paths: packed fp32
+    ]
+    torch.manual_seed(5)
+    seen = set()
+    for cout, k, chans, dims in cases:
+        native = torch.randn(cout, sum(chans), k, k, k, device=DEV)
+        variants = [(None, tc_variant(k, chans, cout, *dims))]
+        variants += [((i, c), tc_variant(k, [cout], c, *dims)) for i, c in enumerate(chans)]
+        outs = []
+        for dgrad_of, tc in variants:
+            seen.add(tc)
+            want = eng._kernel_weights_chain(native, cout, k, chans, tc, dgrad_of, dims)
+            got = eng._kernel_weights(native, cout, k, chans, tc, dgrad_of, dims)
+            outs.append((want, got))
+        eng._flush_gathers()                           # ONE launch for all variants of the layer
+        for want, got in outs:
+            assert want.dtype == got.dtype and want.shape == got.shape
+            assert torch.equal(want, got)
+    assert seen == {0, 1, 2}
