@@ -65,6 +65,10 @@ _WEIGHT_MAPS: Dict[tuple, tuple] = {}     # layer signature -> (idx int32, count
 STREAM_PRIORITIES = os.environ.get("CTU_PRIO", "1") == "1"
 # The weight gradient of a layer waits for that layer's data gradients (it then runs beside the BatchNorm kernels of the layer
 # below) instead of racing them for the SMs.  (A/B: CTU_WGRAD_AFTER=0/1)
+# The ConvTranspose3d weight gradient (a CUDA-core kernel) stays IN the chain: beside it run the tcgen05 weight gradients of
+# the stream next door, which it does not compete with for TMEM; moved onto that stream it queues behind them and the chain
+# is left with data-gradient convolutions that do (measured: 4.30 -> 4.42 ms/step).  (A/B: CTU_CONVT_WGRAD_ASYNC=1)
+CONVT_WGRAD_ASYNC = os.environ.get("CTU_CONVT_WGRAD_ASYNC", "0") == "1"
 WGRAD_AFTER_DGRAD = os.environ.get("CTU_WGRAD_AFTER", "0") == "1"
 _SIDE_HIGH = (0,)          # which: 0 weight preparation, 1 weight gradients, 2 dead branch, 3 network-input gradient
 
@@ -653,33 +657,65 @@ class Engine:
         self._consume(srcs)
         pa, ca, ns = self._src_args(srcs)
         lib = _lib.load()
-        wp = self.f32(lib.ctu_convt_wpack_floats(cout, ns, ca))
-        call("ctu_convt_pack_weight", weight.data_ptr(), wp.data_ptr(), cout, ns, ca, stream_ptr())
+        chans = [s.c for s in srcs]
+        need = list(need_src_grad)
+        want_bwd = self.record
+
+        def prep(eng):
+            # forward weights and (training) the data-gradient weights of every source: parameters only, so they are
+            # prepared on the weight-preparation stream with everything else, off the layer chain
+            ca_ = int_array(chans)
+            wp_ = eng.f32(lib.ctu_convt_wpack_floats(cout, len(chans), ca_))
+            call("ctu_convt_pack_weight", weight.data_ptr(), wp_.data_ptr(), cout, len(chans), ca_, stream_ptr())
+            out = [wp_]
+            for i, c in enumerate(chans):
+                if want_bwd and need[i]:
+                    wpd_ = eng.f32(lib.ctu_convt_wpack_dgrad_floats(cout, c))
+                    call("ctu_convt_pack_weight_dgrad", weight.data_ptr(), wpd_.data_ptr(), cout, len(chans), ca_, i, stream_ptr())
+                    out.append(wpd_)
+                else:
+                    out.append(None)
+            return tuple(out)
+
+        res = self._prepared("convt", prep)
+        wp, wpds = res[0], list(res[1:])
         y = self.new_act(cout, s0.n, 2 * s0.d, 2 * s0.h, 2 * s0.w)
         call("ctu_convt2_fprop", self.dtype, pa, ca, ns, wp.data_ptr(), bias.data_ptr() if bias is not None else None,
              y.ptr, cout, s0.n, s0.d, s0.h, s0.w, stream_ptr())
         if self.record:
             srcs = list(srcs)
-            need = list(need_src_grad)
 
             def bwd():
                 dy = self.agrads.pop(id(y))
                 pa, ca, ns = self._src_args(srcs)
                 if weight.requires_grad:
-                    dwp = torch.empty_like(wp)
-                    db = self._grad_buffer(bias) if (bias is not None and bias.requires_grad) else None
-                    call("ctu_convt2_wgrad", self.dtype, pa, ca, ns, dy.ptr, dwp.data_ptr(),
-                         db.data_ptr() if db is not None else None, cout, s0.n, s0.d, s0.h, s0.w, stream_ptr())
-                    dw = self._grad_buffer(weight)
-                    call("ctu_convt_unpack_wgrad", dwp.data_ptr(), dw.data_ptr(), cout, ns, ca, stream_ptr())
-                    self._add_pgrad(weight, dw)
-                    if db is not None:
-                        self._add_pgrad(bias, db)
+                    def wgrad():
+                        dwp = torch.empty_like(wp)
+                        db = self._grad_buffer(bias) if (bias is not None and bias.requires_grad) else None
+                        call("ctu_convt2_wgrad", self.dtype, pa, ca, ns, dy.ptr, dwp.data_ptr(),
+                             db.data_ptr() if db is not None else None, cout, s0.n, s0.d, s0.h, s0.w, stream_ptr())
+                        dw = self._grad_buffer(weight)
+                        call("ctu_convt_unpack_wgrad", dwp.data_ptr(), dw.data_ptr(), cout, ns, ca, stream_ptr())
+                        self._add_pgrad(weight, dw)
+                        if db is not None:
+                            self._add_pgrad(bias, db)
+
+                    if WGRAD_ASYNC and CONVT_WGRAD_ASYNC:
+                        main = torch.cuda.current_stream()
+                        side = _side_stream(self.device, 1)
+                        side.wait_stream(main)
+                        with torch.cuda.stream(side):
+                            wgrad()
+                        dy.buf.record_stream(side)
+                        for s in srcs:
+                            s.buf.record_stream(side)
+                        self._wgrad_stream = side
+                    else:
+                        wgrad()
                 for i, s in enumerate(srcs):
                     if not need[i]:
                         continue
-                    wpd = self.f32(lib.ctu_convt_wpack_dgrad_floats(cout, s.c))
-                    call("ctu_convt_pack_weight_dgrad", weight.data_ptr(), wpd.data_ptr(), cout, ns, ca, i, stream_ptr())
+                    wpd = wpds[i]
                     dx = self.new_act(s.c, s.n, s.d, s.h, s.w)
                     call("ctu_convt2_dgrad", self.dtype, dy.ptr, wpd.data_ptr(), dx.ptr, cout, s.c,
                          s.n, s.d, s.h, s.w, stream_ptr())
