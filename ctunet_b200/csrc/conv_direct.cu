@@ -410,7 +410,9 @@ int ctu_conv3d_wgrad(int dtype, const void* const* h_srcs, const int* h_src_chan
     CTU_REQUIRE(h_srcs && dy && dwp && cout > 0 && n > 0 && d > 0 && h > 0 && w > 0, "ctu_conv3d_wgrad: bad arguments");
     CTU_REQUIRE(k == 1 || k == 3 || k == 5, "ctu_conv3d_wgrad: kernel size %d unsupported", k);
     const long long nfl = (long long)((cout + 7) / 8) * m.cb_total * k * k * k * 64;
-    cudaError_t e = cudaMemsetAsync(dwp, 0, nfl * sizeof(float), (cudaStream_t)stream);
+    const bool prezeroed = (use_tensor_path & CTU_ACCUM_PREZEROED) != 0;      // dwp (not dbias) was zeroed by the caller
+    use_tensor_path &= ~CTU_ACCUM_PREZEROED;
+    cudaError_t e = prezeroed ? cudaSuccess : cudaMemsetAsync(dwp, 0, nfl * sizeof(float), (cudaStream_t)stream);
     if (e == cudaSuccess && dbias) e = cudaMemsetAsync(dbias, 0, cout * sizeof(float), (cudaStream_t)stream);
     if (e != cudaSuccess) {
         set_error("ctu_conv3d_wgrad: memset: %s", cudaGetErrorString(e));

@@ -68,6 +68,12 @@ STREAM_PRIORITIES = os.environ.get("CTU_PRIO", "1") == "1"
 # The ConvTranspose3d weight gradient (a CUDA-core kernel) stays IN the chain: beside it run the tcgen05 weight gradients of
 # the stream next door, which it does not compete with for TMEM; moved onto that stream it queues behind them and the chain
 # is left with data-gradient convolutions that do (measured: 4.30 -> 4.42 ms/step).  (A/B: CTU_CONVT_WGRAD_ASYNC=1)
+# Leaf tails (gradient un-packing, weight-composition chain rule, BatchNorm buffer updates, head parameter gradients) on a
+# third stream, and the weight-gradient accumulators pre-zeroed in arena chunks: the weight-gradient stream, which is the
+# long pole of the backward pass, carries tcgen05 kernels only.  (A/B: CTU_LEAF_TAIL=0, CTU_WGRAD_ARENA=0)
+LEAF_TAIL_ASYNC = os.environ.get("CTU_LEAF_TAIL", "1") == "1"
+WGRAD_ARENA = os.environ.get("CTU_WGRAD_ARENA", "0") == "1"     # (measured: 4.274 with, 4.258 ms without -- the chunk memsets cost more than they save)
+WACC_CHUNK_FLOATS = 4 * 1024 * 1024
 CONVT_WGRAD_ASYNC = os.environ.get("CTU_CONVT_WGRAD_ASYNC", "0") == "1"
 WGRAD_AFTER_DGRAD = os.environ.get("CTU_WGRAD_AFTER", "0") == "1"
 _SIDE_HIGH = (0,)          # which: 0 weight preparation, 1 weight gradients, 2 dead branch, 3 network-input gradient
@@ -142,6 +148,8 @@ class Engine:
         self._arena = None
         self._arena_used = 0
         self._gjobs = []                           # pending weight-image gathers (see _kernel_weights)
+        self._wacc = {}                            # stream -> [zeroed fp32 arena chunk, floats used] (see wacc)
+        self._leaf_tail_stream = None
         self._dead_stream = None
         # set by trainer.TrainStep: (targets, softmax_for_dice, ce_lambda, dice_lambda, comps, mirror) -- the head then
         # runs fused with the loss (csrc/head.cu: head_loss_*), produces no output tensors and wires its own backward
@@ -265,6 +273,43 @@ class Engine:
         self._arena_used += n16
         t._ctu_prezeroed = True
         return t
+
+    def wacc(self, n: int) -> torch.Tensor:
+        """A ZEROED float32 buffer of ``n`` entries for a weight-gradient kernel (it accumulates with atomics): slices of
+        arena chunks zeroed once on the stream that uses them, instead of one memset node in front of every kernel."""
+        if not WGRAD_ARENA:
+            return self.f32(n)
+        n64 = (n + 63) // 64 * 64
+        if n64 > WACC_CHUNK_FLOATS:
+            t = torch.zeros(n, dtype=torch.float32, device=self.device)
+            t._ctu_prezeroed = True
+            return t
+        key = torch.cuda.current_stream().cuda_stream
+        ent = self._wacc.get(key)
+        if ent is None or ent[1] + n64 > WACC_CHUNK_FLOATS:
+            ent = [torch.zeros(WACC_CHUNK_FLOATS, dtype=torch.float32, device=self.device), 0]
+            self._wacc[key] = ent
+        t = ent[0][ent[1]:ent[1] + n]
+        ent[1] += n64
+        t._ctu_prezeroed = True
+        return t
+
+    def _leaf_tail(self, after_stream, fn, *tensors):
+        """Run ``fn`` (small kernels that finish a LEAF of the backward pass: gradient un-packing, the chain rule of a
+        weight composition, parameter-gradient registration, BatchNorm buffer updates) on the leaf-tail stream once
+        ``after_stream`` has reached this point -- the weight-gradient stream carries tcgen05 kernels only."""
+        if not LEAF_TAIL_ASYNC:
+            with torch.cuda.stream(after_stream):
+                fn()
+            return
+        tail = _side_stream(self.device, 4)
+        tail.wait_stream(after_stream)
+        with torch.cuda.stream(tail):
+            fn()
+        for t in tensors:
+            if isinstance(t, torch.Tensor):
+                t.record_stream(tail)
+        self._leaf_tail_stream = tail
 
     @staticmethod
     def _pz(t) -> int:
@@ -459,14 +504,15 @@ class Engine:
 
         The weight gradient is a leaf of the backward graph (only the optimizer reads it), so it is enqueued on a
         second stream (``WGRAD_ASYNC``): it overlaps the BatchNorm / head kernels of the layers below while the data
-        gradient stays on the critical path.  ``after_wgrad()`` runs behind it on the same stream."""
+        gradient stays on the critical path.  The un-packing into the native layout and ``after_wgrad()`` (small, non-tensor
+        kernels) run behind it on a THIRD stream (``_leaf_tail``), so the next tcgen05 weight gradient is not queued behind them."""
         lib = _lib.load()
         s0 = srcs[0]
         dy = self.agrads.pop(id(y))
         pa, ca, ns = self._src_args(srcs)
         if dw_out is not None:
-            def wgrad():
-                dwp = self.f32(lib.ctu_conv_wpack_floats(cout, k, ns, ca))
+            def wgrad_kernel():
+                dwp = self.wacc(lib.ctu_conv_wpack_floats(cout, k, ns, ca))
                 tc = 0
                 small = (self.use_tc and ns == 1 and not phase_cout
                          and lib.ctu_conv_wide_wgrad_supported(k, srcs[0].c, cout, s0.d, s0.h, s0.w))
@@ -478,7 +524,10 @@ class Engine:
                     tc = 2
                 call("ctu_conv3d_wgrad", self.dtype, pa, ca, ns, dy.ptr, dwp.data_ptr(),
                      db_out.data_ptr() if db_out is not None else None, phase_cout, cout, k, s0.n, s0.d, s0.h, s0.w,
-                     int(tc), stream_ptr())
+                     int(tc) | self._pz(dwp), stream_ptr())
+                return dwp
+
+            def wgrad_tail(dwp):
                 call("ctu_conv_unpack_wgrad", dwp.data_ptr(), dw_out.data_ptr(), cout, k, ns, ca, stream_ptr())
                 if after_wgrad is not None:
                     after_wgrad()
@@ -491,11 +540,12 @@ class Engine:
                 side = _side_stream(self.device, 1)
                 side.wait_stream(main)                      # dy (and everything enqueued before this point) is ready
                 with torch.cuda.stream(side):
-                    wgrad()
+                    dwp = wgrad_kernel()
                 dy.buf.record_stream(side)
                 self._wgrad_stream = side
+                self._leaf_tail(side, lambda: wgrad_tail(dwp), dwp)
             else:
-                wgrad()
+                wgrad_tail(wgrad_kernel())
 
         if not WGRAD_AFTER_DGRAD:
             launch_wgrad()
@@ -796,7 +846,9 @@ class Engine:
                              bn.running_var.data_ptr(), bn.num_batches_tracked.data_ptr(), mom, c, extra_updates,
                              stream_ptr())
 
-                    if WGRAD_ASYNC:
+                    if WGRAD_ASYNC and LEAF_TAIL_ASYNC:
+                        self._leaf_tail(torch.cuda.current_stream(), update, sums)
+                    elif WGRAD_ASYNC:
                         side = _side_stream(self.device, 1)
                         side.wait_stream(torch.cuda.current_stream())
                         with torch.cuda.stream(side):
@@ -935,7 +987,9 @@ class Engine:
                          s0.n, s0.spatial, stream_ptr())
                     self._pgrad_done(((weight, dw), (bias, db)))
 
-                if WGRAD_ASYNC:
+                if WGRAD_ASYNC and LEAF_TAIL_ASYNC:
+                    self._leaf_tail(torch.cuda.current_stream(), params, dlc)       # a CUDA-core kernel: not on the tcgen05 stream
+                elif WGRAD_ASYNC:
                     main = torch.cuda.current_stream()
                     side = _side_stream(self.device, 1)
                     side.wait_stream(main)
@@ -961,6 +1015,9 @@ class Engine:
         if self._input_grad_stream is not None:
             torch.cuda.current_stream().wait_stream(self._input_grad_stream)
             self._input_grad_stream = None
+        if self._leaf_tail_stream is not None:
+            torch.cuda.current_stream().wait_stream(self._leaf_tail_stream)
+            self._leaf_tail_stream = None
 
     def backward(self, g0=None, g1=None):
         # (drop the closure first: it references the engine AND the forward outputs, i.e. the autograd graph -- a cycle

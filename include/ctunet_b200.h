@@ -39,7 +39,8 @@ extern "C" {
 #define CTU_ERR_INVALID (-1)
 #define CTU_ERR_UNSUPPORTED (-2)
 #define CTU_MAX_SRC 4
-/* OR into `use_tensor_path` of ctu_conv3d_fprop, `phases` of ctu_bn_stats or `y_phase_major` of ctu_bn_relu_bwd_reduce:
+/* OR into `use_tensor_path` of ctu_conv3d_fprop / ctu_conv3d_wgrad (there: dwp), `phases` of ctu_bn_stats or `y_phase_major` of
+ * ctu_bn_relu_bwd_reduce:
  * the caller has already zeroed the double accumulators (bn_sums / sums / sums2), so the entry point enqueues no memset of
  * its own.  A step driver zeroes ONE arena for all of a pass's accumulators instead of ~30 memset nodes on the layer chain. */
 #define CTU_ACCUM_PREZEROED 0x100
