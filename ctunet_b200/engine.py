@@ -63,8 +63,11 @@ ACC_ARENA_DOUBLES = 32768   # 256 KB: every BatchNorm accumulator of a pass (for
 WEIGHT_GATHER = os.environ.get("CTU_WEIGHT_GATHER", "1") == "1"
 _WEIGHT_MAPS: Dict[tuple, tuple] = {}     # layer signature -> (idx int32, count, bf16?)
 STREAM_PRIORITIES = os.environ.get("CTU_PRIO", "1") == "1"
-# The weight gradient of a layer waits for that layer's data gradients (it then runs beside the BatchNorm kernels of the layer
-# below) instead of racing them for the SMs.  (A/B: CTU_WGRAD_AFTER=0/1)
+# When does the weight gradient of a stage join the race for the SMs?  A tcgen05 weight gradient and a tcgen05 data gradient
+# cannot share an SM (TMEM), so whichever starts first makes the other wait.  Stages with ONE data gradient: weight gradient
+# enqueued beside it (0).  Stages with two (the concatenated skip + up-sampled sources): behind them (2) -- otherwise it slips
+# in between the two data gradients and the chain waits 150 us for it (CUPTI timeline; 4.254 -> 4.223 ms).  Always behind
+# (1) is worse (4.32).  (A/B: CTU_WGRAD_AFTER=0/1/2)
 # The ConvTranspose3d weight gradient (a CUDA-core kernel) stays IN the chain: beside it run the tcgen05 weight gradients of
 # the stream next door, which it does not compete with for TMEM; moved onto that stream it queues behind them and the chain
 # is left with data-gradient convolutions that do (measured: 4.30 -> 4.42 ms/step).  (A/B: CTU_CONVT_WGRAD_ASYNC=1)
@@ -72,10 +75,11 @@ STREAM_PRIORITIES = os.environ.get("CTU_PRIO", "1") == "1"
 # third stream, and the weight-gradient accumulators pre-zeroed in arena chunks: the weight-gradient stream, which is the
 # long pole of the backward pass, carries tcgen05 kernels only.  (A/B: CTU_LEAF_TAIL=0, CTU_WGRAD_ARENA=0)
 LEAF_TAIL_ASYNC = os.environ.get("CTU_LEAF_TAIL", "1") == "1"
+HEAD_PGRAD_LATE = os.environ.get("CTU_HEAD_PGRAD_LATE", "0") == "1"    # (measured neutral to slightly negative: 4.25 vs 4.25-4.29 ms)
 WGRAD_ARENA = os.environ.get("CTU_WGRAD_ARENA", "0") == "1"     # (measured: 4.274 with, 4.258 ms without -- the chunk memsets cost more than they save)
 WACC_CHUNK_FLOATS = 4 * 1024 * 1024
 CONVT_WGRAD_ASYNC = os.environ.get("CTU_CONVT_WGRAD_ASYNC", "0") == "1"
-WGRAD_AFTER_DGRAD = os.environ.get("CTU_WGRAD_AFTER", "0") == "1"
+WGRAD_AFTER_DGRAD = int(os.environ.get("CTU_WGRAD_AFTER", "2"))      # 0 never, 1 always, 2 only for stages with >= 2 data gradients
 _SIDE_HIGH = (0,)          # which: 0 weight preparation, 1 weight gradients, 2 dead branch, 3 network-input gradient
 
 
@@ -150,6 +154,7 @@ class Engine:
         self._gjobs = []                           # pending weight-image gathers (see _kernel_weights)
         self._wacc = {}                            # stream -> [zeroed fp32 arena chunk, floats used] (see wacc)
         self._leaf_tail_stream = None
+        self._late_leaves = []
         self._dead_stream = None
         # set by trainer.TrainStep: (targets, softmax_for_dice, ce_lambda, dice_lambda, comps, mirror) -- the head then
         # runs fused with the loss (csrc/head.cu: head_loss_*), produces no output tensors and wires its own backward
@@ -547,7 +552,8 @@ class Engine:
             else:
                 wgrad_tail(wgrad_kernel())
 
-        if not WGRAD_AFTER_DGRAD:
+        after = WGRAD_AFTER_DGRAD == 1 or (WGRAD_AFTER_DGRAD == 2 and sum(1 for nd in need if nd) >= 2)
+        if not after:
             launch_wgrad()
 
         def dgrads():
@@ -583,7 +589,7 @@ class Engine:
             self._input_grad_stream = side
         else:
             dgrads()
-        if WGRAD_AFTER_DGRAD:
+        if after:
             launch_wgrad()
 
     def _pgrad_done(self, pairs):
@@ -987,7 +993,11 @@ class Engine:
                          s0.n, s0.spatial, stream_ptr())
                     self._pgrad_done(((weight, dw), (bias, db)))
 
-                if WGRAD_ASYNC and LEAF_TAIL_ASYNC:
+                if WGRAD_ASYNC and LEAF_TAIL_ASYNC and HEAD_PGRAD_LATE:
+                    # enqueued when the whole chain has been: it then runs beside the LAST weight gradients (tcgen05 kernels with
+                    # a small register footprint) instead of taking the SMs from the BatchNorm kernels at the head of the chain
+                    self._late_leaves.append((params, dlc))
+                elif WGRAD_ASYNC and LEAF_TAIL_ASYNC:
                     self._leaf_tail(torch.cuda.current_stream(), params, dlc)       # a CUDA-core kernel: not on the tcgen05 stream
                 elif WGRAD_ASYNC:
                     main = torch.cuda.current_stream()
@@ -1009,6 +1019,9 @@ class Engine:
         for fn in reversed(self.tape):
             fn()
         self.tape = []
+        for fn, keep in self._late_leaves:
+            self._leaf_tail(torch.cuda.current_stream(), fn, keep)
+        self._late_leaves = []
         if self._wgrad_stream is not None:                   # weight gradients -> visible to the optimizer's stream
             torch.cuda.current_stream().wait_stream(self._wgrad_stream)
             self._wgrad_stream = None
