@@ -165,8 +165,12 @@ def test_fused_up_stage_bf16_tensor_path(case):
         rel = ((gg[name] - rg[name]).norm() / rg[name].norm()).item()
         # the transposed convolution's bias gradient is a sum of BatchNorm-centred (zero-mean) gradients over every
         # voxel: a small signal under bf16 storage of dy, checked at fp32 accuracy in the check-mode test above
+        # bn.b = sum(dz) is likewise a cancelling sum whose ReLU mask flips where the bf16-rounded pre-activation crosses
+        # zero: observed 2.0e-2 .. 4.3e-2 over the six cases (and 5.7e-2 under a different fp32 accumulation order of the
+        # convolution), against 3e-2 .. 4e-2 for the weight gradients -- 7e-2 keeps the check meaningful without being flaky
         print("%s: |ref| %.3e  normwise err %.3e" % (name, rg[name].norm().item(), rel))
-        assert rel <= (1.5e-1 if name == "ct.b" else 5e-2), "%s normwise err %.3e" % (name, rel)
+        tol = 1.5e-1 if name == "ct.b" else (7e-2 if name == "bn.b" else 5e-2)
+        assert rel <= tol, "%s normwise err %.3e" % (name, rel)
 
 
 @pytest.mark.parametrize("phase_major", [False, True])
