@@ -191,8 +191,10 @@ struct TcWalk {
 // sum(dz) and sum(dz * xhat) with dz = dA * [scale * y + shift > 0], reading y (16 B per voxel and block) while the
 // gradient tile is still in registers -- the separate reduce pass over y and dA (ctu_bn_relu_bwd_reduce) disappears.
 template <int K, int COB, bool BNRED = false>
-__global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel(const __grid_constant__ TcMaps maps,
-                                                                                 TcParams p) {
+// (one-block variants: at most 88 registers, so that TWO CTAs -- four MMA issuers -- share an SM; for K = 5 that costs 64 bytes
+//  of spills in the epilogue and buys 8 -> 8 at 4x128^3 200 -> 174 us with the balanced shares, recAE_v2_fixed 8.66 -> 8.2 ms)
+__global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB), (COB == 1 && !BNRED) ? 2 : 1)
+    conv3d_tc_kernel(const __grid_constant__ TcMaps maps, TcParams p) {
     constexpr int PAD = K / 2;
     constexpr int HH = TC_TH + K - 1, WW = TC_TW + K - 1;
     constexpr uint32_t ROW = WW * 16;              // bytes per halo row of one channel block
@@ -541,8 +543,9 @@ __global__ void __launch_bounds__(32 * (1 + TC_WB + 4 * TC_WB)) conv3d_tc_kernel
 //   fprop 7->7 at 4x128^3 94.9 -> 84.7, 2->7 95.2 -> 85.6, 64->14 at 4x64^3 88.3 -> 84.5, 14->14 at 4x64^3 47.5 -> 47.6;
 //   but 4-block outputs 146 -> 169 ([14,14,1]->64 at 4x64^3), 53 -> 58 (128->28 at 4x32^3), 30 -> 33 (28->28 at 4x32^3);
 //   wgrad (first formulation) 244 -> 240, 135 -> 127, 84.4 -> 79.5, 49.3 -> 47.0; (kd,kh)-in-N formulation 116 -> 124.
-// (5^3 layers -- four halo planes per segment -- were neutral: recAE_v2_fixed 8.96 -> 9.03, UNet4_2IC 8.74 -> 8.70 ms/step.)
-// Hence: shares for 3^3 fprop / dgrad with <= 2 output blocks per CTA and >= 16 planes per CTA, and for the first wgrad
+// (5^3 layers -- four halo planes per segment: one-block kernel, two CTAs per SM, 8->8 at 4x128^3 194 -> 174 us; two-block
+//  kernel 16->16 at 4x64^3 168 -> 187 us.)
+// Hence: shares for 3^3 fprop / dgrad with <= 2 output blocks per CTA, 5^3 with one, >= 16 planes per CTA, and for the first wgrad
 // formulation; fixed chunks elsewhere.  CTU_TC_BALANCE=0 / 1 forces one mode everywhere (A/B runs).
 static int tc_balance(bool by_rule) {
     static const int forced = getenv("CTU_TC_BALANCE") ? atoi(getenv("CTU_TC_BALANCE")) : -1;
@@ -758,7 +761,7 @@ int conv3d_fprop_tc(const void* const* h_srcs, const int* h_src_channels, int ns
         p.dchunks = (d + dc - 1) / dc;
         p.total_items = tiles * p.dchunks;
         int gx = (148 * occ) / g.ngroups;
-        p.balance = tc_balance(k == 3 && g.cobg <= 2 && (long long)tiles * d >= 16LL * (gx > 0 ? gx : 1));
+        p.balance = tc_balance(((k == 3 && g.cobg <= 2) || (k == 5 && g.cobg == 1)) && (long long)tiles * d >= 16LL * (gx > 0 ? gx : 1));
         const long long units = p.balance ? (long long)tiles * d : (long long)p.total_items;
         if (gx > units) gx = (int)units;
         if (gx < 1) gx = 1;

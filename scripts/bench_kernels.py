@@ -71,6 +71,13 @@ SHAPES = [
     ("L2 up-fused [56,56,1]->256 @16^3", [56, 56, 1], 256, 4, 16, 16, 16),
 ]
 which = sys.argv[1] if len(sys.argv) > 1 else "both"
+if which == "k5":      # the legacy 5^3 family at the benchmarked sizes (recAE_v2_fixed / UNet4_2IC level 0 and 1)
+    for name, chans, cout, n, d, h, w in [("5^3 8->8 @128^3", [8], 8, 4, 128, 128, 128), ("5^3 1->8 @128^3", [1], 8, 4, 128, 128, 128),
+                                          ("5^3 16->16 @64^3", [16], 16, 4, 64, 64, 64)]:
+        t = fprop(chans, cout, n, d, h, w, 5)
+        fl = 2.0 * n * d * h * w * sum(chans) * cout * 125
+        print("%-20s fprop %8.1f us = %6.1f TFLOP/s   wgrad %8.1f us" % (name, t, fl / t / 1e6, wgrad(chans, cout, n, d, h, w, 5)), flush=True)
+    sys.exit(0)
 for name, chans, cout, n, d, h, w in SHAPES:
     line = "%-36s" % name
     if which in ("wgrad", "both"):
