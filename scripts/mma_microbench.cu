@@ -194,7 +194,7 @@ int main() {
     printf("%-4s %-4s %-3s %-3s %-3s | cycles per MMA per warp | aggregate cycles per MMA | tensor floor max(M,128)*N/256\n", "M", "N",
            "W", "A", "MN");
     const int Ms[] = {128, 64};
-    const int Ns[] = {32, 48, 96, 128, 256};
+    const int Ns[] = {32, 40, 48, 64, 80, 96, 128, 256};
     for (int mn = 0; mn < 2; ++mn)
         for (int M : Ms)
             for (int N : Ns)
