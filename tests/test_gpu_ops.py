@@ -528,3 +528,46 @@ def test_weight_gather_equals_packing_chain():
             assert want.dtype == got.dtype and want.shape == got.shape
             assert torch.equal(want, got)
     assert seen == {0, 1, 2}
+
+
+def test_accum_prezeroed_flag_matches_library_memset():
+    """CTU_ACCUM_PREZEROED (include/ctunet_b200.h): with the flag the entry points ADD into accumulators the caller zeroed
+    and enqueue no memset of their own; the sums equal those of the plain calls bit for bit where the reduction order is
+    fixed (ctu_bn_stats) and to rounding where atomics commute (fused conv statistics, backward reduction)."""
+    from ctunet_b200 import _lib
+    from ctunet_b200._lib import CTU_ACCUM_PREZEROED, call, int_array, ptr_array, stream_ptr
+    lib = _lib.load()
+    eng = _eng("bf16")
+    torch.manual_seed(11)
+    n, c, d, h, w = 2, 7, 16, 32, 32
+    cpad = 8
+    x = eng.pack(torch.randn(n, c, d, h, w, device=DEV))
+    # ctu_bn_stats
+    s_plain = torch.full((2 * cpad,), 123.0, dtype=torch.float64, device=DEV)      # garbage: the call must zero it
+    s_flag = torch.zeros(2 * cpad, dtype=torch.float64, device=DEV)
+    call("ctu_bn_stats", eng.dtype, x.ptr, c, 1, n, x.spatial, s_plain.data_ptr(), stream_ptr())
+    call("ctu_bn_stats", eng.dtype, x.ptr, c, 1 | CTU_ACCUM_PREZEROED, n, x.spatial, s_flag.data_ptr(), stream_ptr())
+    assert torch.allclose(s_plain, s_flag, rtol=1e-12, atol=1e-9)
+    # the flag really skips the memset: a second flagged call accumulates on top
+    call("ctu_bn_stats", eng.dtype, x.ptr, c, 1 | CTU_ACCUM_PREZEROED, n, x.spatial, s_flag.data_ptr(), stream_ptr())
+    assert torch.allclose(2 * s_plain, s_flag, rtol=1e-12, atol=1e-9)
+    # fused statistics of the tcgen05 convolution
+    wt = torch.randn(7, c, 3, 3, 3, device=DEV) * 0.1
+    wk = eng._kernel_weights_chain(wt, 7, 3, [c], 1)
+    y = eng.new_act(7, n, d, h, w)
+    sums = []
+    for flag, init in ((0, 55.0), (CTU_ACCUM_PREZEROED, 0.0)):
+        s = torch.full((2 * cpad,), init, dtype=torch.float64, device=DEV)
+        call("ctu_conv3d_fprop", eng.dtype, ptr_array([x.ptr]), int_array([c]), 1, wk.data_ptr(), None, y.ptr, s.data_ptr(), 0,
+             7, 3, n, d, h, w, 1 | flag, stream_ptr())
+        sums.append(s)
+    assert torch.allclose(sums[0], sums[1], rtol=1e-9, atol=1e-6)
+    # BatchNorm backward reduction
+    ss = torch.rand(4 * cpad, device=DEV)
+    dA = eng.pack(torch.randn(n, c, d, h, w, device=DEV))
+    red = []
+    for flag, init in ((0, -7.0), (CTU_ACCUM_PREZEROED, 0.0)):
+        s = torch.full((2 * cpad,), init, dtype=torch.float64, device=DEV)
+        call("ctu_bn_relu_bwd_reduce", eng.dtype, x.ptr, ss.data_ptr(), dA.ptr, None, s.data_ptr(), c, n, d, h, w, 0 | flag, stream_ptr())
+        red.append(s)
+    assert torch.allclose(red[0], red[1], rtol=1e-9, atol=1e-6)
