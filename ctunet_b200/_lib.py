@@ -145,7 +145,15 @@ def call(name: str, *args):
     launches += 1
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_raw_device = getattr(torch._C, "_cuda_getDevice", None)
+
+
 def stream_ptr() -> int:
+    """cudaStream_t of torch's current stream on the current device (what every entry point is enqueued on).  The raw
+    accessors cost ~0.3 us; ``torch.cuda.current_stream()`` builds a Stream object (~4 us, 165 times per eager step)."""
+    if _raw_stream is not None and _raw_device is not None:
+        return _raw_stream(_raw_device())
     return torch.cuda.current_stream().cuda_stream
 
 
