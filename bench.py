@@ -179,7 +179,7 @@ class _Quiet:
         self._cm.__exit__(*a)
 
 
-def reference_trainer(model, device, lr=1e-4, install=False, data_parallel="keep"):
+def reference_trainer(model, device, lr=1e-4, install=False, data_parallel="keep", graph=False):
     """The UNMODIFIED reference trainer object (oracle/ref_harness.py) configured like the benchmarked example .ini:
     Adam(amsgrad) lr 1e-4, dice_lambda = ce_lambda = 1, scheduler on, metrics off (they are reporting-only and run on the
     host through monai in the reference).  ``install``: with ctunet_b200.install() applied (the drop-in)."""
@@ -189,7 +189,7 @@ def reference_trainer(model, device, lr=1e-4, install=False, data_parallel="keep
     MM = load_reference(with_trainer=True)[4]
     if install:
         import ctunet_b200
-        ctunet_b200.install(MM, data_parallel=data_parallel)
+        ctunet_b200.install(MM, data_parallel=data_parallel, graph=graph)
     params = dict(model_class=model, problem_handler="FlapRecWithShapePriorDoubleOut" if HANDLER[model] == "double"
                   else "FlapRecWithShapePrior", optimizer="adam", learning_rate=lr, momentum=0.99, weight_decay=0.0,
                   dice_lambda=1.0, ce_lambda=1.0, save_dice_plots=False, save_hd_plots=False, scheduler=True)
@@ -742,6 +742,16 @@ def run_b200_arm(a):
                           "first_loss": first,
                           "note": "the reference's own Model.forward_pass (Model.py:324-380: host batch, torch.optim.Adam, "
                                   "ReduceLROnPlateau on the host, float() per loss component) with ctunet_b200.install() applied"}
+                del m
+                C.uninstall()
+                torch.cuda.empty_cache()
+                # the same with install(graph=True): the installed modules replay captured forward / backward graphs
+                m = reference_trainer(a.model, "cuda", install=True, data_parallel="single", graph=True)
+                torch.autograd.set_detect_anomaly(False)
+                sec, first = reference_forward_pass_time(m, sample, steps=10, warmup=4, sync=torch.cuda.synchronize)
+                dropin["dropin_graph_forward_pass_ms"] = sec * 1e3
+                dropin["note"] += ("; dropin_graph_forward_pass_ms: install(graph=True) -- forward and backward replayed from "
+                                   "CUDA graphs inside the reference's loop (its 201 MB host batch, optimizer and scheduler unchanged)")
                 del m
                 C.uninstall()
                 torch.cuda.empty_cache()

@@ -41,7 +41,7 @@ def uninstall() -> int:
     return n
 
 
-def install(trainer_module=None, replace_losses: bool = True, data_parallel: str = "keep"):
+def install(trainer_module=None, replace_losses: bool = True, data_parallel: str = "keep", graph: bool = False):
     """Rebind the reference's model (and optionally loss-handler) names to the B200 classes.
 
     ``trainer_module`` defaults to ``ctunet.pytorch.Model`` (must be importable).  The reference's handler classes are
@@ -55,12 +55,15 @@ def install(trainer_module=None, replace_losses: bool = True, data_parallel: str
     ``data_parallel``: 'keep' leaves ``Model.new_model`` alone -- with several visible GPUs the reference wraps the model
     in ``nn.DataParallel`` (Model.py:481-486), which these modules support (replicas read the broadcast weights);
     'single' patches ``new_model`` to build the bare module on the current device, for one-process-per-GPU launches
-    (torchrun + ``parallel.GradSync``).  Returns the list of rebound names."""
+    (torchrun + ``parallel.GradSync``).  ``graph``: the installed modules replay captured CUDA graphs for the forward and
+    the backward pass of a training iteration (``models._GraphNetFn``; the third iteration of a batch shape captures) -- the
+    eager launch stream is host-bound behind the reference's own step driver.  Returns the list of rebound names."""
     import importlib
     if trainer_module is None:
         trainer_module = importlib.import_module("ctunet.pytorch.Model")
     if data_parallel not in ("keep", "single"):
         raise ValueError("data_parallel: 'keep' or 'single'")
+    _rebind(models, "DROPIN_GRAPH", bool(graph))
     done = []
     for name in MODEL_CLASSES:
         _rebind(trainer_module, name, getattr(models, name))
