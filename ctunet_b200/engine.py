@@ -75,7 +75,10 @@ STREAM_PRIORITIES = os.environ.get("CTU_PRIO", "1") == "1"
 # third stream, and the weight-gradient accumulators pre-zeroed in arena chunks: the weight-gradient stream, which is the
 # long pole of the backward pass, carries tcgen05 kernels only.  (A/B: CTU_LEAF_TAIL=0, CTU_WGRAD_ARENA=0)
 LEAF_TAIL_ASYNC = os.environ.get("CTU_LEAF_TAIL", "1") == "1"
-HEAD_PGRAD_LATE = os.environ.get("CTU_HEAD_PGRAD_LATE", "0") == "1"    # (measured neutral to slightly negative: 4.25 vs 4.25-4.29 ms)
+DEFER_BIG_WGRAD = os.environ.get("CTU_DEFER_WGRAD", "1") == "1"
+DEFER_MIN_VOXELS = int(os.environ.get("CTU_DEFER_MIN_VOXELS", str(4 * 64 ** 3)))       # low-resolution voxels of the fused stage
+DEFER_WINDOW_VOXELS = int(os.environ.get("CTU_DEFER_WINDOW_VOXELS", str(4 * 128 ** 3)))  # voxels x channel blocks of the BatchNorm
+HEAD_PGRAD_LATE = int(os.environ.get("CTU_HEAD_PGRAD_LATE", "0"))   # 1: at the end of the tape; 2: beside the first data-gradient convolution    # (measured neutral to slightly negative: 4.25 vs 4.25-4.29 ms)
 WGRAD_ARENA = os.environ.get("CTU_WGRAD_ARENA", "0") == "1"     # (measured: 4.274 with, 4.258 ms without -- the chunk memsets cost more than they save)
 WACC_CHUNK_FLOATS = 4 * 1024 * 1024
 CONVT_WGRAD_ASYNC = os.environ.get("CTU_CONVT_WGRAD_ASYNC", "0") == "1"
@@ -155,6 +158,7 @@ class Engine:
         self._wacc = {}                            # stream -> [zeroed fp32 arena chunk, floats used] (see wacc)
         self._leaf_tail_stream = None
         self._late_leaves = []
+        self._deferred_wgrads = []
         self._dead_stream = None
         # set by trainer.TrainStep: (targets, softmax_for_dice, ce_lambda, dice_lambda, comps, mirror) -- the head then
         # runs fused with the loss (csrc/head.cu: head_loss_*), produces no output tensors and wires its own backward
@@ -537,18 +541,26 @@ class Engine:
                 if after_wgrad is not None:
                     after_wgrad()
 
+        def enqueue_wgrad():
+            main = torch.cuda.current_stream()
+            side = _side_stream(self.device, 1)
+            side.wait_stream(main)                      # dy (and everything enqueued before this point) is ready
+            with torch.cuda.stream(side):
+                dwp = wgrad_kernel()
+            dy.buf.record_stream(side)
+            self._wgrad_stream = side
+            self._leaf_tail(side, lambda: wgrad_tail(dwp), dwp)
+
         def launch_wgrad():
             if dw_out is None:
                 return
             if WGRAD_ASYNC:
-                main = torch.cuda.current_stream()
-                side = _side_stream(self.device, 1)
-                side.wait_stream(main)                      # dy (and everything enqueued before this point) is ready
-                with torch.cuda.stream(side):
-                    dwp = wgrad_kernel()
-                dy.buf.record_stream(side)
-                self._wgrad_stream = side
-                self._leaf_tail(side, lambda: wgrad_tail(dwp), dwp)
+                # The long weight gradients of the fused up stages at the top levels are held back until the chain reaches
+                # a long BatchNorm-backward window (see _release_deferred_wgrad): tensor work under non-tensor work.
+                if DEFER_BIG_WGRAD and phase_cout and s0.n * s0.d * s0.h * s0.w >= DEFER_MIN_VOXELS:
+                    self._deferred_wgrads.append(enqueue_wgrad)
+                else:
+                    enqueue_wgrad()
             else:
                 wgrad_tail(wgrad_kernel())
 
@@ -557,6 +569,10 @@ class Engine:
             launch_wgrad()
 
         def dgrads():
+            if HEAD_PGRAD_LATE == 2 and self._late_leaves and any(need):
+                for fn, keep in self._late_leaves:          # (CUDA-core leaves beside a tensor kernel, not beside BatchNorm)
+                    self._leaf_tail(torch.cuda.current_stream(), fn, keep)
+                self._late_leaves = []
             for i, s in enumerate(srcs):
                 if not need[i]:
                     continue
@@ -842,6 +858,8 @@ class Engine:
                 dP = self.agrads.pop(id(pooled), None) if pool else None
                 if dA is None and dP is None:
                     raise RuntimeError("internal: BatchNorm stage received no gradient")
+                if self._deferred_wgrads and count * ((c + 7) // 8) >= DEFER_WINDOW_VOXELS:
+                    self._deferred_wgrads.pop(0)()          # a long HBM-bound window starts: run a held-back weight gradient under it
                 st = stream_ptr()
                 if extra_updates > 0 and bn.track_running_stats and bn.running_mean is not None:
                     # buffers only (nothing in this step reads them): beside the weight gradients, off the critical path
@@ -1022,6 +1040,8 @@ class Engine:
         for fn, keep in self._late_leaves:
             self._leaf_tail(torch.cuda.current_stream(), fn, keep)
         self._late_leaves = []
+        while self._deferred_wgrads:
+            self._deferred_wgrads.pop(0)()
         if self._wgrad_stream is not None:                   # weight gradients -> visible to the optimizer's stream
             torch.cuda.current_stream().wait_stream(self._wgrad_stream)
             self._wgrad_stream = None
